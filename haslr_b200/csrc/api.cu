@@ -1,0 +1,56 @@
+// Context management of the C ABI (include/haslr_b200.h).
+#include "common.cuh"
+
+extern "C" int hgpu_abi_version(void) { return 1; }
+
+extern "C" const char* hgpu_strerror(int code) {
+    switch (code) {
+        case HGPU_OK: return "ok";
+        case HGPU_E_INVALID: return "invalid argument";
+        case HGPU_E_CUDA: return "CUDA runtime error";
+        case HGPU_E_NOMEM: return "out of memory";
+        case HGPU_E_NOSPACE: return "output capacity too small";
+        case HGPU_E_UNSUPPORTED: return "unsupported request";
+        case HGPU_E_INTERNAL: return "internal inconsistency";
+        default: return "unknown error";
+    }
+}
+
+extern "C" int hgpu_create(int device, hgpu_t** out) {
+    if (!out) return HGPU_E_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return HGPU_E_CUDA;   // no silent CPU path: the product needs a GPU
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) return HGPU_E_CUDA; }
+    if (device >= n) return HGPU_E_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return HGPU_E_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return HGPU_E_CUDA;
+    if (prop.major < 10) return HGPU_E_UNSUPPORTED;       // built for sm_100a only
+    hgpu_ctx* c = new hgpu_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    *out = c;
+    return HGPU_OK;
+}
+
+extern "C" void hgpu_destroy(hgpu_t* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    poa_state_destroy(ctx->poa);
+    k12_state_destroy(ctx->k12);
+    delete ctx;
+}
+
+extern "C" int hgpu_set_stream(hgpu_t* ctx, void* cuda_stream) {
+    if (!ctx) return HGPU_E_INVALID;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return HGPU_OK;
+}
+
+extern "C" const char* hgpu_last_error(const hgpu_t* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+extern "C" uint64_t hgpu_launch_count(const hgpu_t* ctx) { return ctx ? ctx->launches : 0; }

@@ -1,0 +1,494 @@
+// Host side of the batched POA path: edge scheduler, memory plan, C ABI (hgpu_poa_*).
+//
+// Replaces the pthread edge queue of the reference (src/haslr_assemble/src/Assemble.cpp:365-434,562-605):
+// instead of T threads pulling one edge each from a mutex-guarded cursor and calling SPOA, all edges of a call
+// are queued on the device and pulled by the warps of one persistent kernel (poa_device.cuh).
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <numeric>
+#include <vector>
+
+#include "common.cuh"
+#include "poa_device.cuh"
+
+using namespace hgpu;
+
+struct PoaPass {                 // one scheduling pass keeps its consensus pool alive until the results are gathered
+    DevBuf<uint8_t> pool;
+};
+
+struct PoaState {
+    DevBuf<uint8_t> arena, ws, d_bases, d_out;
+    DevBuf<uint64_t> seg_ptr, cons_pos, d_off;
+    DevBuf<uint32_t> seg_len, e_seg_off, items, status, cons_len, out_nodes, counters;
+    DevBuf<unsigned long long> stats, pool_cursor;
+    std::vector<std::unique_ptr<PoaPass>> passes;
+    hgpu_poa_stats st{};
+    bool timing = false;
+    uint64_t cfg_arena_bytes = 0;
+    uint32_t cfg_max_warps = 0;
+    uint32_t last_n_edges = 0;
+    uint64_t last_total = 0;
+    WsLayout last_wl{};          // layout / slot size of the most recent launch (debug inspection)
+    uint64_t last_slot = 0;
+    bool have_result = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+void poa_state_destroy(PoaState* s) {
+    if (!s) return;
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    delete s;
+}
+
+static PoaState* poa_state(hgpu_t* ctx) {
+    if (!ctx->poa) ctx->poa = new PoaState();
+    return ctx->poa;
+}
+
+static int make_scores(hgpu_t* ctx, int8_t match, int8_t mismatch, int8_t gap, DpScores* sc) {
+    sc->sm = (int)match - (int)gap;
+    sc->sx = (int)mismatch - (int)gap;
+    sc->g = gap;
+    int lo = std::min(std::min(sc->sm, sc->sx), sc->g);
+    sc->lo_step = lo < 0 ? -lo : 0;
+    int hi = std::max(sc->sm, sc->sx);
+    sc->hi_step = hi > 0 ? hi : 0;
+    // the packed int16 fill assumes a non-positive gap and small scores; anything else runs in int32
+    if (gap > 0 || std::abs(sc->sm) > 127 || std::abs(sc->sx) > 127) sc->hi_step = 1 << 20;
+    (void)ctx;
+    return HGPU_OK;
+}
+
+namespace {
+struct EdgeEst {
+    uint32_t edge;
+    uint32_t ncap;       // node capacity needed (estimate)
+    uint64_t slot;       // score-matrix bytes needed (estimate)
+};
+
+// Node-count growth model: every later segment adds about `growth` new nodes per base (SURVEY.md §8(d):
+// |V| grows ~ L * (ins + sub) per read). growth >= 1 means the worst case (every base a new node).
+void estimate_edge(const uint32_t* len, uint32_t R, double growth, const DpScores& sc, EdgeEst* out) {
+    double V = len[0];
+    uint64_t slot = 0;
+    uint32_t lmax = len[0];
+    for (uint32_t k = 1; k < R; ++k) {
+        uint32_t Vi = (uint32_t)std::min<double>(V + 1.0, 4.0e9);
+        bool p16 = dp_fits16(Vi, len[k], sc);
+        slot = std::max(slot, dp_slot_bytes(Vi, len[k], p16));
+        // overhang beyond the graph's current span also becomes new nodes
+        double over = len[k] > V ? (double)len[k] - V : 0.0;
+        V += growth >= 1.0 ? (double)len[k] : std::min<double>(len[k], growth * len[k] + over + 8.0);
+        lmax = std::max(lmax, len[k]);
+    }
+    double ncap = V + lmax + 64.0;
+    out->ncap = (uint32_t)std::min<double>(ncap, 4.0e9);
+    out->slot = slot + 4096;
+}
+}  // namespace
+
+struct PoaRunOpts {
+    uint32_t stop_round = 0xFFFFFFFFu;
+    int force_i32 = 0;
+    uint32_t max_warps = 0;
+};
+
+// Runs all edges to consensus. d_bases is a device pointer; seg_off / edge_seg_off are host arrays.
+// Leaves per-edge status/cons_len/cons_pos on the device and in `status_h`/`len_h`.
+static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off, const uint32_t* edge_seg_off, uint32_t n_edges,
+                   const DpScores& sc, const PoaRunOpts& opt, std::vector<uint32_t>& status_h, std::vector<uint32_t>& len_h) {
+    PoaState* S = poa_state(ctx);
+    cudaStream_t st = ctx->stream;
+    S->passes.clear();
+    S->have_result = false;
+    memset(&S->st, 0, sizeof S->st);
+
+    // ---- non-empty segments, CSR by edge (Assemble.cpp:537 skips empty ones)
+    std::vector<uint64_t> seg_ptr; std::vector<uint32_t> seg_len; std::vector<uint32_t> e_off(n_edges + 1, 0);
+    seg_ptr.reserve(edge_seg_off[n_edges]); seg_len.reserve(edge_seg_off[n_edges]);
+    for (uint32_t e = 0; e < n_edges; ++e) {
+        e_off[e] = (uint32_t)seg_len.size();
+        for (uint32_t s = edge_seg_off[e]; s < edge_seg_off[e + 1]; ++s) {
+            uint64_t b = seg_off[s], en = seg_off[s + 1];
+            if (en < b || en - b > 0x7FFFFFFFull) HGPU_FAIL(ctx, HGPU_E_INVALID, "segment %u has invalid bounds", s);
+            if (en > b) { seg_ptr.push_back(b); seg_len.push_back((uint32_t)(en - b)); }
+        }
+    }
+    e_off[n_edges] = (uint32_t)seg_len.size();
+    const size_t n_seg = seg_len.size();
+
+    HGPU_CUDA(ctx, S->seg_ptr.ensure(n_seg + 1)); HGPU_CUDA(ctx, S->seg_len.ensure(n_seg + 1));
+    HGPU_CUDA(ctx, S->e_seg_off.ensure(n_edges + 1)); HGPU_CUDA(ctx, S->items.ensure(n_edges + 1));
+    HGPU_CUDA(ctx, S->status.ensure(n_edges + 1)); HGPU_CUDA(ctx, S->cons_len.ensure(n_edges + 1));
+    HGPU_CUDA(ctx, S->cons_pos.ensure(n_edges + 1)); HGPU_CUDA(ctx, S->out_nodes.ensure(n_edges + 1));
+    HGPU_CUDA(ctx, S->stats.ensure(8)); HGPU_CUDA(ctx, S->pool_cursor.ensure(1)); HGPU_CUDA(ctx, S->counters.ensure(256));
+    if (n_seg) {
+        HGPU_CUDA(ctx, cudaMemcpyAsync(S->seg_ptr.p, seg_ptr.data(), n_seg * 8, cudaMemcpyHostToDevice, st));
+        HGPU_CUDA(ctx, cudaMemcpyAsync(S->seg_len.p, seg_len.data(), n_seg * 4, cudaMemcpyHostToDevice, st));
+    }
+    HGPU_CUDA(ctx, cudaMemcpyAsync(S->e_seg_off.p, e_off.data(), (size_t)(n_edges + 1) * 4, cudaMemcpyHostToDevice, st));
+    HGPU_CUDA(ctx, cudaMemsetAsync(S->stats.p, 0, 8 * sizeof(unsigned long long), st));
+    HGPU_CUDA(ctx, cudaMemsetAsync(S->status.p, 0, (size_t)(n_edges + 1) * 4, st));
+    HGPU_CUDA(ctx, cudaMemsetAsync(S->cons_len.p, 0, (size_t)(n_edges + 1) * 4, st));
+    HGPU_CUDA(ctx, cudaMemsetAsync(S->cons_pos.p, 0, (size_t)(n_edges + 1) * 8, st));
+
+    status_h.assign(n_edges, 0); len_h.assign(n_edges, 0);
+    if (n_edges == 0) return HGPU_OK;
+
+    // ---- resident warps and memory budget
+    int blocks_per_sm = 0;
+    const size_t smem = (size_t)DP_WARPS_PER_BLOCK * DP_SMEM_PER_WARP;
+    HGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_poa_edges, 32 * DP_WARPS_PER_BLOCK, smem));
+    if (blocks_per_sm < 1) HGPU_FAIL(ctx, HGPU_E_INTERNAL, "k_poa_edges cannot be resident");
+    uint32_t max_warps = (uint32_t)ctx->sm_count * blocks_per_sm * DP_WARPS_PER_BLOCK;
+    if (S->cfg_max_warps) max_warps = std::min(max_warps, S->cfg_max_warps);
+    if (opt.max_warps) max_warps = std::min(max_warps, opt.max_warps);
+    max_warps = std::max<uint32_t>(DP_WARPS_PER_BLOCK, max_warps / DP_WARPS_PER_BLOCK * DP_WARPS_PER_BLOCK);
+    uint64_t budget = S->cfg_arena_bytes;
+    if (!budget) {
+        size_t fr = 0, tot = 0;
+        HGPU_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
+        fr += S->arena.n + S->ws.n;   // what we already hold can be reused
+        budget = (uint64_t)(fr * 0.80);
+        budget = std::min<uint64_t>(budget, 96ull << 30);
+    }
+
+    std::vector<uint32_t> pending(n_edges);
+    std::iota(pending.begin(), pending.end(), 0u);
+    double growth = 0.15;
+    std::vector<EdgeEst> est;
+    std::vector<uint32_t> items_h;
+    for (int attempt = 0; attempt < 5 && !pending.empty(); ++attempt) {
+        // ---- estimates, largest first (also the LPT order for load balance)
+        est.resize(pending.size());
+        uint64_t pool_cap = 0;
+        for (size_t i = 0; i < pending.size(); ++i) {
+            uint32_t e = pending[i];
+            uint32_t R = e_off[e + 1] - e_off[e];
+            est[i].edge = e;
+            if (R == 0) { est[i].ncap = 64; est[i].slot = 4096; continue; }
+            estimate_edge(seg_len.data() + e_off[e], R, growth, sc, &est[i]);
+            uint64_t sum = 0; uint32_t lmax = 0;
+            for (uint32_t k = 0; k < R; ++k) { sum += seg_len[e_off[e] + k]; lmax = std::max(lmax, seg_len[e_off[e] + k]); }
+            pool_cap += growth >= 1.0 ? sum : std::min<uint64_t>(sum, (uint64_t)(2.0 * lmax * (1.0 + growth)) + 256);
+        }
+        std::sort(est.begin(), est.end(), [](const EdgeEst& a, const EdgeEst& b) {
+            if (a.slot != b.slot) return a.slot > b.slot;
+            return a.edge < b.edge;
+        });
+        items_h.resize(est.size());
+        for (size_t i = 0; i < est.size(); ++i) items_h[i] = est[i].edge;
+        HGPU_CUDA(ctx, cudaMemcpyAsync(S->items.p, items_h.data(), items_h.size() * 4, cudaMemcpyHostToDevice, st));
+
+        std::unique_ptr<PoaPass> pass(new PoaPass());
+        HGPU_CUDA(ctx, pass->pool.alloc(pool_cap + 256));
+        HGPU_CUDA(ctx, cudaMemsetAsync(S->pool_cursor.p, 0, sizeof(unsigned long long), st));
+        HGPU_CUDA(ctx, cudaMemsetAsync(S->counters.p, 0, 256 * 4, st));
+
+        // ---- size classes: a class ends where the slot estimate has halved, unless memory is no constraint
+        struct Cls { size_t a, b; uint64_t slot; WsLayout wl; uint32_t warps; };
+        std::vector<Cls> classes;
+        size_t i = 0;
+        while (i < est.size()) {
+            Cls c; c.a = i; c.slot = (est[i].slot + 127) / 128 * 128;
+            auto plan = [&](size_t a, size_t b, Cls& cc) {
+                uint32_t nc = 64;
+                for (size_t q = a; q < b; ++q) nc = std::max(nc, est[q].ncap);
+                uint32_t ec = nc + nc / 4 + 64;
+                cc.wl = ws_layout(nc, ec);
+                uint64_t per = cc.slot + cc.wl.bytes;
+                uint64_t w = budget / per;
+                cc.warps = (uint32_t)std::min<uint64_t>(w, max_warps);
+            };
+            plan(i, est.size(), c);
+            size_t j = est.size();
+            if (c.warps < max_warps) {
+                j = i + 1;
+                while (j < est.size() && est[j].slot * 2 > c.slot) ++j;
+                plan(i, j, c);
+            }
+            c.b = j;
+            classes.push_back(c);
+            i = j;
+        }
+        if (classes.size() > 256) HGPU_FAIL(ctx, HGPU_E_INTERNAL, "too many size classes (%zu)", classes.size());
+
+        for (size_t ci = 0; ci < classes.size(); ++ci) {
+            Cls& c = classes[ci];
+            const uint32_t n_items = (uint32_t)(c.b - c.a);
+            if (c.warps == 0) {
+                // does not fit the device budget even alone: report per edge, keep going
+                std::vector<uint32_t> code(1, ST_TOO_LARGE);
+                for (size_t q = c.a; q < c.b; ++q)
+                    HGPU_CUDA(ctx, cudaMemcpyAsync(S->status.p + est[q].edge, code.data(), 4, cudaMemcpyHostToDevice, st));
+                HGPU_CUDA(ctx, cudaStreamSynchronize(st));
+                continue;
+            }
+            uint32_t warps = std::min<uint32_t>(c.warps, (n_items + 0) ? n_items : 1);
+            uint32_t blocks = (warps + DP_WARPS_PER_BLOCK - 1) / DP_WARPS_PER_BLOCK;
+            warps = blocks * DP_WARPS_PER_BLOCK;
+            if ((uint64_t)warps > c.warps && c.warps >= (uint32_t)DP_WARPS_PER_BLOCK) { blocks = c.warps / DP_WARPS_PER_BLOCK; warps = blocks * DP_WARPS_PER_BLOCK; }
+            HGPU_CUDA(ctx, S->arena.ensure((size_t)warps * c.slot));
+            HGPU_CUDA(ctx, S->ws.ensure((size_t)warps * c.wl.bytes));
+            S->st.arena_bytes = std::max<uint64_t>(S->st.arena_bytes, (uint64_t)warps * c.slot);
+            PoaArgs a{};
+            a.bases = d_bases; a.seg_ptr = S->seg_ptr.p; a.seg_len = S->seg_len.p; a.e_seg_off = S->e_seg_off.p;
+            a.items = S->items.p + c.a; a.n_items = n_items; a.counter = S->counters.p + ci;
+            a.status = S->status.p; a.cons_len = S->cons_len.p; a.cons_pos = S->cons_pos.p; a.out_nodes = S->out_nodes.p;
+            a.pool = pass->pool.p; a.pool_cap = pass->pool.n; a.pool_cursor = S->pool_cursor.p;
+            a.ws = S->ws.p; a.wl = c.wl; a.arena = S->arena.p; a.slot_bytes = c.slot;
+            S->last_wl = c.wl; S->last_slot = c.slot;
+            a.sc = sc; a.stats = S->stats.p; a.stop_round = opt.stop_round; a.force_i32 = opt.force_i32;
+            if (S->timing) HGPU_CUDA(ctx, cudaEventRecord(S->ev0, st));
+            k_poa_edges<<<blocks, 32 * DP_WARPS_PER_BLOCK, smem, st>>>(a);
+            HGPU_CUDA(ctx, cudaGetLastError());
+            ctx->launches++; S->st.dp_launches++;
+            if (S->timing) {
+                HGPU_CUDA(ctx, cudaEventRecord(S->ev1, st));
+                HGPU_CUDA(ctx, cudaEventSynchronize(S->ev1));
+                float ms = 0; cudaEventElapsedTime(&ms, S->ev0, S->ev1);
+                S->st.ms_dp += ms;
+            }
+        }
+        HGPU_CUDA(ctx, cudaMemcpyAsync(status_h.data(), S->status.p, (size_t)n_edges * 4, cudaMemcpyDeviceToHost, st));
+        HGPU_CUDA(ctx, cudaStreamSynchronize(st));
+        S->passes.push_back(std::move(pass));
+        // pool cursor of this pass is only meaningful for the pass; retry whatever did not fit
+        std::vector<uint32_t> next;
+        for (uint32_t e : pending) {
+            uint32_t s_ = status_h[e];
+            if (s_ == ST_CAPACITY || s_ == ST_TOO_LARGE || s_ == ST_POOL) next.push_back(e);
+        }
+        if (opt.stop_round != 0xFFFFFFFFu) break;
+        if (growth >= 1.0) break;     // worst case already tried
+        pending.swap(next);
+        growth = attempt >= 2 ? 1.0 : growth * 2.5;
+    }
+    HGPU_CUDA(ctx, cudaMemcpyAsync(len_h.data(), S->cons_len.p, (size_t)n_edges * 4, cudaMemcpyDeviceToHost, st));
+    unsigned long long sth[8];
+    HGPU_CUDA(ctx, cudaMemcpyAsync(sth, S->stats.p, sizeof sth, cudaMemcpyDeviceToHost, st));
+    HGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    S->st.cells = sth[0]; S->st.cells_padded = sth[1]; S->st.alignments = sth[2]; S->st.alignments_i32 = sth[3]; S->st.bases_in = sth[4];
+    return HGPU_OK;
+}
+
+// offsets + gather into d_out (device) ; returns total bytes in *total
+static int poa_gather(hgpu_t* ctx, uint32_t n_edges, const std::vector<uint32_t>& len_h, uint64_t* out_cons_off,
+                      uint8_t* d_out, uint64_t out_cap, uint64_t* total) {
+    PoaState* S = poa_state(ctx);
+    cudaStream_t st = ctx->stream;
+    uint64_t off = 0;
+    for (uint32_t e = 0; e < n_edges; ++e) { out_cons_off[e] = off; off += len_h[e]; }
+    out_cons_off[n_edges] = off;
+    *total = off;
+    S->st.bases_out = off;
+    if (n_edges == 0 || off == 0) return HGPU_OK;
+    HGPU_CUDA(ctx, S->d_off.ensure(n_edges + 1));
+    HGPU_CUDA(ctx, cudaMemcpyAsync(S->d_off.p, out_cons_off, (size_t)(n_edges + 1) * 8, cudaMemcpyHostToDevice, st));
+    uint32_t blocks = std::min<uint32_t>(n_edges, (uint32_t)ctx->sm_count * 16);
+    k_poa_gather<<<blocks, 256, 0, st>>>(S->cons_pos.p, S->cons_len.p, S->d_off.p, n_edges, d_out, out_cap);
+    HGPU_CUDA(ctx, cudaGetLastError());
+    ctx->launches++; S->st.other_launches++;
+    return HGPU_OK;
+}
+
+static int poa_prepare(hgpu_t* ctx, const uint64_t* seg_off, const uint32_t* edge_seg_off, uint32_t n_edges, uint32_t band,
+                       uint64_t* out_cons_off, uint32_t* out_status) {
+    if (!ctx) return HGPU_E_INVALID;
+    if (!edge_seg_off || !out_cons_off || !out_status || (!seg_off && n_edges && edge_seg_off[n_edges]))
+        HGPU_FAIL(ctx, HGPU_E_INVALID, "null argument");
+    if (band != 0) HGPU_FAIL(ctx, HGPU_E_UNSUPPORTED, "band must be 0: the reference runs SPOA's full (unbanded) DP");
+    for (uint32_t e = 0; e < n_edges; ++e)
+        if (edge_seg_off[e + 1] < edge_seg_off[e]) HGPU_FAIL(ctx, HGPU_E_INVALID, "edge_seg_off not monotone at %u", e);
+    HGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    PoaState* S = poa_state(ctx);
+    if (!S->ev0) { HGPU_CUDA(ctx, cudaEventCreate(&S->ev0)); HGPU_CUDA(ctx, cudaEventCreate(&S->ev1)); }
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_poa_batch_dev(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off, const uint32_t* edge_seg_off,
+                                  uint32_t n_edges, int8_t match, int8_t mismatch, int8_t gap, uint32_t band,
+                                  uint8_t* d_out_cons, uint64_t out_cons_cap, uint64_t* out_cons_off, uint32_t* out_status) {
+    int rc = poa_prepare(ctx, seg_off, edge_seg_off, n_edges, band, out_cons_off, out_status);
+    if (rc) return rc;
+    PoaState* S = poa_state(ctx);
+    DpScores sc; make_scores(ctx, match, mismatch, gap, &sc);
+    std::vector<uint32_t> status_h, len_h;
+    rc = poa_run(ctx, d_bases, seg_off, edge_seg_off, n_edges, sc, PoaRunOpts(), status_h, len_h);
+    if (rc) return rc;
+    for (uint32_t e = 0; e < n_edges; ++e) out_status[e] = status_h[e];
+    uint64_t total = 0;
+    S->last_n_edges = n_edges;
+    // offsets first: the caller learns the needed size even when its buffer is too small
+    uint64_t off = 0;
+    for (uint32_t e = 0; e < n_edges; ++e) off += len_h[e];
+    S->last_total = off; S->have_result = true;
+    if (off > out_cons_cap || (off && !d_out_cons)) {
+        uint64_t o = 0;
+        for (uint32_t e = 0; e < n_edges; ++e) { out_cons_off[e] = o; o += len_h[e]; }
+        out_cons_off[n_edges] = o;
+        HGPU_FAIL(ctx, HGPU_E_NOSPACE, "consensus needs %llu bytes, caller gave %llu", (unsigned long long)off, (unsigned long long)out_cons_cap);
+    }
+    rc = poa_gather(ctx, n_edges, len_h, out_cons_off, d_out_cons, out_cons_cap, &total);
+    if (rc) return rc;
+    HGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_poa_batch(hgpu_t* ctx, const uint8_t* bases, const uint64_t* seg_off, const uint32_t* edge_seg_off,
+                              uint32_t n_edges, int8_t match, int8_t mismatch, int8_t gap, uint32_t band,
+                              uint8_t* out_cons, uint64_t out_cons_cap, uint64_t* out_cons_off, uint32_t* out_status) {
+    int rc = poa_prepare(ctx, seg_off, edge_seg_off, n_edges, band, out_cons_off, out_status);
+    if (rc) return rc;
+    PoaState* S = poa_state(ctx);
+    const uint64_t n_bases = n_edges ? seg_off[edge_seg_off[n_edges]] : 0;
+    if (n_bases && !bases) HGPU_FAIL(ctx, HGPU_E_INVALID, "null bases");
+    HGPU_CUDA(ctx, S->d_bases.ensure(n_bases + 16));
+    if (n_bases) HGPU_CUDA(ctx, cudaMemcpyAsync(S->d_bases.p, bases, n_bases, cudaMemcpyHostToDevice, ctx->stream));
+    HGPU_CUDA(ctx, S->d_out.ensure(out_cons_cap + 16));
+    rc = hgpu_poa_batch_dev(ctx, S->d_bases.p, seg_off, edge_seg_off, n_edges, match, mismatch, gap, band,
+                            S->d_out.p, out_cons_cap, out_cons_off, out_status);
+    if (rc) return rc;
+    const uint64_t total = out_cons_off[n_edges];
+    if (total) {
+        if (!out_cons) HGPU_FAIL(ctx, HGPU_E_INVALID, "null out_cons");
+        HGPU_CUDA(ctx, cudaMemcpyAsync(out_cons, S->d_out.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    HGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_poa_fetch(hgpu_t* ctx, uint8_t* out_cons, uint64_t out_cons_cap) {
+    if (!ctx) return HGPU_E_INVALID;
+    PoaState* S = poa_state(ctx);
+    if (!S->have_result) HGPU_FAIL(ctx, HGPU_E_INVALID, "no POA result to fetch");
+    if (S->last_total > out_cons_cap) HGPU_FAIL(ctx, HGPU_E_NOSPACE, "consensus needs %llu bytes", (unsigned long long)S->last_total);
+    if (S->last_total == 0) return HGPU_OK;
+    if (!out_cons) HGPU_FAIL(ctx, HGPU_E_INVALID, "null out_cons");
+    HGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t n_edges = S->last_n_edges;
+    std::vector<uint32_t> len_h(n_edges);
+    HGPU_CUDA(ctx, cudaMemcpyAsync(len_h.data(), S->cons_len.p, (size_t)n_edges * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<uint64_t> off(n_edges + 1);
+    HGPU_CUDA(ctx, S->d_out.ensure(S->last_total + 16));
+    uint64_t total = 0;
+    int rc = poa_gather(ctx, n_edges, len_h, off.data(), S->d_out.p, S->last_total, &total);
+    if (rc) return rc;
+    HGPU_CUDA(ctx, cudaMemcpyAsync(out_cons, S->d_out.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    HGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_poa_get_stats(const hgpu_t* ctx, hgpu_poa_stats* out) {
+    if (!ctx || !out) return HGPU_E_INVALID;
+    if (!ctx->poa) { memset(out, 0, sizeof *out); return HGPU_OK; }
+    *out = ctx->poa->st;
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_poa_set_timing(hgpu_t* ctx, int enabled) {
+    if (!ctx) return HGPU_E_INVALID;
+    poa_state(ctx)->timing = enabled != 0;
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_poa_configure(hgpu_t* ctx, uint64_t arena_bytes, uint32_t max_warps) {
+    if (!ctx) return HGPU_E_INVALID;
+    PoaState* S = poa_state(ctx);
+    S->cfg_arena_bytes = arena_bytes;
+    S->cfg_max_warps = max_warps;
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_poa_debug(hgpu_t* ctx, const uint8_t* bases, const uint64_t* seg_off, uint32_t n_segs, uint32_t n_prior,
+                              int8_t match, int8_t mismatch, int8_t gap, int force_i32, int reserved,
+                              int32_t* H, uint64_t H_cap, int32_t* aln_node, int32_t* aln_pos, uint32_t aln_cap,
+                              uint32_t* rank2node, uint8_t* node_code, uint32_t* pred_off, uint32_t* pred_node, uint32_t* pred_weight,
+                              uint32_t node_cap, uint32_t edge_cap, hgpu_poa_dbg_sizes* sizes) {
+    (void)reserved;
+    if (!ctx || !seg_off || !sizes) return HGPU_E_INVALID;
+    if (n_prior == 0) HGPU_FAIL(ctx, HGPU_E_INVALID, "n_prior must be >= 1");
+    uint32_t edge_seg_off[2] = {0, n_segs};
+    uint64_t dummy_off[2]; uint32_t dummy_status[1];
+    int rc = poa_prepare(ctx, seg_off, edge_seg_off, 1, 0, dummy_off, dummy_status);
+    if (rc) return rc;
+    PoaState* S = poa_state(ctx);
+    cudaStream_t st = ctx->stream;
+    const uint64_t n_bases = seg_off[n_segs];
+    HGPU_CUDA(ctx, S->d_bases.ensure(n_bases + 16));
+    if (n_bases) HGPU_CUDA(ctx, cudaMemcpyAsync(S->d_bases.p, bases, n_bases, cudaMemcpyHostToDevice, st));
+    DpScores sc; make_scores(ctx, match, mismatch, gap, &sc);
+    PoaRunOpts opt; opt.stop_round = n_prior; opt.force_i32 = force_i32; opt.max_warps = DP_WARPS_PER_BLOCK;
+    std::vector<uint32_t> status_h, len_h;
+    rc = poa_run(ctx, S->d_bases.p, seg_off, edge_seg_off, 1, sc, opt, status_h, len_h);
+    if (rc) return rc;
+    if (status_h[0] != ST_OK) HGPU_FAIL(ctx, HGPU_E_INTERNAL, "debug edge ended with status %u", status_h[0]);
+    std::vector<uint32_t> lens;
+    for (uint32_t s = 0; s < n_segs; ++s) if (seg_off[s + 1] > seg_off[s]) lens.push_back((uint32_t)(seg_off[s + 1] - seg_off[s]));
+    if (lens.empty()) { memset(sizes, 0, sizeof *sizes); return HGPU_OK; }
+    // any of the block's warps may have pulled the edge: find the workspace that holds a graph
+    const WsLayout wl = S->last_wl;
+    const uint64_t slot = S->last_slot;
+    std::vector<uint8_t> wsh;
+    wsh.resize(wl.bytes * DP_WARPS_PER_BLOCK);
+    HGPU_CUDA(ctx, cudaMemcpyAsync(wsh.data(), S->ws.p, wsh.size(), cudaMemcpyDeviceToHost, st));
+    HGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    int w = -1;
+    for (int q = 0; q < DP_WARPS_PER_BLOCK; ++q) {
+        const uint32_t* hdr = reinterpret_cast<const uint32_t*>(wsh.data() + (size_t)q * wl.bytes + wl.o_hdr);
+        if (hdr[HDR_N_NODES] != 0 && hdr[HDR_N_NODES] <= wl.ncap) { w = q; break; }
+    }
+    if (w < 0) HGPU_FAIL(ctx, HGPU_E_INTERNAL, "debug: no workspace holds a graph");
+    uint8_t* base = wsh.data() + (size_t)w * wl.bytes;
+    GraphView g = bind_graph(base, wl);
+    const uint32_t* hdr = reinterpret_cast<const uint32_t*>(base + wl.o_hdr);
+    const uint32_t N = *g.n_nodes, NE = *g.n_edges;
+    if (N > node_cap || NE > edge_cap) HGPU_FAIL(ctx, HGPU_E_NOSPACE, "debug: graph has %u nodes / %u edges", N, NE);
+    sizes->n_nodes = N; sizes->n_edges = NE; sizes->aln_len = 0; sizes->L = 0;
+    uint32_t pe = 0;
+    for (uint32_t r = 0; r < N; ++r) {
+        uint32_t v = g.rank2node[r];
+        if (rank2node) rank2node[r] = v;
+        if (pred_off) pred_off[r] = pe;
+        for (uint32_t x = g.in_head[v]; x != NIL; x = g.e_next_in[x]) {
+            if (pred_node) pred_node[pe] = g.e_begin[x];
+            if (pred_weight) pred_weight[pe] = g.e_w[x];
+            ++pe;
+        }
+    }
+    if (pred_off) pred_off[N] = pe;
+    if (node_code) for (uint32_t i = 0; i < N; ++i) node_code[i] = (uint8_t)"ACGT"[g.code[i]];
+    if (lens.size() <= n_prior) return HGPU_OK;      // graph only
+    const uint32_t V = hdr[HDR_LAST_V], L = hdr[HDR_LAST_L];
+    const bool p16 = hdr[HDR_LAST_P16] != 0;
+    const int bias = (int)hdr[HDR_LAST_BIAS];
+    sizes->L = L;
+    const uint32_t n = *g.aln_len;
+    sizes->aln_len = n;
+    if (aln_node && aln_pos) {
+        if (n > aln_cap) HGPU_FAIL(ctx, HGPU_E_NOSPACE, "debug: alignment has %u pairs", n);
+        for (uint32_t t = 0; t < n; ++t) {   // stored last pair first
+            int32_t rk = g.aln_rank[n - 1 - t];
+            aln_node[t] = rk < 0 ? -1 : (int32_t)g.rank2node[rk];
+            aln_pos[t] = g.aln_pos[n - 1 - t];
+        }
+    }
+    if (H) {
+        const uint64_t cells = (uint64_t)(V + 1) * (L + 1);
+        if (cells > H_cap) HGPU_FAIL(ctx, HGPU_E_NOSPACE, "debug: H needs %llu cells", (unsigned long long)cells);
+        DevBuf<int32_t> dH;
+        HGPU_CUDA(ctx, dH.alloc(cells));
+        uint8_t* slot_p = S->arena.p + (uint64_t)w * slot;
+        if (p16) k_poa_dump_H<DP_NW16, true><<<ctx->sm_count * 4, 256, 0, st>>>(slot_p, V, L, bias, sc.g, dH.p);
+        else k_poa_dump_H<DP_NW32, false><<<ctx->sm_count * 4, 256, 0, st>>>(slot_p, V, L, bias, sc.g, dH.p);
+        HGPU_CUDA(ctx, cudaGetLastError());
+        ctx->launches++;
+        HGPU_CUDA(ctx, cudaMemcpyAsync(H, dH.p, cells * 4, cudaMemcpyDeviceToHost, st));
+        HGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    return HGPU_OK;
+}

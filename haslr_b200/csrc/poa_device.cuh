@@ -1,0 +1,684 @@
+// Batched partial-order-alignment kernel for sm_100a.
+//
+// Replaces SPOA's graph-NW engine + graph update + consensus as driven by asm_calc_single_cns_seq
+// (reference src/haslr_assemble/src/Assemble.cpp:499-554) and the pthread edge queue around it
+// (Assemble.cpp:365-434,562-605). ONE persistent kernel, k_poa_edges: every warp pulls backbone edges from
+// a device-side queue and takes one edge from its first supporting segment to its consensus string:
+//
+//   chain graph of segment 0  ->  for each further segment { graph-NW fill, traceback, add_alignment,
+//   topological sort, per-rank DP records }  ->  heaviest-bundle consensus  ->  bytes into the output pool
+//
+// so warps in their (serial, latency-bound) graph-update phase overlap with warps in the (throughput-bound)
+// score-matrix fill, and no host round trip sits between the R alignments of an edge.
+//
+// Score matrix ("H") layout and arithmetic of the fill — see DESIGN.md:
+//  * rows = nodes in topological order (+ virtual row 0), columns = sequence positions; every lane owns CPL
+//    consecutive columns of a stripe of SW = 32*CPL columns and keeps the previous row in registers, so the
+//    common case (single predecessor = previous rank) touches no memory for its inputs;
+//  * cells are stored in "gap-hat" space  Hhat[i][j] = H[i][j] - j*gap (+ bias): the horizontal gap recurrence
+//    becomes a plain prefix maximum, done per lane in registers then across lanes with warp shuffles;
+//  * int16 cells packed two per 32-bit register, updated with the packed-int16 DPX instructions
+//    (VIADD.16x2 / VIADDMNMX.S16x2 / VIMNMX3.S16x2); an int32 instantiation takes alignments whose score
+//    range does not fit (SPOA makes the same switch);
+//  * every finished row is streamed to the warp's slot of the HBM arena as 512-byte lane-interleaved
+//    units (coalesced 16-byte stores); non-adjacent predecessors and the traceback read it back.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "poa_graph.cuh"
+
+namespace hgpu {
+
+enum : uint32_t { ST_OK = 0, ST_CAPACITY = 1, ST_TOPOSORT = 2, ST_TRACEBACK = 3, ST_TOO_LARGE = 4, ST_POOL = 5 };
+
+// Scores in gap-hat space (host computes them once per call).
+struct DpScores {
+    int32_t sm;      // match - gap      (diagonal step, bases equal)
+    int32_t sx;      // mismatch - gap   (diagonal step, bases differ)
+    int32_t g;       // gap              (vertical step); horizontal steps cost 0 in hat space
+    int32_t lo_step; // most negative change of Hhat per consumed row (>= 0, magnitude)
+    int32_t hi_step; // most positive change of Hhat per consumed column (>= 0)
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-warp workspace: the POA graph of the edge the warp currently owns + update/consensus scratch.
+// ---------------------------------------------------------------------------------------------------------
+struct WsLayout {
+    uint32_t ncap, ecap, scap;
+    uint64_t o_hdr, o_code, o_in_head, o_in_tail, o_out_head, o_aligned, o_e_begin, o_e_end, o_e_w, o_e_next_in, o_e_next_out,
+        o_rank2node, o_node2rank, o_meta0, o_meta1, o_pred_off, o_pred_rank, o_aln_rank, o_aln_pos, o_mark, o_check, o_stack,
+        o_score, o_pred;
+    uint64_t bytes;
+};
+
+__host__ __device__ inline WsLayout ws_layout(uint32_t ncap, uint32_t ecap) {
+    WsLayout w;
+    w.ncap = ncap; w.ecap = ecap; w.scap = ecap + 4 * ncap + 8;
+    uint64_t o = 0;
+    auto take = [&](uint64_t bytes) { uint64_t r = o; o += (bytes + 15) / 16 * 16; return r; };
+    const uint64_t n = ncap, e = ecap;
+    w.o_hdr = take(64);
+    w.o_code = take(n);
+    w.o_in_head = take(4 * n); w.o_in_tail = take(4 * n); w.o_out_head = take(4 * n);
+    w.o_aligned = take(12 * n);
+    w.o_e_begin = take(4 * e); w.o_e_end = take(4 * e); w.o_e_w = take(4 * e); w.o_e_next_in = take(4 * e); w.o_e_next_out = take(4 * e);
+    w.o_rank2node = take(4 * n); w.o_node2rank = take(4 * n);
+    w.o_meta0 = take(4 * n); w.o_meta1 = take(4 * n);
+    w.o_pred_off = take(4 * (n + 1)); w.o_pred_rank = take(4 * e);
+    w.o_aln_rank = take(4 * n); w.o_aln_pos = take(4 * n);
+    w.o_mark = take(n); w.o_check = take(n);
+    w.o_stack = take(4 * (uint64_t)w.scap);
+    w.o_score = take(8 * n); w.o_pred = take(4 * n);
+    w.bytes = (o + 127) / 128 * 128;
+    return w;
+}
+
+// header words of a workspace
+enum : int { HDR_N_NODES = 0, HDR_N_EDGES = 1, HDR_ALN_LEN = 2, HDR_LAST_P16 = 3, HDR_LAST_V = 4, HDR_LAST_L = 5, HDR_LAST_BIAS = 6 };
+
+__host__ __device__ inline GraphView bind_graph(uint8_t* base, const WsLayout& w) {
+    GraphView g;
+    g.ncap = w.ncap; g.ecap = w.ecap;
+    uint32_t* hdr = reinterpret_cast<uint32_t*>(base + w.o_hdr);
+    g.n_nodes = hdr + HDR_N_NODES; g.n_edges = hdr + HDR_N_EDGES; g.aln_len = hdr + HDR_ALN_LEN;
+    g.code = base + w.o_code;
+    g.in_head = reinterpret_cast<uint32_t*>(base + w.o_in_head);
+    g.in_tail = reinterpret_cast<uint32_t*>(base + w.o_in_tail);
+    g.out_head = reinterpret_cast<uint32_t*>(base + w.o_out_head);
+    g.aligned = reinterpret_cast<uint32_t*>(base + w.o_aligned);
+    g.e_begin = reinterpret_cast<uint32_t*>(base + w.o_e_begin);
+    g.e_end = reinterpret_cast<uint32_t*>(base + w.o_e_end);
+    g.e_w = reinterpret_cast<uint32_t*>(base + w.o_e_w);
+    g.e_next_in = reinterpret_cast<uint32_t*>(base + w.o_e_next_in);
+    g.e_next_out = reinterpret_cast<uint32_t*>(base + w.o_e_next_out);
+    g.rank2node = reinterpret_cast<uint32_t*>(base + w.o_rank2node);
+    g.node2rank = reinterpret_cast<uint32_t*>(base + w.o_node2rank);
+    g.meta0 = reinterpret_cast<uint32_t*>(base + w.o_meta0);
+    g.meta1 = reinterpret_cast<uint32_t*>(base + w.o_meta1);
+    g.pred_off = reinterpret_cast<uint32_t*>(base + w.o_pred_off);
+    g.pred_rank = reinterpret_cast<uint32_t*>(base + w.o_pred_rank);
+    g.aln_rank = reinterpret_cast<int32_t*>(base + w.o_aln_rank);
+    g.aln_pos = reinterpret_cast<int32_t*>(base + w.o_aln_pos);
+    return g;
+}
+
+__host__ __device__ inline GraphScratch bind_scratch(uint8_t* base, const WsLayout& w) {
+    GraphScratch s;
+    s.mark = base + w.o_mark; s.check = base + w.o_check;
+    s.stack = reinterpret_cast<uint32_t*>(base + w.o_stack); s.stack_cap = w.scap;
+    s.score = reinterpret_cast<int64_t*>(base + w.o_score);
+    s.pred = reinterpret_cast<int32_t*>(base + w.o_pred);
+    return s;
+}
+
+static constexpr unsigned FULL = 0xFFFFFFFFu;
+static constexpr int TB_ROWS = 32, TB_COLS = 32;
+static constexpr int TB_SMEM_BYTES = TB_ROWS * TB_COLS * 4 + TB_ROWS * 8 + TB_COLS;  // tile + meta0/1 + seq codes
+
+// Geometry of one alignment inside a slot. P16: two int16 cells per word; I32: one int32 cell per word.
+template <int NW, bool P16>
+struct Geo {
+    static constexpr int CPL = P16 ? 2 * NW : NW;   // columns per lane per stripe
+    static constexpr int SW = 32 * CPL;             // columns per stripe
+    static constexpr int UNITS = NW / 4;            // 16-byte units per lane per stripe row
+    static constexpr int NEGV = P16 ? (-32768 + 256) : -(1 << 29);
+    static constexpr int PROF_BYTES = 4 * NW * 32 * 4;
+    __host__ __device__ static uint32_t stripes(uint32_t L) { return (L + 1 + SW - 1) / SW; }
+    // bytes of a slot for V nodes and L columns: (V+1) rows * NS stripes * NW*128 B, then NS*(V+1) int32 boundary column
+    __host__ __device__ static uint64_t slot_bytes(uint32_t V, uint32_t L) {
+        uint64_t ns = stripes(L);
+        uint64_t h = (uint64_t)(V + 1) * ns * NW * 128;
+        uint64_t bc = ((uint64_t)(V + 1) * ns * 4 + 15) / 16 * 16;
+        return h + bc;
+    }
+    __host__ __device__ static int32_t bias(uint32_t V, const DpScores& sc) {
+        return P16 ? (-32768 + 1024 + (int32_t)(V + 2) * sc.lo_step) : 0;
+    }
+};
+
+// does the int16 range hold for this alignment? (stored = Hhat + bias must stay inside [-32768+1024, 32767-512])
+__host__ __device__ inline bool dp_fits16(uint32_t V, uint32_t L, const DpScores& sc) {
+    int64_t up = (int64_t)(L + 1) * sc.hi_step;
+    return up + (int64_t)(V + 2) * sc.lo_step + 1024 + 512 < 65536;
+}
+
+static constexpr int DP_NW16 = 8;   // int16 kernel: 16 columns per lane, 512-column stripes
+static constexpr int DP_NW32 = 8;   // int32 kernel:  8 columns per lane, 256-column stripes
+static constexpr int DP_SMEM_PER_WARP = 4480;  // max(profile 4 KB, traceback tile 4384 B), 128-byte multiple
+static constexpr int DP_WARPS_PER_BLOCK = 4;
+
+__host__ __device__ inline uint64_t dp_slot_bytes(uint32_t V, uint32_t L, bool p16) {
+    return p16 ? Geo<DP_NW16, true>::slot_bytes(V, L) : Geo<DP_NW32, false>::slot_bytes(V, L);
+}
+
+struct PoaArgs {
+    // input segments (non-empty ones only), CSR by edge
+    const uint8_t* bases;
+    const uint64_t* seg_ptr;     // offset into bases
+    const uint32_t* seg_len;
+    const uint32_t* e_seg_off;   // [n_edges+1]
+    // work queue
+    const uint32_t* items;       // edge ids in processing order
+    uint32_t n_items;
+    uint32_t* counter;           // cursor, zeroed before the launch
+    // per-edge results
+    uint32_t* status;
+    uint32_t* cons_len;
+    uint64_t* cons_pos;          // device address of the edge's consensus bytes (inside some pass's pool)
+    uint32_t* out_nodes;         // final node count (may be null)
+    uint8_t* pool; uint64_t pool_cap; unsigned long long* pool_cursor;
+    // per-warp storage
+    uint8_t* ws; WsLayout wl;
+    uint8_t* arena; uint64_t slot_bytes;
+    DpScores sc;
+    unsigned long long* stats;   // [0] cells [1] cells computed incl. padding [2] alignments [3] int32 alignments [4] bases in
+    uint32_t stop_round;         // debug: stop after the fill+traceback of this round (0xFFFFFFFF = run to consensus)
+    int force_i32;
+};
+
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ uint32_t pack2(int v) { return ((uint32_t)v & 0xFFFFu) * 0x10001u; }
+
+template <int NW, bool P16>
+struct SlotView {
+    using G = Geo<NW, P16>;
+    uint32_t* H;       // score words
+    int32_t* bcol;     // [NS][V+1] last column of each stripe (stored space)
+    uint32_t V, L, NS;
+    __device__ __forceinline__ void bind(uint8_t* slot, uint32_t V_, uint32_t L_) {
+        V = V_; L = L_; NS = G::stripes(L_);
+        H = reinterpret_cast<uint32_t*>(slot);
+        bcol = reinterpret_cast<int32_t*>(slot + (uint64_t)(V + 1) * NS * NW * 128);
+    }
+    __device__ __forceinline__ uint4* row_units(uint32_t i, uint32_t s, int lane) const {
+        return reinterpret_cast<uint4*>(H) + ((uint64_t)i * NS + s) * G::UNITS * 32 + lane;
+    }
+    // one cell, stored space
+    __device__ __forceinline__ int load(uint32_t i, uint32_t j) const {
+        uint32_t s = j / G::SW, jj = j - s * G::SW, ln = jj / G::CPL, c = jj - ln * G::CPL;
+        uint32_t k = P16 ? (c >> 1) : c;
+        uint32_t w = H[(((uint64_t)i * NS + s) * G::UNITS + (k >> 2)) * 128 + ln * 4 + (k & 3)];
+        if (P16) return (c & 1) ? (int)(int16_t)(w >> 16) : (int)(int16_t)(w & 0xFFFFu);
+        return (int)w;
+    }
+};
+
+template <int NW, bool P16>
+struct RowOps {
+    using G = Geo<NW, P16>;
+    // h := max over {diag from src shifted by one column, vert from src}, src being the row held in h itself
+    __device__ __forceinline__ static void from_regs(uint32_t (&h)[NW], uint32_t left, const uint32_t* pf, uint32_t g2, int g) {
+        if (P16) {
+#pragma unroll
+            for (int k = NW - 1; k >= 0; --k) {
+                uint32_t hs = __byte_perm(k ? h[k > 0 ? k - 1 : 0] : left, h[k], 0x5432);
+                uint32_t d = __vadd2(hs, pf[k * 32]);
+                h[k] = __viaddmax_s16x2(h[k], g2, d);
+            }
+        } else {
+#pragma unroll
+            for (int k = NW - 1; k >= 0; --k) {
+                int hs = (int)(k ? h[k > 0 ? k - 1 : 0] : left);
+                int d = hs + (int)pf[k * 32];
+                h[k] = (uint32_t)max((int)h[k] + g, d);
+            }
+        }
+    }
+    // t := max(t, diag/vert from one source word w at position k with its left neighbour `prev`)
+    __device__ __forceinline__ static uint32_t acc(uint32_t t, uint32_t prev, uint32_t w, uint32_t pfw, uint32_t g2, int g) {
+        if (P16) {
+            uint32_t hs = __byte_perm(prev, w, 0x5432);
+            return __vimax3_s16x2(t, __vadd2(hs, pfw), __vadd2(w, g2));
+        } else {
+            return (uint32_t)max((int)t, max((int)prev + (int)pfw, (int)w + g));
+        }
+    }
+    // in-lane inclusive prefix maximum; returns the lane total (max of all the lane's cells)
+    __device__ __forceinline__ static int scan(uint32_t (&h)[NW]) {
+        if (P16) {
+            const uint32_t neg2 = pack2(G::NEGV);
+            uint32_t run = neg2;
+#pragma unroll
+            for (int k = 0; k < NW; ++k) {
+                uint32_t tsh = __byte_perm(h[k], neg2, 0x1054);   // (lo = NEG, hi = h.lo)
+                uint32_t rb = __byte_perm(run, 0, 0x3232);        // broadcast run.hi
+                run = __vimax3_s16x2(h[k], tsh, rb);
+                h[k] = run;
+            }
+            return (int)(int16_t)(run >> 16);
+        } else {
+            int run = G::NEGV;
+#pragma unroll
+            for (int k = 0; k < NW; ++k) { run = max(run, (int)h[k]); h[k] = (uint32_t)run; }
+            return run;
+        }
+    }
+    __device__ __forceinline__ static void apply_carry(uint32_t (&h)[NW], int c) {
+        if (P16) {
+            uint32_t c2 = pack2(c);
+#pragma unroll
+            for (int k = 0; k < NW; ++k) h[k] = __vmaxs2(h[k], c2);
+        } else {
+#pragma unroll
+            for (int k = 0; k < NW; ++k) h[k] = (uint32_t)max((int)h[k], c);
+        }
+    }
+    __device__ __forceinline__ static int last_cell(const uint32_t (&h)[NW]) {
+        return P16 ? (int)(int16_t)(h[NW - 1] >> 16) : (int)h[NW - 1];
+    }
+    // the word a lane hands to its right neighbour as diagonal source: only the LAST cell matters
+    __device__ __forceinline__ static uint32_t left_from_cell(int v) { return P16 ? ((uint32_t)v << 16) : (uint32_t)v; }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Graph-NW of one segment against the warp's graph: fill the slot, trace back into gv.aln_rank/aln_pos
+// (traceback order, graph side as ranks). Returns false if the traceback found no predecessor.
+// ---------------------------------------------------------------------------------------------------------
+template <int NW, bool P16>
+__device__ __noinline__ bool dp_align(const GraphView& gv, uint8_t* slot, uint8_t* wsm, const uint8_t* seq,
+                                      uint32_t V, uint32_t L, const DpScores sc, int lane) {
+    using G = Geo<NW, P16>;
+    using R = RowOps<NW, P16>;
+    uint32_t* prof = reinterpret_cast<uint32_t*>(wsm);                 // [4][NW][32]
+    const int g = sc.g;
+    const uint32_t g2 = P16 ? pack2(g) : (uint32_t)g;
+    SlotView<NW, P16> sv;
+    sv.bind(slot, V, L);
+    const int bias = G::bias(V, sc);
+    const uint32_t NS = sv.NS;
+
+    // =============================== fill ===============================
+    for (uint32_t s = 0; s < NS; ++s) {
+        __syncwarp();
+        // --- sequence profile of this stripe: prof[code][k][lane] = hat-score(s) of the lane's k-th word
+        {
+            const uint32_t j0 = s * G::SW + lane * G::CPL;   // first column owned by this lane
+#pragma unroll 4
+            for (int k = 0; k < NW; ++k) {
+                uint32_t w[4];
+                if (P16) {
+                    uint32_t ja = j0 + 2 * k, jb = ja + 1;
+                    int ca = (ja >= 1 && ja <= L) ? (int)base_code(seq[ja - 1]) : -1;
+                    int cb = (jb >= 1 && jb <= L) ? (int)base_code(seq[jb - 1]) : -1;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        int va = ca < 0 ? 0 : (ca == c ? sc.sm : sc.sx);
+                        int vb = cb < 0 ? 0 : (cb == c ? sc.sm : sc.sx);
+                        w[c] = ((uint32_t)va & 0xFFFFu) | ((uint32_t)vb << 16);
+                    }
+                } else {
+                    uint32_t ja = j0 + k;
+                    int ca = (ja >= 1 && ja <= L) ? (int)base_code(seq[ja - 1]) : -1;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) w[c] = (uint32_t)(ca < 0 ? 0 : (ca == c ? sc.sm : sc.sx));
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) prof[(c * NW + k) * 32 + lane] = w[c];
+            }
+        }
+        __syncwarp();
+        const int32_t* bc_prev = (s > 0) ? sv.bcol + (uint64_t)(s - 1) * (V + 1) : nullptr;
+        int32_t* bc_cur = sv.bcol + (uint64_t)s * (V + 1);
+
+        // --- row 0: Hhat = 0 everywhere
+        uint32_t h[NW];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) h[k] = P16 ? pack2(bias) : (uint32_t)bias;
+        {
+            uint4* dst = sv.row_units(0, s, lane);
+#pragma unroll
+            for (int u = 0; u < G::UNITS; ++u) dst[u * 32] = make_uint4(h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
+            if (lane == 31) bc_cur[0] = bias;
+        }
+
+        for (uint32_t r0 = 0; r0 < V; r0 += 32) {
+            // batched per-rank records: lane q holds rank r0+q
+            const uint32_t rr = r0 + lane;
+            uint32_t mm0 = 0, mm1 = 0;
+            int bcd = G::NEGV, bcc = G::NEGV;
+            if (rr < V) {
+                mm0 = gv.meta0[rr]; mm1 = gv.meta1[rr];
+                if (s > 0) { bcd = bc_prev[rr]; bcc = bc_prev[rr + 1]; }
+            }
+            const int nb = (V - r0) < 32u ? (int)(V - r0) : 32;
+            for (int q = 0; q < nb; ++q) {
+                const uint32_t r = r0 + q, i = r + 1;
+                const uint32_t m0 = __shfl_sync(FULL, mm0, q);
+                const uint32_t m1 = __shfl_sync(FULL, mm1, q);
+                const int diag_in = __shfl_sync(FULL, bcd, q);     // Hhat[i-1][first col of stripe - 1]
+                const int carry_in = __shfl_sync(FULL, bcc, q);    // Hhat[i][first col of stripe - 1]
+                const uint32_t code = m0 & 3u, npc = (m0 >> 3) & 3u, d0 = m0 >> 5;
+                const uint32_t* pf = prof + code * NW * 32 + lane;
+                if ((npc == 1 && d0 == 1) || (npc == 0 && r == 0)) {
+                    uint32_t left = __shfl_up_sync(FULL, h[NW - 1], 1);
+                    if (lane == 0) left = R::left_from_cell(diag_in);
+                    R::from_regs(h, left, pf, g2, g);
+                } else {
+                    uint32_t t[NW];
+#pragma unroll
+                    for (int k = 0; k < NW; ++k) t[k] = P16 ? pack2(G::NEGV) : (uint32_t)G::NEGV;
+                    uint32_t np = npc, cs = 0;
+                    if (npc == 0) np = 1;
+                    if (npc == 3) { cs = gv.pred_off[r]; np = gv.pred_off[r + 1] - cs; }
+                    for (uint32_t x = 0; x < np; ++x) {
+                        uint32_t prow;
+                        if (npc == 0) prow = 0;
+                        else if (npc == 3) prow = gv.pred_rank[cs + x] + 1;
+                        else prow = i - (x == 0 ? d0 : m1);
+                        if (prow == i - 1) {
+                            uint32_t left = __shfl_up_sync(FULL, h[NW - 1], 1);
+                            if (lane == 0) left = R::left_from_cell(diag_in);
+#pragma unroll
+                            for (int k = 0; k < NW; ++k) t[k] = R::acc(t[k], k ? h[k > 0 ? k - 1 : 0] : left, h[k], pf[k * 32], g2, g);
+                        } else {
+                            const uint4* src = sv.row_units(prow, s, lane);
+                            uint4 lastu = src[(G::UNITS - 1) * 32];
+                            uint32_t left = __shfl_up_sync(FULL, lastu.w, 1);
+                            if (lane == 0) left = R::left_from_cell(s > 0 ? bc_prev[prow - 0] : G::NEGV);
+                            uint32_t prev = left;
+#pragma unroll
+                            for (int u = 0; u < G::UNITS; ++u) {
+                                uint4 v = src[u * 32];
+                                t[4 * u] = R::acc(t[4 * u], prev, v.x, pf[(4 * u) * 32], g2, g);
+                                t[4 * u + 1] = R::acc(t[4 * u + 1], v.x, v.y, pf[(4 * u + 1) * 32], g2, g);
+                                t[4 * u + 2] = R::acc(t[4 * u + 2], v.y, v.z, pf[(4 * u + 2) * 32], g2, g);
+                                t[4 * u + 3] = R::acc(t[4 * u + 3], v.z, v.w, pf[(4 * u + 3) * 32], g2, g);
+                                prev = v.w;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < NW; ++k) h[k] = t[k];
+                }
+                // horizontal gaps = prefix maximum in hat space
+                int incl = R::scan(h);
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int v = __shfl_up_sync(FULL, incl, d);
+                    if (lane >= d) incl = max(incl, v);
+                }
+                int excl = __shfl_up_sync(FULL, incl, 1);
+                excl = (lane == 0) ? carry_in : max(excl, carry_in);
+                R::apply_carry(h, excl);
+                // stream the row out
+                uint4* dst = sv.row_units(i, s, lane);
+#pragma unroll
+                for (int u = 0; u < G::UNITS; ++u) dst[u * 32] = make_uint4(h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
+                if (lane == 31) bc_cur[i] = R::last_cell(h);
+            }
+        }
+        __syncwarp();
+    }
+    __threadfence_block();
+    __syncwarp();
+
+    // =============================== traceback ===============================
+    // end cell: best Hhat[i][L] over sink nodes, first maximum in rank order (SPOA kNW)
+    int best = INT32_MIN; uint32_t best_i = 0;
+    for (uint32_t r = lane; r < V; r += 32) {
+        if (gv.meta0[r] & META_SINK) {
+            int v = sv.load(r + 1, L);
+            if (v > best) { best = v; best_i = r + 1; }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        int ov = __shfl_xor_sync(FULL, best, d);
+        uint32_t oi = __shfl_xor_sync(FULL, best_i, d);
+        if (oi != 0 && (best_i == 0 || ov > best || (ov == best && oi < best_i))) { best = ov; best_i = oi; }
+    }
+    int* tile = reinterpret_cast<int*>(wsm);                              // [TB_ROWS][TB_COLS]
+    uint32_t* tm0 = reinterpret_cast<uint32_t*>(wsm + TB_ROWS * TB_COLS * 4);
+    uint32_t* tm1 = tm0 + TB_ROWS;
+    uint8_t* tseq = reinterpret_cast<uint8_t*>(tm1 + TB_ROWS);
+    uint32_t ci = best_i, cj = L, n_out = 0;
+    bool bad = (best_i == 0);
+    while (!bad && !(ci == 0 && cj == 0)) {
+        const uint32_t it = ci, jt = cj;
+        __syncwarp();
+        if (it >= (uint32_t)lane) {
+            const uint32_t row = it - lane;
+#pragma unroll 8
+            for (int c = 0; c < TB_COLS; ++c) if (jt >= (uint32_t)c) tile[lane * TB_COLS + c] = sv.load(row, jt - c);
+            if (row >= 1) { tm0[lane] = gv.meta0[row - 1]; tm1[lane] = gv.meta1[row - 1]; }
+        }
+        if (jt >= (uint32_t)lane + 1) tseq[lane] = (uint8_t)base_code(seq[jt - lane - 1]);
+        __syncwarp();
+        if (lane == 0) {
+            uint32_t i = ci, j = cj;
+            while (true) {
+                if (i == 0 && j == 0) break;
+                const uint32_t li = it - i, lj = jt - j;
+                if ((li >= (uint32_t)TB_ROWS - 1 || lj >= (uint32_t)TB_COLS - 1) && (li != 0 || lj != 0)) break;
+                auto getH = [&](uint32_t ii, uint32_t jj) -> int {
+                    uint32_t a_ = it - ii, b_ = jt - jj;   // ii <= it, jj <= jt always hold on a walk up/left
+                    if (a_ < (uint32_t)TB_ROWS && b_ < (uint32_t)TB_COLS) return tile[a_ * TB_COLS + b_];
+                    return sv.load(ii, jj);
+                };
+                const int val = tile[li * TB_COLS + lj];
+                uint32_t pi = i, pj = j;
+                bool found = false;
+                if (i != 0) {
+                    const uint32_t m0 = tm0[li], m1 = tm1[li];
+                    const uint32_t code = m0 & 3u, npc = (m0 >> 3) & 3u, d0 = m0 >> 5;
+                    uint32_t np = npc, cs = 0;
+                    if (npc == 0) np = 1;
+                    if (npc == 3) { cs = gv.pred_off[i - 1]; np = gv.pred_off[i] - cs; }
+                    if (j != 0) {
+                        const int dsc = (tseq[lj] == code) ? sc.sm : sc.sx;
+                        for (uint32_t x = 0; x < np && !found; ++x) {
+                            uint32_t prow = npc == 0 ? 0 : npc == 3 ? gv.pred_rank[cs + x] + 1 : i - (x == 0 ? d0 : m1);
+                            if (val == getH(prow, j - 1) + dsc) { pi = prow; pj = j - 1; found = true; }
+                        }
+                    }
+                    for (uint32_t x = 0; x < np && !found; ++x) {
+                        uint32_t prow = npc == 0 ? 0 : npc == 3 ? gv.pred_rank[cs + x] + 1 : i - (x == 0 ? d0 : m1);
+                        if (val == getH(prow, j) + g) { pi = prow; pj = j; found = true; }
+                    }
+                }
+                if (!found && j != 0 && val == getH(i, j - 1)) { pi = i; pj = j - 1; found = true; }
+                if (!found || n_out >= gv.ncap) { bad = true; break; }
+                gv.aln_rank[n_out] = (pi == i) ? -1 : (int32_t)(i - 1);
+                gv.aln_pos[n_out] = (pj == j) ? -1 : (int32_t)(j - 1);
+                ++n_out;
+                i = pi; j = pj;
+            }
+            ci = i; cj = j;
+        }
+        ci = __shfl_sync(FULL, ci, 0); cj = __shfl_sync(FULL, cj, 0);
+        n_out = __shfl_sync(FULL, n_out, 0);
+        bad = __shfl_sync(FULL, (int)bad, 0) != 0;
+    }
+    if (lane == 0) *gv.aln_len = bad ? 0 : n_out;
+    __syncwarp();
+    return !bad;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Lane-parallel pieces of the graph update.
+// ---------------------------------------------------------------------------------------------------------
+// chain graph of the first segment: ranks = node ids
+__device__ __forceinline__ void w_init_chain(GraphView& g, const uint8_t* seq, uint32_t L, int lane) {
+    for (uint32_t i = lane; i < L; i += 32) {
+        uint32_t c = base_code(seq[i]);
+        g.code[i] = (uint8_t)c;
+        g.in_head[i] = g.in_tail[i] = (i > 0) ? i - 1 : NIL;
+        g.out_head[i] = (i + 1 < L) ? i : NIL;
+        g.aligned[3 * i] = g.aligned[3 * i + 1] = g.aligned[3 * i + 2] = NIL;
+        if (i + 1 < L) { g.e_begin[i] = i; g.e_end[i] = i + 1; g.e_w[i] = 2; g.e_next_in[i] = NIL; g.e_next_out[i] = NIL; }
+        g.rank2node[i] = i; g.node2rank[i] = i;
+        g.meta0[i] = c | ((i + 1 < L) ? 0u : META_SINK) | ((i > 0) ? ((1u << 3) | (1u << 5)) : 0u);
+        g.meta1[i] = 0;
+        g.pred_off[i] = (i > 0) ? i - 1 : 0;
+        if (i > 0) g.pred_rank[i - 1] = i - 1;
+    }
+    if (lane == 0) {
+        g.pred_off[L] = L - 1;
+        *g.n_nodes = L; *g.n_edges = L - 1; *g.aln_len = 0;
+    }
+    __syncwarp();
+}
+
+// per-rank DP records (meta0/meta1/pred CSR) from rank2node/node2rank + in-lists; same content as g_build_meta
+__device__ __forceinline__ void w_build_meta(GraphView& g, int lane) {
+    const uint32_t N = *g.n_nodes;
+    uint32_t running = 0;
+    for (uint32_t r0 = 0; r0 < N; r0 += 32) {
+        const uint32_t r = r0 + lane;
+        uint32_t deg = 0, v = 0;
+        if (r < N) {
+            v = g.rank2node[r];
+            for (uint32_t x = g.in_head[v]; x != NIL; x = g.e_next_in[x]) ++deg;
+        }
+        uint32_t incl = deg;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += o;
+        }
+        const uint32_t off = running + incl - deg;
+        if (r < N) {
+            uint32_t m0 = g.code[v] | (g.out_head[v] == NIL ? META_SINK : 0u), m1 = 0;
+            g.pred_off[r] = off;
+            uint32_t np = 0;
+            for (uint32_t x = g.in_head[v]; x != NIL; x = g.e_next_in[x]) {
+                uint32_t pr = g.node2rank[g.e_begin[x]];
+                g.pred_rank[off + np] = pr;
+                if (np == 0) m0 |= (r - pr) << 5;
+                if (np == 1) m1 = r - pr;
+                ++np;
+            }
+            m0 |= (np > 3 ? 3u : np) << 3;
+            g.meta0[r] = m0; g.meta1[r] = m1;
+        }
+        running += __shfl_sync(FULL, incl, 31);
+    }
+    if (lane == 0) g.pred_off[N] = running;
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_poa_edges: the persistent per-edge kernel.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, 8) k_poa_edges(PoaArgs a) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const uint32_t gw = blockIdx.x * DP_WARPS_PER_BLOCK + wib;
+    uint8_t* wsm = smem_raw + (size_t)wib * DP_SMEM_PER_WARP;
+    uint8_t* slot = a.arena + (uint64_t)gw * a.slot_bytes;
+    uint8_t* wsb = a.ws + (uint64_t)gw * a.wl.bytes;
+    GraphView gv = bind_graph(wsb, a.wl);
+    GraphScratch gs = bind_scratch(wsb, a.wl);
+    uint32_t* hdr = reinterpret_cast<uint32_t*>(wsb + a.wl.o_hdr);
+    unsigned long long st_cells = 0, st_padded = 0, st_aln = 0, st_aln32 = 0, st_bases = 0;
+
+    while (true) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(a.counter, 1u);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= a.n_items) break;
+        const uint32_t e = a.items[item];
+        const uint32_t s0 = a.e_seg_off[e];
+        const uint32_t R = a.e_seg_off[e + 1] - s0;
+        uint32_t st = ST_OK;
+        uint32_t n_cons = 0;
+        bool debug_stop = false;
+        if (R == 0) {
+            if (lane == 0) { *gv.n_nodes = 0; *gv.n_edges = 0; *gv.aln_len = 0; }
+        } else {
+            const uint32_t L0 = a.seg_len[s0];
+            if (L0 > gv.ncap || L0 > gv.ecap) st = ST_CAPACITY;
+            else { w_init_chain(gv, a.bases + a.seg_ptr[s0], L0, lane); st_bases += L0; }
+            for (uint32_t k = 1; k < R && st == ST_OK; ++k) {
+                const uint32_t V = *gv.n_nodes;
+                const uint32_t NE = *gv.n_edges;
+                const uint32_t L = a.seg_len[s0 + k];
+                const uint8_t* seq = a.bases + a.seg_ptr[s0 + k];
+                const bool p16 = !a.force_i32 && dp_fits16(V, L, a.sc);
+                if ((uint64_t)V + L > gv.ncap || (uint64_t)NE + L + 1 > gv.ecap) { st = ST_CAPACITY; break; }
+                if (dp_slot_bytes(V, L, p16) > a.slot_bytes) { st = ST_TOO_LARGE; break; }
+                bool ok = p16 ? dp_align<DP_NW16, true>(gv, slot, wsm, seq, V, L, a.sc, lane)
+                              : dp_align<DP_NW32, false>(gv, slot, wsm, seq, V, L, a.sc, lane);
+                if (lane == 0) {
+                    hdr[HDR_LAST_P16] = p16 ? 1u : 0u; hdr[HDR_LAST_V] = V; hdr[HDR_LAST_L] = L;
+                    hdr[HDR_LAST_BIAS] = (uint32_t)(p16 ? Geo<DP_NW16, true>::bias(V, a.sc) : 0);
+                }
+                st_cells += (unsigned long long)(V + 1) * (L + 1);
+                st_padded += (unsigned long long)(V + 1) *
+                             (p16 ? Geo<DP_NW16, true>::stripes(L) * Geo<DP_NW16, true>::SW : Geo<DP_NW32, false>::stripes(L) * Geo<DP_NW32, false>::SW);
+                st_aln += 1; st_aln32 += p16 ? 0 : 1; st_bases += L;
+                if (!ok) { st = ST_TRACEBACK; break; }
+                if (k == a.stop_round) { debug_stop = true; break; }
+                // fold the alignment into the graph (serial, SPOA order), re-sort, rebuild the DP records
+                uint32_t ust = ST_OK;
+                if (lane == 0) {
+                    if (!g_add_alignment(gv, seq, L)) ust = ST_CAPACITY;
+                    else if (!g_toposort(gv, gs)) ust = ST_TOPOSORT;
+                }
+                ust = __shfl_sync(FULL, ust, 0);
+                __syncwarp();
+                if (ust != ST_OK) { st = ust; break; }
+                w_build_meta(gv, lane);
+            }
+            if (a.stop_round != 0xFFFFFFFFu) debug_stop = true;
+            // heaviest-bundle consensus; node ids land in aln_rank
+            if (st == ST_OK && !debug_stop) {
+                if (lane == 0) n_cons = g_consensus(gv, gs, reinterpret_cast<uint32_t*>(gv.aln_rank));
+                n_cons = __shfl_sync(FULL, n_cons, 0);
+                __syncwarp();
+            }
+        }
+        // publish
+        unsigned long long pos = 0;
+        if (lane == 0 && n_cons > 0) {
+            pos = atomicAdd(a.pool_cursor, (unsigned long long)n_cons);
+            if (pos + n_cons > a.pool_cap) st = ST_POOL;
+        }
+        pos = __shfl_sync(FULL, pos, 0);
+        st = __shfl_sync(FULL, st, 0);
+        if (st == ST_OK && n_cons > 0) {
+            const uint32_t* ids = reinterpret_cast<const uint32_t*>(gv.aln_rank);
+            for (uint32_t i = lane; i < n_cons; i += 32) a.pool[pos + i] = (uint8_t)"ACGT"[gv.code[ids[i]]];
+        }
+        if (lane == 0) {
+            a.status[e] = st;
+            a.cons_len[e] = (st == ST_OK) ? n_cons : 0;
+            a.cons_pos[e] = (uint64_t)(uintptr_t)(a.pool + pos);
+            if (a.out_nodes) a.out_nodes[e] = *gv.n_nodes;
+        }
+        __syncwarp();
+    }
+    if (lane == 0 && a.stats) {
+        atomicAdd(a.stats + 0, st_cells); atomicAdd(a.stats + 1, st_padded); atomicAdd(a.stats + 2, st_aln);
+        atomicAdd(a.stats + 3, st_aln32); atomicAdd(a.stats + 4, st_bases);
+    }
+}
+
+// out[off[e] .. off[e]+len[e]) = consensus bytes of edge e
+__global__ void __launch_bounds__(256) k_poa_gather(const uint64_t* cons_pos, const uint32_t* cons_len,
+                                                    const uint64_t* off, uint32_t n_edges, uint8_t* out, uint64_t out_cap) {
+    for (uint32_t e = blockIdx.x; e < n_edges; e += gridDim.x) {
+        const uint32_t n = cons_len[e];
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(cons_pos[e]);
+        const uint64_t o = off[e];
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) if (o + i < out_cap) out[o + i] = src[i];
+    }
+}
+
+// Debug: export the score matrix of warp 0's last alignment in the reference's H space (row-major (V+1)*(L+1) int32).
+template <int NW, bool P16>
+__global__ void k_poa_dump_H(uint8_t* slot, uint32_t V, uint32_t L, int bias, int gap, int32_t* H) {
+    SlotView<NW, P16> sv;
+    sv.bind(slot, V, L);
+    const uint64_t total = (uint64_t)(V + 1) * (L + 1);
+    for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total; idx += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t i = (uint32_t)(idx / (L + 1)), j = (uint32_t)(idx % (L + 1));
+        H[idx] = sv.load(i, j) - bias + (int)j * gap;
+    }
+}
+
+#endif  // __CUDACC__
+}  // namespace hgpu

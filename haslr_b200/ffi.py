@@ -1,0 +1,195 @@
+"""ctypes binding of the C ABI declared in include/haslr_b200.h (one entry per exported function)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+u8p, u32p, u64p, i32p, f64p = (C.POINTER(t) for t in (C.c_uint8, C.c_uint32, C.c_uint64, C.c_int32, C.c_double))
+
+HGPU_OK, HGPU_E_INVALID, HGPU_E_CUDA, HGPU_E_NOMEM, HGPU_E_NOSPACE, HGPU_E_UNSUPPORTED, HGPU_E_INTERNAL = 0, -1, -2, -3, -4, -5, -6
+
+# every symbol include/haslr_b200.h declares (tests check the library exports all of them)
+EXPORTS = (
+    "hgpu_create", "hgpu_destroy", "hgpu_set_stream", "hgpu_strerror", "hgpu_last_error", "hgpu_abi_version",
+    "hgpu_launch_count", "hgpu_compact_lr", "hgpu_backbone_edges", "hgpu_poa_batch", "hgpu_poa_batch_dev",
+    "hgpu_poa_fetch", "hgpu_poa_get_stats", "hgpu_poa_set_timing", "hgpu_poa_configure", "hgpu_poa_debug",
+)
+
+
+class HgpuError(RuntimeError):
+    def __init__(self, code, detail):
+        super().__init__(f"hgpu error {code}: {detail}")
+        self.code = code
+
+
+class HitsT(C.Structure):
+    _fields_ = [("n_hits", C.c_uint32)] + [(n, u32p) for n in
+                ("q_start", "q_end", "t_id", "t_len", "t_start", "t_end", "n_match", "n_block")] + \
+               [("is_rev", u8p), ("mapq", u8p), ("cg_off", u32p), ("cg_ops", u32p)]
+
+
+class K1Params(C.Structure):
+    _fields_ = [("min_aln_sim", C.c_double), ("uniq_freq", C.c_double), ("max_uniq_dev", C.c_double),
+                ("min_aln_block", C.c_uint32), ("min_aln_mapq", C.c_uint32)]
+
+
+class PoaStats(C.Structure):
+    _fields_ = [("cells", C.c_uint64), ("cells_padded", C.c_uint64), ("alignments", C.c_uint64),
+                ("alignments_i32", C.c_uint64), ("bases_in", C.c_uint64), ("bases_out", C.c_uint64),
+                ("dp_launches", C.c_uint64), ("update_launches", C.c_uint64), ("other_launches", C.c_uint64),
+                ("ms_dp", C.c_float), ("ms_update", C.c_float), ("ms_other", C.c_float), ("arena_bytes", C.c_uint64)]
+
+
+class DbgSizes(C.Structure):
+    _fields_ = [("n_nodes", C.c_uint32), ("n_edges", C.c_uint32), ("aln_len", C.c_uint32), ("L", C.c_uint32)]
+
+
+CL_ELEM = np.dtype([(n, "<u4") for n in ("hit", "q_start", "q_end", "t_start", "t_end", "n_match", "n_block",
+                                         "cg_lo", "cg_lo_len", "cg_hi", "cg_hi_len")])
+EDGE_SUPP = np.dtype([("lr_id_strand", "<u4"), ("cmp_head", "<u4"), ("cmp_tail", "<u4")])
+
+
+def lib_path():
+    return os.path.join(_HERE, "libhaslr_b200.so")
+
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library. Raises if it has not been built (python __graft_entry__.py / make)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise ImportError(f"{p} is missing: build it with `make` (nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(p)
+    L.hgpu_create.restype = C.c_int; L.hgpu_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.hgpu_destroy.restype = None; L.hgpu_destroy.argtypes = [C.c_void_p]
+    L.hgpu_set_stream.restype = C.c_int; L.hgpu_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.hgpu_strerror.restype = C.c_char_p; L.hgpu_strerror.argtypes = [C.c_int]
+    L.hgpu_last_error.restype = C.c_char_p; L.hgpu_last_error.argtypes = [C.c_void_p]
+    L.hgpu_abi_version.restype = C.c_int; L.hgpu_abi_version.argtypes = []
+    L.hgpu_launch_count.restype = C.c_uint64; L.hgpu_launch_count.argtypes = [C.c_void_p]
+    L.hgpu_compact_lr.restype = C.c_int
+    L.hgpu_compact_lr.argtypes = [C.c_void_p, C.POINTER(HitsT), u32p, C.c_uint32, f64p, C.c_uint32, C.POINTER(K1Params),
+                                  C.c_void_p, u32p, u64p]
+    L.hgpu_backbone_edges.restype = C.c_int
+    L.hgpu_backbone_edges.argtypes = [C.c_void_p, u32p, u8p, u32p, C.c_uint32, C.c_uint32, u64p, u32p, C.c_void_p, u8p, u64p]
+    poa_sig = [C.c_void_p, C.c_void_p, u64p, u32p, C.c_uint32, C.c_int8, C.c_int8, C.c_int8, C.c_uint32,
+               C.c_void_p, C.c_uint64, u64p, u32p]
+    L.hgpu_poa_batch.restype = C.c_int; L.hgpu_poa_batch.argtypes = poa_sig
+    L.hgpu_poa_batch_dev.restype = C.c_int; L.hgpu_poa_batch_dev.argtypes = poa_sig
+    L.hgpu_poa_fetch.restype = C.c_int; L.hgpu_poa_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    L.hgpu_poa_get_stats.restype = C.c_int; L.hgpu_poa_get_stats.argtypes = [C.c_void_p, C.POINTER(PoaStats)]
+    L.hgpu_poa_set_timing.restype = C.c_int; L.hgpu_poa_set_timing.argtypes = [C.c_void_p, C.c_int]
+    L.hgpu_poa_configure.restype = C.c_int; L.hgpu_poa_configure.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32]
+    L.hgpu_poa_debug.restype = C.c_int
+    L.hgpu_poa_debug.argtypes = [C.c_void_p, u8p, u64p, C.c_uint32, C.c_uint32, C.c_int8, C.c_int8, C.c_int8, C.c_int, C.c_int,
+                                 i32p, C.c_uint64, i32p, i32p, C.c_uint32, u32p, u8p, u32p, u32p, u32p,
+                                 C.c_uint32, C.c_uint32, C.POINTER(DbgSizes)]
+    _lib = L
+    return L
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+class Context:
+    """One hgpu context = one GPU. Mirrors the reference's stage functions (see include/haslr_b200.h)."""
+
+    def __init__(self, device=-1):
+        self.L = load()
+        h = C.c_void_p()
+        rc = self.L.hgpu_create(device, C.byref(h))
+        if rc != 0:
+            raise HgpuError(rc, self.L.hgpu_strerror(rc).decode() + " (hgpu_create: a B200-class GPU is required; no CPU fallback)")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.hgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise HgpuError(rc, self.L.hgpu_last_error(self.h).decode())
+
+    def set_stream(self, stream_ptr):
+        self._check(self.L.hgpu_set_stream(self.h, C.c_void_p(stream_ptr)))
+
+    def launch_count(self):
+        return int(self.L.hgpu_launch_count(self.h))
+
+    # ---- (iii) batched POA -------------------------------------------------------------------------------
+    def poa_batch(self, bases, seg_off, edge_seg_off, match=5, mismatch=-4, gap=-8, band=0, out=None):
+        """Host buffers in, host buffers out (copies inside). Returns (cons uint8[], cons_off uint64[n+1], status uint32[n])."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        seg_off = np.ascontiguousarray(seg_off, dtype=np.uint64)
+        edge_seg_off = np.ascontiguousarray(edge_seg_off, dtype=np.uint32)
+        n = len(edge_seg_off) - 1
+        cap = int(seg_off[-1]) + 64 if out is None else len(out)
+        if out is None:
+            out = np.empty(cap, dtype=np.uint8)
+        off = np.zeros(n + 1, dtype=np.uint64)
+        status = np.zeros(max(n, 1), dtype=np.uint32)
+        rc = self.L.hgpu_poa_batch(self.h, bases.ctypes.data, _p(seg_off, u64p), _p(edge_seg_off, u32p), n, match, mismatch, gap, band,
+                                   out.ctypes.data, cap, _p(off, u64p), _p(status, u32p))
+        self._check(rc)
+        return out[: int(off[n])], off, status[:n]
+
+    def poa_batch_dev(self, d_bases_ptr, seg_off, edge_seg_off, d_out_ptr, out_cap, match=5, mismatch=-4, gap=-8, band=0):
+        """Bases and consensus already/still on the device (raw pointers). Returns (cons_off, status)."""
+        seg_off = np.ascontiguousarray(seg_off, dtype=np.uint64)
+        edge_seg_off = np.ascontiguousarray(edge_seg_off, dtype=np.uint32)
+        n = len(edge_seg_off) - 1
+        off = np.zeros(n + 1, dtype=np.uint64)
+        status = np.zeros(max(n, 1), dtype=np.uint32)
+        rc = self.L.hgpu_poa_batch_dev(self.h, C.c_void_p(d_bases_ptr), _p(seg_off, u64p), _p(edge_seg_off, u32p), n, match, mismatch, gap,
+                                       band, C.c_void_p(d_out_ptr), out_cap, _p(off, u64p), _p(status, u32p))
+        self._check(rc)
+        return off, status[:n]
+
+    def poa_stats(self):
+        s = PoaStats()
+        self._check(self.L.hgpu_poa_get_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in PoaStats._fields_}
+
+    def poa_set_timing(self, on):
+        self._check(self.L.hgpu_poa_set_timing(self.h, int(on)))
+
+    def poa_configure(self, arena_bytes=0, max_warps=0):
+        self._check(self.L.hgpu_poa_configure(self.h, arena_bytes, max_warps))
+
+    def poa_debug(self, bases, seg_off, n_prior, match=5, mismatch=-4, gap=-8, force_i32=False, want_H=True):
+        """Graph after n_prior segments (rank order) + score matrix / alignment of the next one; same dict as the oracle's."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        seg_off = np.ascontiguousarray(seg_off, dtype=np.uint64)
+        n_segs = len(seg_off) - 1
+        cap_n = int(seg_off[-1]) + 1
+        lens = np.diff(seg_off.astype(np.int64))
+        Lmax = int(lens.max()) if n_segs else 0
+        H = np.zeros((cap_n + 1) * (Lmax + 1) if want_H else 1, dtype=np.int32)
+        aln_cap = cap_n + Lmax + 2
+        an = np.zeros(aln_cap, dtype=np.int32); ap = np.zeros(aln_cap, dtype=np.int32)
+        r2n = np.zeros(cap_n, dtype=np.uint32); code = np.zeros(cap_n, dtype=np.uint8)
+        poff = np.zeros(cap_n + 1, dtype=np.uint32); pn = np.zeros(2 * cap_n + n_segs + 8, dtype=np.uint32); pw = np.zeros_like(pn)
+        sz = DbgSizes()
+        rc = self.L.hgpu_poa_debug(self.h, _p(bases, u8p), _p(seg_off, u64p), n_segs, n_prior, match, mismatch, gap, int(force_i32), 0,
+                                   _p(H, i32p) if want_H else None, len(H) if want_H else 0, _p(an, i32p), _p(ap, i32p), aln_cap,
+                                   _p(r2n, u32p), _p(code, u8p), _p(poff, u32p), _p(pn, u32p), _p(pw, u32p), cap_n, len(pn), C.byref(sz))
+        self._check(rc)
+        V, L = sz.n_nodes, sz.L
+        return dict(V=V, L=L, H=H[: (V + 1) * (L + 1)].reshape(V + 1, L + 1) if want_H else None,
+                    aln_node=an[: sz.aln_len].copy(), aln_pos=ap[: sz.aln_len].copy(), rank2node=r2n[:V].copy(),
+                    code=code[:V].copy(), pred_off=poff[: V + 1].copy(), pred_node=pn[: int(poff[V])].copy(),
+                    pred_weight=pw[: int(poff[V])].copy())

@@ -1,0 +1,147 @@
+/* haslr_b200 — C ABI of the B200-native haslr_assemble hot path.
+ *
+ * The reference (vpc-ccg/haslr) has no plugin/FFI layer; its hot path is reached through C++ stage functions
+ * called from src/haslr_assemble/src/main.cpp. Each entry point below names the reference interface it
+ * replaces (file:line relative to /root/reference/src/haslr_assemble/src). INTEGRATION.md shows the binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes, no C++ or torch types; every function returns HGPU_OK (0) or a
+ * negative HGPU_E_* code and never calls exit(); hgpu_last_error() gives the detail string. One context per
+ * GPU; a context is not thread-safe. Unless a function says "_dev", all pointers are HOST pointers and the
+ * call copies host->device and device->host itself. All kernels of a call are ordered on the context's stream
+ * (hgpu_set_stream; default: the legacy default stream).
+ */
+#ifndef HASLR_B200_H
+#define HASLR_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HGPU_OK             0
+#define HGPU_E_INVALID     -1   /* bad argument */
+#define HGPU_E_CUDA        -2   /* CUDA runtime error (see hgpu_last_error) */
+#define HGPU_E_NOMEM       -3   /* device or host allocation failed */
+#define HGPU_E_NOSPACE     -4   /* caller-provided output capacity too small */
+#define HGPU_E_UNSUPPORTED -5   /* valid request this build cannot serve (e.g. band != 0) */
+#define HGPU_E_INTERNAL    -6   /* a kernel reported an inconsistent state */
+
+typedef struct hgpu_ctx hgpu_t;
+
+int         hgpu_create(int device /* -1 = current */, hgpu_t** out);
+void        hgpu_destroy(hgpu_t* ctx);
+int         hgpu_set_stream(hgpu_t* ctx, void* cuda_stream /* cudaStream_t, NULL = default */);
+const char* hgpu_strerror(int code);
+const char* hgpu_last_error(const hgpu_t* ctx);
+int         hgpu_abi_version(void);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t    hgpu_launch_count(const hgpu_t* ctx);
+
+/* ---- (i) PAF hits -> compact long reads ------------------------------------------------------------------
+ * Replaces, per long read: load_alignment's filters F1-F4 and per-read sort (Longread.cpp:234-302),
+ * process_lr_alignment_group (Longread.cpp:182-232), fix_overlapping_alignments (Longread.cpp:430-512) and
+ * build_compact_longreads / find_best_scheduling (Longread.cpp:514-624; Longread.hpp:89).
+ * Hits of read r are rows read_off[r] .. read_off[r+1) of the column arrays, in PAF order; reads in ascending id.
+ */
+typedef struct {
+    uint32_t n_hits;
+    const uint32_t* q_start; const uint32_t* q_end;          /* PAF col 3,4 */
+    const uint32_t* t_id; const uint32_t* t_len;             /* PAF col 6 (integer name), 7 */
+    const uint32_t* t_start; const uint32_t* t_end;          /* PAF col 8,9 */
+    const uint32_t* n_match; const uint32_t* n_block;        /* PAF col 10,11 */
+    const uint8_t* is_rev; const uint8_t* mapq;              /* PAF col 5 == '-', col 12 */
+    const uint32_t* cg_off;   /* n_hits+1 offsets into cg_ops */
+    const uint32_t* cg_ops;   /* run-length cg:Z: ops: (len << 2) | op, op 0 = M, 1 = I, 2 = D/other */
+} hgpu_hits_t;
+
+typedef struct {
+    double   min_aln_sim;     /* --aln-sim, default 0.85  (Commandline.cpp:46-66) */
+    double   uniq_freq;       /* calc_uniq_freq, Contig.cpp:162-174 */
+    double   max_uniq_dev;    /* --uniq-dev, default 0.15 */
+    uint32_t min_aln_block;   /* --aln-block, default 500 */
+    uint32_t min_aln_mapq;    /* 55 */
+} hgpu_k1_params;
+
+/* One element of a compact long read, coordinates after the overlap fix; the kept part of the hit's CIGAR is
+ * ops [cg_lo .. cg_hi], the first with length cg_lo_len and the last with cg_hi_len. */
+typedef struct {
+    uint32_t hit;
+    uint32_t q_start, q_end, t_start, t_end, n_match, n_block;
+    uint32_t cg_lo, cg_lo_len, cg_hi, cg_hi_len;
+} hgpu_cl_elem;
+
+/* out_elems: capacity n_hits. out_read_off: n_reads+1. *out_n = number of elements written. */
+int hgpu_compact_lr(hgpu_t* ctx, const hgpu_hits_t* hits, const uint32_t* read_off, uint32_t n_reads,
+                    const double* mean_kmer, uint32_t n_contigs, const hgpu_k1_params* prm,
+                    hgpu_cl_elem* out_elems, uint32_t* out_read_off, uint64_t* out_n);
+
+/* ---- (ii) compact long reads -> backbone edge table -----------------------------------------------------
+ * Replaces bbg_build_graph + bbg_add_edge (Backbone_graph.cpp:148-171,10-25; Backbone_graph.hpp:60) and the
+ * rule of bbg_remove_weak_edges (Backbone_graph.cpp:348-375; Backbone_graph.hpp:63).
+ * Output: directed entries (each undirected edge appears as edge and twin) sorted by
+ * key64 = ((node1<<1|rev1) << 32) | (node2<<1|rev2)  — the iteration order of the reference's
+ * graph[node].edges[rev] std::maps; supports of an entry in ascending (read id, element index) order;
+ * out_keep[e] = 1 iff the entry survives bbg_remove_weak_edges. Capacities: 2*n_pairs entries (+1 for
+ * out_supp_off) and 2*n_pairs supports, n_pairs = sum over reads of max(len-1, 0). */
+typedef struct { uint32_t lr_id_strand; /* lr_id | lr_strand << 31 */ uint32_t cmp_head; uint32_t cmp_tail; } hgpu_edge_supp;
+
+int hgpu_backbone_edges(hgpu_t* ctx, const uint32_t* cl_tid, const uint8_t* cl_rev, const uint32_t* cl_read_off,
+                        uint32_t n_reads, uint32_t min_edge_sup,
+                        uint64_t* out_key, uint32_t* out_supp_off, hgpu_edge_supp* out_supp, uint8_t* out_keep,
+                        uint64_t* out_n_entries);
+
+/* ---- (iii) batched POA consensus -------------------------------------------------------------------------
+ * Replaces the body of asm_calc_single_cns_seq (Assemble.cpp:499-554), i.e. per backbone edge the five SPOA
+ * calls createAlignmentEngine(kNW, match, mismatch, gap), createGraph(), align_sequence_with_graph(),
+ * add_alignment(), generate_consensus(), and the pthread edge queue around it (Assemble.cpp:365-434,562-605).
+ * bases: ASCII, non-ACGT reads as 'A' (Compressed_sequence.cpp:57). Segment s = bases[seg_off[s] .. seg_off[s+1]);
+ * edge e owns segments edge_seg_off[e] .. edge_seg_off[e+1) in the order they are fed to the graph; empty
+ * segments are skipped (Assemble.cpp:537). band must be 0 (full DP, as SPOA).
+ * out_cons (capacity out_cons_cap bytes) receives the concatenated consensus strings, out_cons_off n_edges+1
+ * offsets, out_status n_edges per-edge codes (0 = ok). If out_cons_cap is too small the call returns
+ * HGPU_E_NOSPACE, out_cons_off[n_edges] holds the needed size, and hgpu_poa_fetch can still collect the result.
+ */
+int hgpu_poa_batch(hgpu_t* ctx, const uint8_t* bases, const uint64_t* seg_off, const uint32_t* edge_seg_off,
+                   uint32_t n_edges, int8_t match, int8_t mismatch, int8_t gap, uint32_t band,
+                   uint8_t* out_cons, uint64_t out_cons_cap, uint64_t* out_cons_off, uint32_t* out_status);
+
+/* Same, with `bases` and `out_cons` already DEVICE pointers (seg_off/edge_seg_off/out_cons_off/out_status stay
+ * host arrays: they are metadata the host scheduler needs). */
+int hgpu_poa_batch_dev(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off, const uint32_t* edge_seg_off,
+                       uint32_t n_edges, int8_t match, int8_t mismatch, int8_t gap, uint32_t band,
+                       uint8_t* d_out_cons, uint64_t out_cons_cap, uint64_t* out_cons_off, uint32_t* out_status);
+
+int hgpu_poa_fetch(hgpu_t* ctx, uint8_t* out_cons, uint64_t out_cons_cap);
+
+typedef struct {
+    uint64_t cells;            /* sum over alignments of (|V|+1)*(L+1): the algorithmic DP cells */
+    uint64_t cells_padded;     /* cells actually computed (stripe padding included) */
+    uint64_t alignments;       /* graph-NW alignments run */
+    uint64_t alignments_i32;   /* of which in the int32 kernel (score range too wide for int16) */
+    uint64_t bases_in;         /* segment bases consumed */
+    uint64_t bases_out;        /* consensus bases produced */
+    uint64_t dp_launches, update_launches, other_launches;
+    float    ms_dp, ms_update, ms_other;   /* CUDA-event time per kernel family, only if timing enabled */
+    uint64_t arena_bytes;      /* score-matrix arena size used */
+} hgpu_poa_stats;
+int hgpu_poa_get_stats(const hgpu_t* ctx, hgpu_poa_stats* out);
+/* Per-kernel-family CUDA-event timing (serialises the families; leave off when measuring whole-job throughput). */
+int hgpu_poa_set_timing(hgpu_t* ctx, int enabled);
+/* Tuning knobs: arena_bytes = score-matrix arena (0 = auto), max_batch_edges (0 = auto). */
+int hgpu_poa_configure(hgpu_t* ctx, uint64_t arena_bytes, uint32_t max_batch_edges);
+
+/* Debug/inspection (used by the parity tests): graph after the first n_prior non-empty segments of ONE edge, in
+ * rank order, plus the score matrix and alignment of the next segment. H is written in the reference's H space
+ * (row-major (V+1)*(L+1) int32). force_i32 != 0 runs the int32 kernel; force_nw selects the stripe width
+ * (words per lane: 8/16/24/32, 0 = auto). Any output may be NULL. */
+typedef struct { uint32_t n_nodes, n_edges, aln_len, L; } hgpu_poa_dbg_sizes;
+int hgpu_poa_debug(hgpu_t* ctx, const uint8_t* bases, const uint64_t* seg_off, uint32_t n_segs, uint32_t n_prior,
+                   int8_t match, int8_t mismatch, int8_t gap, int force_i32, int force_nw,
+                   int32_t* H, uint64_t H_cap, int32_t* aln_node, int32_t* aln_pos, uint32_t aln_cap,
+                   uint32_t* rank2node, uint8_t* node_code, uint32_t* pred_off, uint32_t* pred_node, uint32_t* pred_weight,
+                   uint32_t node_cap, uint32_t edge_cap, hgpu_poa_dbg_sizes* sizes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HASLR_B200_H */

