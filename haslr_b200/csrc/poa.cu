@@ -71,13 +71,13 @@ struct EdgeEst {
 
 // Node-count growth model: every later segment adds about `growth` new nodes per base (SURVEY.md §8(d):
 // |V| grows ~ L * (ins + sub) per read). growth >= 1 means the worst case (every base a new node).
-void estimate_edge(const uint32_t* len, uint32_t R, double growth, const DpScores& sc, EdgeEst* out) {
+void estimate_edge(const uint32_t* len, uint32_t R, double growth, const DpScores& sc, bool force_i32, EdgeEst* out) {
     double V = len[0];
     uint64_t slot = 0;
     uint32_t lmax = len[0];
     for (uint32_t k = 1; k < R; ++k) {
         uint32_t Vi = (uint32_t)std::min<double>(V + 1.0, 4.0e9);
-        bool p16 = dp_fits16(Vi, len[k], sc);
+        bool p16 = !force_i32 && dp_fits16(Vi, len[k], sc);
         slot = std::max(slot, dp_slot_bytes(Vi, len[k], p16));
         // overhang beyond the graph's current span also becomes new nodes
         double over = len[k] > V ? (double)len[k] - V : 0.0;
@@ -170,7 +170,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
             uint32_t R = e_off[e + 1] - e_off[e];
             est[i].edge = e;
             if (R == 0) { est[i].ncap = 64; est[i].slot = 4096; continue; }
-            estimate_edge(seg_len.data() + e_off[e], R, growth, sc, &est[i]);
+            estimate_edge(seg_len.data() + e_off[e], R, growth, sc, opt.force_i32 != 0, &est[i]);
             uint64_t sum = 0; uint32_t lmax = 0;
             for (uint32_t k = 0; k < R; ++k) { sum += seg_len[e_off[e] + k]; lmax = std::max(lmax, seg_len[e_off[e] + k]); }
             pool_cap += growth >= 1.0 ? sum : std::min<uint64_t>(sum, (uint64_t)(2.0 * lmax * (1.0 + growth)) + 256);
@@ -234,6 +234,8 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
             HGPU_CUDA(ctx, S->arena.ensure((size_t)warps * c.slot));
             HGPU_CUDA(ctx, S->ws.ensure((size_t)warps * c.wl.bytes));
             S->st.arena_bytes = std::max<uint64_t>(S->st.arena_bytes, (uint64_t)warps * c.slot);
+            if (opt.stop_round != 0xFFFFFFFFu)   // debug inspection looks for the one workspace that holds a graph
+                HGPU_CUDA(ctx, cudaMemsetAsync(S->ws.p, 0, (size_t)warps * c.wl.bytes, st));
             PoaArgs a{};
             a.bases = d_bases; a.seg_ptr = S->seg_ptr.p; a.seg_len = S->seg_len.p; a.e_seg_off = S->e_seg_off.p;
             a.items = S->items.p + c.a; a.n_items = n_items; a.counter = S->counters.p + ci;
@@ -262,7 +264,6 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
             uint32_t s_ = status_h[e];
             if (s_ == ST_CAPACITY || s_ == ST_TOO_LARGE || s_ == ST_POOL) next.push_back(e);
         }
-        if (opt.stop_round != 0xFFFFFFFFu) break;
         if (growth >= 1.0) break;     // worst case already tried
         pending.swap(next);
         growth = attempt >= 2 ? 1.0 : growth * 2.5;

@@ -586,12 +586,13 @@ __global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, 8) k_poa_edges(PoaArg
         uint32_t st = ST_OK;
         uint32_t n_cons = 0;
         bool debug_stop = false;
+        unsigned long long e_cells = 0, e_padded = 0, e_aln = 0, e_aln32 = 0, e_bases = 0;   // counted only if the edge completes
         if (R == 0) {
             if (lane == 0) { *gv.n_nodes = 0; *gv.n_edges = 0; *gv.aln_len = 0; }
         } else {
             const uint32_t L0 = a.seg_len[s0];
             if (L0 > gv.ncap || L0 > gv.ecap) st = ST_CAPACITY;
-            else { w_init_chain(gv, a.bases + a.seg_ptr[s0], L0, lane); st_bases += L0; }
+            else { w_init_chain(gv, a.bases + a.seg_ptr[s0], L0, lane); e_bases += L0; }
             for (uint32_t k = 1; k < R && st == ST_OK; ++k) {
                 const uint32_t V = *gv.n_nodes;
                 const uint32_t NE = *gv.n_edges;
@@ -606,10 +607,10 @@ __global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, 8) k_poa_edges(PoaArg
                     hdr[HDR_LAST_P16] = p16 ? 1u : 0u; hdr[HDR_LAST_V] = V; hdr[HDR_LAST_L] = L;
                     hdr[HDR_LAST_BIAS] = (uint32_t)(p16 ? Geo<DP_NW16, true>::bias(V, a.sc) : 0);
                 }
-                st_cells += (unsigned long long)(V + 1) * (L + 1);
-                st_padded += (unsigned long long)(V + 1) *
+                e_cells += (unsigned long long)(V + 1) * (L + 1);
+                e_padded += (unsigned long long)(V + 1) *
                              (p16 ? Geo<DP_NW16, true>::stripes(L) * Geo<DP_NW16, true>::SW : Geo<DP_NW32, false>::stripes(L) * Geo<DP_NW32, false>::SW);
-                st_aln += 1; st_aln32 += p16 ? 0 : 1; st_bases += L;
+                e_aln += 1; e_aln32 += p16 ? 0 : 1; e_bases += L;
                 if (!ok) { st = ST_TRACEBACK; break; }
                 if (k == a.stop_round) { debug_stop = true; break; }
                 // fold the alignment into the graph (serial, SPOA order), re-sort, rebuild the DP records
@@ -643,6 +644,7 @@ __global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, 8) k_poa_edges(PoaArg
             const uint32_t* ids = reinterpret_cast<const uint32_t*>(gv.aln_rank);
             for (uint32_t i = lane; i < n_cons; i += 32) a.pool[pos + i] = (uint8_t)"ACGT"[gv.code[ids[i]]];
         }
+        if (st == ST_OK) { st_cells += e_cells; st_padded += e_padded; st_aln += e_aln; st_aln32 += e_aln32; st_bases += e_bases; }
         if (lane == 0) {
             a.status[e] = st;
             a.cons_len[e] = (st == ST_OK) ? n_cons : 0;
