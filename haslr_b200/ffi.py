@@ -193,3 +193,56 @@ class Context:
                     aln_node=an[: sz.aln_len].copy(), aln_pos=ap[: sz.aln_len].copy(), rank2node=r2n[:V].copy(),
                     code=code[:V].copy(), pred_off=poff[: V + 1].copy(), pred_node=pn[: int(poff[V])].copy(),
                     pred_weight=pw[: int(poff[V])].copy())
+
+
+# ---- (i) / (ii): methods attached to Context ----------------------------------------------------------------
+def _hits_struct(h):
+    s = HitsT()
+    s.n_hits = len(h["q_start"])
+    keep = []
+    for n in ("q_start", "q_end", "t_id", "t_len", "t_start", "t_end", "n_match", "n_block", "cg_off", "cg_ops"):
+        a = np.ascontiguousarray(h[n], dtype=np.uint32); keep.append(a)
+        setattr(s, n, _p(a, u32p))
+    for n in ("is_rev", "mapq"):
+        a = np.ascontiguousarray(h[n], dtype=np.uint8); keep.append(a)
+        setattr(s, n, _p(a, u8p))
+    return s, keep
+
+
+def _compact_lr(self, hits, read_off, mean_kmer, uniq_freq, min_aln_block=500, min_aln_sim=0.85, min_aln_mapq=55, max_uniq_dev=0.15):
+    """build_compact_longreads (Longread.hpp:89) incl. the load filters / sort / overlap fix. Returns (elems CL_ELEM[], read_off)."""
+    hs, keep = _hits_struct(hits)
+    read_off = np.ascontiguousarray(read_off, dtype=np.uint32)
+    mean_kmer = np.ascontiguousarray(mean_kmer, dtype=np.float64)
+    n_reads = len(read_off) - 1
+    prm = K1Params(min_aln_sim, uniq_freq, max_uniq_dev, min_aln_block, min_aln_mapq)
+    elems = np.zeros(max(hs.n_hits, 1), dtype=CL_ELEM)
+    out_off = np.zeros(n_reads + 1, dtype=np.uint32)
+    n = C.c_uint64(0)
+    rc = self.L.hgpu_compact_lr(self.h, C.byref(hs), _p(read_off, u32p), n_reads, _p(mean_kmer, f64p), len(mean_kmer), C.byref(prm),
+                                elems.ctypes.data, _p(out_off, u32p), C.byref(n))
+    self._check(rc)
+    return elems[: n.value].copy(), out_off
+
+
+def _backbone_edges(self, cl_tid, cl_rev, cl_read_off, min_edge_sup=3):
+    """bbg_build_graph + the weak-edge rule (Backbone_graph.hpp:60,63). Returns (key64[], supp_off[], supp EDGE_SUPP[], keep[])."""
+    cl_tid = np.ascontiguousarray(cl_tid, dtype=np.uint32)
+    cl_rev = np.ascontiguousarray(cl_rev, dtype=np.uint8)
+    cl_read_off = np.ascontiguousarray(cl_read_off, dtype=np.uint32)
+    n_reads = len(cl_read_off) - 1
+    cnt = np.diff(cl_read_off.astype(np.int64))
+    n_pairs = int(np.maximum(cnt - 1, 0).sum())
+    cap = max(2 * n_pairs, 1)
+    key = np.zeros(cap, dtype=np.uint64); soff = np.zeros(cap + 1, dtype=np.uint32)
+    supp = np.zeros(cap, dtype=EDGE_SUPP); keep = np.zeros(cap, dtype=np.uint8)
+    n = C.c_uint64(0)
+    rc = self.L.hgpu_backbone_edges(self.h, _p(cl_tid, u32p), _p(cl_rev, u8p), _p(cl_read_off, u32p), n_reads, min_edge_sup,
+                                    _p(key, u64p), _p(soff, u32p), supp.ctypes.data, _p(keep, u8p), C.byref(n))
+    self._check(rc)
+    n = n.value
+    return key[:n].copy(), soff[: n + 1].copy(), supp[: int(soff[n])].copy(), keep[:n].copy()
+
+
+Context.compact_lr = _compact_lr
+Context.backbone_edges = _backbone_edges
