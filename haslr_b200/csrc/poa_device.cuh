@@ -560,6 +560,231 @@ __device__ __forceinline__ void w_build_meta(GraphView& g, int lane) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// w_add_alignment: SPOA Graph::add_alignment (unit weights), lane-parallel.
+// A global (kNW) alignment consumes every sequence position exactly once, so the work is indexed by sequence
+// position j: (A) resolve the node j lands on (existing node with the same base, an aligned sibling with that
+// base, or a new node), (B) number the new nodes in alignment order (= SPOA's creation order) with a warp scan,
+// initialise them and cross-link aligned sets, (C) add or bump the edge (node[j-1] -> node[j]). A path visits a
+// node at most once and at most one member of an aligned set, so lanes never touch the same list; an in-list
+// receives at most one new edge per alignment, so in-edge ORDER (what fixes every tie-break downstream) is the
+// same as in the serial version; edge ids differ, which nothing observes.
+// Returns ST_OK, or ST_CAPACITY; 0xFFFFFFFF = "not a full-coverage alignment, use the serial version".
+// ---------------------------------------------------------------------------------------------------------
+static constexpr uint32_t ABSENT = 0xFFFFFFFEu;
+
+__device__ __noinline__ uint32_t w_add_alignment(GraphView& g, GraphScratch& s, const uint8_t* seq, uint32_t L, int lane) {
+    const uint32_t n = *g.aln_len, N0 = *g.n_nodes, E0 = *g.n_edges;
+    if (n == 0 || 3ull * L > s.stack_cap) return 0xFFFFFFFFu;
+    if ((uint64_t)N0 + L > g.ncap || (uint64_t)E0 + L + 1 > g.ecap) return ST_CAPACITY;
+    uint32_t* by_j = s.stack; uint32_t* nid = by_j + L; uint32_t* alto = nid + L;
+    for (uint32_t j = lane; j < L; j += 32) by_j[j] = ABSENT;
+    __syncwarp();
+    for (uint32_t t = lane; t < n; t += 32) {
+        const int32_t pos = g.aln_pos[t];
+        if (pos != -1) by_j[pos] = (uint32_t)g.aln_rank[t];     // rank, or 0xFFFFFFFF for an insertion
+    }
+    __syncwarp();
+    // (A)+(B): node of every position; new nodes numbered in alignment order
+    uint32_t n_new = 0;
+    bool full = true;
+    for (uint32_t j0 = 0; j0 < L; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        bool isnew = false; uint32_t node = NIL, al = NIL;
+        if (j < L) {
+            const uint32_t rk = by_j[j];
+            const uint32_t c = base_code(seq[j]);
+            if (rk == ABSENT) full = false;
+            else if (rk == 0xFFFFFFFFu) isnew = true;
+            else {
+                const uint32_t a = g.rank2node[rk];
+                if (g.code[a] == c) node = a;
+                else {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const uint32_t o = g.aligned[3 * a + q];
+                        if (o == NIL) break;
+                        if (g.code[o] == c) { node = o; break; }
+                    }
+                    if (node == NIL) { isnew = true; al = a; }
+                }
+            }
+        }
+        const unsigned m = __ballot_sync(FULL, isnew);
+        if (isnew) node = N0 + n_new + __popc(m & ((1u << lane) - 1));
+        n_new += __popc(m);
+        if (j < L) { nid[j] = node; alto[j] = al; }
+    }
+    if (__any_sync(FULL, !full)) return 0xFFFFFFFFu;             // nothing modified yet
+    __syncwarp();
+    // (B2): initialise new nodes, cross-link aligned sets (SPOA order: existing members first, then the node aligned to)
+    for (uint32_t j = lane; j < L; j += 32) {
+        const uint32_t v = nid[j];
+        if (v < N0) continue;
+        g.code[v] = (uint8_t)base_code(seq[j]);
+        g.in_head[v] = NIL; g.in_tail[v] = NIL; g.out_head[v] = NIL;
+        uint32_t a3[3] = {NIL, NIL, NIL};
+        const uint32_t a = alto[j];
+        if (a != NIL) {
+            int cnt = 0;
+            for (int q = 0; q < 3; ++q) {
+                const uint32_t o = g.aligned[3 * a + q];
+                if (o == NIL) break;
+                a3[cnt++] = o;
+                for (int z = 0; z < 3; ++z) if (g.aligned[3 * o + z] == NIL) { g.aligned[3 * o + z] = v; break; }
+            }
+            a3[cnt] = a;
+            for (int z = 0; z < 3; ++z) if (g.aligned[3 * a + z] == NIL) { g.aligned[3 * a + z] = v; break; }
+        }
+        g.aligned[3 * v] = a3[0]; g.aligned[3 * v + 1] = a3[1]; g.aligned[3 * v + 2] = a3[2];
+    }
+    __syncwarp();
+    // (C): edges between consecutive positions, weight 2 (both bases contribute 1)
+    uint32_t e_new = 0;
+    for (uint32_t j0 = 1; j0 < L; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        bool need = false; uint32_t b = NIL, e = NIL;
+        if (j < L) {
+            b = nid[j - 1]; e = nid[j];
+            need = true;
+            for (uint32_t x = g.out_head[b]; x != NIL; x = g.e_next_out[x])
+                if (g.e_end[x] == e) { g.e_w[x] += 2; need = false; break; }
+        }
+        const unsigned m = __ballot_sync(FULL, need);
+        if (need) {
+            const uint32_t x = E0 + e_new + __popc(m & ((1u << lane) - 1));
+            g.e_begin[x] = b; g.e_end[x] = e; g.e_w[x] = 2;
+            g.e_next_in[x] = NIL;
+            g.e_next_out[x] = g.out_head[b];
+            g.out_head[b] = x;
+            const uint32_t tl = g.in_tail[e];
+            if (tl == NIL) g.in_head[e] = x; else g.e_next_in[tl] = x;
+            g.in_tail[e] = x;
+        }
+        e_new += __popc(m);
+    }
+    if (lane == 0) { *g.n_nodes = N0 + n_new; *g.n_edges = E0 + e_new; }
+    __syncwarp();
+    return ST_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// w_toposort: SPOA Graph::topological_sort, same order, mostly lane-parallel.
+// SPOA walks roots i = 0..N-1 in id order and runs a DFS over in-edges / aligned nodes from every unmarked one.
+// A root whose predecessors are all emitted and that has no aligned nodes is emitted on the spot — that is the
+// bulk of a POA graph, and it is decided here for 32 consecutive ids at a time from registers and two shared-memory
+// bitmaps (emitted, "do not check aligned"): the longest prefix of the batch whose nodes are emitted already or
+// emit-on-the-spot is ranked with one ballot. Only the first node that breaks the prefix (an aligned set, a
+// branch whose nodes have larger ids) runs SPOA's DFS verbatim on one lane, then the batch resumes behind it.
+// Returns 1 ok, 0 failed (stack overflow / step guard): the caller falls back to the serial g_toposort.
+// ---------------------------------------------------------------------------------------------------------
+static constexpr uint32_t TOPO_BM_WORDS = 400;                    // 12,800 nodes per bitmap
+static constexpr uint32_t TOPO_STACK = (DP_SMEM_PER_WARP - 2 * TOPO_BM_WORDS * 4) / 4;   // 320 entries
+
+__device__ __noinline__ int w_toposort(GraphView& g, uint8_t* wsm, int lane) {
+    const uint32_t N = *g.n_nodes;
+    if (N > TOPO_BM_WORDS * 32) return 0;
+    uint32_t* perm = reinterpret_cast<uint32_t*>(wsm);
+    uint32_t* nochk = perm + TOPO_BM_WORDS;
+    uint32_t* stk = nochk + TOPO_BM_WORDS;
+    for (uint32_t w = lane; w < (N + 31) / 32; w += 32) { perm[w] = 0; nochk[w] = 0; }
+    __syncwarp();
+    auto is_perm = [&](uint32_t v) -> bool { return (perm[v >> 5] >> (v & 31)) & 1u; };
+    uint32_t nr = 0;
+    int okflag = 1;
+    for (uint32_t i0 = 0; i0 < N && okflag; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const bool valid = i < N;
+        uint32_t np = 0, p0 = NIL, p1 = NIL;
+        bool slow = false;                                        // aligned nodes or more than two predecessors
+        if (valid) {
+            uint32_t x = g.in_head[i];
+            if (x != NIL) {
+                p0 = g.e_begin[x]; np = 1; x = g.e_next_in[x];
+                if (x != NIL) { p1 = g.e_begin[x]; np = 2; if (g.e_next_in[x] != NIL) slow = true; }
+            }
+            if (g.aligned[3 * i] != NIL) slow = true;
+        }
+        uint32_t pos = 0;
+        while (true) {
+            const uint32_t lo = i0 + pos;
+            const bool marked = valid && is_perm(i);
+            bool ok = valid && (uint32_t)lane >= pos && !marked && !slow;
+            if (ok && np >= 1) ok = is_perm(p0) || (p0 >= lo && p0 < i);
+            if (ok && np >= 2) ok = is_perm(p1) || (p1 >= lo && p1 < i);
+            const bool pass = (uint32_t)lane < pos || !valid || marked || ok;
+            const unsigned failmask = __ballot_sync(FULL, !pass);
+            const uint32_t f = failmask ? (uint32_t)(__ffs(failmask) - 1) : 32u;
+            const bool emit = ok && (uint32_t)lane < f;
+            const unsigned em = __ballot_sync(FULL, emit);
+            if (emit) {
+                const uint32_t r = nr + __popc(em & ((1u << lane) - 1));
+                g.rank2node[r] = i; g.node2rank[i] = r;
+            }
+            if (lane == 0 && em) perm[i0 >> 5] |= em;
+            nr += __popc(em);
+            __syncwarp();
+            if (f >= 32) break;
+            // SPOA's DFS from root i0+f, verbatim, on one lane
+            if (lane == 0) {
+                uint32_t sp = 0, guard = 0;
+                const uint32_t limit = 16u * (N + *g.n_edges) + 1024u;
+                stk[sp++] = i0 + f;
+                while (sp > 0) {
+                    if (++guard > limit) { okflag = 0; break; }
+                    const uint32_t v = stk[sp - 1];
+                    bool vvalid = true;
+                    if (!is_perm(v)) {
+                        const bool chk = !((nochk[v >> 5] >> (v & 31)) & 1u);
+                        for (uint32_t x = g.in_head[v]; x != NIL; x = g.e_next_in[x]) {
+                            const uint32_t b = g.e_begin[x];
+                            if (!is_perm(b)) {
+                                if (sp >= TOPO_STACK) { okflag = 0; break; }
+                                stk[sp++] = b; vvalid = false;
+                            }
+                        }
+                        if (!okflag) break;
+                        uint32_t al[3] = {NIL, NIL, NIL};
+                        if (chk) {
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) {
+                                const uint32_t o = g.aligned[3 * v + q];
+                                if (o == NIL) break;
+                                al[q] = o;
+                                if (!is_perm(o)) {
+                                    if (sp >= TOPO_STACK) { okflag = 0; break; }
+                                    stk[sp++] = o; nochk[o >> 5] |= 1u << (o & 31); vvalid = false;
+                                }
+                            }
+                            if (!okflag) break;
+                        }
+                        if (vvalid) {
+                            perm[v >> 5] |= 1u << (v & 31);
+                            if (chk) {
+                                g.rank2node[nr] = v; g.node2rank[v] = nr; ++nr;
+#pragma unroll
+                                for (int q = 0; q < 3; ++q) {
+                                    if (al[q] == NIL) break;
+                                    g.rank2node[nr] = al[q]; g.node2rank[al[q]] = nr; ++nr;
+                                }
+                            }
+                        }
+                    }
+                    if (vvalid) --sp;
+                }
+            }
+            nr = __shfl_sync(FULL, nr, 0);
+            okflag = __shfl_sync(FULL, okflag, 0);
+            __syncwarp();
+            if (!okflag) break;
+            pos = f + 1;
+            if (pos >= 32) break;
+        }
+    }
+    if (okflag && nr != N) okflag = 0;
+    return okflag;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // k_poa_edges: the persistent per-edge kernel.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, 8) k_poa_edges(PoaArgs a) {
@@ -613,15 +838,22 @@ __global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, 8) k_poa_edges(PoaArg
                 e_aln += 1; e_aln32 += p16 ? 0 : 1; e_bases += L;
                 if (!ok) { st = ST_TRACEBACK; break; }
                 if (k == a.stop_round) { debug_stop = true; break; }
-                // fold the alignment into the graph (serial, SPOA order), re-sort, rebuild the DP records
-                uint32_t ust = ST_OK;
-                if (lane == 0) {
-                    if (!g_add_alignment(gv, seq, L)) ust = ST_CAPACITY;
-                    else if (!g_toposort(gv, gs)) ust = ST_TOPOSORT;
+                // fold the alignment into the graph, re-sort, rebuild the DP records (same results as SPOA's serial code)
+                uint32_t ust = w_add_alignment(gv, gs, seq, L, lane);
+                if (ust == 0xFFFFFFFFu) {                 // not a full-coverage alignment: serial restatement
+                    ust = ST_OK;
+                    if (lane == 0 && !g_add_alignment(gv, seq, L)) ust = ST_CAPACITY;
+                    ust = __shfl_sync(FULL, ust, 0);
+                    __syncwarp();
                 }
-                ust = __shfl_sync(FULL, ust, 0);
-                __syncwarp();
                 if (ust != ST_OK) { st = ust; break; }
+                if (!w_toposort(gv, wsm, lane)) {          // too large for the shared-memory bitmaps / deep DFS: serial
+                    ust = ST_OK;
+                    if (lane == 0 && !g_toposort(gv, gs)) ust = ST_TOPOSORT;
+                    ust = __shfl_sync(FULL, ust, 0);
+                    __syncwarp();
+                    if (ust != ST_OK) { st = ust; break; }
+                }
                 w_build_meta(gv, lane);
             }
             if (a.stop_round != 0xFFFFFFFFu) debug_stop = true;
