@@ -191,6 +191,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     ctx = haslr_b200.Context(local)
     ctx.poa_set_timing(True)
+    if os.environ.get("HGPU_MAX_WARPS"):   # developer knob for occupancy experiments
+        ctx.poa_configure(0, int(os.environ["HGPU_MAX_WARPS"]))
     n_edges = args.edges
 
     # ---- synthetic cfg3 shard of this rank, resident in HBM and mirrored in pinned host memory

@@ -113,6 +113,16 @@ __host__ __device__ inline GraphScratch bind_scratch(uint8_t* base, const WsLayo
 }
 
 static constexpr unsigned FULL = 0xFFFFFFFFu;
+#ifndef HGPU_STCS
+#define HGPU_STCS 1
+#endif
+__device__ __forceinline__ void st_row(uint4* p, uint4 v) {
+#if HGPU_STCS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
 static constexpr int TB_ROWS = 32, TB_COLS = 32;
 static constexpr int TB_SMEM_BYTES = TB_ROWS * TB_COLS * 4 + TB_ROWS * 8 + TB_COLS;  // tile + meta0/1 + seq codes
 
@@ -145,7 +155,10 @@ __host__ __device__ inline bool dp_fits16(uint32_t V, uint32_t L, const DpScores
 
 static constexpr int DP_NW16 = 8;   // int16 kernel: 16 columns per lane, 512-column stripes
 static constexpr int DP_NW32 = 8;   // int32 kernel:  8 columns per lane, 256-column stripes
-static constexpr int DP_SMEM_PER_WARP = 4480;  // max(profile 4 KB, traceback tile 4384 B), 128-byte multiple
+#ifndef HGPU_RING
+#define HGPU_RING 0
+#endif
+static constexpr int DP_SMEM_PER_WARP = HGPU_RING ? 6144 : 4480;  // profile 4 KB + two-row ring 2 KB; reused by the traceback tile (4384 B) and the sort bitmaps
 static constexpr int DP_WARPS_PER_BLOCK = 4;
 
 __host__ __device__ inline uint64_t dp_slot_bytes(uint32_t V, uint32_t L, bool p16) {
@@ -276,12 +289,21 @@ struct RowOps {
 // Graph-NW of one segment against the warp's graph: fill the slot, trace back into gv.aln_rank/aln_pos
 // (traceback order, graph side as ranks). Returns false if the traceback found no predecessor.
 // ---------------------------------------------------------------------------------------------------------
+#ifndef HGPU_INLINE_DP
+#define HGPU_INLINE_DP 1
+#endif
+#if HGPU_INLINE_DP
+#define DP_INLINE __forceinline__
+#else
+#define DP_INLINE __noinline__
+#endif
 template <int NW, bool P16>
-__device__ __noinline__ bool dp_align(const GraphView& gv, uint8_t* slot, uint8_t* wsm, const uint8_t* seq,
+__device__ DP_INLINE bool dp_align(const GraphView& gv, uint8_t* slot, uint8_t* wsm, const uint8_t* seq,
                                       uint32_t V, uint32_t L, const DpScores sc, int lane) {
     using G = Geo<NW, P16>;
     using R = RowOps<NW, P16>;
     uint32_t* prof = reinterpret_cast<uint32_t*>(wsm);                 // [4][NW][32]
+    uint4* ring = reinterpret_cast<uint4*>(wsm + G::PROF_BYTES);      // [2][UNITS][32]: rows i-2 / i-3 of the current stripe
     const int g = sc.g;
     const uint32_t g2 = P16 ? pack2(g) : (uint32_t)g;
     SlotView<NW, P16> sv;
@@ -333,6 +355,7 @@ __device__ __noinline__ bool dp_align(const GraphView& gv, uint8_t* slot, uint8_
             if (lane == 31) bc_cur[0] = bias;
         }
 
+        const bool has_next_stripe = s + 1 < NS;
         for (uint32_t r0 = 0; r0 < V; r0 += 32) {
             // batched per-rank records: lane q holds rank r0+q
             const uint32_t rr = r0 + lane;
@@ -344,69 +367,104 @@ __device__ __noinline__ bool dp_align(const GraphView& gv, uint8_t* slot, uint8_
             }
             const int nb = (V - r0) < 32u ? (int)(V - r0) : 32;
             for (int q = 0; q < nb; ++q) {
-                const uint32_t r = r0 + q, i = r + 1;
+                const uint32_t i = r0 + q + 1;
                 const uint32_t m0 = __shfl_sync(FULL, mm0, q);
-                const uint32_t m1 = __shfl_sync(FULL, mm1, q);
-                const int diag_in = __shfl_sync(FULL, bcd, q);     // Hhat[i-1][first col of stripe - 1]
-                const int carry_in = __shfl_sync(FULL, bcc, q);    // Hhat[i][first col of stripe - 1]
-                const uint32_t code = m0 & 3u, npc = (m0 >> 3) & 3u, d0 = m0 >> 5;
-                const uint32_t* pf = prof + code * NW * 32 + lane;
-                if ((npc == 1 && d0 == 1) || (npc == 0 && r == 0)) {
+                int diag_in = G::NEGV, carry_in = G::NEGV;
+                if (s > 0) {
+                    diag_in = __shfl_sync(FULL, bcd, q);      // Hhat[i-1][first col of stripe - 1]
+                    carry_in = __shfl_sync(FULL, bcc, q);     // Hhat[i][first col of stripe - 1]
+                }
+                const uint32_t* pf = prof + (m0 & 3u) * (NW * 32) + lane;
+                // ring slot of row i-1 (the row in h); it replaces row i-3 there, so ring reads come first
+                uint4* ring_wr = ring + ((i - 1) & 1u) * (G::UNITS * 32) + lane;
+                if ((m0 & META_FAST) != 0) {                  // single predecessor = previous rank: registers only
+                    if (HGPU_RING) {
+#pragma unroll
+                        for (int u = 0; u < G::UNITS; ++u) ring_wr[u * 32] = make_uint4(h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
+                    }
                     uint32_t left = __shfl_up_sync(FULL, h[NW - 1], 1);
                     if (lane == 0) left = R::left_from_cell(diag_in);
                     R::from_regs(h, left, pf, g2, g);
                 } else {
+                    const uint32_t npc = (m0 >> 3) & 3u, d0 = m0 >> META_D0_SHIFT;
                     uint32_t t[NW];
 #pragma unroll
                     for (int k = 0; k < NW; ++k) t[k] = P16 ? pack2(G::NEGV) : (uint32_t)G::NEGV;
-                    uint32_t np = npc, cs = 0;
+                    uint32_t np = npc, cs = 0, d1 = 0;
                     if (npc == 0) np = 1;
-                    if (npc == 3) { cs = gv.pred_off[r]; np = gv.pred_off[r + 1] - cs; }
+                    if (npc >= 2) d1 = __shfl_sync(FULL, mm1, q);
+                    if (npc == 3) { cs = gv.pred_off[i - 1]; np = gv.pred_off[i] - cs; }
                     for (uint32_t x = 0; x < np; ++x) {
-                        uint32_t prow;
-                        if (npc == 0) prow = 0;
-                        else if (npc == 3) prow = gv.pred_rank[cs + x] + 1;
-                        else prow = i - (x == 0 ? d0 : m1);
-                        if (prow == i - 1) {
+                        uint32_t dist;                         // rank distance to this predecessor row
+                        if (npc == 0) dist = i;
+                        else if (npc == 3) dist = i - (gv.pred_rank[cs + x] + 1);
+                        else dist = x == 0 ? d0 : d1;
+                        if (dist == 1) {
                             uint32_t left = __shfl_up_sync(FULL, h[NW - 1], 1);
                             if (lane == 0) left = R::left_from_cell(diag_in);
 #pragma unroll
                             for (int k = 0; k < NW; ++k) t[k] = R::acc(t[k], k ? h[k > 0 ? k - 1 : 0] : left, h[k], pf[k * 32], g2, g);
                         } else {
-                            const uint4* src = sv.row_units(prow, s, lane);
-                            uint4 lastu = src[(G::UNITS - 1) * 32];
-                            uint32_t left = __shfl_up_sync(FULL, lastu.w, 1);
-                            if (lane == 0) left = R::left_from_cell(s > 0 ? bc_prev[prow - 0] : G::NEGV);
+                            const uint32_t prow = i - dist;
+                            // rows i-2 and i-3 live in the shared-memory ring, older ones are re-read from the slot
+                            const uint4* src = (HGPU_RING && dist <= 3) ? ring + (prow & 1u) * (G::UNITS * 32) + lane : sv.row_units(prow, s, lane);
+                            const uint32_t ustride = 32;
+                            uint4 v[G::UNITS];
+#pragma unroll
+                            for (int u = 0; u < G::UNITS; ++u) v[u] = src[u * ustride];
+                            uint32_t left = __shfl_up_sync(FULL, v[G::UNITS - 1].w, 1);
+                            int bl = G::NEGV;                  // Hhat[prow][first col of stripe - 1]
+                            if (s > 0) {
+                                const int ql = q + 1 - (int)dist;
+                                bl = ql >= 0 ? __shfl_sync(FULL, bcd, ql & 31) : bc_prev[prow];
+                            }
+                            if (lane == 0) left = R::left_from_cell(bl);
                             uint32_t prev = left;
 #pragma unroll
                             for (int u = 0; u < G::UNITS; ++u) {
-                                uint4 v = src[u * 32];
-                                t[4 * u] = R::acc(t[4 * u], prev, v.x, pf[(4 * u) * 32], g2, g);
-                                t[4 * u + 1] = R::acc(t[4 * u + 1], v.x, v.y, pf[(4 * u + 1) * 32], g2, g);
-                                t[4 * u + 2] = R::acc(t[4 * u + 2], v.y, v.z, pf[(4 * u + 2) * 32], g2, g);
-                                t[4 * u + 3] = R::acc(t[4 * u + 3], v.z, v.w, pf[(4 * u + 3) * 32], g2, g);
-                                prev = v.w;
+                                t[4 * u] = R::acc(t[4 * u], prev, v[u].x, pf[(4 * u) * 32], g2, g);
+                                t[4 * u + 1] = R::acc(t[4 * u + 1], v[u].x, v[u].y, pf[(4 * u + 1) * 32], g2, g);
+                                t[4 * u + 2] = R::acc(t[4 * u + 2], v[u].y, v[u].z, pf[(4 * u + 2) * 32], g2, g);
+                                t[4 * u + 3] = R::acc(t[4 * u + 3], v[u].z, v[u].w, pf[(4 * u + 3) * 32], g2, g);
+                                prev = v[u].w;
                             }
                         }
+                    }
+                    if (HGPU_RING) {
+#pragma unroll
+                        for (int u = 0; u < G::UNITS; ++u) ring_wr[u * 32] = make_uint4(h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
                     }
 #pragma unroll
                     for (int k = 0; k < NW; ++k) h[k] = t[k];
                 }
                 // horizontal gaps = prefix maximum in hat space
-                int incl = R::scan(h);
+                // Across lanes the exclusive prefix is needed. Lane totals almost always rise up to the lane holding the
+                // row maximum and everything right of it inherits that maximum, so: neighbour total (1 SHFL) + row maximum
+                // (1 REDUX) + two ballots decide the common case exactly; any violation falls back to the 5-step scan.
+                const int tot = R::scan(h);
+                const int nbv = __shfl_up_sync(FULL, tot, 1);
+                const int rowmax = __reduce_max_sync(FULL, tot);
+                const int prevv = (lane == 0) ? carry_in : nbv;
+                const int amax = __ffs(__ballot_sync(FULL, tot == rowmax)) - 1;     // first lane holding the maximum
+                int excl;
+                if (__ballot_sync(FULL, lane <= amax && tot < prevv) == 0) {
+                    excl = (lane <= amax) ? prevv : rowmax;
+                } else {
+                    int incl = tot;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    int v = __shfl_up_sync(FULL, incl, d);
-                    if (lane >= d) incl = max(incl, v);
+                    for (int d = 1; d < 32; d <<= 1) {
+                        int v = __shfl_up_sync(FULL, incl, d);
+                        if (lane >= d) incl = max(incl, v);
+                    }
+                    excl = __shfl_up_sync(FULL, incl, 1);
+                    excl = (lane == 0) ? carry_in : max(excl, carry_in);
                 }
-                int excl = __shfl_up_sync(FULL, incl, 1);
-                excl = (lane == 0) ? carry_in : max(excl, carry_in);
                 R::apply_carry(h, excl);
                 // stream the row out
                 uint4* dst = sv.row_units(i, s, lane);
 #pragma unroll
-                for (int u = 0; u < G::UNITS; ++u) dst[u * 32] = make_uint4(h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
-                if (lane == 31) bc_cur[i] = R::last_cell(h);
+                for (int u = 0; u < G::UNITS; ++u) st_row(dst + u * 32, make_uint4(h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]));
+                if (has_next_stripe && lane == 31) bc_cur[i] = R::last_cell(h);
             }
         }
         __syncwarp();
@@ -436,6 +494,7 @@ __device__ __noinline__ bool dp_align(const GraphView& gv, uint8_t* slot, uint8_
     uint32_t ci = best_i, cj = L, n_out = 0;
     bool bad = (best_i == 0);
     while (!bad && !(ci == 0 && cj == 0)) {
+        // tile of the stored matrix with (ci, cj) in its corner: tile[a][b] = Hhat[it - a][jt - b]
         const uint32_t it = ci, jt = cj;
         __syncwarp();
         if (it >= (uint32_t)lane) {
@@ -446,12 +505,35 @@ __device__ __noinline__ bool dp_align(const GraphView& gv, uint8_t* slot, uint8_
         }
         if (jt >= (uint32_t)lane + 1) tseq[lane] = (uint8_t)base_code(seq[jt - lane - 1]);
         __syncwarp();
-        if (lane == 0) {
-            uint32_t i = ci, j = cj;
-            while (true) {
-                if (i == 0 && j == 0) break;
-                const uint32_t li = it - i, lj = jt - j;
-                if ((li >= (uint32_t)TB_ROWS - 1 || lj >= (uint32_t)TB_COLS - 1) && (li != 0 || lj != 0)) break;
+        while (true) {
+            if (ci == 0 && cj == 0) break;
+            const uint32_t li = it - ci, lj = jt - cj;
+            if (li >= (uint32_t)TB_ROWS - 1 || lj >= (uint32_t)TB_COLS - 1) break;     // reload the tile around (ci, cj)
+            // (1) a run of diagonal moves through rows whose only predecessor is the previous rank: SPOA tries the
+            //     diagonal of the first predecessor first, so every lane can test "its" step of the run independently
+            {
+                const uint32_t a_ = li + lane, b_ = lj + lane;
+                bool cond = a_ + 1 < (uint32_t)TB_ROWS && b_ + 1 < (uint32_t)TB_COLS && ci > (uint32_t)lane && cj > (uint32_t)lane;
+                if (cond) {
+                    const uint32_t m0 = tm0[a_];
+                    const int dsc = (tseq[b_] == (m0 & 3u)) ? sc.sm : sc.sx;
+                    cond = (m0 & META_FAST) != 0 && tile[a_ * TB_COLS + b_] == tile[(a_ + 1) * TB_COLS + b_ + 1] + dsc;
+                }
+                const unsigned fm = __ballot_sync(FULL, !cond);
+                const uint32_t run = fm ? (uint32_t)(__ffs(fm) - 1) : 32u;
+                if (run > 0) {
+                    if ((uint64_t)n_out + run > gv.ncap) { bad = true; break; }
+                    if ((uint32_t)lane < run) {
+                        gv.aln_rank[n_out + lane] = (int32_t)(ci - lane - 1);
+                        gv.aln_pos[n_out + lane] = (int32_t)(cj - lane - 1);
+                    }
+                    n_out += run; ci -= run; cj -= run;
+                    continue;
+                }
+            }
+            // (2) one generic step in SPOA's preference order: diagonal over predecessors (in-edge order), vertical, horizontal
+            if (lane == 0) {
+                const uint32_t i = ci, j = cj;
                 auto getH = [&](uint32_t ii, uint32_t jj) -> int {
                     uint32_t a_ = it - ii, b_ = jt - jj;   // ii <= it, jj <= jt always hold on a walk up/left
                     if (a_ < (uint32_t)TB_ROWS && b_ < (uint32_t)TB_COLS) return tile[a_ * TB_COLS + b_];
@@ -462,7 +544,7 @@ __device__ __noinline__ bool dp_align(const GraphView& gv, uint8_t* slot, uint8_
                 bool found = false;
                 if (i != 0) {
                     const uint32_t m0 = tm0[li], m1 = tm1[li];
-                    const uint32_t code = m0 & 3u, npc = (m0 >> 3) & 3u, d0 = m0 >> 5;
+                    const uint32_t code = m0 & 3u, npc = (m0 >> 3) & 3u, d0 = m0 >> META_D0_SHIFT;
                     uint32_t np = npc, cs = 0;
                     if (npc == 0) np = 1;
                     if (npc == 3) { cs = gv.pred_off[i - 1]; np = gv.pred_off[i] - cs; }
@@ -479,17 +561,19 @@ __device__ __noinline__ bool dp_align(const GraphView& gv, uint8_t* slot, uint8_
                     }
                 }
                 if (!found && j != 0 && val == getH(i, j - 1)) { pi = i; pj = j - 1; found = true; }
-                if (!found || n_out >= gv.ncap) { bad = true; break; }
-                gv.aln_rank[n_out] = (pi == i) ? -1 : (int32_t)(i - 1);
-                gv.aln_pos[n_out] = (pj == j) ? -1 : (int32_t)(j - 1);
-                ++n_out;
-                i = pi; j = pj;
+                if (!found || n_out >= gv.ncap) { bad = true; }
+                else {
+                    gv.aln_rank[n_out] = (pi == i) ? -1 : (int32_t)(i - 1);
+                    gv.aln_pos[n_out] = (pj == j) ? -1 : (int32_t)(j - 1);
+                    ++n_out;
+                    ci = pi; cj = pj;
+                }
             }
-            ci = i; cj = j;
+            ci = __shfl_sync(FULL, ci, 0); cj = __shfl_sync(FULL, cj, 0);
+            n_out = __shfl_sync(FULL, n_out, 0);
+            bad = __shfl_sync(FULL, (int)bad, 0) != 0;
+            if (bad) break;
         }
-        ci = __shfl_sync(FULL, ci, 0); cj = __shfl_sync(FULL, cj, 0);
-        n_out = __shfl_sync(FULL, n_out, 0);
-        bad = __shfl_sync(FULL, (int)bad, 0) != 0;
     }
     if (lane == 0) *gv.aln_len = bad ? 0 : n_out;
     __syncwarp();
@@ -509,7 +593,7 @@ __device__ __forceinline__ void w_init_chain(GraphView& g, const uint8_t* seq, u
         g.aligned[3 * i] = g.aligned[3 * i + 1] = g.aligned[3 * i + 2] = NIL;
         if (i + 1 < L) { g.e_begin[i] = i; g.e_end[i] = i + 1; g.e_w[i] = 2; g.e_next_in[i] = NIL; g.e_next_out[i] = NIL; }
         g.rank2node[i] = i; g.node2rank[i] = i;
-        g.meta0[i] = c | ((i + 1 < L) ? 0u : META_SINK) | ((i > 0) ? ((1u << 3) | (1u << 5)) : 0u);
+        g.meta0[i] = c | ((i + 1 < L) ? 0u : META_SINK) | META_FAST | ((i > 0) ? ((1u << 3) | (1u << META_D0_SHIFT)) : 0u);
         g.meta1[i] = 0;
         g.pred_off[i] = (i > 0) ? i - 1 : 0;
         if (i > 0) g.pred_rank[i - 1] = i - 1;
@@ -546,11 +630,12 @@ __device__ __forceinline__ void w_build_meta(GraphView& g, int lane) {
             for (uint32_t x = g.in_head[v]; x != NIL; x = g.e_next_in[x]) {
                 uint32_t pr = g.node2rank[g.e_begin[x]];
                 g.pred_rank[off + np] = pr;
-                if (np == 0) m0 |= (r - pr) << 5;
+                if (np == 0) m0 |= (r - pr) << META_D0_SHIFT;
                 if (np == 1) m1 = r - pr;
                 ++np;
             }
             m0 |= (np > 3 ? 3u : np) << 3;
+            if ((np == 1 && (m0 >> META_D0_SHIFT) == 1) || (np == 0 && r == 0)) m0 |= META_FAST;
             g.meta0[r] = m0; g.meta1[r] = m1;
         }
         running += __shfl_sync(FULL, incl, 31);
@@ -677,8 +762,8 @@ __device__ __noinline__ uint32_t w_add_alignment(GraphView& g, GraphScratch& s, 
 // branch whose nodes have larger ids) runs SPOA's DFS verbatim on one lane, then the batch resumes behind it.
 // Returns 1 ok, 0 failed (stack overflow / step guard): the caller falls back to the serial g_toposort.
 // ---------------------------------------------------------------------------------------------------------
-static constexpr uint32_t TOPO_BM_WORDS = 400;                    // 12,800 nodes per bitmap
-static constexpr uint32_t TOPO_STACK = (DP_SMEM_PER_WARP - 2 * TOPO_BM_WORDS * 4) / 4;   // 320 entries
+static constexpr uint32_t TOPO_BM_WORDS = HGPU_RING ? 576 : 400;     // nodes per bitmap = 32x
+static constexpr uint32_t TOPO_STACK = (DP_SMEM_PER_WARP - 2 * TOPO_BM_WORDS * 4) / 4;   // 384 entries
 
 __device__ __noinline__ int w_toposort(GraphView& g, uint8_t* wsm, int lane) {
     const uint32_t N = *g.n_nodes;
@@ -787,7 +872,10 @@ __device__ __noinline__ int w_toposort(GraphView& g, uint8_t* wsm, int lane) {
 // ---------------------------------------------------------------------------------------------------------
 // k_poa_edges: the persistent per-edge kernel.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, 8) k_poa_edges(PoaArgs a) {
+#ifndef HGPU_MINBLOCKS
+#define HGPU_MINBLOCKS 7
+#endif
+__global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, HGPU_MINBLOCKS) k_poa_edges(PoaArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;

@@ -24,9 +24,12 @@ static constexpr uint32_t NIL = 0xFFFFFFFFu;
 //   bits 0-1  node code (A,C,G,T = 0..3)
 //   bit  2    sink (no out-edges)
 //   bits 3-4  predecessor class: 0 none, 1 one, 2 two, 3 three or more (walk the CSR)
-//   bits 5-31 rank distance to the first predecessor (classes 1..3)
+//   bit  5    fast row: its only predecessor is the previous rank (or it is rank 0 without predecessors)
+//   bits 6-31 rank distance to the first predecessor (classes 1..3)
 // meta1: rank distance to the second predecessor (classes 2..3)
 static constexpr uint32_t META_SINK = 4u;
+static constexpr uint32_t META_FAST = 32u;
+static constexpr int META_D0_SHIFT = 6;
 
 struct GraphView {
     uint32_t ncap;        // capacity in nodes (== capacity of the aln arrays)
@@ -229,11 +232,12 @@ HGPU_HD void g_build_meta(GraphView& g) {
         for (uint32_t x = g.in_head[v]; x != NIL; x = g.e_next_in[x]) {
             uint32_t pr = g.node2rank[g.e_begin[x]];
             g.pred_rank[pe++] = pr;
-            if (np == 0) m0 |= (r - pr) << 5;
+            if (np == 0) m0 |= (r - pr) << META_D0_SHIFT;
             if (np == 1) m1 = r - pr;
             ++np;
         }
         m0 |= (np > 3 ? 3u : np) << 3;
+        if ((np == 1 && (m0 >> META_D0_SHIFT) == 1) || (np == 0 && r == 0)) m0 |= META_FAST;
         g.meta0[r] = m0; g.meta1[r] = m1;
     }
     g.pred_off[N] = pe;

@@ -51,7 +51,8 @@ EDGE_SUPP = np.dtype([("lr_id_strand", "<u4"), ("cmp_head", "<u4"), ("cmp_tail",
 
 
 def lib_path():
-    return os.path.join(_HERE, "libhaslr_b200.so")
+    # HASLR_B200_LIB: developer override to A/B-test another build of the same library
+    return os.environ.get("HASLR_B200_LIB") or os.path.join(_HERE, "libhaslr_b200.so")
 
 
 _lib = None

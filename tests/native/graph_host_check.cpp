@@ -43,7 +43,7 @@ struct Store {
 // predecessor rows (1-based H rows) of rank r from the packed records, exactly as the CUDA fill decodes them
 void pred_rows(const GraphView& g, uint32_t r, std::vector<uint32_t>& out) {
     out.clear();
-    const uint32_t m0 = g.meta0[r], m1 = g.meta1[r], npc = (m0 >> 3) & 3u, d0 = m0 >> 5, i = r + 1;
+    const uint32_t m0 = g.meta0[r], m1 = g.meta1[r], npc = (m0 >> 3) & 3u, d0 = m0 >> META_D0_SHIFT, i = r + 1;
     if (npc == 0) { out.push_back(0); return; }
     if (npc == 3) { for (uint32_t x = g.pred_off[r]; x < g.pred_off[r + 1]; ++x) out.push_back(g.pred_rank[x] + 1); return; }
     out.push_back(i - d0);
