@@ -8,7 +8,15 @@ LIB      := haslr_b200/libhaslr_b200.so
 TUS      := api poa k12
 HDRS     := $(wildcard $(CSRC)/*.cuh) include/haslr_b200.h
 
-all: $(LIB)
+HOSTSRC  := $(wildcard haslr_b200/host/*.cpp)
+BIN      := bin/haslr_assemble
+
+all: $(LIB) $(BIN)
+
+# the drop-in binary: C++ host code above the C ABI
+$(BIN): $(HOSTSRC) haslr_b200/host/haslr.hpp $(LIB)
+	@mkdir -p bin
+	g++ -std=c++17 -O2 -Wall -o $@ $(HOSTSRC) -Lhaslr_b200 -lhaslr_b200 -Wl,-rpath,'$$ORIGIN/../haslr_b200' -lz -lpthread
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJDIR)
@@ -18,6 +26,6 @@ $(LIB): $(foreach t,$(TUS),$(OBJDIR)/$(t).o)
 	$(NVCC) $(ARCH) -shared -o $@ $^ -lcudart
 
 clean:
-	rm -rf build $(LIB)
+	rm -rf build $(LIB) $(BIN)
 
 .PHONY: all clean

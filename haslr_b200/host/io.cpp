@@ -1,0 +1,211 @@
+// Input side: FASTA/FASTQ (plain or gzip), PAF, plus the small shared helpers.
+#include <zlib.h>
+
+#include <algorithm>
+#include <cerrno>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+
+#include "haslr.hpp"
+
+namespace haslr {
+
+FILE* open_write(const std::string& path) {
+    FILE* fp = fopen(path.c_str(), "w");
+    if (!fp) { fprintf(stderr, "[ERROR] could not open file for writing: %s\n", path.c_str()); exit(EXIT_FAILURE); }
+    return fp;
+}
+FILE* open_append(const std::string& path) {
+    FILE* fp = fopen(path.c_str(), "a");
+    if (!fp) { fprintf(stderr, "[ERROR] could not open file for appending: %s\n", path.c_str()); exit(EXIT_FAILURE); }
+    return fp;
+}
+
+// what a base reads back as after the reference's 2-bit round trip (Compressed_sequence.cpp:10-19,46-62)
+static inline char fold_base(unsigned char c) {
+    switch (c) {
+        case 'A': case 'a': return 'A';
+        case 'C': case 'c': return 'C';
+        case 'G': case 'g': return 'G';
+        case 'T': case 't': return 'T';
+        default: return 'A';
+    }
+}
+
+std::string revcomp(const std::string& s) {      // Common.cpp:186-193 (inputs here are pure ACGT)
+    std::string r(s.size(), 'N');
+    for (size_t i = 0; i < s.size(); ++i) {
+        char c = s[s.size() - 1 - i];
+        r[i] = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : 'N';
+    }
+    return r;
+}
+
+namespace {
+struct GzLines {
+    gzFile fp; std::vector<char> buf; size_t beg = 0, end = 0; bool eof = false;
+    explicit GzLines(const std::string& path) : buf(1 << 20) {
+        fp = gzopen(path.c_str(), "r");
+        if (!fp) { fprintf(stderr, "[ERROR] could not open file: %s\n", path.c_str()); exit(EXIT_FAILURE); }
+    }
+    ~GzLines() { gzclose(fp); }
+    // next line without its terminator; false at end of file
+    bool next(std::string& line) {
+        line.clear();
+        while (true) {
+            if (beg == end) {
+                if (eof) return !line.empty();
+                int n = gzread(fp, buf.data(), (unsigned)buf.size());
+                if (n <= 0) { eof = true; return !line.empty(); }
+                beg = 0; end = (size_t)n;
+            }
+            char* nl = (char*)memchr(buf.data() + beg, '\n', end - beg);
+            if (nl) {
+                line.append(buf.data() + beg, nl - (buf.data() + beg));
+                beg = (size_t)(nl - buf.data()) + 1;
+                if (!line.empty() && line.back() == '\r') line.pop_back();
+                return true;
+            }
+            line.append(buf.data() + beg, end - beg);
+            beg = end;
+        }
+    }
+};
+}  // namespace
+
+// FASTA or FASTQ, multi-line, optionally gzipped (what kseq.h accepts). Record i gets id i (file order), as in
+// load_contig_compressed / load_longread_compressed (Contig.cpp:43-107, Longread.cpp:109-162).
+void load_fasta(const std::string& path, SeqStore& out, ContigStore* meta) {
+    GzLines in(path);
+    std::string line;
+    if (out.off.empty()) out.off.push_back(0);
+    bool have = in.next(line);
+    while (have) {
+        if (line.empty()) { have = in.next(line); continue; }
+        if (line[0] != '>' && line[0] != '@') { fprintf(stderr, "[ERROR] %s: not a FASTA/FASTQ header: %.40s\n", path.c_str(), line.c_str()); exit(EXIT_FAILURE); }
+        const bool fastq = line[0] == '@';
+        if (meta) {
+            // KC:i: and km:f: from the header comment (Contig.cpp:63-66; the reference dereferences a NULL strstr when absent)
+            size_t sp = line.find_first_of(" \t");
+            const char* comment = sp == std::string::npos ? "" : line.c_str() + sp + 1;
+            const char* p1 = strstr(comment, "KC:i:");
+            const char* p2 = strstr(comment, "km:f:");
+            if (!p1 || !p2) { fprintf(stderr, "[ERROR] %s: contig header without KC:i:/km:f: tags: %.60s\n", path.c_str(), line.c_str()); exit(EXIT_FAILURE); }
+            meta->kmer_count.push_back((uint32_t)strtoul(p1 + 5, NULL, 10));
+            meta->mean_kmer.push_back(strtod(p2 + 5, NULL));
+        }
+        size_t start = out.seq.size();
+        have = in.next(line);
+        while (have && !(line.size() && (line[0] == '>' || (fastq && line[0] == '+') || (!fastq && line[0] == '@')))) {
+            for (char c : line) if (c != ' ' && c != '\t') out.seq.push_back(fold_base((unsigned char)c));
+            have = in.next(line);
+        }
+        if (fastq && have && line[0] == '+') {     // skip the quality block: as many characters as the sequence
+            size_t need = out.seq.size() - start, got = 0;
+            while (got < need && (have = in.next(line))) got += line.size();
+            have = in.next(line);
+        }
+        out.off.push_back(out.seq.size());
+    }
+}
+
+void load_fofn(const std::string& path, std::vector<std::string>& files) {
+    std::ifstream fin(path.c_str());
+    if (!fin.is_open()) { fprintf(stderr, "[ERROR] could not open file: %s\n", path.c_str()); exit(EXIT_FAILURE); }
+    std::string line;
+    while (getline(fin, line)) if (!line.empty()) files.push_back(line);
+}
+
+static inline uint32_t parse_u32(const char* b, const char* e) {
+    uint64_t v = 0;
+    for (; b < e && *b >= '0' && *b <= '9'; ++b) v = v * 10 + (uint64_t)(*b - '0');
+    return (uint32_t)v;
+}
+
+// minimap2 PAF with cg:Z: (Longread.cpp:234-302 reads columns 1-12 and the cg tag). All rows are kept: the load
+// filters run on the GPU. The file is mapped whole and tokenised by hand — no per-field string objects.
+void load_paf(const std::string& path, PafTable& paf) {
+    FILE* fp = fopen(path.c_str(), "rb");
+    if (!fp) { fprintf(stderr, "[ERROR] (load_paf) could not open file: %s\n", path.c_str()); exit(EXIT_FAILURE); }
+    std::vector<char> buf(1 << 24);
+    std::string carry;
+    auto parse_line = [&](const char* b, const char* e) {
+        if (b == e) return;
+        const char* f[13]; int nf = 0;
+        f[nf++] = b;
+        for (const char* p = b; p < e && nf < 13; ++p) if (*p == '\t') f[nf++] = p + 1;
+        if (nf < 12) { fprintf(stderr, "[ERROR] (load_paf) line with %d columns\n", nf); exit(EXIT_FAILURE); }
+        auto fe = [&](int i) { return i + 1 < nf ? f[i + 1] - 1 : e; };
+        paf.q_id.push_back(parse_u32(f[0], fe(0))); paf.q_len.push_back(parse_u32(f[1], fe(1)));
+        paf.q_start.push_back(parse_u32(f[2], fe(2))); paf.q_end.push_back(parse_u32(f[3], fe(3)));
+        paf.is_rev.push_back(*f[4] == '-' ? 1 : 0);
+        paf.t_id.push_back(parse_u32(f[5], fe(5))); paf.t_len.push_back(parse_u32(f[6], fe(6)));
+        paf.t_start.push_back(parse_u32(f[7], fe(7))); paf.t_end.push_back(parse_u32(f[8], fe(8)));
+        paf.n_match.push_back(parse_u32(f[9], fe(9))); paf.n_block.push_back(parse_u32(f[10], fe(10)));
+        paf.mapq.push_back((uint8_t)parse_u32(f[11], fe(11)));
+        // first cg:Z: tag among the optional columns
+        const char* p = nf > 12 ? f[12] : e;
+        while (p < e) {
+            const char* t = (const char*)memchr(p, '\t', e - p);
+            const char* te = t ? t : e;
+            if (te - p >= 5 && memcmp(p, "cg:Z:", 5) == 0) {
+                const char* c = p + 5;
+                while (c < te) {
+                    uint32_t n = 0;
+                    while (c < te && *c >= '0' && *c <= '9') n = n * 10 + (uint32_t)(*c++ - '0');
+                    if (c >= te) break;
+                    const char op = *c++;
+                    paf.cg_ops.push_back((n << 2) | (op == 'M' ? 0u : op == 'I' ? 1u : 2u));
+                }
+                break;
+            }
+            p = te + 1;
+        }
+        paf.cg_off.push_back((uint32_t)paf.cg_ops.size());
+    };
+    while (true) {
+        size_t n = fread(buf.data(), 1, buf.size(), fp);
+        if (n == 0) break;
+        const char* b = buf.data(); const char* end = b + n;
+        while (b < end) {
+            const char* nl = (const char*)memchr(b, '\n', end - b);
+            if (!nl) { carry.append(b, end - b); break; }
+            if (!carry.empty()) { carry.append(b, nl - b); parse_line(carry.data(), carry.data() + carry.size()); carry.clear(); }
+            else parse_line(b, nl);
+            b = nl + 1;
+        }
+    }
+    if (!carry.empty()) parse_line(carry.data(), carry.data() + carry.size());
+    fclose(fp);
+}
+
+// rows must be grouped by read with read ids ascending (the reference silently assumes it: update_longreads,
+// Longread.cpp:57-84, slices the hit array by cumulative counts in read-id order)
+void finish_paf(PafTable& paf, size_t n_reads) {
+    for (size_t i = 1; i < paf.size(); ++i)
+        if (paf.q_id[i] < paf.q_id[i - 1]) {
+            fprintf(stderr, "[ERROR] (load_paf) PAF rows are not grouped by ascending read id (row %zu: read %u after read %u)\n", i, paf.q_id[i], paf.q_id[i - 1]);
+            exit(EXIT_FAILURE);
+        }
+    if (paf.size() && paf.q_id.back() >= n_reads) {
+        fprintf(stderr, "[ERROR] (load_paf) PAF names read %u but only %zu reads were loaded\n", paf.q_id.back(), n_reads);
+        exit(EXIT_FAILURE);
+    }
+    paf.read_off.assign(n_reads + 1, 0);
+    for (size_t i = 0; i < paf.size(); ++i) paf.read_off[paf.q_id[i] + 1]++;
+    for (size_t r = 0; r < n_reads; ++r) paf.read_off[r + 1] += paf.read_off[r];
+}
+
+// mean km of the 20 longest contigs, pairs ordered descending by (len, km) — Contig.cpp:162-174
+double calc_uniq_freq(const ContigStore& c) {
+    std::vector<std::pair<uint32_t, double>> v(c.size());
+    for (size_t i = 0; i < c.size(); ++i) v[i] = {c.len(i), c.mean_kmer[i]};
+    std::sort(v.begin(), v.end(), std::greater<std::pair<uint32_t, double>>());
+    double freq = 0;
+    size_t i = 0;
+    for (; i < 20 && i < v.size(); ++i) freq += v[i].second;
+    return freq / (double)i;
+}
+
+}  // namespace haslr

@@ -1,0 +1,222 @@
+// haslr_assemble — drop-in for the reference binary of the same name (reference src/haslr_assemble/src/main.cpp).
+// Same options (Commandline.cpp:68-242), same files in the output directory; stages (i)-(iii) run on the GPU.
+#include <getopt.h>
+#include <sys/resource.h>
+#include <sys/stat.h>
+#include <sys/time.h>
+
+#include <cerrno>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+
+#include "haslr.hpp"
+
+using namespace haslr;
+
+static double cpu_time() {
+    struct rusage t; getrusage(RUSAGE_SELF, &t);
+    return t.ru_utime.tv_sec + t.ru_utime.tv_usec / 1e6 + t.ru_stime.tv_sec + t.ru_stime.tv_usec / 1e6;
+}
+static double real_time() { struct timeval t; gettimeofday(&t, nullptr); return t.tv_sec + t.tv_usec / 1e6; }
+
+static void help_short() { fprintf(stderr, "usage: haslr_assemble -c contig.fasta -l longread.fasta -m lr2contig.paf -d outdir [options]\n"); }
+static void help(const Options& o) {
+    help_short();
+    fprintf(stderr, "\nRequired options:\n"
+                    "    -c STR            Path to contigs file (also --contig)\n"
+                    "    -l STR            Path to long read dataset (also --long)\n"
+                    "    -m STR            Path to mappings of long reads onto contigs (also --mapping)\n"
+                    "    -d STR            Path to the output directory (also --dir)\n\nAdvanced options:\n");
+    fprintf(stderr, "    --aln-block       Minimum length of alignment block [%d]\n", o.min_aln_block);
+    fprintf(stderr, "    --aln-sim         Minimum alignment similarity [%.2lf]\n", o.min_aln_sim);
+    fprintf(stderr, "    --uniq-dev        Maximum deviation from mean frequency of uniq contigs [%.2lf]\n", o.max_uniq_dev);
+    fprintf(stderr, "    --edge-sup        Minimum number of long read supporting each edge [%d]\n", o.min_edge_sup);
+    fprintf(stderr, "\nOther options:\n"
+                    "    -t INT            Number of CPU cores to use (also --threads)\n"
+                    "    --gpus INT        Number of GPUs the consensus edges are sharded over [1]\n"
+                    "    --no-logs         Do not write log_coordinate.txt / log_consensus.txt\n"
+                    "    --long-fofn       The file passed by -l is fofn\n"
+                    "    --mapping-fofn    The file passed by -m is fofn\n");
+    fprintf(stderr, "    --version         Prints version (%s)\n    -h                Prints this help message (also --help)\n\n", o.prog_version.c_str());
+}
+
+static bool parse(int argc, char** argv, Options& o, bool& logs) {
+    if (argc == 1) { help_short(); return false; }
+    static struct option lo[] = {
+        {"contig", required_argument, 0, 'c'}, {"long", required_argument, 0, 'l'}, {"mapping", required_argument, 0, 'm'},
+        {"dir", required_argument, 0, 'd'}, {"help", no_argument, 0, 'h'}, {"threads", required_argument, 0, 't'},
+        {"version", no_argument, 0, 0}, {"long-fofn", no_argument, 0, 0}, {"mapping-fofn", no_argument, 0, 0},
+        {"aln-block", required_argument, 0, 0}, {"aln-sim", required_argument, 0, 0}, {"uniq-dev", required_argument, 0, 0},
+        {"edge-sup", required_argument, 0, 0}, {"gpus", required_argument, 0, 0}, {"no-logs", no_argument, 0, 0}, {0, 0, 0, 0}};
+    int c, idx;
+    while ((c = getopt_long(argc, argv, "c:l:m:d:t:h", lo, &idx)) != -1) {
+        switch (c) {
+            case 'c': o.contig_path = optarg; break;
+            case 'l': o.long_path = optarg; break;
+            case 'm': o.mapping_path = optarg; break;
+            case 'd': o.out_dir = optarg; break;
+            case 't': {
+                int v = atoi(optarg), hw = (int)std::thread::hardware_concurrency();
+                o.num_threads = v < 1 ? 1 : (v > hw ? hw : v);
+                break;
+            }
+            case 'h': help(o); exit(EXIT_SUCCESS);
+            case 0:
+                if (idx == 6) { fprintf(stdout, "%s\n", o.prog_version.c_str()); exit(EXIT_SUCCESS); }
+                else if (idx == 7) o.long_fofn = true;
+                else if (idx == 8) o.mapping_fofn = true;
+                else if (idx == 9) { int v = atoi(optarg); o.min_aln_block = v < 0 ? 500 : v; }
+                else if (idx == 10) { o.min_aln_sim = atof(optarg); if (o.min_aln_sim < 0 || o.min_aln_sim > 1) o.min_aln_sim = 0.85; }
+                else if (idx == 11) o.max_uniq_dev = atof(optarg);
+                else if (idx == 12) { int v = atoi(optarg); o.min_edge_sup = v < 0 ? 3 : v; }
+                else if (idx == 13) { int v = atoi(optarg); o.gpus = v < 1 ? 1 : v; }
+                else if (idx == 14) logs = false;
+                else { help_short(); return false; }
+                break;
+            default: help_short(); return false;
+        }
+    }
+    const char* need[4][2] = {{"-c", o.contig_path.c_str()}, {"-l", o.long_path.c_str()}, {"-m", o.mapping_path.c_str()}, {"-d", o.out_dir.c_str()}};
+    for (auto& n : need) if (!*n[1]) { fprintf(stderr, "[ERROR] (CommandLine:parseCommandLine) option %s is required!\n", n[0]); help_short(); return false; }
+    errno = 0;
+    if (mkdir(o.out_dir.c_str(), S_IRWXU | S_IRWXG | S_IROTH | S_IXOTH) == -1 && errno != EEXIST) return false;
+    fprintf(stderr, "\n");
+    return true;
+}
+
+int main(int argc, char** argv) {
+    Options opt;
+    bool logs = true;
+    if (!parse(argc, argv, opt, logs)) return EXIT_FAILURE;
+    const double c0 = cpu_time(), r0 = real_time();
+    auto lap = [&]() { fprintf(stderr, "       elapsed time %.2lf CPU seconds (%.2lf real seconds)\n\n", cpu_time() - c0, real_time() - r0); };
+    const std::string& d = opt.out_dir;
+
+    std::vector<hgpu_t*> ctxs;
+    for (int i = 0; i < opt.gpus; ++i) {
+        hgpu_t* h = nullptr;
+        int rc = hgpu_create(opt.gpus == 1 ? -1 : i, &h);
+        if (rc != HGPU_OK) { fprintf(stderr, "[ERROR] hgpu_create(device %d): %s — this build needs a B200-class GPU\n", i, hgpu_strerror(rc)); return EXIT_FAILURE; }
+        ctxs.push_back(h);
+    }
+    fprintf(stderr, "[NOTE] number of threads: %d, GPUs: %d\n\n", opt.num_threads, opt.gpus);
+
+    fprintf(stderr, "[NOTE] loading contig sequences...\n");
+    ContigStore contigs;
+    load_fasta(opt.contig_path, contigs, &contigs);
+    fprintf(stderr, "       loaded %zu contigs\n", contigs.size());
+    lap();
+    fprintf(stderr, "[NOTE] calculating kmer frequency of unique contigs\n");
+    opt.uniq_freq = calc_uniq_freq(contigs);
+    fprintf(stderr, "       mean: %.2lf\n", opt.uniq_freq);
+    lap();
+
+    fprintf(stderr, "[NOTE] loading long read sequences...\n");
+    SeqStore reads;
+    {
+        std::vector<std::string> files;
+        if (opt.long_fofn) load_fofn(opt.long_path, files); else files.push_back(opt.long_path);
+        for (const auto& f : files) load_fasta(f, reads, nullptr);
+    }
+    fprintf(stderr, "       loaded %zu long reads\n", reads.size());
+    lap();
+    fprintf(stderr, "[NOTE] loading alignment between contigs and long reads...\n");
+    PafTable paf;
+    {
+        std::vector<std::string> files;
+        if (opt.mapping_fofn) load_fofn(opt.mapping_path, files); else files.push_back(opt.mapping_path);
+        for (const auto& f : files) load_paf(f, paf);
+        finish_paf(paf, reads.size());
+    }
+    fprintf(stderr, "       loaded %zu alignment rows\n", paf.size());
+    lap();
+
+    // (i) filters + per-read sort + overlap fix + chaining, on the GPU
+    fprintf(stderr, "[NOTE] fixing overlapping alignments and building compact long reads (GPU)...\n");
+    CompactReads cl;
+    {
+        hgpu_hits_t h{(uint32_t)paf.size(), paf.q_start.data(), paf.q_end.data(), paf.t_id.data(), paf.t_len.data(), paf.t_start.data(),
+                      paf.t_end.data(), paf.n_match.data(), paf.n_block.data(), paf.is_rev.data(), paf.mapq.data(), paf.cg_off.data(),
+                      paf.cg_ops.empty() ? paf.cg_off.data() : paf.cg_ops.data()};
+        hgpu_k1_params p{opt.min_aln_sim, opt.uniq_freq, opt.max_uniq_dev, opt.min_aln_block, opt.min_aln_mapq};
+        cl.elems.resize(paf.size() + 1); cl.off.resize(reads.size() + 1);
+        uint64_t n = 0;
+        int rc = hgpu_compact_lr(ctxs[0], &h, paf.read_off.data(), (uint32_t)reads.size(), contigs.mean_kmer.data(), (uint32_t)contigs.size(), &p,
+                                 cl.elems.data(), cl.off.data(), &n);
+        if (rc != HGPU_OK) { fprintf(stderr, "[ERROR] hgpu_compact_lr: %s\n", hgpu_last_error(ctxs[0])); return EXIT_FAILURE; }
+        cl.elems.resize(n);
+    }
+    write_compact(cl, paf, d + "/compact_uniq.txt");
+    lap();
+
+    // (ii) edge table on the GPU, graph container on the host
+    fprintf(stderr, "[NOTE] building the backbone graph (GPU)...\n");
+    Graph g;
+    {
+        std::vector<uint32_t> tid(cl.elems.size()); std::vector<uint8_t> rev(cl.elems.size());
+        for (size_t j = 0; j < cl.elems.size(); ++j) { tid[j] = paf.t_id[cl.elems[j].hit]; rev[j] = paf.is_rev[cl.elems[j].hit]; }
+        uint64_t pairs = 0;
+        for (size_t r = 0; r + 1 < cl.off.size(); ++r) if (cl.off[r + 1] - cl.off[r] > 1) pairs += cl.off[r + 1] - cl.off[r] - 1;
+        const size_t cap = 2 * pairs + 1;
+        std::vector<uint64_t> key(cap); std::vector<uint32_t> soff(cap + 1); std::vector<hgpu_edge_supp> supp(cap); std::vector<uint8_t> keep(cap);
+        uint64_t n = 0;
+        int rc = hgpu_backbone_edges(ctxs[0], tid.data(), rev.data(), cl.off.data(), (uint32_t)reads.size(), opt.min_edge_sup,
+                                     key.data(), soff.data(), supp.data(), keep.data(), &n);
+        if (rc != HGPU_OK) { fprintf(stderr, "[ERROR] hgpu_backbone_edges: %s\n", hgpu_last_error(ctxs[0])); return EXIT_FAILURE; }
+        key.resize(n); soff.resize(n + 1); keep.resize(n);
+        graph_from_edge_table(g, contigs.size(), key, soff, supp, nullptr);
+    }
+    write_stats(g, contigs, d + "/backbone.01.init.stat");
+    write_gfa(g, contigs, d + "/backbone.01.init.gfa");
+    lap();
+    fprintf(stderr, "[NOTE] cleaning weak edges...\n");
+    fprintf(stderr, "       removed %d edges\n", remove_weak_edges(g, opt.min_edge_sup));
+    write_stats(g, contigs, d + "/backbone.02.weakEdge.stat");
+    write_gfa(g, contigs, d + "/backbone.02.weakEdge.gfa");
+    lap();
+
+    fprintf(stderr, "[NOTE] cleaning tips...\n");
+    int nb = clean_tips(g, 1, d + "/backbone.03.tip.log");
+    nb += clean_tips(g, 2, d + "/backbone.03.tip.log");
+    nb += clean_tips(g, 3, d + "/backbone.03.tip.log");
+    fprintf(stderr, "       removed %d tips\n", nb);
+    write_stats(g, contigs, d + "/backbone.03.tip.stat");
+    write_gfa(g, contigs, d + "/backbone.03.tip.gfa");
+    lap();
+    fprintf(stderr, "[NOTE] cleaning simple bubbles...\n");
+    fprintf(stderr, "       removed %d simple bubbles\n", clean_simple_bubbles(g, 4, d + "/backbone.04.simplebubble.log"));
+    write_stats(g, contigs, d + "/backbone.04.simplebubble.stat");
+    write_gfa(g, contigs, d + "/backbone.04.simplebubble.gfa");
+    lap();
+    fprintf(stderr, "[NOTE] cleaning super bubbles...\n");
+    fprintf(stderr, "       removed %d super bubbles\n", clean_super_bubbles(g, d + "/backbone.05.superbubble.log"));
+    write_stats(g, contigs, d + "/backbone.05.superbubble.stat");
+    write_gfa(g, contigs, d + "/backbone.05.superbubble.gfa");
+    lap();
+    fprintf(stderr, "[NOTE] cleaning small bubbles...\n");
+    fprintf(stderr, "       removed %d small bubbles\n", clean_small_bubbles(g, d + "/backbone.06.smallbubble.log"));
+    write_stats(g, contigs, d + "/backbone.06.smallbubble.stat");
+    write_gfa(g, contigs, d + "/backbone.06.smallbubble.gfa");
+    lap();
+    report_branching(g, d + "/backbone.branching.log");
+
+    fprintf(stderr, "[NOTE] calculating long read coordinates between anchors...\n");
+    std::vector<EdgeRef> edges;
+    enumerate_edges(g, 11, edges);
+    calc_edge_coordinates(g, edges, contigs, reads, cl, paf, logs ? d + "/log_coordinate.txt" : std::string());
+    lap();
+
+    // (iii) all edges in one batched POA call per GPU
+    fprintf(stderr, "[NOTE] calling consensus sequence between anchors (GPU, %zu edges)...\n", edges.size());
+    enumerate_edges(g, 12, edges);
+    if (!edges.empty() && call_consensus(g, edges, reads, ctxs, d + "/log_consensus.txt", logs) != 0) return EXIT_FAILURE;
+    lap();
+
+    fprintf(stderr, "[NOTE] generating the assembly from the cleaned backbone graph...\n");
+    write_assembly(g, contigs, d);
+    lap();
+    for (hgpu_t* h : ctxs) hgpu_destroy(h);
+    fprintf(stderr, "[NOTE] elapsed time %.2lf CPU seconds (%.2lf real seconds)\n\n*** BYE ***\n\n", cpu_time() - c0, real_time() - r0);
+    return EXIT_SUCCESS;
+}
