@@ -9,6 +9,7 @@
 #include <iterator>
 #include <set>
 #include <thread>
+#include <ctime>
 
 #include "haslr.hpp"
 
@@ -197,9 +198,12 @@ static void append_segment(const SeqStore& reads, const CnsSupp& s, std::string&
     }
 }
 
+static double now_s() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + t.tv_nsec * 1e-9; }
+
 int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& reads, const std::vector<hgpu_t*>& ctxs,
                    const std::string& logpath, bool write_log) {
     const size_t n = edges.size();
+    const double t0 = now_s();
     std::string bases;
     std::vector<uint64_t> seg_off{0};
     std::vector<uint32_t> edge_seg_off{0};
@@ -236,6 +240,7 @@ int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& 
     }
     std::vector<std::string> cons(n);
     std::vector<int> rc(G, 0);
+    const double t1 = now_s();
     auto run = [&](size_t gi) {
         const std::vector<uint32_t>& my = shard[gi];
         if (my.empty()) return;
@@ -250,9 +255,15 @@ int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& 
         std::vector<uint8_t> out(b.size() + 64);
         std::vector<uint64_t> off(my.size() + 1);
         std::vector<uint32_t> status(my.size());
+        hgpu_poa_set_timing(ctxs[gi], 1);
         int r = hgpu_poa_batch(ctxs[gi], (const uint8_t*)b.data(), so.data(), eso.data(), (uint32_t)my.size(), 5, -4, -8, 0,   // Assemble.cpp:8-11
                                out.data(), out.size(), off.data(), status.data());
         if (r != HGPU_OK) { fprintf(stderr, "[ERROR] hgpu_poa_batch (gpu %zu): %s\n", gi, hgpu_last_error(ctxs[gi])); rc[gi] = r; return; }
+        hgpu_poa_stats st;
+        if (hgpu_poa_get_stats(ctxs[gi], &st) == HGPU_OK)
+            fprintf(stderr, "       gpu %zu: %zu edges, %llu alignments (%llu int32), %.1f Mbases in, %.3e DP cells, kernel %.1f ms (%.0f GCUPS), %llu launches\n",
+                    gi, my.size(), (unsigned long long)st.alignments, (unsigned long long)st.alignments_i32, st.bases_in / 1e6, (double)st.cells,
+                    st.ms_dp, st.ms_dp > 0 ? st.cells / (st.ms_dp * 1e6) : 0.0, (unsigned long long)st.dp_launches);
         for (size_t k = 0; k < my.size(); ++k) {
             if (status[k] != 0) { fprintf(stderr, "[ERROR] POA failed for edge %u with status %u\n", my[k], status[k]); rc[gi] = HGPU_E_INTERNAL; }
             cons[my[k]].assign((const char*)out.data() + off[k], off[k + 1] - off[k]);
@@ -265,6 +276,8 @@ int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& 
         for (auto& t : th) t.join();
     }
     for (int r : rc) if (r) return r;
+    const double t2 = now_s();
+    fprintf(stderr, "       %zu segments gathered in %.2f s, POA calls %.2f s\n", seg_off.size() - 1, t1 - t0, t2 - t1);
     FILE* fp = write_log ? open_write(logpath) : nullptr;
     for (size_t e = 0; e < n; ++e) {
         const EdgeRef& er = edges[e];

@@ -33,6 +33,8 @@ static inline char fold_base(unsigned char c) {
     }
 }
 
+namespace { struct FoldTable { char t[256]; FoldTable() { for (int i = 0; i < 256; ++i) t[i] = fold_base((unsigned char)i); } } FOLD; }
+
 std::string revcomp(const std::string& s) {      // Common.cpp:186-193 (inputs here are pure ACGT)
     std::string r(s.size(), 'N');
     for (size_t i = 0; i < s.size(); ++i) {
@@ -98,7 +100,14 @@ void load_fasta(const std::string& path, SeqStore& out, ContigStore* meta) {
         size_t start = out.seq.size();
         have = in.next(line);
         while (have && !(line.size() && (line[0] == '>' || (fastq && line[0] == '+') || (!fastq && line[0] == '@')))) {
-            for (char c : line) if (c != ' ' && c != '\t') out.seq.push_back(fold_base((unsigned char)c));
+            {   // bulk append, then fold in place (sequence lines carry no blanks in practice; strip them if they do)
+                const size_t at = out.seq.size();
+                out.seq.append(line);
+                char* p = &out.seq[at];
+                size_t w = 0;
+                for (size_t k = 0; k < line.size(); ++k) { const unsigned char c = (unsigned char)p[k]; if (c != ' ' && c != '\t') p[w++] = FOLD.t[c]; }
+                out.seq.resize(at + w);
+            }
             have = in.next(line);
         }
         if (fastq && have && line[0] == '+') {     // skip the quality block: as many characters as the sequence
