@@ -181,6 +181,7 @@ def main():
     import torch
     import torch.distributed as dist
     import haslr_b200
+    from haslr_b200 import sharding
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
@@ -206,15 +207,9 @@ def main():
     torch.cuda.synchronize()
 
     def gather_consensus(off):
-        """Final exchange of the path: every rank ends up with every shard's consensus (NCCL all-gather)."""
-        if world == 1:
-            return
-        n = torch.tensor([int(off[-1])], dtype=torch.int64, device=dev)
-        sizes = [torch.zeros_like(n) for _ in range(world)]
-        dist.all_gather(sizes, n)
-        mx = int(max(int(s.item()) for s in sizes))
-        bufs = [torch.empty(mx, dtype=torch.uint8, device=dev) for _ in range(world)]
-        dist.all_gather(bufs, d_out[:mx] if mx <= out_cap else torch.nn.functional.pad(d_out, (0, mx - out_cap)))
+        """Final exchange of the path: every rank ends up with every shard's consensus (one NCCL all-gather)."""
+        if world > 1:
+            sharding.all_gather_consensus(dist, d_out, off, dev, to_host=False)
 
     def step_dev():
         off, status = ctx.poa_batch_dev(d_bases.data_ptr(), seg_off, eso, d_out.data_ptr(), out_cap, *SCORES)
