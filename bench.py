@@ -287,15 +287,17 @@ def main():
     peak, peak_src = peaks()
     alg_bytes = 4 * cells + bases_in + bases_out           # 4 B per DP cell + 1 B per base in + consensus out
     achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "k_poa_edges_traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
             tj = json.load(f)
-        if tj.get("edges_per_launch") == n_edges:
-            traffic = tj.get("dram_bytes_per_launch")
+        # ncu cannot replay the 2.3 s / 40 GB launch; DRAM traffic is linear in DP cells, so scale the profiled per-cell figure
+        traffic = tj["dram_bytes_per_dp_cell"] * cells / max(1, args.steps * klaunch)
+        traffic_src = "profiles/k_poa_edges_traffic.json: %.3f DRAM B per DP cell (ncu, %d-edge launch) x cells of this launch" % (
+            tj["dram_bytes_per_dp_cell"], tj["edges_in_profiled_launch"])
     roofline = {"kernel": "k_poa_edges", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "gcups": cells / (kernel_ms / 1e3) / 1e9,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "gcups": cells / (kernel_ms / 1e3) / 1e9,
                 "kernel_ms_per_launch": kernel_ms / max(1, args.steps * klaunch), "launches_per_step": klaunch,
                 "algorithmic_bytes_per_launch": alg_bytes / max(1, args.steps * klaunch)}
 
