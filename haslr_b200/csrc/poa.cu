@@ -4,6 +4,7 @@
 // instead of T threads pulling one edge each from a mutex-guarded cursor and calling SPOA, all edges of a call
 // are queued on the device and pulled by the warps of one persistent kernel (poa_device.cuh).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <numeric>
@@ -19,7 +20,7 @@ struct PoaPass {                 // one scheduling pass keeps its consensus pool
 };
 
 struct PoaState {
-    DevBuf<uint8_t> arena, ws, d_bases, d_out;
+    DevBuf<uint8_t> arena, ws, arena_team, ws_team, d_bases, d_out;
     DevBuf<uint64_t> seg_ptr, cons_pos, d_off;
     DevBuf<uint32_t> seg_len, e_seg_off, items, status, cons_len, out_nodes, counters;
     DevBuf<unsigned long long> stats, pool_cursor;
@@ -33,18 +34,29 @@ struct PoaState {
     WsLayout last_wl{};          // layout / slot size of the most recent launch (debug inspection)
     uint64_t last_slot = 0;
     bool have_result = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t stream2 = nullptr;   // the team kernel (few huge edges) runs beside the warp-per-edge kernel
+    uint32_t cfg_team = 8;            // 0 disables the team kernel
+    double cfg_team_min_cells = 2.0e8;
 };
 
 void poa_state_destroy(PoaState* s) {
     if (!s) return;
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
+    if (s->stream2) cudaStreamDestroy(s->stream2);
     delete s;
 }
 
 static PoaState* poa_state(hgpu_t* ctx) {
-    if (!ctx->poa) ctx->poa = new PoaState();
+    if (!ctx->poa) {
+        ctx->poa = new PoaState();
+        // developer knobs (tests force the team kernel onto small inputs with these)
+        if (const char* e = getenv("HGPU_TEAM")) ctx->poa->cfg_team = (uint32_t)atoi(e);
+        if (const char* e = getenv("HGPU_TEAM_MIN_CELLS")) ctx->poa->cfg_team_min_cells = atof(e);
+    }
     return ctx->poa;
 }
 
@@ -67,18 +79,21 @@ struct EdgeEst {
     uint32_t edge;
     uint32_t ncap;       // node capacity needed (estimate)
     uint64_t slot;       // score-matrix bytes needed (estimate)
+    double cells;        // DP cells (estimate)
+    uint32_t lmax;       // longest segment
 };
 
 // Node-count growth model: every later segment adds about `growth` new nodes per base (SURVEY.md §8(d):
 // |V| grows ~ L * (ins + sub) per read). growth >= 1 means the worst case (every base a new node).
 void estimate_edge(const uint32_t* len, uint32_t R, double growth, const DpScores& sc, bool force_i32, EdgeEst* out) {
-    double V = len[0];
+    double V = len[0], cells = 0;
     uint64_t slot = 0;
     uint32_t lmax = len[0];
     for (uint32_t k = 1; k < R; ++k) {
         uint32_t Vi = (uint32_t)std::min<double>(V + 1.0, 4.0e9);
         bool p16 = !force_i32 && dp_fits16(Vi, len[k], sc);
         slot = std::max(slot, dp_slot_bytes(Vi, len[k], p16));
+        cells += (V + 1.0) * (len[k] + 1.0);
         // overhang beyond the graph's current span also becomes new nodes
         double over = len[k] > V ? (double)len[k] - V : 0.0;
         V += growth >= 1.0 ? (double)len[k] : std::min<double>(len[k], growth * len[k] + over + 8.0);
@@ -87,6 +102,8 @@ void estimate_edge(const uint32_t* len, uint32_t R, double growth, const DpScore
     double ncap = V + lmax + 64.0;
     out->ncap = (uint32_t)std::min<double>(ncap, 4.0e9);
     out->slot = slot + 4096;
+    out->cells = cells;
+    out->lmax = lmax;
 }
 }  // namespace
 
@@ -161,7 +178,9 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
     double growth = 0.15;
     std::vector<EdgeEst> est;
     std::vector<uint32_t> items_h;
+    const uint64_t budget_total = budget;
     for (int attempt = 0; attempt < 5 && !pending.empty(); ++attempt) {
+        budget = budget_total;
         // ---- estimates, largest first (also the LPT order for load balance)
         est.resize(pending.size());
         uint64_t pool_cap = 0;
@@ -169,24 +188,79 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
             uint32_t e = pending[i];
             uint32_t R = e_off[e + 1] - e_off[e];
             est[i].edge = e;
-            if (R == 0) { est[i].ncap = 64; est[i].slot = 4096; continue; }
+            if (R == 0) { est[i].ncap = 64; est[i].slot = 4096; est[i].cells = 0; est[i].lmax = 0; continue; }
             estimate_edge(seg_len.data() + e_off[e], R, growth, sc, opt.force_i32 != 0, &est[i]);
             uint64_t sum = 0; uint32_t lmax = 0;
             for (uint32_t k = 0; k < R; ++k) { sum += seg_len[e_off[e] + k]; lmax = std::max(lmax, seg_len[e_off[e] + k]); }
             pool_cap += growth >= 1.0 ? sum : std::min<uint64_t>(sum, (uint64_t)(2.0 * lmax * (1.0 + growth)) + 256);
         }
-        std::sort(est.begin(), est.end(), [](const EdgeEst& a, const EdgeEst& b) {
+        // ---- edges so large that one warp would be the tail of the whole pass go to the team kernel (a block per edge):
+        //      a lone warp fills ~2.4 G cells/s against ~1 T cells/s for the device, so "large" = more than 1/400 of the work
+        std::vector<EdgeEst> team;
+        if (S->cfg_team >= 2 && opt.stop_round == 0xFFFFFFFFu) {
+            double total = 0;
+            for (const EdgeEst& x : est) total += x.cells;
+            const double thr = std::max(total / 400.0, S->cfg_team_min_cells);
+            std::vector<EdgeEst> rest;
+            for (const EdgeEst& x : est) {
+                const bool wide = x.lmax >= 2u * (uint32_t)Geo<DP_NW16, true>::SW - 1;     // at least 3 stripes to spread
+                if (wide && x.cells > thr) team.push_back(x); else rest.push_back(x);
+            }
+            est.swap(rest);
+        }
+        auto by_size = [](const EdgeEst& a, const EdgeEst& b) {
             if (a.slot != b.slot) return a.slot > b.slot;
             return a.edge < b.edge;
-        });
-        items_h.resize(est.size());
+        };
+        std::sort(est.begin(), est.end(), by_size);
+        std::sort(team.begin(), team.end(), [](const EdgeEst& a, const EdgeEst& b) { return a.cells != b.cells ? a.cells > b.cells : a.edge < b.edge; });
+        items_h.resize(est.size() + team.size());
         for (size_t i = 0; i < est.size(); ++i) items_h[i] = est[i].edge;
+        for (size_t i = 0; i < team.size(); ++i) items_h[est.size() + i] = team[i].edge;
         HGPU_CUDA(ctx, cudaMemcpyAsync(S->items.p, items_h.data(), items_h.size() * 4, cudaMemcpyHostToDevice, st));
 
         std::unique_ptr<PoaPass> pass(new PoaPass());
         HGPU_CUDA(ctx, pass->pool.alloc(pool_cap + 256));
         HGPU_CUDA(ctx, cudaMemsetAsync(S->pool_cursor.p, 0, sizeof(unsigned long long), st));
         HGPU_CUDA(ctx, cudaMemsetAsync(S->counters.p, 0, 256 * 4, st));
+
+        if (S->timing) HGPU_CUDA(ctx, cudaEventRecord(S->ev0, st));
+        bool team_launched = false;
+        if (!team.empty()) {
+            constexpr int TEAM = 8;
+            uint64_t tslot = 0; uint32_t nc = 64;
+            for (const EdgeEst& x : team) { tslot = std::max(tslot, x.slot); nc = std::max(nc, x.ncap); }
+            tslot = (tslot + 127) / 128 * 128;
+            const WsLayout twl = ws_layout(nc, nc + nc / 4 + 64);
+            const uint64_t tbudget = budget / 2;              // the other half stays with the warp-per-edge kernel
+            uint32_t teams = (uint32_t)std::min<uint64_t>({(uint64_t)team.size(), (uint64_t)ctx->sm_count * 3, tbudget / (tslot + twl.bytes)});
+            if (teams == 0) {
+                for (const EdgeEst& x : team) est.push_back(x);          // does not fit even once: let the classes report it
+                std::sort(est.begin(), est.end(), by_size);
+                for (size_t i = 0; i < est.size(); ++i) items_h[i] = est[i].edge;
+                HGPU_CUDA(ctx, cudaMemcpyAsync(S->items.p, items_h.data(), items_h.size() * 4, cudaMemcpyHostToDevice, st));
+                team.clear();
+            } else {
+                budget -= (uint64_t)teams * (tslot + twl.bytes);
+                HGPU_CUDA(ctx, S->arena_team.ensure((size_t)teams * tslot));
+                HGPU_CUDA(ctx, S->ws_team.ensure((size_t)teams * twl.bytes));
+                PoaArgs a{};
+                a.bases = d_bases; a.seg_ptr = S->seg_ptr.p; a.seg_len = S->seg_len.p; a.e_seg_off = S->e_seg_off.p;
+                a.items = S->items.p + est.size(); a.n_items = (uint32_t)team.size(); a.counter = S->counters.p + 255;
+                a.status = S->status.p; a.cons_len = S->cons_len.p; a.cons_pos = S->cons_pos.p; a.out_nodes = S->out_nodes.p;
+                a.pool = pass->pool.p; a.pool_cap = pass->pool.n; a.pool_cursor = S->pool_cursor.p;
+                a.ws = S->ws_team.p; a.wl = twl; a.arena = S->arena_team.p; a.slot_bytes = tslot;
+                a.sc = sc; a.stats = S->stats.p; a.stop_round = opt.stop_round; a.force_i32 = opt.force_i32;
+                const size_t tsmem = (size_t)TEAM * DP_SMEM_PER_WARP + (TEAM + 4) * 4;
+                HGPU_CUDA(ctx, cudaEventRecord(S->ev_fork, st));          // uploads and memsets above are on `st`
+                HGPU_CUDA(ctx, cudaStreamWaitEvent(S->stream2, S->ev_fork, 0));
+                k_poa_edges_team<TEAM><<<teams, 32 * TEAM, tsmem, S->stream2>>>(a);
+                HGPU_CUDA(ctx, cudaGetLastError());
+                HGPU_CUDA(ctx, cudaEventRecord(S->ev_join, S->stream2));
+                ctx->launches++; S->st.dp_launches++;
+                team_launched = true;
+            }
+        }
 
         // ---- size classes: a class ends where the slot estimate has halved, unless memory is no constraint
         struct Cls { size_t a, b; uint64_t slot; WsLayout wl; uint32_t warps; };
@@ -244,16 +318,16 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
             a.ws = S->ws.p; a.wl = c.wl; a.arena = S->arena.p; a.slot_bytes = c.slot;
             S->last_wl = c.wl; S->last_slot = c.slot;
             a.sc = sc; a.stats = S->stats.p; a.stop_round = opt.stop_round; a.force_i32 = opt.force_i32;
-            if (S->timing) HGPU_CUDA(ctx, cudaEventRecord(S->ev0, st));
             k_poa_edges<<<blocks, 32 * DP_WARPS_PER_BLOCK, smem, st>>>(a);
             HGPU_CUDA(ctx, cudaGetLastError());
             ctx->launches++; S->st.dp_launches++;
-            if (S->timing) {
-                HGPU_CUDA(ctx, cudaEventRecord(S->ev1, st));
-                HGPU_CUDA(ctx, cudaEventSynchronize(S->ev1));
-                float ms = 0; cudaEventElapsedTime(&ms, S->ev0, S->ev1);
-                S->st.ms_dp += ms;
-            }
+        }
+        if (team_launched) HGPU_CUDA(ctx, cudaStreamWaitEvent(st, S->ev_join, 0));
+        if (S->timing) {
+            HGPU_CUDA(ctx, cudaEventRecord(S->ev1, st));
+            HGPU_CUDA(ctx, cudaEventSynchronize(S->ev1));
+            float ms = 0; cudaEventElapsedTime(&ms, S->ev0, S->ev1);
+            S->st.ms_dp += ms;
         }
         HGPU_CUDA(ctx, cudaMemcpyAsync(status_h.data(), S->status.p, (size_t)n_edges * 4, cudaMemcpyDeviceToHost, st));
         HGPU_CUDA(ctx, cudaStreamSynchronize(st));
@@ -306,7 +380,11 @@ static int poa_prepare(hgpu_t* ctx, const uint64_t* seg_off, const uint32_t* edg
         if (edge_seg_off[e + 1] < edge_seg_off[e]) HGPU_FAIL(ctx, HGPU_E_INVALID, "edge_seg_off not monotone at %u", e);
     HGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     PoaState* S = poa_state(ctx);
-    if (!S->ev0) { HGPU_CUDA(ctx, cudaEventCreate(&S->ev0)); HGPU_CUDA(ctx, cudaEventCreate(&S->ev1)); }
+    if (!S->ev0) {
+        HGPU_CUDA(ctx, cudaEventCreate(&S->ev0)); HGPU_CUDA(ctx, cudaEventCreate(&S->ev1));
+        HGPU_CUDA(ctx, cudaEventCreateWithFlags(&S->ev_fork, cudaEventDisableTiming)); HGPU_CUDA(ctx, cudaEventCreateWithFlags(&S->ev_join, cudaEventDisableTiming));
+        HGPU_CUDA(ctx, cudaStreamCreateWithFlags(&S->stream2, cudaStreamNonBlocking));
+    }
     return HGPU_OK;
 }
 

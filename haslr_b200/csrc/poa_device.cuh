@@ -30,7 +30,7 @@
 
 namespace hgpu {
 
-enum : uint32_t { ST_OK = 0, ST_CAPACITY = 1, ST_TOPOSORT = 2, ST_TRACEBACK = 3, ST_TOO_LARGE = 4, ST_POOL = 5 };
+enum : uint32_t { ST_OK = 0, ST_CAPACITY = 1, ST_TOPOSORT = 2, ST_TRACEBACK = 3, ST_TOO_LARGE = 4, ST_POOL = 5, ST_SYNC = 6 };
 
 // Scores in gap-hat space (host computes them once per call).
 struct DpScores {
@@ -297,11 +297,35 @@ struct RowOps {
 #else
 #define DP_INLINE __noinline__
 #endif
+// Team mode (k_poa_edges_team): the warps of a team share one alignment; warp `trank` of `tsize` fills stripes
+// trank, trank+tsize, ... and stripe s can start a batch of 32 rows once stripe s-1 has published those rows'
+// boundary column. vprog[w] = (stripe * (V+1) + rows done) of warp w, monotone, in shared memory.
+__device__ __forceinline__ void team_publish(volatile uint32_t* vprog, uint32_t trank, uint32_t value, int lane) {
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) vprog[trank] = value;
+}
+__device__ __forceinline__ bool team_wait(volatile uint32_t* vprog, uint32_t who, uint32_t need, int lane) {
+    int ok = 1;
+    if (lane == 0) {
+        uint32_t spins = 0;
+        while (vprog[who] < need) {
+            __nanosleep(64);
+            if (++spins > (1u << 25)) { ok = 0; break; }      // never hang the GPU: give up, the edge reports ST_SYNC
+        }
+    }
+    ok = __shfl_sync(FULL, ok, 0);
+    __threadfence_block();
+    return ok != 0;
+}
+
 template <int NW, bool P16>
-__device__ DP_INLINE bool dp_align(const GraphView& gv, uint8_t* slot, uint8_t* wsm, const uint8_t* seq,
-                                      uint32_t V, uint32_t L, const DpScores sc, int lane) {
+__device__ DP_INLINE bool dp_fill(const GraphView& gv, uint8_t* slot, uint8_t* wsm, const uint8_t* seq,
+                                  uint32_t V, uint32_t L, const DpScores sc, int lane,
+                                  uint32_t trank, uint32_t tsize, volatile uint32_t* vprog) {
     using G = Geo<NW, P16>;
     using R = RowOps<NW, P16>;
+    bool sync_ok = true;
     uint32_t* prof = reinterpret_cast<uint32_t*>(wsm);                 // [4][NW][32]
     uint4* ring = reinterpret_cast<uint4*>(wsm + G::PROF_BYTES);      // [2][UNITS][32]: rows i-2 / i-3 of the current stripe
     const int g = sc.g;
@@ -312,7 +336,7 @@ __device__ DP_INLINE bool dp_align(const GraphView& gv, uint8_t* slot, uint8_t* 
     const uint32_t NS = sv.NS;
 
     // =============================== fill ===============================
-    for (uint32_t s = 0; s < NS; ++s) {
+    for (uint32_t s = trank; s < NS; s += tsize) {
         __syncwarp();
         // --- sequence profile of this stripe: prof[code][k][lane] = hat-score(s) of the lane's k-th word
         {
@@ -354,6 +378,7 @@ __device__ DP_INLINE bool dp_align(const GraphView& gv, uint8_t* slot, uint8_t* 
             for (int u = 0; u < G::UNITS; ++u) dst[u * 32] = make_uint4(h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
             if (lane == 31) bc_cur[0] = bias;
         }
+        if (tsize > 1) team_publish(vprog, trank, s * (V + 1) + 1, lane);
 
         const bool has_next_stripe = s + 1 < NS;
         for (uint32_t r0 = 0; r0 < V; r0 += 32) {
@@ -361,6 +386,10 @@ __device__ DP_INLINE bool dp_align(const GraphView& gv, uint8_t* slot, uint8_t* 
             const uint32_t rr = r0 + lane;
             uint32_t mm0 = 0, mm1 = 0;
             int bcd = G::NEGV, bcc = G::NEGV;
+            if (tsize > 1 && s > 0) {       // rows r0 .. r0+32 of the stripe to the left must be complete
+                const uint32_t need_rows = (r0 + 33 < V + 1) ? r0 + 33 : V + 1;
+                if (!team_wait(vprog, (trank + tsize - 1) % tsize, (s - 1) * (V + 1) + need_rows, lane)) sync_ok = false;
+            }
             if (rr < V) {
                 mm0 = gv.meta0[rr]; mm1 = gv.meta1[rr];
                 if (s > 0) { bcd = bc_prev[rr]; bcc = bc_prev[rr + 1]; }
@@ -466,12 +495,22 @@ __device__ DP_INLINE bool dp_align(const GraphView& gv, uint8_t* slot, uint8_t* 
                 for (int u = 0; u < G::UNITS; ++u) st_row(dst + u * 32, make_uint4(h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]));
                 if (has_next_stripe && lane == 31) bc_cur[i] = R::last_cell(h);
             }
+            if (tsize > 1) team_publish(vprog, trank, s * (V + 1) + ((r0 + 32 < V) ? r0 + 32 : V) + 1, lane);
         }
         __syncwarp();
     }
     __threadfence_block();
     __syncwarp();
+    return sync_ok;
+}
 
+template <int NW, bool P16>
+__device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8_t* wsm, const uint8_t* seq,
+                                       uint32_t V, uint32_t L, const DpScores sc, int lane) {
+    using G = Geo<NW, P16>;
+    const int g = sc.g;
+    SlotView<NW, P16> sv;
+    sv.bind(slot, V, L);
     // =============================== traceback ===============================
     // end cell: best Hhat[i][L] over sink nodes, first maximum in rank order (SPOA kNW)
     int best = INT32_MIN; uint32_t best_i = 0;
@@ -578,6 +617,13 @@ __device__ DP_INLINE bool dp_align(const GraphView& gv, uint8_t* slot, uint8_t* 
     if (lane == 0) *gv.aln_len = bad ? 0 : n_out;
     __syncwarp();
     return !bad;
+}
+
+template <int NW, bool P16>
+__device__ DP_INLINE bool dp_align(const GraphView& gv, uint8_t* slot, uint8_t* wsm, const uint8_t* seq,
+                                   uint32_t V, uint32_t L, const DpScores sc, int lane) {
+    dp_fill<NW, P16>(gv, slot, wsm, seq, V, L, sc, lane, 0, 1, nullptr);
+    return dp_traceback<NW, P16>(gv, slot, wsm, seq, V, L, sc, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -974,6 +1020,132 @@ __global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, HGPU_MINBLOCKS) k_poa
         __syncwarp();
     }
     if (lane == 0 && a.stats) {
+        atomicAdd(a.stats + 0, st_cells); atomicAdd(a.stats + 1, st_padded); atomicAdd(a.stats + 2, st_aln);
+        atomicAdd(a.stats + 3, st_aln32); atomicAdd(a.stats + 4, st_bases);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_poa_edges_team<TEAM>: one BLOCK of TEAM warps per backbone edge, for edges whose score matrices are so large
+// that a single warp would become the tail of the whole batch (deep coverage x long gap). The fill of one
+// alignment is spread over the team stripe by stripe (pipelined through the boundary columns, see dp_fill);
+// traceback, graph update and consensus run on warp 0 exactly as in k_poa_edges, so results are identical.
+// ---------------------------------------------------------------------------------------------------------
+template <int TEAM>
+__global__ void __launch_bounds__(32 * TEAM, 768 / (32 * TEAM)) k_poa_edges_team(PoaArgs a) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const uint32_t wib = threadIdx.x >> 5;                  // = rank in the team
+    const uint32_t gw = blockIdx.x;                          // one slot / workspace per team
+    uint8_t* wsm = smem_raw + (size_t)wib * DP_SMEM_PER_WARP;
+    volatile uint32_t* vprog = reinterpret_cast<volatile uint32_t*>(smem_raw + (size_t)TEAM * DP_SMEM_PER_WARP);   // [TEAM]
+    volatile uint32_t* bcast = vprog + TEAM;                 // [4]: item, status, flag, spare
+    uint8_t* slot = a.arena + (uint64_t)gw * a.slot_bytes;
+    uint8_t* wsb = a.ws + (uint64_t)gw * a.wl.bytes;
+    GraphView gv = bind_graph(wsb, a.wl);
+    GraphScratch gs = bind_scratch(wsb, a.wl);
+    uint32_t* hdr = reinterpret_cast<uint32_t*>(wsb + a.wl.o_hdr);
+    unsigned long long st_cells = 0, st_padded = 0, st_aln = 0, st_aln32 = 0, st_bases = 0;
+    const bool lead = wib == 0;
+
+    while (true) {
+        if (threadIdx.x == 0) bcast[0] = atomicAdd(a.counter, 1u);
+        __syncthreads();
+        const uint32_t item = bcast[0];
+        if (item >= a.n_items) break;
+        const uint32_t e = a.items[item];
+        const uint32_t s0 = a.e_seg_off[e];
+        const uint32_t R = a.e_seg_off[e + 1] - s0;
+        uint32_t st = ST_OK;
+        uint32_t n_cons = 0;
+        bool debug_stop = false;
+        unsigned long long e_cells = 0, e_padded = 0, e_aln = 0, e_aln32 = 0, e_bases = 0;
+        if (R == 0) {
+            if (threadIdx.x == 0) { *gv.n_nodes = 0; *gv.n_edges = 0; *gv.aln_len = 0; }
+        } else {
+            const uint32_t L0 = a.seg_len[s0];
+            if (L0 > gv.ncap || L0 > gv.ecap) st = ST_CAPACITY;
+            else if (lead) { w_init_chain(gv, a.bases + a.seg_ptr[s0], L0, lane); e_bases += L0; }
+            for (uint32_t k = 1; k < R && st == ST_OK; ++k) {
+                if (threadIdx.x < TEAM) vprog[threadIdx.x] = 0;
+                __syncthreads();                              // graph of round k-1 complete, progress words cleared
+                const uint32_t V = *gv.n_nodes;
+                const uint32_t NE = *gv.n_edges;
+                const uint32_t L = a.seg_len[s0 + k];
+                const uint8_t* seq = a.bases + a.seg_ptr[s0 + k];
+                const bool p16 = !a.force_i32 && dp_fits16(V, L, a.sc);
+                if ((uint64_t)V + L > gv.ncap || (uint64_t)NE + L + 1 > gv.ecap) { st = ST_CAPACITY; break; }
+                if (dp_slot_bytes(V, L, p16) > a.slot_bytes) { st = ST_TOO_LARGE; break; }
+                const bool fill_ok = p16 ? dp_fill<DP_NW16, true>(gv, slot, wsm, seq, V, L, a.sc, lane, wib, TEAM, vprog)
+                                         : dp_fill<DP_NW32, false>(gv, slot, wsm, seq, V, L, a.sc, lane, wib, TEAM, vprog);
+                const int all_ok = __syncthreads_and(fill_ok ? 1 : 0);    // every stripe stored (and no wait gave up)
+                if (!all_ok) { st = ST_SYNC; break; }
+                uint32_t rst = ST_OK;
+                if (lead) {
+                    bool ok = p16 ? dp_traceback<DP_NW16, true>(gv, slot, wsm, seq, V, L, a.sc, lane)
+                                  : dp_traceback<DP_NW32, false>(gv, slot, wsm, seq, V, L, a.sc, lane);
+                    if (lane == 0) {
+                        hdr[HDR_LAST_P16] = p16 ? 1u : 0u; hdr[HDR_LAST_V] = V; hdr[HDR_LAST_L] = L;
+                        hdr[HDR_LAST_BIAS] = (uint32_t)(p16 ? Geo<DP_NW16, true>::bias(V, a.sc) : 0);
+                    }
+                    e_cells += (unsigned long long)(V + 1) * (L + 1);
+                    e_padded += (unsigned long long)(V + 1) *
+                                 (p16 ? Geo<DP_NW16, true>::stripes(L) * Geo<DP_NW16, true>::SW : Geo<DP_NW32, false>::stripes(L) * Geo<DP_NW32, false>::SW);
+                    e_aln += 1; e_aln32 += p16 ? 0 : 1; e_bases += L;
+                    if (!ok) rst = ST_TRACEBACK;
+                    else if (k != a.stop_round) {
+                        uint32_t ust = w_add_alignment(gv, gs, seq, L, lane);
+                        if (ust == 0xFFFFFFFFu) {
+                            ust = ST_OK;
+                            if (lane == 0 && !g_add_alignment(gv, seq, L)) ust = ST_CAPACITY;
+                            ust = __shfl_sync(FULL, ust, 0);
+                            __syncwarp();
+                        }
+                        if (ust == ST_OK && !w_toposort(gv, wsm, lane)) {
+                            if (lane == 0 && !g_toposort(gv, gs)) ust = ST_TOPOSORT;
+                            ust = __shfl_sync(FULL, ust, 0);
+                            __syncwarp();
+                        }
+                        if (ust == ST_OK) w_build_meta(gv, lane);
+                        rst = ust;
+                    }
+                    if (lane == 0) bcast[1] = rst;
+                }
+                __syncthreads();
+                rst = bcast[1];
+                if (rst != ST_OK) { st = rst; break; }
+                if (k == a.stop_round) { debug_stop = true; break; }
+            }
+            if (a.stop_round != 0xFFFFFFFFu) debug_stop = true;
+            if (st == ST_OK && !debug_stop && lead) {
+                if (lane == 0) n_cons = g_consensus(gv, gs, reinterpret_cast<uint32_t*>(gv.aln_rank));
+                n_cons = __shfl_sync(FULL, n_cons, 0);
+                __syncwarp();
+            }
+        }
+        if (lead) {
+            unsigned long long pos = 0;
+            if (lane == 0 && n_cons > 0) {
+                pos = atomicAdd(a.pool_cursor, (unsigned long long)n_cons);
+                if (pos + n_cons > a.pool_cap) st = ST_POOL;
+            }
+            pos = __shfl_sync(FULL, pos, 0);
+            st = __shfl_sync(FULL, st, 0);
+            if (st == ST_OK && n_cons > 0) {
+                const uint32_t* ids = reinterpret_cast<const uint32_t*>(gv.aln_rank);
+                for (uint32_t i = lane; i < n_cons; i += 32) a.pool[pos + i] = (uint8_t)"ACGT"[gv.code[ids[i]]];
+            }
+            if (st == ST_OK) { st_cells += e_cells; st_padded += e_padded; st_aln += e_aln; st_aln32 += e_aln32; st_bases += e_bases; }
+            if (lane == 0) {
+                a.status[e] = st;
+                a.cons_len[e] = (st == ST_OK) ? n_cons : 0;
+                a.cons_pos[e] = (uint64_t)(uintptr_t)(a.pool + pos);
+                if (a.out_nodes) a.out_nodes[e] = *gv.n_nodes;
+            }
+        }
+        __syncthreads();                                      // bcast[0] may be rewritten now
+    }
+    if (threadIdx.x == 0 && a.stats) {
         atomicAdd(a.stats + 0, st_cells); atomicAdd(a.stats + 1, st_padded); atomicAdd(a.stats + 2, st_aln);
         atomicAdd(a.stats + 3, st_aln32); atomicAdd(a.stats + 4, st_bases);
     }

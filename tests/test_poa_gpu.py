@@ -122,3 +122,24 @@ def test_roundtrip_property_large(ctx):
     assert (status == 0).all()
     for e, t in enumerate(truths):
         assert cons[int(off[e]): int(off[e + 1])].tobytes() == t.tobytes()
+
+
+def test_team_kernel_matches_oracle(oracle, monkeypatch):
+    """Edges large enough for the block-per-edge kernel (forced here with a low threshold): multi-stripe score matrices
+    filled by 8 warps in a pipeline must give the same consensus as the warp-per-edge kernel and the oracle."""
+    import haslr_b200
+    monkeypatch.setenv("HGPU_TEAM", "8")
+    monkeypatch.setenv("HGPU_TEAM_MIN_CELLS", "1000")
+    c = haslr_b200.Context(0)
+    try:
+        # mixed batch: long gaps (4-10 stripes, some int32) go to the team kernel, short ones stay warp-per-edge
+        b1, so1, es1, _ = synth.poa_batch(31, 6, depth=5, length=2600, length_jitter=0.3)
+        b2, so2, es2, _ = synth.poa_batch(32, 40, depth=6, length=300, length_jitter=0.3)
+        b3, so3, es3, _ = synth.poa_batch(33, 2, depth=3, length=5200)
+        bases = np.concatenate((b1, b2, b3))
+        seg_off = np.concatenate((so1, so2[1:] + so1[-1], so3[1:] + so1[-1] + so2[-1])).astype(np.uint64)
+        eso = np.concatenate((es1, es2[1:] + es1[-1], es3[1:] + es1[-1] + es2[-1])).astype(np.uint32)
+        st = check_batch(c, oracle, bases, seg_off, eso)
+        assert st["dp_launches"] >= 2          # team kernel + warp-per-edge kernel
+    finally:
+        c.close()
