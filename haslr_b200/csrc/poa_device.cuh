@@ -18,8 +18,10 @@
 //  * cells are stored in "gap-hat" space  Hhat[i][j] = H[i][j] - j*gap (+ bias): the horizontal gap recurrence
 //    becomes a plain prefix maximum, done per lane in registers then across lanes with warp shuffles;
 //  * int16 cells packed two per 32-bit register, updated with the packed-int16 DPX instructions
-//    (VIADD.16x2 / VIADDMNMX.S16x2 / VIMNMX3.S16x2); an int32 instantiation takes alignments whose score
-//    range does not fit (SPOA makes the same switch);
+//    (VIADD.16x2 / VIADDMNMX.S16x2 / VIMNMX.S16x2). A lane's 16 columns are two runs of 8: word k packs column k
+//    (low half) with column k+8 (high half), so the one-column shift of the diagonal move is "the previous word"
+//    (no byte permutes) and the in-lane prefix maximum is ONE 7-step chain that scans both runs at once;
+//    an int32 instantiation takes alignments whose score range does not fit (SPOA makes the same switch);
 //  * every finished row is streamed to the warp's slot of the HBM arena as 512-byte lane-interleaved
 //    units (coalesced 16-byte stores); non-adjacent predecessors and the traceback read it back.
 #pragma once
@@ -47,7 +49,7 @@ struct DpScores {
 struct WsLayout {
     uint32_t ncap, ecap, scap;
     uint64_t o_hdr, o_code, o_in_head, o_in_tail, o_out_head, o_aligned, o_e_begin, o_e_end, o_e_w, o_e_next_in, o_e_next_out,
-        o_rank2node, o_node2rank, o_meta0, o_meta1, o_pred_off, o_pred_rank, o_aln_rank, o_aln_pos, o_mark, o_check, o_stack,
+        o_rank2node, o_node2rank, o_meta0, o_pred_off, o_pred_rank, o_aln_rank, o_aln_pos, o_mark, o_check, o_stack,
         o_score, o_pred;
     uint64_t bytes;
 };
@@ -64,7 +66,7 @@ __host__ __device__ inline WsLayout ws_layout(uint32_t ncap, uint32_t ecap) {
     w.o_aligned = take(12 * n);
     w.o_e_begin = take(4 * e); w.o_e_end = take(4 * e); w.o_e_w = take(4 * e); w.o_e_next_in = take(4 * e); w.o_e_next_out = take(4 * e);
     w.o_rank2node = take(4 * n); w.o_node2rank = take(4 * n);
-    w.o_meta0 = take(4 * n); w.o_meta1 = take(4 * n);
+    w.o_meta0 = take(4 * n);
     w.o_pred_off = take(4 * (n + 1)); w.o_pred_rank = take(4 * e);
     w.o_aln_rank = take(4 * n); w.o_aln_pos = take(4 * n);
     w.o_mark = take(n); w.o_check = take(n);
@@ -95,7 +97,6 @@ __host__ __device__ inline GraphView bind_graph(uint8_t* base, const WsLayout& w
     g.rank2node = reinterpret_cast<uint32_t*>(base + w.o_rank2node);
     g.node2rank = reinterpret_cast<uint32_t*>(base + w.o_node2rank);
     g.meta0 = reinterpret_cast<uint32_t*>(base + w.o_meta0);
-    g.meta1 = reinterpret_cast<uint32_t*>(base + w.o_meta1);
     g.pred_off = reinterpret_cast<uint32_t*>(base + w.o_pred_off);
     g.pred_rank = reinterpret_cast<uint32_t*>(base + w.o_pred_rank);
     g.aln_rank = reinterpret_cast<int32_t*>(base + w.o_aln_rank);
@@ -124,7 +125,8 @@ __device__ __forceinline__ void st_row(uint4* p, uint4 v) {
 #endif
 }
 static constexpr int TB_ROWS = 32, TB_COLS = 32;
-static constexpr int TB_SMEM_BYTES = TB_ROWS * TB_COLS * 4 + TB_ROWS * 8 + TB_COLS;  // tile + meta0/1 + seq codes
+static constexpr int TB_LD = TB_COLS + 1;        // tile row stride in words: odd, so a column of the tile spreads over all banks
+static constexpr int TB_SMEM_BYTES = TB_ROWS * TB_LD * 4 + TB_ROWS * 4 + TB_COLS;  // tile + meta0 + seq codes
 
 // Geometry of one alignment inside a slot. P16: two int16 cells per word; I32: one int32 cell per word.
 template <int NW, bool P16>
@@ -211,9 +213,9 @@ struct SlotView {
     // one cell, stored space
     __device__ __forceinline__ int load(uint32_t i, uint32_t j) const {
         uint32_t s = j / G::SW, jj = j - s * G::SW, ln = jj / G::CPL, c = jj - ln * G::CPL;
-        uint32_t k = P16 ? (c >> 1) : c;
+        uint32_t k = P16 ? (c & (uint32_t)(NW - 1)) : c;      // P16: word k = columns k (low half) and k+NW (high half)
         uint32_t w = H[(((uint64_t)i * NS + s) * G::UNITS + (k >> 2)) * 128 + ln * 4 + (k & 3)];
-        if (P16) return (c & 1) ? (int)(int16_t)(w >> 16) : (int)(int16_t)(w & 0xFFFFu);
+        if (P16) return (c >= (uint32_t)NW) ? (int)(int16_t)(w >> 16) : (int)(int16_t)(w & 0xFFFFu);
         return (int)w;
     }
 };
@@ -384,14 +386,14 @@ __device__ DP_INLINE bool dp_fill(const GraphView& gv, uint8_t* slot, uint8_t* w
         for (uint32_t r0 = 0; r0 < V; r0 += 32) {
             // batched per-rank records: lane q holds rank r0+q
             const uint32_t rr = r0 + lane;
-            uint32_t mm0 = 0, mm1 = 0;
+            uint32_t mm0 = 0;
             int bcd = G::NEGV, bcc = G::NEGV;
             if (tsize > 1 && s > 0) {       // rows r0 .. r0+32 of the stripe to the left must be complete
                 const uint32_t need_rows = (r0 + 33 < V + 1) ? r0 + 33 : V + 1;
                 if (!team_wait(vprog, (trank + tsize - 1) % tsize, (s - 1) * (V + 1) + need_rows, lane)) sync_ok = false;
             }
             if (rr < V) {
-                mm0 = gv.meta0[rr]; mm1 = gv.meta1[rr];
+                mm0 = gv.meta0[rr];
                 if (s > 0) { bcd = bc_prev[rr]; bcc = bc_prev[rr + 1]; }
             }
             const int nb = (V - r0) < 32u ? (int)(V - r0) : 32;
@@ -415,13 +417,13 @@ __device__ DP_INLINE bool dp_fill(const GraphView& gv, uint8_t* slot, uint8_t* w
                     if (lane == 0) left = R::left_from_cell(diag_in);
                     R::from_regs(h, left, pf, g2, g);
                 } else {
-                    const uint32_t npc = (m0 >> 3) & 3u, d0 = m0 >> META_D0_SHIFT;
+                    const uint32_t npc = (m0 >> 3) & 3u, d0 = meta_d0(m0);
                     uint32_t t[NW];
 #pragma unroll
                     for (int k = 0; k < NW; ++k) t[k] = P16 ? pack2(G::NEGV) : (uint32_t)G::NEGV;
                     uint32_t np = npc, cs = 0, d1 = 0;
                     if (npc == 0) np = 1;
-                    if (npc >= 2) d1 = __shfl_sync(FULL, mm1, q);
+                    if (npc == 2) d1 = meta_d1(m0);
                     if (npc == 3) { cs = gv.pred_off[i - 1]; np = gv.pred_off[i] - cs; }
                     for (uint32_t x = 0; x < np; ++x) {
                         uint32_t dist;                         // rank distance to this predecessor row
@@ -504,6 +506,328 @@ __device__ DP_INLINE bool dp_fill(const GraphView& gv, uint8_t* slot, uint8_t* w
     return sync_ok;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// int16 fill. One warp, stripes of 512 columns, 16 columns per lane as 8 words; word k = column k (low half) and
+// column k+8 (high half). Rows i-1 and i-2 of the current stripe stay in registers (A/B, swapping roles every
+// row), which serves every fast row and ~85 % of the other rows (a second predecessor two ranks back is what a
+// substitution or an indel bubble produces) without touching memory; older predecessor rows are re-read from the
+// slot. Shared-memory and slot addresses are carried as plain integers through inline PTX so that the row loop
+// holds no address arithmetic beyond one add per pointer.
+// ---------------------------------------------------------------------------------------------------------
+template <int OFF>
+__device__ __forceinline__ uint32_t lds_off(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ void stg_cs_v4(uint64_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void stg_cs_v4_512(uint64_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.global.cs.v4.u32 [%0+512], {%1, %2, %3, %4};" :: "l"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void stg_u32(uint64_t addr, uint32_t v) {
+    asm volatile("st.global.u32 [%0], %1;" :: "l"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ldg_v4(uint64_t addr, int off512) {
+    uint4 v;
+    if (off512) asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4+512];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(addr) : "memory");
+    else asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(addr) : "memory");
+    return v;
+}
+
+struct Fill16 {
+    static constexpr int NW = DP_NW16;
+    using G = Geo<DP_NW16, true>;
+    static constexpr uint32_t NEG2 = ((uint32_t)(G::NEGV & 0xFFFF)) * 0x10001u;
+
+    // t[k] := max(t[k], diagonal from src shifted one column, vertical from src); hs0 = the word left of src[0]
+    __device__ __forceinline__ static void acc(uint32_t (&t)[8], const uint32_t (&src)[8], uint32_t hs0, uint32_t pf, uint32_t g2) {
+        t[0] = __vimax3_s16x2(t[0], __vadd2(hs0, lds_off<0>(pf)), __vadd2(src[0], g2));
+        t[1] = __vimax3_s16x2(t[1], __vadd2(src[0], lds_off<128>(pf)), __vadd2(src[1], g2));
+        t[2] = __vimax3_s16x2(t[2], __vadd2(src[1], lds_off<256>(pf)), __vadd2(src[2], g2));
+        t[3] = __vimax3_s16x2(t[3], __vadd2(src[2], lds_off<384>(pf)), __vadd2(src[3], g2));
+        t[4] = __vimax3_s16x2(t[4], __vadd2(src[3], lds_off<512>(pf)), __vadd2(src[4], g2));
+        t[5] = __vimax3_s16x2(t[5], __vadd2(src[4], lds_off<640>(pf)), __vadd2(src[5], g2));
+        t[6] = __vimax3_s16x2(t[6], __vadd2(src[5], lds_off<768>(pf)), __vadd2(src[6], g2));
+        t[7] = __vimax3_s16x2(t[7], __vadd2(src[6], lds_off<896>(pf)), __vadd2(src[7], g2));
+    }
+    // the word "one column to the left" of src[0]: low half = column 15 of the lane to the left (or the stripe
+    // boundary value for lane 0), high half = this lane's column 7
+    __device__ __forceinline__ static uint32_t left_word(const uint32_t (&src)[8], int boundary, int lane) {
+        uint32_t left = __shfl_up_sync(FULL, src[7], 1);
+        if (lane == 0) left = (uint32_t)boundary << 16;
+        return __byte_perm(left, src[7], 0x5432);
+    }
+};
+
+// Cold per-alignment state of the int16 fill lives in the warp's shared memory (behind the 4 KB profile) instead of
+// registers; the row loop reads it only on its rare paths (batch header, >= 3 predecessors, far predecessor rows).
+struct FillFrame16 {
+    unsigned long long meta0, pred_off, pred_rank, bc_prev, bc_cur;
+};
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t addr) {
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldg_u32(unsigned long long base, uint32_t index) {
+    uint32_t v;
+    asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(base + 4ull * index) : "memory");
+    return v;
+}
+#define FRAME16(field) ((uint32_t)offsetof(FillFrame16, field))
+
+// One row, in place: A = row i-1 on entry and row i on exit (stored to the slot as well). B holds row i-2 whenever row i
+// has a predecessor two ranks back; `save` says that row i+1 has one, so row i-1 is parked in B before A is overwritten.
+// The body is kept small on purpose (one instance of each piece): the kernel is instruction-cache bound otherwise.
+struct Row16State {
+    uint32_t pf_lane;        // shared address of prof[0][0][lane]
+    uint32_t frame;          // shared address of the FillFrame16
+    uint32_t g2;             // packed gap
+    uint32_t row_bytes;      // distance between consecutive rows of the stripe in the slot
+    uint64_t dst;            // slot address of this lane's first unit of row i
+    uint32_t bcx;            // batch register: lane q holds the boundary value of row r0+q+1 in the stripe to the left
+    uint32_t bco;            // batch register: lane q collects the last cell of row r0+q+1 (boundary for the next stripe)
+    int lane; bool has_prev, has_next;
+};
+
+__device__ __forceinline__ void row16(uint32_t (&A)[8], uint32_t (&B)[8], Row16State& S, uint32_t m0, int q, uint32_t i,
+                                      int diag_in, int carry_in, bool save) {
+    using F = Fill16;
+    const int lane = S.lane;
+    const uint32_t g2 = S.g2;
+    const uint32_t pf = S.pf_lane + (m0 & 3u) * (uint32_t)(F::NW * 32 * 4);
+    if ((m0 & META_FAST) != 0) {                                    // single predecessor = previous rank: registers only
+        const uint32_t hs0 = F::left_word(A, diag_in, lane);
+        if (save) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) B[k] = A[k];
+        }
+        A[7] = __viaddmax_s16x2(A[7], g2, __vadd2(A[6], lds_off<896>(pf)));
+        A[6] = __viaddmax_s16x2(A[6], g2, __vadd2(A[5], lds_off<768>(pf)));
+        A[5] = __viaddmax_s16x2(A[5], g2, __vadd2(A[4], lds_off<640>(pf)));
+        A[4] = __viaddmax_s16x2(A[4], g2, __vadd2(A[3], lds_off<512>(pf)));
+        A[3] = __viaddmax_s16x2(A[3], g2, __vadd2(A[2], lds_off<384>(pf)));
+        A[2] = __viaddmax_s16x2(A[2], g2, __vadd2(A[1], lds_off<256>(pf)));
+        A[1] = __viaddmax_s16x2(A[1], g2, __vadd2(A[0], lds_off<128>(pf)));
+        A[0] = __viaddmax_s16x2(A[0], g2, __vadd2(hs0, lds_off<0>(pf)));
+    } else {
+        const uint32_t npc = (m0 >> 3) & 3u;
+        uint32_t t[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t[k] = F::NEG2;
+        uint32_t np = npc == 0 ? 1u : npc, cs = 0;
+        unsigned long long prank = 0;
+        if (npc == 3) {
+            const unsigned long long poff = lds_u64(S.frame + FRAME16(pred_off));
+            prank = lds_u64(S.frame + FRAME16(pred_rank));
+            cs = ldg_u32(poff, i - 1);
+            np = ldg_u32(poff, i) - cs;
+        }
+#pragma unroll 1
+        for (uint32_t x = 0; x < np; ++x) {
+            uint32_t dist;                                          // rank distance to this predecessor row
+            if (npc == 3) dist = i - (ldg_u32(prank, cs + x) + 1);
+            else if (npc == 0) dist = i;                            // no predecessor: the virtual row 0
+            else dist = x == 0 ? meta_d0(m0) : meta_d1(m0);
+            uint32_t gg = g2, pfl = pf;
+            asm volatile("" : "+r"(gg), "+r"(pfl));                 // nothing of the body is hoisted out of the loop (it would only spill)
+            if (dist == 1) {
+                F::acc(t, A, F::left_word(A, diag_in, lane), pfl, gg);
+            } else {
+                int bl = F::G::NEGV;                                // Hhat[i - dist][first column of the stripe - 1]
+                if (S.has_prev) {
+                    const int ql = q - (int)dist;                   // bcx lane that holds row i - dist
+                    bl = ql >= 0 ? __shfl_sync(FULL, (int)S.bcx, ql & 31) : (int)ldg_u32(lds_u64(S.frame + FRAME16(bc_prev)), i - dist);
+                }
+                if (dist == 2) {
+                    F::acc(t, B, F::left_word(B, bl, lane), pfl, gg);
+                } else {
+                    const uint64_t src = S.dst - (uint64_t)dist * S.row_bytes;
+                    const uint4 v0 = ldg_v4(src, 0), v1 = ldg_v4(src, 1);
+                    const uint32_t v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                    F::acc(t, v, F::left_word(v, bl, lane), pfl, gg);
+                }
+            }
+        }
+        if (save) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) B[k] = A[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) A[k] = t[k];
+    }
+    // horizontal gaps = prefix maximum in hat space. In the lane: one chain scans columns 0..7 (low halves) and 8..15
+    // (high halves) together; the high run then also takes the low run's total.
+#pragma unroll
+    for (int k = 1; k < 8; ++k) A[k] = __vmaxs2(A[k], A[k - 1]);
+    const uint32_t both = __vmaxs2(A[7], __byte_perm(A[7], 0, 0x1032));
+    const int tot = (int)(int16_t)(both & 0xFFFFu);                // the lane's maximum
+    // Across lanes the exclusive prefix is needed. Lane totals almost always rise up to the lane holding the row
+    // maximum and everything right of it inherits that maximum, so: neighbour total (1 SHFL) + row maximum (1 REDUX)
+    // + two ballots decide the common case exactly; any violation falls back to the 5-step scan.
+    const int nbv = __shfl_up_sync(FULL, tot, 1);
+    const int rowmax = __reduce_max_sync(FULL, tot);
+    const int prevv = (lane == 0) ? carry_in : nbv;
+    const int amax = __ffs(__ballot_sync(FULL, tot == rowmax)) - 1;   // first lane holding the maximum
+    int excl;
+    if (__ballot_sync(FULL, lane <= amax && tot < prevv) == 0) {
+        excl = (lane <= amax) ? prevv : rowmax;
+    } else {
+        int incl = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int v = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl = max(incl, v);
+        }
+        excl = __shfl_up_sync(FULL, incl, 1);
+        excl = (lane == 0) ? carry_in : max(excl, carry_in);
+    }
+    const uint32_t mid = __byte_perm(A[7], F::NEG2, 0x1054);        // (low = NEG, high = total of the low run)
+    const uint32_t cc = __vmaxs2(mid, __byte_perm((uint32_t)excl, 0, 0x1010));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) A[k] = __vmaxs2(A[k], cc);
+    // stream the row out; its last cell (lane 31) is parked in lane q of bco until the batch ends
+    stg_cs_v4(S.dst, A[0], A[1], A[2], A[3]);
+    stg_cs_v4_512(S.dst, A[4], A[5], A[6], A[7]);
+    S.dst += S.row_bytes;
+    if (S.has_next) {
+        const uint32_t last = __shfl_sync(FULL, A[7], 31);
+        if (lane == q) S.bco = (uint32_t)((int32_t)last >> 16);
+    }
+}
+
+// does the rank with record m0 read the row two ranks back? (class 3 walks the CSR: assume yes)
+__device__ __forceinline__ bool meta_reads_two_back(uint32_t m0) {
+    const uint32_t npc = (m0 >> 3) & 3u;
+    if (npc == 0) return (m0 & META_FAST) == 0;      // a later rank without predecessors reads the virtual row 0
+    return npc == 3 || meta_d0(m0) == 2 || (npc == 2 && meta_d1(m0) == 2);
+}
+
+#ifndef HGPU_INLINE_FILL16
+#define HGPU_INLINE_FILL16 0
+#endif
+#if HGPU_INLINE_FILL16
+#define FILL16_INLINE __forceinline__
+#else
+#define FILL16_INLINE __noinline__      // own register allocation: the edge loop's graph pointers are not live in here
+#endif
+struct FillGraph { const uint32_t* meta0; const uint32_t* pred_off; const uint32_t* pred_rank; };
+
+__device__ FILL16_INLINE bool dp_fill16(const FillGraph gv, uint8_t* slot, uint8_t* wsm, const uint8_t* seq,
+                                        uint32_t V, uint32_t L, const DpScores sc, int lane,
+                                        uint32_t trank, uint32_t tsize, volatile uint32_t* vprog) {
+    constexpr int NW = DP_NW16;
+    using G = Geo<NW, true>;
+    bool sync_ok = true;
+    uint32_t* prof = reinterpret_cast<uint32_t*>(wsm);                 // [4][NW][32]
+    FillFrame16* frame = reinterpret_cast<FillFrame16*>(wsm + G::PROF_BYTES);
+    SlotView<NW, true> sv;
+    sv.bind(slot, V, L);
+    const int bias = G::bias(V, sc);
+    const uint32_t NS = sv.NS;
+    Row16State S;
+    S.lane = lane;
+    S.g2 = pack2(sc.g);
+    S.pf_lane = (uint32_t)__cvta_generic_to_shared(prof + lane);
+    S.frame = (uint32_t)__cvta_generic_to_shared(frame);
+    S.row_bytes = NS * (uint32_t)(G::UNITS * 32 * 16);
+    S.bcx = 0; S.bco = 0;
+    if (lane == 0) {
+        frame->meta0 = (unsigned long long)(uintptr_t)gv.meta0;
+        frame->pred_off = (unsigned long long)(uintptr_t)gv.pred_off;
+        frame->pred_rank = (unsigned long long)(uintptr_t)gv.pred_rank;
+    }
+    asm volatile("" : "+r"(S.pf_lane), "+r"(S.frame), "+r"(S.g2), "+r"(S.row_bytes));   // kept in registers, never recomputed in the row loop
+
+    for (uint32_t s = trank; s < NS; s += tsize) {
+        __syncwarp();
+        // --- sequence profile of this stripe: prof[code][k][lane] = hat scores of the lane's k-th word (columns k, k+8)
+        {
+            const uint32_t j0 = s * G::SW + lane * G::CPL;   // first column owned by this lane
+#pragma unroll 4
+            for (int k = 0; k < NW; ++k) {
+                const uint32_t ja = j0 + k, jb = ja + NW;
+                const int ca = (ja >= 1 && ja <= L) ? (int)base_code(seq[ja - 1]) : -1;
+                const int cb = (jb >= 1 && jb <= L) ? (int)base_code(seq[jb - 1]) : -1;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int va = ca < 0 ? 0 : (ca == c ? sc.sm : sc.sx);
+                    const int vb = cb < 0 ? 0 : (cb == c ? sc.sm : sc.sx);
+                    prof[(c * NW + k) * 32 + lane] = ((uint32_t)va & 0xFFFFu) | ((uint32_t)vb << 16);
+                }
+            }
+        }
+        const int32_t* bc_prev = (s > 0) ? sv.bcol + (uint64_t)(s - 1) * (V + 1) : nullptr;
+        int32_t* bc_cur = sv.bcol + (uint64_t)s * (V + 1);
+        if (lane == 0) {
+            frame->bc_prev = (unsigned long long)(uintptr_t)bc_prev;
+            frame->bc_cur = (unsigned long long)(uintptr_t)bc_cur;
+        }
+        __syncwarp();
+        asm volatile("" : "+r"(S.pf_lane) :: "memory");              // profile loads below may not move above / be merged across this point
+        S.has_prev = s > 0;
+        S.has_next = s + 1 < NS;
+
+        // --- row 0: Hhat = 0 everywhere
+        uint32_t A[NW], B[NW];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) { A[k] = pack2(bias); B[k] = Fill16::NEG2; }
+        {
+            uint4* dst = sv.row_units(0, s, lane);
+#pragma unroll
+            for (int u = 0; u < G::UNITS; ++u) dst[u * 32] = make_uint4(A[4 * u], A[4 * u + 1], A[4 * u + 2], A[4 * u + 3]);
+            if (lane == 31) bc_cur[0] = bias;
+        }
+        if (tsize > 1) team_publish(vprog, trank, s * (V + 1) + 1, lane);
+        S.dst = (uint64_t)(uintptr_t)sv.row_units(1, s, lane);
+        asm volatile("" : "+l"(S.dst));
+
+        // per-rank records of the first batch; later batches are fetched one batch ahead
+        uint32_t nm0 = ((uint32_t)lane < V) ? gv.meta0[lane] : 0u;
+        int diag = G::NEGV;                                           // boundary value of row i-1: starts at row 0
+        if (s > 0) {
+            if (tsize > 1 && !team_wait(vprog, (trank + tsize - 1) % tsize, (s - 1) * (V + 1) + 1, lane)) sync_ok = false;
+            diag = bc_prev[0];
+        }
+        for (uint32_t r0 = 0; r0 < V; r0 += 32) {
+            const uint32_t rr = r0 + lane;
+            const uint32_t mm0 = nm0;
+            if (rr + 32 < V) nm0 = ldg_u32(lds_u64(S.frame + FRAME16(meta0)), rr + 32);
+            if (s > 0) {
+                if (tsize > 1) {            // rows r0 .. r0+32 of the stripe to the left must be complete
+                    const uint32_t need_rows = (r0 + 33 < V + 1) ? r0 + 33 : V + 1;
+                    if (!team_wait(vprog, (trank + tsize - 1) % tsize, (s - 1) * (V + 1) + need_rows, lane)) sync_ok = false;
+                }
+                S.bcx = (rr < V) ? ldg_u32(lds_u64(S.frame + FRAME16(bc_prev)), rr + 1) : 0u;
+            }
+            const int nb = (V - r0) < 32u ? (int)(V - r0) : 32;
+            // bit q of save_mask: row r0+q+1 parks row r0+q in B before overwriting it, because row r0+q+2 reads two ranks back
+            const uint32_t save_mask = __ballot_sync(FULL, meta_reads_two_back(mm0)) >> 1;
+#pragma unroll 1
+            for (int q = 0; q < nb; ++q) {
+                const uint32_t m0 = __shfl_sync(FULL, mm0, q);
+                int carry = G::NEGV;
+                if (S.has_prev) carry = __shfl_sync(FULL, (int)S.bcx, q);
+                bool save = ((save_mask >> q) & 1u) != 0;
+                if (q == 31) save = (__ballot_sync(FULL, rr + 32 < V && meta_reads_two_back(nm0)) & 1u) != 0;   // first row of the next batch
+                row16(A, B, S, m0, q, r0 + q + 1, diag, carry, save);
+                diag = carry;
+            }
+            if (S.has_next && lane < nb) {
+                const unsigned long long bc = lds_u64(S.frame + FRAME16(bc_cur));
+                asm volatile("st.global.u32 [%0], %1;" :: "l"(bc + 4ull * (rr + 1)), "r"(S.bco) : "memory");
+            }
+            if (tsize > 1) team_publish(vprog, trank, s * (V + 1) + ((r0 + 32 < V) ? r0 + 32 : V) + 1, lane);
+        }
+        __syncwarp();
+    }
+    __threadfence_block();
+    __syncwarp();
+    return sync_ok;
+}
+
 template <int NW, bool P16>
 __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8_t* wsm, const uint8_t* seq,
                                        uint32_t V, uint32_t L, const DpScores sc, int lane) {
@@ -526,10 +850,9 @@ __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8
         uint32_t oi = __shfl_xor_sync(FULL, best_i, d);
         if (oi != 0 && (best_i == 0 || ov > best || (ov == best && oi < best_i))) { best = ov; best_i = oi; }
     }
-    int* tile = reinterpret_cast<int*>(wsm);                              // [TB_ROWS][TB_COLS]
-    uint32_t* tm0 = reinterpret_cast<uint32_t*>(wsm + TB_ROWS * TB_COLS * 4);
-    uint32_t* tm1 = tm0 + TB_ROWS;
-    uint8_t* tseq = reinterpret_cast<uint8_t*>(tm1 + TB_ROWS);
+    int* tile = reinterpret_cast<int*>(wsm);                              // [TB_ROWS][TB_LD]
+    uint32_t* tm0 = reinterpret_cast<uint32_t*>(wsm + TB_ROWS * TB_LD * 4);
+    uint8_t* tseq = reinterpret_cast<uint8_t*>(tm0 + TB_ROWS);
     uint32_t ci = best_i, cj = L, n_out = 0;
     bool bad = (best_i == 0);
     while (!bad && !(ci == 0 && cj == 0)) {
@@ -539,8 +862,8 @@ __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8
         if (it >= (uint32_t)lane) {
             const uint32_t row = it - lane;
 #pragma unroll 8
-            for (int c = 0; c < TB_COLS; ++c) if (jt >= (uint32_t)c) tile[lane * TB_COLS + c] = sv.load(row, jt - c);
-            if (row >= 1) { tm0[lane] = gv.meta0[row - 1]; tm1[lane] = gv.meta1[row - 1]; }
+            for (int c = 0; c < TB_COLS; ++c) if (jt >= (uint32_t)c) tile[lane * TB_LD + c] = sv.load(row, jt - c);
+            if (row >= 1) tm0[lane] = gv.meta0[row - 1];
         }
         if (jt >= (uint32_t)lane + 1) tseq[lane] = (uint8_t)base_code(seq[jt - lane - 1]);
         __syncwarp();
@@ -556,7 +879,7 @@ __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8
                 if (cond) {
                     const uint32_t m0 = tm0[a_];
                     const int dsc = (tseq[b_] == (m0 & 3u)) ? sc.sm : sc.sx;
-                    cond = (m0 & META_FAST) != 0 && tile[a_ * TB_COLS + b_] == tile[(a_ + 1) * TB_COLS + b_ + 1] + dsc;
+                    cond = (m0 & META_FAST) != 0 && tile[a_ * TB_LD + b_] == tile[(a_ + 1) * TB_LD + b_ + 1] + dsc;
                 }
                 const unsigned fm = __ballot_sync(FULL, !cond);
                 const uint32_t run = fm ? (uint32_t)(__ffs(fm) - 1) : 32u;
@@ -575,15 +898,15 @@ __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8
                 const uint32_t i = ci, j = cj;
                 auto getH = [&](uint32_t ii, uint32_t jj) -> int {
                     uint32_t a_ = it - ii, b_ = jt - jj;   // ii <= it, jj <= jt always hold on a walk up/left
-                    if (a_ < (uint32_t)TB_ROWS && b_ < (uint32_t)TB_COLS) return tile[a_ * TB_COLS + b_];
+                    if (a_ < (uint32_t)TB_ROWS && b_ < (uint32_t)TB_COLS) return tile[a_ * TB_LD + b_];
                     return sv.load(ii, jj);
                 };
-                const int val = tile[li * TB_COLS + lj];
+                const int val = tile[li * TB_LD + lj];
                 uint32_t pi = i, pj = j;
                 bool found = false;
                 if (i != 0) {
-                    const uint32_t m0 = tm0[li], m1 = tm1[li];
-                    const uint32_t code = m0 & 3u, npc = (m0 >> 3) & 3u, d0 = m0 >> META_D0_SHIFT;
+                    const uint32_t m0 = tm0[li];
+                    const uint32_t code = m0 & 3u, npc = (m0 >> 3) & 3u, d0 = meta_d0(m0), m1 = meta_d1(m0);
                     uint32_t np = npc, cs = 0;
                     if (npc == 0) np = 1;
                     if (npc == 3) { cs = gv.pred_off[i - 1]; np = gv.pred_off[i] - cs; }
@@ -622,7 +945,8 @@ __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8
 template <int NW, bool P16>
 __device__ DP_INLINE bool dp_align(const GraphView& gv, uint8_t* slot, uint8_t* wsm, const uint8_t* seq,
                                    uint32_t V, uint32_t L, const DpScores sc, int lane) {
-    dp_fill<NW, P16>(gv, slot, wsm, seq, V, L, sc, lane, 0, 1, nullptr);
+    if (P16) dp_fill16(FillGraph{gv.meta0, gv.pred_off, gv.pred_rank}, slot, wsm, seq, V, L, sc, lane, 0, 1, nullptr);
+    else dp_fill<NW, false>(gv, slot, wsm, seq, V, L, sc, lane, 0, 1, nullptr);
     return dp_traceback<NW, P16>(gv, slot, wsm, seq, V, L, sc, lane);
 }
 
@@ -639,8 +963,7 @@ __device__ __forceinline__ void w_init_chain(GraphView& g, const uint8_t* seq, u
         g.aligned[3 * i] = g.aligned[3 * i + 1] = g.aligned[3 * i + 2] = NIL;
         if (i + 1 < L) { g.e_begin[i] = i; g.e_end[i] = i + 1; g.e_w[i] = 2; g.e_next_in[i] = NIL; g.e_next_out[i] = NIL; }
         g.rank2node[i] = i; g.node2rank[i] = i;
-        g.meta0[i] = c | ((i + 1 < L) ? 0u : META_SINK) | META_FAST | ((i > 0) ? ((1u << 3) | (1u << META_D0_SHIFT)) : 0u);
-        g.meta1[i] = 0;
+        g.meta0[i] = meta_pack(c | ((i + 1 < L) ? 0u : META_SINK), i, i > 0 ? 1u : 0u, 1u, 0u);
         g.pred_off[i] = (i > 0) ? i - 1 : 0;
         if (i > 0) g.pred_rank[i - 1] = i - 1;
     }
@@ -651,7 +974,7 @@ __device__ __forceinline__ void w_init_chain(GraphView& g, const uint8_t* seq, u
     __syncwarp();
 }
 
-// per-rank DP records (meta0/meta1/pred CSR) from rank2node/node2rank + in-lists; same content as g_build_meta
+// per-rank DP records (meta0 / pred CSR) from rank2node/node2rank + in-lists; same content as g_build_meta
 __device__ __forceinline__ void w_build_meta(GraphView& g, int lane) {
     const uint32_t N = *g.n_nodes;
     uint32_t running = 0;
@@ -670,19 +993,17 @@ __device__ __forceinline__ void w_build_meta(GraphView& g, int lane) {
         }
         const uint32_t off = running + incl - deg;
         if (r < N) {
-            uint32_t m0 = g.code[v] | (g.out_head[v] == NIL ? META_SINK : 0u), m1 = 0;
+            const uint32_t base = g.code[v] | (g.out_head[v] == NIL ? META_SINK : 0u);
             g.pred_off[r] = off;
-            uint32_t np = 0;
+            uint32_t np = 0, d0 = 0, d1 = 0;
             for (uint32_t x = g.in_head[v]; x != NIL; x = g.e_next_in[x]) {
                 uint32_t pr = g.node2rank[g.e_begin[x]];
                 g.pred_rank[off + np] = pr;
-                if (np == 0) m0 |= (r - pr) << META_D0_SHIFT;
-                if (np == 1) m1 = r - pr;
+                if (np == 0) d0 = r - pr;
+                if (np == 1) d1 = r - pr;
                 ++np;
             }
-            m0 |= (np > 3 ? 3u : np) << 3;
-            if ((np == 1 && (m0 >> META_D0_SHIFT) == 1) || (np == 0 && r == 0)) m0 |= META_FAST;
-            g.meta0[r] = m0; g.meta1[r] = m1;
+            g.meta0[r] = meta_pack(base, r, np, d0, d1);
         }
         running += __shfl_sync(FULL, incl, 31);
     }
@@ -921,9 +1242,14 @@ __device__ __noinline__ int w_toposort(GraphView& g, uint8_t* wsm, int lane) {
 #ifndef HGPU_MINBLOCKS
 #define HGPU_MINBLOCKS 7
 #endif
+__device__ __forceinline__ int lane_id() {       // read once, never rematerialised from S2R inside the hot loops
+    const int l = (int)(threadIdx.x & 31u);
+    return __shfl_sync(FULL, l, l);                 // a shuffle result is opaque to ptxas, S2R is not
+}
+
 __global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, HGPU_MINBLOCKS) k_poa_edges(PoaArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    const int lane = threadIdx.x & 31;
+    const int lane = lane_id();
     const int wib = threadIdx.x >> 5;
     const uint32_t gw = blockIdx.x * DP_WARPS_PER_BLOCK + wib;
     uint8_t* wsm = smem_raw + (size_t)wib * DP_SMEM_PER_WARP;
@@ -1034,7 +1360,7 @@ __global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, HGPU_MINBLOCKS) k_poa
 template <int TEAM>
 __global__ void __launch_bounds__(32 * TEAM, 768 / (32 * TEAM)) k_poa_edges_team(PoaArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    const int lane = threadIdx.x & 31;
+    const int lane = lane_id();
     const uint32_t wib = threadIdx.x >> 5;                  // = rank in the team
     const uint32_t gw = blockIdx.x;                          // one slot / workspace per team
     uint8_t* wsm = smem_raw + (size_t)wib * DP_SMEM_PER_WARP;
@@ -1076,7 +1402,7 @@ __global__ void __launch_bounds__(32 * TEAM, 768 / (32 * TEAM)) k_poa_edges_team
                 const bool p16 = !a.force_i32 && dp_fits16(V, L, a.sc);
                 if ((uint64_t)V + L > gv.ncap || (uint64_t)NE + L + 1 > gv.ecap) { st = ST_CAPACITY; break; }
                 if (dp_slot_bytes(V, L, p16) > a.slot_bytes) { st = ST_TOO_LARGE; break; }
-                const bool fill_ok = p16 ? dp_fill<DP_NW16, true>(gv, slot, wsm, seq, V, L, a.sc, lane, wib, TEAM, vprog)
+                const bool fill_ok = p16 ? dp_fill16(FillGraph{gv.meta0, gv.pred_off, gv.pred_rank}, slot, wsm, seq, V, L, a.sc, lane, wib, TEAM, vprog)
                                          : dp_fill<DP_NW32, false>(gv, slot, wsm, seq, V, L, a.sc, lane, wib, TEAM, vprog);
                 const int all_ok = __syncthreads_and(fill_ok ? 1 : 0);    // every stripe stored (and no wait gave up)
                 if (!all_ok) { st = ST_SYNC; break; }

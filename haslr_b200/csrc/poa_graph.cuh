@@ -15,6 +15,7 @@
 #else
 #define HGPU_HD inline
 #endif
+#define HGPU_HD_FWD HGPU_HD
 
 namespace hgpu {
 
@@ -23,13 +24,23 @@ static constexpr uint32_t NIL = 0xFFFFFFFFu;
 // meta0 layout (one word per rank, consumed by the DP/traceback kernel)
 //   bits 0-1  node code (A,C,G,T = 0..3)
 //   bit  2    sink (no out-edges)
-//   bits 3-4  predecessor class: 0 none, 1 one, 2 two, 3 three or more (walk the CSR)
+//   bits 3-4  predecessor class: 0 none, 1 one, 2 two, 3 walk the CSR (three or more, or a distance >= 8192)
 //   bit  5    fast row: its only predecessor is the previous rank (or it is rank 0 without predecessors)
-//   bits 6-31 rank distance to the first predecessor (classes 1..3)
-// meta1: rank distance to the second predecessor (classes 2..3)
+//   bits 6-18  rank distance to the first predecessor  (classes 1, 2)
+//   bits 19-31 rank distance to the second predecessor (class 2)
 static constexpr uint32_t META_SINK = 4u;
 static constexpr uint32_t META_FAST = 32u;
-static constexpr int META_D0_SHIFT = 6;
+static constexpr int META_D0_SHIFT = 6, META_D1_SHIFT = 19;
+static constexpr uint32_t META_DMAX = 1u << 13;
+HGPU_HD_FWD uint32_t meta_d0(uint32_t m0) { return (m0 >> META_D0_SHIFT) & (META_DMAX - 1u); }
+HGPU_HD_FWD uint32_t meta_d1(uint32_t m0) { return m0 >> META_D1_SHIFT; }
+// record of a rank with code/sink bits `base`, np predecessors, the first two at distances d0, d1
+HGPU_HD_FWD uint32_t meta_pack(uint32_t base, uint32_t rank, uint32_t np, uint32_t d0, uint32_t d1) {
+    if (np == 0) return base | (rank == 0 ? META_FAST : 0u);
+    if (np > 2 || d0 >= META_DMAX || (np == 2 && d1 >= META_DMAX)) return base | (3u << 3);
+    if (np == 1) return base | (1u << 3) | (d0 << META_D0_SHIFT) | (d0 == 1 ? META_FAST : 0u);
+    return base | (2u << 3) | (d0 << META_D0_SHIFT) | (d1 << META_D1_SHIFT);
+}
 
 struct GraphView {
     uint32_t ncap;        // capacity in nodes (== capacity of the aln arrays)
@@ -47,7 +58,6 @@ struct GraphView {
     uint32_t* rank2node;  // [ncap]
     uint32_t* node2rank;  // [ncap]
     uint32_t* meta0;      // [ncap] by rank
-    uint32_t* meta1;      // [ncap] by rank
     uint32_t* pred_off;   // [ncap+1] by rank, CSR into pred_rank
     uint32_t* pred_rank;  // [ecap]
     int32_t* aln_rank;    // [ncap] alignment, traceback order (last pair first): rank or -1
@@ -226,19 +236,17 @@ HGPU_HD void g_build_meta(GraphView& g) {
     uint32_t pe = 0;
     for (uint32_t r = 0; r < N; ++r) {
         uint32_t v = g.rank2node[r];
-        uint32_t m0 = g.code[v] | (g.out_head[v] == NIL ? META_SINK : 0u), m1 = 0;
+        const uint32_t base = g.code[v] | (g.out_head[v] == NIL ? META_SINK : 0u);
         g.pred_off[r] = pe;
-        uint32_t np = 0;
+        uint32_t np = 0, d0 = 0, d1 = 0;
         for (uint32_t x = g.in_head[v]; x != NIL; x = g.e_next_in[x]) {
             uint32_t pr = g.node2rank[g.e_begin[x]];
             g.pred_rank[pe++] = pr;
-            if (np == 0) m0 |= (r - pr) << META_D0_SHIFT;
-            if (np == 1) m1 = r - pr;
+            if (np == 0) d0 = r - pr;
+            if (np == 1) d1 = r - pr;
             ++np;
         }
-        m0 |= (np > 3 ? 3u : np) << 3;
-        if ((np == 1 && (m0 >> META_D0_SHIFT) == 1) || (np == 0 && r == 0)) m0 |= META_FAST;
-        g.meta0[r] = m0; g.meta1[r] = m1;
+        g.meta0[r] = meta_pack(base, r, np, d0, d1);
     }
     g.pred_off[N] = pe;
 }

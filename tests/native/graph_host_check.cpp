@@ -16,14 +16,14 @@ namespace {
 struct Store {
     std::vector<uint8_t> code, mark, check;
     std::vector<uint32_t> in_head, in_tail, out_head, aligned, e_begin, e_end, e_w, e_next_in, e_next_out, rank2node, node2rank,
-        meta0, meta1, pred_off, pred_rank, stack;
+        meta0, pred_off, pred_rank, stack;
     std::vector<int32_t> aln_rank, aln_pos, pred;
     std::vector<int64_t> score;
     uint32_t n_nodes = 0, n_edges = 0, aln_len = 0;
     GraphView g; GraphScratch s;
     Store(uint32_t ncap, uint32_t ecap) {
         code.resize(ncap); mark.resize(ncap); check.resize(ncap);
-        for (auto* v : {&in_head, &in_tail, &out_head, &rank2node, &node2rank, &meta0, &meta1}) v->resize(ncap);
+        for (auto* v : {&in_head, &in_tail, &out_head, &rank2node, &node2rank, &meta0}) v->resize(ncap);
         aligned.resize(3 * (size_t)ncap); pred_off.resize(ncap + 1);
         for (auto* v : {&e_begin, &e_end, &e_w, &e_next_in, &e_next_out, &pred_rank}) v->resize(ecap);
         stack.resize(ecap + 4 * (size_t)ncap + 8);
@@ -32,7 +32,7 @@ struct Store {
         g.code = code.data(); g.in_head = in_head.data(); g.in_tail = in_tail.data(); g.out_head = out_head.data();
         g.aligned = aligned.data(); g.e_begin = e_begin.data(); g.e_end = e_end.data(); g.e_w = e_w.data();
         g.e_next_in = e_next_in.data(); g.e_next_out = e_next_out.data(); g.rank2node = rank2node.data();
-        g.node2rank = node2rank.data(); g.meta0 = meta0.data(); g.meta1 = meta1.data(); g.pred_off = pred_off.data();
+        g.node2rank = node2rank.data(); g.meta0 = meta0.data(); g.pred_off = pred_off.data();
         g.pred_rank = pred_rank.data(); g.aln_rank = aln_rank.data(); g.aln_pos = aln_pos.data();
         g.n_nodes = &n_nodes; g.n_edges = &n_edges; g.aln_len = &aln_len;
         s.mark = mark.data(); s.check = check.data(); s.stack = stack.data(); s.stack_cap = (uint32_t)stack.size();
@@ -43,7 +43,7 @@ struct Store {
 // predecessor rows (1-based H rows) of rank r from the packed records, exactly as the CUDA fill decodes them
 void pred_rows(const GraphView& g, uint32_t r, std::vector<uint32_t>& out) {
     out.clear();
-    const uint32_t m0 = g.meta0[r], m1 = g.meta1[r], npc = (m0 >> 3) & 3u, d0 = m0 >> META_D0_SHIFT, i = r + 1;
+    const uint32_t m0 = g.meta0[r], m1 = meta_d1(m0), npc = (m0 >> 3) & 3u, d0 = meta_d0(m0), i = r + 1;
     if (npc == 0) { out.push_back(0); return; }
     if (npc == 3) { for (uint32_t x = g.pred_off[r]; x < g.pred_off[r + 1]; ++x) out.push_back(g.pred_rank[x] + 1); return; }
     out.push_back(i - d0);

@@ -43,3 +43,37 @@ if len(sys.argv) > 2 and sys.argv[2] != '-':
     json.dump({"headline": head, "total_samples": ts, "total_inst": ti,
                "top_lines": [{"file": f, "line": l, "samples_pct": 100*s/ts, "inst_pct": 100*i/ti, "src": t}
                              for (f, l), (s, i, t) in sorted(lines.items(), key=lambda kv: -kv[1][0])[:60]]}, open(sys.argv[2], "w"), indent=1)
+
+# ---- per-function / per-phase attribution (function = nearest preceding definition in the same file)
+import os
+import re
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+defs = {}
+SUBPHASE = [("--- sequence profile of this stripe", "fill.profile"), ("--- row 0: Hhat = 0", "fill.row0"),
+            ("batched per-rank records", "fill.batch_hdr"), ("const uint32_t i = r0 + q + 1;", "fill.row_hdr"),
+            ("if ((m0 & META_FAST) != 0) {", "fill.fast_row"), ("const uint32_t npc = (m0 >> 3) & 3u, d0 = m0 >> META_D0_SHIFT;", "fill.slow_row"),
+            ("// horizontal gaps = prefix maximum", "fill.scan"), ("// stream the row out", "fill.store"),
+            ("// end cell: best Hhat", "tb.endcell"), ("// tile of the stored matrix", "tb.tile_load"),
+            ("// (1) a run of diagonal moves", "tb.diag_run"), ("// (2) one generic step", "tb.generic"),
+            ("// SPOA's DFS from root", "topo.dfs"), ("// (A)+(B): node of every position", "add.AB"), ("// (B2): initialise new nodes", "add.B2"),
+            ("// (C): edges between consecutive", "add.C"), ("// heaviest-bundle consensus; node ids", "edge.consensus"), ("// publish", "edge.publish")]
+for fn in ("poa_device.cuh", "poa_graph.cuh"):
+    marks = []
+    for n, text in enumerate(open(os.path.join(ROOT, "haslr_b200", "csrc", fn)), 1):
+        m = re.match(r"^(?:template.*>\s*)?(?:__device__|__global__|HGPU_HD|__host__ __device__)[^;]*?\b([a-zA-Z_0-9]+)\s*\(", text)
+        if m and not text.strip().endswith(";"):
+            marks.append((n, m.group(1)))
+        for pat, nm in SUBPHASE:
+            if pat in text:
+                marks.append((n, nm))
+    defs[fn] = marks
+phase = collections.Counter(); phase_i = collections.Counter()
+for (f, l), (s, i, t) in lines.items():
+    name = f or "?"
+    for n, nm in defs.get(f, []):
+        if n <= l:
+            name = nm
+    phase[name] += s; phase_i[name] += i
+print("--- by function/phase (samples %, instructions %)")
+for k, v in phase.most_common(40):
+    print(f"{k:28s} samp {100*v/ts:5.1f}%  inst {100*phase_i[k]/ti:5.1f}%")
