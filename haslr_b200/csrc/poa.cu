@@ -252,6 +252,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
                 a.ws = S->ws_team.p; a.wl = twl; a.arena = S->arena_team.p; a.slot_bytes = tslot;
                 a.sc = sc; a.stats = S->stats.p; a.stop_round = opt.stop_round; a.force_i32 = opt.force_i32;
                 const size_t tsmem = (size_t)TEAM * DP_SMEM_PER_WARP + (TEAM + 4) * 4;
+                HGPU_CUDA(ctx, cudaFuncSetAttribute(k_poa_edges_team<TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
                 HGPU_CUDA(ctx, cudaEventRecord(S->ev_fork, st));          // uploads and memsets above are on `st`
                 HGPU_CUDA(ctx, cudaStreamWaitEvent(S->stream2, S->ev_fork, 0));
                 k_poa_edges_team<TEAM><<<teams, 32 * TEAM, tsmem, S->stream2>>>(a);
@@ -318,6 +319,8 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
             a.ws = S->ws.p; a.wl = c.wl; a.arena = S->arena.p; a.slot_bytes = c.slot;
             S->last_wl = c.wl; S->last_slot = c.slot;
             a.sc = sc; a.stats = S->stats.p; a.stop_round = opt.stop_round; a.force_i32 = opt.force_i32;
+            if (const char* e = getenv("HGPU_PROBE")) { a.probe = (uint32_t)atoi(e); a.probe_round = 1; }
+            if (const char* e = getenv("HGPU_PROBE_ROUND")) a.probe_round = (uint32_t)atoi(e);
             k_poa_edges<<<blocks, 32 * DP_WARPS_PER_BLOCK, smem, st>>>(a);
             HGPU_CUDA(ctx, cudaGetLastError());
             ctx->launches++; S->st.dp_launches++;

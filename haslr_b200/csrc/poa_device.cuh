@@ -160,7 +160,7 @@ static constexpr int DP_NW32 = 8;   // int32 kernel:  8 columns per lane, 256-co
 #ifndef HGPU_RING
 #define HGPU_RING 0
 #endif
-static constexpr int DP_SMEM_PER_WARP = HGPU_RING ? 6144 : 4480;  // profile 4 KB + two-row ring 2 KB; reused by the traceback tile (4384 B) and the sort bitmaps
+static constexpr int DP_SMEM_PER_WARP = 6272;  // int16 fill: profile 4 KB + frame 128 B + two parked rows 2 KB; reused by the traceback tile (4384 B) and the sort bitmaps
 static constexpr int DP_WARPS_PER_BLOCK = 4;
 
 __host__ __device__ inline uint64_t dp_slot_bytes(uint32_t V, uint32_t L, bool p16) {
@@ -190,6 +190,8 @@ struct PoaArgs {
     unsigned long long* stats;   // [0] cells [1] cells computed incl. padding [2] alignments [3] int32 alignments [4] bases in
     uint32_t stop_round;         // debug: stop after the fill+traceback of this round (0xFFFFFFFF = run to consensus)
     int force_i32;
+    uint32_t probe, probe_round; // developer timing probes (HGPU_PROBE=phase, HGPU_PROBE_ROUND=k): the edge ends in round k after 1 fill, 2 traceback,
+                                 // 3 add_alignment, 4 topological sort, 5 DP records; results are invalid
 };
 
 #if defined(__CUDACC__)
@@ -529,6 +531,11 @@ __device__ __forceinline__ void stg_cs_v4_512(uint64_t addr, uint32_t x, uint32_
 __device__ __forceinline__ void stg_u32(uint64_t addr, uint32_t v) {
     asm volatile("st.global.u32 [%0], %1;" :: "l"(addr), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t ldg_w(uint64_t addr, int off) {
+    uint32_t v;
+    asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(addr + (uint64_t)off) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint4 ldg_v4(uint64_t addr, int off512) {
     uint4 v;
     if (off512) asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4+512];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(addr) : "memory");
@@ -564,8 +571,14 @@ struct Fill16 {
 // Cold per-alignment state of the int16 fill lives in the warp's shared memory (behind the 4 KB profile) instead of
 // registers; the row loop reads it only on its rare paths (batch header, >= 3 predecessors, far predecessor rows).
 struct FillFrame16 {
-    unsigned long long meta0, pred_off, pred_rank, bc_prev, bc_cur;
+    unsigned long long meta0, pred_off, pred_rank, bc_prev, bc_cur, seq, H, bcol;
+    uint32_t V, L, NS; int32_t sm, sx, bias;
 };
+__device__ __forceinline__ uint32_t lds_u32v(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ unsigned long long lds_u64(uint32_t addr) {
     unsigned long long v;
     asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
@@ -578,12 +591,15 @@ __device__ __forceinline__ uint32_t ldg_u32(unsigned long long base, uint32_t in
 }
 #define FRAME16(field) ((uint32_t)offsetof(FillFrame16, field))
 
-// One row, in place: A = row i-1 on entry and row i on exit (stored to the slot as well). B holds row i-2 whenever row i
-// has a predecessor two ranks back; `save` says that row i+1 has one, so row i-1 is parked in B before A is overwritten.
-// The body is kept small on purpose (one instance of each piece): the kernel is instruction-cache bound otherwise.
+// One row, in place: A = row i-1 on entry and row i on exit (stored to the slot as well). Rows are "parked" in the warp's
+// shared memory (two slots, by row parity) when a later row reads them two ranks back: `save` says that row i+1 does, so
+// row i-1 is parked before A is overwritten. Predecessor rows other than i-1 stream through two registers, from the
+// parked copy (two ranks back, ~85 % of such rows) or from the slot, and are folded into A in place - no second row of
+// registers. The body is one small code path on purpose: the kernel is instruction-cache bound otherwise, and a spill
+// reload in this loop costs an L2 round trip.
 struct Row16State {
     uint32_t pf_lane;        // shared address of prof[0][0][lane]
-    uint32_t frame;          // shared address of the FillFrame16
+    uint32_t frame;          // shared address of the FillFrame16; parked row r is at frame + 128 + (r & 1) * 1024 + lane * 4, word k at + k * 128
     uint32_t g2;             // packed gap
     uint32_t row_bytes;      // distance between consecutive rows of the stripe in the slot
     uint64_t dst;            // slot address of this lane's first unit of row i
@@ -591,19 +607,39 @@ struct Row16State {
     uint32_t bco;            // batch register: lane q collects the last cell of row r0+q+1 (boundary for the next stripe)
     int lane; bool has_prev, has_next;
 };
+static constexpr uint32_t FILL16_PARKED = 128;      // byte offset of the parked rows behind the frame
 
-__device__ __forceinline__ void row16(uint32_t (&A)[8], uint32_t (&B)[8], Row16State& S, uint32_t m0, int q, uint32_t i,
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ void row16(uint32_t (&A)[8], Row16State& S, uint32_t m0, int q, uint32_t i,
                                       int diag_in, int carry_in, bool save) {
     using F = Fill16;
     const int lane = S.lane;
     const uint32_t g2 = S.g2;
     const uint32_t pf = S.pf_lane + (m0 & 3u) * (uint32_t)(F::NW * 32 * 4);
-    if ((m0 & META_FAST) != 0) {                                    // single predecessor = previous rank: registers only
-        const uint32_t hs0 = F::left_word(A, diag_in, lane);
-        if (save) {
+    const uint32_t parked = S.frame + FILL16_PARKED + (uint32_t)lane * 4u;
+    const uint32_t npc = (m0 >> 3) & 3u;
+    const bool fast = (m0 & META_FAST) != 0;
+    // ---- predecessor list; is row i-1 one of them?
+    uint32_t np = npc == 0 ? 1u : npc, cs = 0;
+    unsigned long long prank = 0;
+    bool has1 = fast || (npc != 3 && npc != 0 && (meta_d0(m0) == 1 || (npc == 2 && meta_d1(m0) == 1)));
+    if (npc == 3) {
+        const unsigned long long poff = lds_u64(S.frame + FRAME16(pred_off));
+        prank = lds_u64(S.frame + FRAME16(pred_rank));
+        cs = ldg_u32(poff, i - 1);
+        np = ldg_u32(poff, i) - cs;
+        for (uint32_t x = 0; x < np; ++x) has1 = has1 || ldg_u32(prank, cs + x) + 2 == i;
+    }
+    const uint32_t hs0 = F::left_word(A, diag_in, lane);
+    if (save) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) B[k] = A[k];
-        }
+        for (int k = 0; k < 8; ++k) sts_u32(parked + ((i - 1) & 1u) * 1024u + k * 128, A[k]);
+    }
+    // ---- row i-1 (registers): diagonal and vertical moves, in place
+    if (has1) {
         A[7] = __viaddmax_s16x2(A[7], g2, __vadd2(A[6], lds_off<896>(pf)));
         A[6] = __viaddmax_s16x2(A[6], g2, __vadd2(A[5], lds_off<768>(pf)));
         A[5] = __viaddmax_s16x2(A[5], g2, __vadd2(A[4], lds_off<640>(pf)));
@@ -613,50 +649,38 @@ __device__ __forceinline__ void row16(uint32_t (&A)[8], uint32_t (&B)[8], Row16S
         A[1] = __viaddmax_s16x2(A[1], g2, __vadd2(A[0], lds_off<128>(pf)));
         A[0] = __viaddmax_s16x2(A[0], g2, __vadd2(hs0, lds_off<0>(pf)));
     } else {
-        const uint32_t npc = (m0 >> 3) & 3u;
-        uint32_t t[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) t[k] = F::NEG2;
-        uint32_t np = npc == 0 ? 1u : npc, cs = 0;
-        unsigned long long prank = 0;
-        if (npc == 3) {
-            const unsigned long long poff = lds_u64(S.frame + FRAME16(pred_off));
-            prank = lds_u64(S.frame + FRAME16(pred_rank));
-            cs = ldg_u32(poff, i - 1);
-            np = ldg_u32(poff, i) - cs;
-        }
+        for (int k = 0; k < 8; ++k) A[k] = F::NEG2;
+    }
+    // ---- every other predecessor row streams through two registers and is folded into A
+    if (!fast) {
 #pragma unroll 1
         for (uint32_t x = 0; x < np; ++x) {
             uint32_t dist;                                          // rank distance to this predecessor row
             if (npc == 3) dist = i - (ldg_u32(prank, cs + x) + 1);
             else if (npc == 0) dist = i;                            // no predecessor: the virtual row 0
             else dist = x == 0 ? meta_d0(m0) : meta_d1(m0);
-            uint32_t gg = g2, pfl = pf;
-            asm volatile("" : "+r"(gg), "+r"(pfl));                 // nothing of the body is hoisted out of the loop (it would only spill)
-            if (dist == 1) {
-                F::acc(t, A, F::left_word(A, diag_in, lane), pfl, gg);
-            } else {
-                int bl = F::G::NEGV;                                // Hhat[i - dist][first column of the stripe - 1]
-                if (S.has_prev) {
-                    const int ql = q - (int)dist;                   // bcx lane that holds row i - dist
-                    bl = ql >= 0 ? __shfl_sync(FULL, (int)S.bcx, ql & 31) : (int)ldg_u32(lds_u64(S.frame + FRAME16(bc_prev)), i - dist);
-                }
-                if (dist == 2) {
-                    F::acc(t, B, F::left_word(B, bl, lane), pfl, gg);
-                } else {
-                    const uint64_t src = S.dst - (uint64_t)dist * S.row_bytes;
-                    const uint4 v0 = ldg_v4(src, 0), v1 = ldg_v4(src, 1);
-                    const uint32_t v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                    F::acc(t, v, F::left_word(v, bl, lane), pfl, gg);
-                }
+            if (dist == 1) continue;
+            int bl = F::G::NEGV;                                    // Hhat[i - dist][first column of the stripe - 1]
+            if (S.has_prev) {
+                const int ql = q - (int)dist;                       // bcx lane that holds row i - dist
+                bl = ql >= 0 ? __shfl_sync(FULL, (int)S.bcx, ql & 31) : (int)ldg_u32(lds_u64(S.frame + FRAME16(bc_prev)), i - dist);
             }
-        }
-        if (save) {
+            const bool near = dist == 2;
+            const uint32_t psrc = parked + (i & 1u) * 1024u;        // parked row i-2
+            const uint64_t src = S.dst - (uint64_t)dist * S.row_bytes;
+            uint32_t hi = near ? lds_u32v(psrc + 7 * 128) : ldg_w(src, 512 + 12);
+            uint32_t left = __shfl_up_sync(FULL, hi, 1);
+            if (lane == 0) left = (uint32_t)bl << 16;
+            const uint32_t h0 = __byte_perm(left, hi, 0x5432);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) B[k] = A[k];
+            for (int k = 7; k >= 1; --k) {
+                const uint32_t lo = near ? lds_u32v(psrc + (k - 1) * 128) : ldg_w(src, ((k - 1) >> 2) * 512 + ((k - 1) & 3) * 4);
+                A[k] = __vimax3_s16x2(A[k], __vadd2(lo, lds_u32v(pf + k * 128)), __vadd2(hi, g2));
+                hi = lo;
+            }
+            A[0] = __vimax3_s16x2(A[0], __vadd2(h0, lds_u32v(pf)), __vadd2(hi, g2));
         }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) A[k] = t[k];
     }
     // horizontal gaps = prefix maximum in hat space. In the lane: one chain scans columns 0..7 (low halves) and 8..15
     // (high halves) together; the high run then also takes the low run's total.
@@ -705,104 +729,109 @@ __device__ __forceinline__ bool meta_reads_two_back(uint32_t m0) {
     return npc == 3 || meta_d0(m0) == 2 || (npc == 2 && meta_d1(m0) == 2);
 }
 
-#ifndef HGPU_INLINE_FILL16
-#define HGPU_INLINE_FILL16 0
-#endif
-#if HGPU_INLINE_FILL16
-#define FILL16_INLINE __forceinline__
-#else
-#define FILL16_INLINE __noinline__      // own register allocation: the edge loop's graph pointers are not live in here
-#endif
-struct FillGraph { const uint32_t* meta0; const uint32_t* pred_off; const uint32_t* pred_rank; };
+// sequence profile of stripe s: prof[code][k][lane] = hat scores of the lane's k-th word (columns k, k+8)
+__device__ __noinline__ void fill16_profile(uint32_t* prof, const FillFrame16* frame, uint32_t s, int lane) {
+    constexpr int NW = DP_NW16;
+    using G = Geo<NW, true>;
+    const uint8_t* seq = reinterpret_cast<const uint8_t*>((uintptr_t)frame->seq);
+    const uint32_t L = frame->L;
+    const int sm = frame->sm, sx = frame->sx;
+    const uint32_t j0 = s * G::SW + lane * G::CPL;   // first column owned by this lane
+#pragma unroll 2
+    for (int k = 0; k < NW; ++k) {
+        const uint32_t ja = j0 + k, jb = ja + NW;
+        const int ca = (ja >= 1 && ja <= L) ? (int)base_code(seq[ja - 1]) : -1;
+        const int cb = (jb >= 1 && jb <= L) ? (int)base_code(seq[jb - 1]) : -1;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int va = ca < 0 ? 0 : (ca == c ? sm : sx);
+            const int vb = cb < 0 ? 0 : (cb == c ? sm : sx);
+            prof[(c * NW + k) * 32 + lane] = ((uint32_t)va & 0xFFFFu) | ((uint32_t)vb << 16);
+        }
+    }
+}
 
-__device__ FILL16_INLINE bool dp_fill16(const FillGraph gv, uint8_t* slot, uint8_t* wsm, const uint8_t* seq,
-                                        uint32_t V, uint32_t L, const DpScores sc, int lane,
-                                        uint32_t trank, uint32_t tsize, volatile uint32_t* vprog) {
+// The fill of one alignment. Everything that is not needed row by row (graph arrays, slot geometry, the sequence, the
+// scores) is parked in the shared-memory frame first, so the row loop keeps its working set in registers.
+template <bool TEAM>
+__device__ __noinline__ bool dp_fill16(const uint32_t* meta0, const uint32_t* pred_off, const uint32_t* pred_rank, uint8_t* slot, uint8_t* wsm,
+                                       const uint8_t* seq, uint32_t V, uint32_t L, int sm, int sx, int gap, int bias, int lane,
+                                       uint32_t trank, uint32_t tsize, volatile uint32_t* vprog) {
     constexpr int NW = DP_NW16;
     using G = Geo<NW, true>;
     bool sync_ok = true;
     uint32_t* prof = reinterpret_cast<uint32_t*>(wsm);                 // [4][NW][32]
     FillFrame16* frame = reinterpret_cast<FillFrame16*>(wsm + G::PROF_BYTES);
-    SlotView<NW, true> sv;
-    sv.bind(slot, V, L);
-    const int bias = G::bias(V, sc);
-    const uint32_t NS = sv.NS;
+    const uint32_t NS = G::stripes(L);
+    __syncwarp();
+    if (lane == 0) {
+        frame->meta0 = (unsigned long long)(uintptr_t)meta0;
+        frame->pred_off = (unsigned long long)(uintptr_t)pred_off;
+        frame->pred_rank = (unsigned long long)(uintptr_t)pred_rank;
+        frame->seq = (unsigned long long)(uintptr_t)seq;
+        frame->H = (unsigned long long)(uintptr_t)slot;
+        frame->bcol = (unsigned long long)(uintptr_t)(slot + (uint64_t)(V + 1) * NS * NW * 128);
+        frame->V = V; frame->L = L; frame->NS = NS; frame->sm = sm; frame->sx = sx; frame->bias = bias;
+    }
     Row16State S;
     S.lane = lane;
-    S.g2 = pack2(sc.g);
+    S.g2 = pack2(gap);
     S.pf_lane = (uint32_t)__cvta_generic_to_shared(prof + lane);
     S.frame = (uint32_t)__cvta_generic_to_shared(frame);
     S.row_bytes = NS * (uint32_t)(G::UNITS * 32 * 16);
     S.bcx = 0; S.bco = 0;
-    if (lane == 0) {
-        frame->meta0 = (unsigned long long)(uintptr_t)gv.meta0;
-        frame->pred_off = (unsigned long long)(uintptr_t)gv.pred_off;
-        frame->pred_rank = (unsigned long long)(uintptr_t)gv.pred_rank;
-    }
     asm volatile("" : "+r"(S.pf_lane), "+r"(S.frame), "+r"(S.g2), "+r"(S.row_bytes));   // kept in registers, never recomputed in the row loop
 
-    for (uint32_t s = trank; s < NS; s += tsize) {
+    for (uint32_t s = TEAM ? trank : 0u; s < lds_u32v(S.frame + FRAME16(NS)); s += TEAM ? tsize : 1u) {
         __syncwarp();
-        // --- sequence profile of this stripe: prof[code][k][lane] = hat scores of the lane's k-th word (columns k, k+8)
+        fill16_profile(prof, frame, s, lane);
+        const uint32_t Vs = lds_u32v(S.frame + FRAME16(V));
         {
-            const uint32_t j0 = s * G::SW + lane * G::CPL;   // first column owned by this lane
-#pragma unroll 4
-            for (int k = 0; k < NW; ++k) {
-                const uint32_t ja = j0 + k, jb = ja + NW;
-                const int ca = (ja >= 1 && ja <= L) ? (int)base_code(seq[ja - 1]) : -1;
-                const int cb = (jb >= 1 && jb <= L) ? (int)base_code(seq[jb - 1]) : -1;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int va = ca < 0 ? 0 : (ca == c ? sc.sm : sc.sx);
-                    const int vb = cb < 0 ? 0 : (cb == c ? sc.sm : sc.sx);
-                    prof[(c * NW + k) * 32 + lane] = ((uint32_t)va & 0xFFFFu) | ((uint32_t)vb << 16);
-                }
+            const unsigned long long bcol = lds_u64(S.frame + FRAME16(bcol));
+            if (lane == 0) {
+                frame->bc_prev = s > 0 ? bcol + 4ull * (s - 1) * (Vs + 1) : 0ull;
+                frame->bc_cur = bcol + 4ull * s * (Vs + 1);
             }
-        }
-        const int32_t* bc_prev = (s > 0) ? sv.bcol + (uint64_t)(s - 1) * (V + 1) : nullptr;
-        int32_t* bc_cur = sv.bcol + (uint64_t)s * (V + 1);
-        if (lane == 0) {
-            frame->bc_prev = (unsigned long long)(uintptr_t)bc_prev;
-            frame->bc_cur = (unsigned long long)(uintptr_t)bc_cur;
         }
         __syncwarp();
         asm volatile("" : "+r"(S.pf_lane) :: "memory");              // profile loads below may not move above / be merged across this point
         S.has_prev = s > 0;
-        S.has_next = s + 1 < NS;
+        S.has_next = s + 1 < lds_u32v(S.frame + FRAME16(NS));
 
         // --- row 0: Hhat = 0 everywhere
-        uint32_t A[NW], B[NW];
-#pragma unroll
-        for (int k = 0; k < NW; ++k) { A[k] = pack2(bias); B[k] = Fill16::NEG2; }
+        uint32_t A[NW];
         {
-            uint4* dst = sv.row_units(0, s, lane);
+            const uint32_t b2 = pack2((int)lds_u32v(S.frame + FRAME16(bias)));
 #pragma unroll
-            for (int u = 0; u < G::UNITS; ++u) dst[u * 32] = make_uint4(A[4 * u], A[4 * u + 1], A[4 * u + 2], A[4 * u + 3]);
-            if (lane == 31) bc_cur[0] = bias;
+            for (int k = 0; k < NW; ++k) A[k] = b2;
+            S.dst = lds_u64(S.frame + FRAME16(H)) + ((uint64_t)s * (G::UNITS * 32) + lane) * 16;       // row 0 of this stripe
+            stg_cs_v4(S.dst, b2, b2, b2, b2);
+            stg_cs_v4_512(S.dst, b2, b2, b2, b2);
+            S.dst += S.row_bytes;
+            if (lane == 31) asm volatile("st.global.u32 [%0], %1;" :: "l"(lds_u64(S.frame + FRAME16(bc_cur))), "r"(lds_u32v(S.frame + FRAME16(bias))) : "memory");
         }
-        if (tsize > 1) team_publish(vprog, trank, s * (V + 1) + 1, lane);
-        S.dst = (uint64_t)(uintptr_t)sv.row_units(1, s, lane);
-        asm volatile("" : "+l"(S.dst));
+        if (TEAM) team_publish(vprog, trank, s * (Vs + 1) + 1, lane);
 
         // per-rank records of the first batch; later batches are fetched one batch ahead
-        uint32_t nm0 = ((uint32_t)lane < V) ? gv.meta0[lane] : 0u;
+        uint32_t nm0 = ((uint32_t)lane < Vs) ? ldg_u32(lds_u64(S.frame + FRAME16(meta0)), lane) : 0u;
         int diag = G::NEGV;                                           // boundary value of row i-1: starts at row 0
         if (s > 0) {
-            if (tsize > 1 && !team_wait(vprog, (trank + tsize - 1) % tsize, (s - 1) * (V + 1) + 1, lane)) sync_ok = false;
-            diag = bc_prev[0];
+            if (TEAM && !team_wait(vprog, (trank + tsize - 1) % tsize, (s - 1) * (Vs + 1) + 1, lane)) sync_ok = false;
+            diag = (int)ldg_u32(lds_u64(S.frame + FRAME16(bc_prev)), 0);
         }
-        for (uint32_t r0 = 0; r0 < V; r0 += 32) {
+#pragma unroll 1
+        for (uint32_t r0 = 0; r0 < Vs; r0 += 32) {
             const uint32_t rr = r0 + lane;
             const uint32_t mm0 = nm0;
-            if (rr + 32 < V) nm0 = ldg_u32(lds_u64(S.frame + FRAME16(meta0)), rr + 32);
+            if (rr + 32 < Vs) nm0 = ldg_u32(lds_u64(S.frame + FRAME16(meta0)), rr + 32);
             if (s > 0) {
-                if (tsize > 1) {            // rows r0 .. r0+32 of the stripe to the left must be complete
-                    const uint32_t need_rows = (r0 + 33 < V + 1) ? r0 + 33 : V + 1;
-                    if (!team_wait(vprog, (trank + tsize - 1) % tsize, (s - 1) * (V + 1) + need_rows, lane)) sync_ok = false;
+                if (TEAM) {                 // rows r0 .. r0+32 of the stripe to the left must be complete
+                    const uint32_t need_rows = (r0 + 33 < Vs + 1) ? r0 + 33 : Vs + 1;
+                    if (!team_wait(vprog, (trank + tsize - 1) % tsize, (s - 1) * (Vs + 1) + need_rows, lane)) sync_ok = false;
                 }
-                S.bcx = (rr < V) ? ldg_u32(lds_u64(S.frame + FRAME16(bc_prev)), rr + 1) : 0u;
+                S.bcx = (rr < Vs) ? ldg_u32(lds_u64(S.frame + FRAME16(bc_prev)), rr + 1) : 0u;
             }
-            const int nb = (V - r0) < 32u ? (int)(V - r0) : 32;
+            const int nb = (Vs - r0) < 32u ? (int)(Vs - r0) : 32;
             // bit q of save_mask: row r0+q+1 parks row r0+q in B before overwriting it, because row r0+q+2 reads two ranks back
             const uint32_t save_mask = __ballot_sync(FULL, meta_reads_two_back(mm0)) >> 1;
 #pragma unroll 1
@@ -811,15 +840,15 @@ __device__ FILL16_INLINE bool dp_fill16(const FillGraph gv, uint8_t* slot, uint8
                 int carry = G::NEGV;
                 if (S.has_prev) carry = __shfl_sync(FULL, (int)S.bcx, q);
                 bool save = ((save_mask >> q) & 1u) != 0;
-                if (q == 31) save = (__ballot_sync(FULL, rr + 32 < V && meta_reads_two_back(nm0)) & 1u) != 0;   // first row of the next batch
-                row16(A, B, S, m0, q, r0 + q + 1, diag, carry, save);
+                if (q == 31) save = (__ballot_sync(FULL, rr + 32 < Vs && meta_reads_two_back(nm0)) & 1u) != 0;   // first row of the next batch
+                row16(A, S, m0, q, r0 + q + 1, diag, carry, save);
                 diag = carry;
             }
             if (S.has_next && lane < nb) {
                 const unsigned long long bc = lds_u64(S.frame + FRAME16(bc_cur));
                 asm volatile("st.global.u32 [%0], %1;" :: "l"(bc + 4ull * (rr + 1)), "r"(S.bco) : "memory");
             }
-            if (tsize > 1) team_publish(vprog, trank, s * (V + 1) + ((r0 + 32 < V) ? r0 + 32 : V) + 1, lane);
+            if (TEAM) team_publish(vprog, trank, s * (Vs + 1) + ((r0 + 32 < Vs) ? r0 + 32 : Vs) + 1, lane);
         }
         __syncwarp();
     }
@@ -945,7 +974,7 @@ __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8
 template <int NW, bool P16>
 __device__ DP_INLINE bool dp_align(const GraphView& gv, uint8_t* slot, uint8_t* wsm, const uint8_t* seq,
                                    uint32_t V, uint32_t L, const DpScores sc, int lane) {
-    if (P16) dp_fill16(FillGraph{gv.meta0, gv.pred_off, gv.pred_rank}, slot, wsm, seq, V, L, sc, lane, 0, 1, nullptr);
+    if (P16) dp_fill16<false>(gv.meta0, gv.pred_off, gv.pred_rank, slot, wsm, seq, V, L, sc.sm, sc.sx, sc.g, Geo<DP_NW16, true>::bias(V, sc), lane, 0, 1, nullptr);
     else dp_fill<NW, false>(gv, slot, wsm, seq, V, L, sc, lane, 0, 1, nullptr);
     return dp_traceback<NW, P16>(gv, slot, wsm, seq, V, L, sc, lane);
 }
@@ -1240,7 +1269,7 @@ __device__ __noinline__ int w_toposort(GraphView& g, uint8_t* wsm, int lane) {
 // k_poa_edges: the persistent per-edge kernel.
 // ---------------------------------------------------------------------------------------------------------
 #ifndef HGPU_MINBLOCKS
-#define HGPU_MINBLOCKS 7
+#define HGPU_MINBLOCKS 8
 #endif
 __device__ __forceinline__ int lane_id() {       // read once, never rematerialised from S2R inside the hot loops
     const int l = (int)(threadIdx.x & 31u);
@@ -1286,8 +1315,15 @@ __global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, HGPU_MINBLOCKS) k_poa
                 const bool p16 = !a.force_i32 && dp_fits16(V, L, a.sc);
                 if ((uint64_t)V + L > gv.ncap || (uint64_t)NE + L + 1 > gv.ecap) { st = ST_CAPACITY; break; }
                 if (dp_slot_bytes(V, L, p16) > a.slot_bytes) { st = ST_TOO_LARGE; break; }
+                const uint32_t probe = (k == a.probe_round) ? a.probe : 0u;
+                if (probe == 1) {
+                    if (p16) dp_fill16<false>(gv.meta0, gv.pred_off, gv.pred_rank, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, Geo<DP_NW16, true>::bias(V, a.sc), lane, 0, 1, nullptr);
+                    e_cells += (unsigned long long)(V + 1) * (L + 1);
+                    debug_stop = true; break;
+                }
                 bool ok = p16 ? dp_align<DP_NW16, true>(gv, slot, wsm, seq, V, L, a.sc, lane)
                               : dp_align<DP_NW32, false>(gv, slot, wsm, seq, V, L, a.sc, lane);
+                if (probe == 2) { e_cells += (unsigned long long)(V + 1) * (L + 1); debug_stop = true; break; }
                 if (lane == 0) {
                     hdr[HDR_LAST_P16] = p16 ? 1u : 0u; hdr[HDR_LAST_V] = V; hdr[HDR_LAST_L] = L;
                     hdr[HDR_LAST_BIAS] = (uint32_t)(p16 ? Geo<DP_NW16, true>::bias(V, a.sc) : 0);
@@ -1307,6 +1343,7 @@ __global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, HGPU_MINBLOCKS) k_poa
                     __syncwarp();
                 }
                 if (ust != ST_OK) { st = ust; break; }
+                if (probe == 3) { debug_stop = true; break; }
                 if (!w_toposort(gv, wsm, lane)) {          // too large for the shared-memory bitmaps / deep DFS: serial
                     ust = ST_OK;
                     if (lane == 0 && !g_toposort(gv, gs)) ust = ST_TOPOSORT;
@@ -1314,7 +1351,9 @@ __global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, HGPU_MINBLOCKS) k_poa
                     __syncwarp();
                     if (ust != ST_OK) { st = ust; break; }
                 }
+                if (probe == 4) { debug_stop = true; break; }
                 w_build_meta(gv, lane);
+                if (probe == 5) { debug_stop = true; break; }
             }
             if (a.stop_round != 0xFFFFFFFFu) debug_stop = true;
             // heaviest-bundle consensus; node ids land in aln_rank
@@ -1402,7 +1441,7 @@ __global__ void __launch_bounds__(32 * TEAM, 768 / (32 * TEAM)) k_poa_edges_team
                 const bool p16 = !a.force_i32 && dp_fits16(V, L, a.sc);
                 if ((uint64_t)V + L > gv.ncap || (uint64_t)NE + L + 1 > gv.ecap) { st = ST_CAPACITY; break; }
                 if (dp_slot_bytes(V, L, p16) > a.slot_bytes) { st = ST_TOO_LARGE; break; }
-                const bool fill_ok = p16 ? dp_fill16(FillGraph{gv.meta0, gv.pred_off, gv.pred_rank}, slot, wsm, seq, V, L, a.sc, lane, wib, TEAM, vprog)
+                const bool fill_ok = p16 ? dp_fill16<true>(gv.meta0, gv.pred_off, gv.pred_rank, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, Geo<DP_NW16, true>::bias(V, a.sc), lane, wib, TEAM, vprog)
                                          : dp_fill<DP_NW32, false>(gv, slot, wsm, seq, V, L, a.sc, lane, wib, TEAM, vprog);
                 const int all_ok = __syncthreads_and(fill_ok ? 1 : 0);    // every stripe stored (and no wait gave up)
                 if (!all_ok) { st = ST_SYNC; break; }
