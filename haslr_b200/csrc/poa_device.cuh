@@ -125,8 +125,6 @@ __device__ __forceinline__ void st_row(uint4* p, uint4 v) {
 #endif
 }
 static constexpr int TB_ROWS = 32, TB_COLS = 32;
-static constexpr int TB_LD = TB_COLS + 1;        // tile row stride in words: odd, so a column of the tile spreads over all banks
-static constexpr int TB_SMEM_BYTES = TB_ROWS * TB_LD * 4 + TB_ROWS * 4 + TB_COLS;  // tile + meta0 + seq codes
 
 // Geometry of one alignment inside a slot. P16: two int16 cells per word; I32: one int32 cell per word.
 template <int NW, bool P16>
@@ -857,14 +855,33 @@ __device__ __noinline__ bool dp_fill16(const uint32_t* meta0, const uint32_t* pr
     return sync_ok;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Traceback. The stored matrix is read in tiles of 32 rows x 32 columns with the current cell in the corner. A
+// tile is kept as the raw 16-byte units of the slot (6 or 10 coalesced LDG.128 + STS.128 per lane, no unpacking),
+// and the rows the walk will most likely need next are prefetched into L2 while the current tile is walked.
+// Inside a tile every lane t decides the move of "its" cell (ci - t, cj - t) in SPOA's preference order (diagonal
+// over the predecessors in in-edge order, then vertical, then horizontal): as long as the lanes before it all moved
+// to the previous rank diagonally, its cell is on the path, so one ballot consumes the whole run of such moves
+// plus the first move of another kind. Only rows with three or more predecessors, or predecessors outside the
+// tile, take the one-lane generic step.
+// ---------------------------------------------------------------------------------------------------------
+template <int NW, bool P16>
+struct TbTile {
+    using G = Geo<NW, P16>;
+    static constexpr int NG = (TB_COLS + G::CPL - 2) / G::CPL + 1;        // column groups a 32-column window can touch (3 / 5)
+    static constexpr int LDW = NG * NW + 4;                               // row stride in words (16-byte multiple, spreads banks)
+    static constexpr int BYTES = TB_ROWS * LDW * 4 + TB_ROWS * 4 + TB_COLS;
+    static_assert(BYTES <= DP_SMEM_PER_WARP, "traceback tile does not fit the warp's shared memory");
+};
+
 template <int NW, bool P16>
 __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8_t* wsm, const uint8_t* seq,
                                        uint32_t V, uint32_t L, const DpScores sc, int lane) {
     using G = Geo<NW, P16>;
+    using T = TbTile<NW, P16>;
     const int g = sc.g;
     SlotView<NW, P16> sv;
     sv.bind(slot, V, L);
-    // =============================== traceback ===============================
     // end cell: best Hhat[i][L] over sink nodes, first maximum in rank order (SPOA kNW)
     int best = INT32_MIN; uint32_t best_i = 0;
     for (uint32_t r = lane; r < V; r += 32) {
@@ -879,68 +896,131 @@ __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8
         uint32_t oi = __shfl_xor_sync(FULL, best_i, d);
         if (oi != 0 && (best_i == 0 || ov > best || (ov == best && oi < best_i))) { best = ov; best_i = oi; }
     }
-    int* tile = reinterpret_cast<int*>(wsm);                              // [TB_ROWS][TB_LD]
-    uint32_t* tm0 = reinterpret_cast<uint32_t*>(wsm + TB_ROWS * TB_LD * 4);
+    uint32_t* tile = reinterpret_cast<uint32_t*>(wsm);                    // [TB_ROWS][LDW] raw words: row it - a, groups g0 ..
+    uint32_t* tm0 = tile + TB_ROWS * T::LDW;
     uint8_t* tseq = reinterpret_cast<uint8_t*>(tm0 + TB_ROWS);
+    const uint4* Hu = reinterpret_cast<const uint4*>(sv.H);
+    const uint32_t NS = sv.NS;
     uint32_t ci = best_i, cj = L, n_out = 0;
     bool bad = (best_i == 0);
     while (!bad && !(ci == 0 && cj == 0)) {
-        // tile of the stored matrix with (ci, cj) in its corner: tile[a][b] = Hhat[it - a][jt - b]
+        // ---- tile with (ci, cj) in its corner: rows it-31 .. it, columns jt-31 .. jt
         const uint32_t it = ci, jt = cj;
+        const uint32_t g0 = (jt >= (uint32_t)(TB_COLS - 1) ? jt - (TB_COLS - 1) : 0u) / G::CPL;   // first column group of the tile
         __syncwarp();
         if (it >= (uint32_t)lane) {
             const uint32_t row = it - lane;
-#pragma unroll 8
-            for (int c = 0; c < TB_COLS; ++c) if (jt >= (uint32_t)c) tile[lane * TB_LD + c] = sv.load(row, jt - c);
+#pragma unroll
+            for (int gi = 0; gi < T::NG; ++gi) {
+                const uint32_t gg = g0 + gi;
+                if (gg * G::CPL <= jt) {
+                    const uint4* src = Hu + ((uint64_t)row * NS + gg / 32u) * (G::UNITS * 32) + (gg & 31u);
+                    uint4* dst = reinterpret_cast<uint4*>(tile + lane * T::LDW + gi * NW);
+#pragma unroll
+                    for (int u = 0; u < G::UNITS; ++u) dst[u] = src[u * 32];
+                }
+            }
             if (row >= 1) tm0[lane] = gv.meta0[row - 1];
         }
         if (jt >= (uint32_t)lane + 1) tseq[lane] = (uint8_t)base_code(seq[jt - lane - 1]);
+        // prefetch what the walk will most likely read next: the rows above the tile, one tile to the left
+        if (it >= (uint32_t)(TB_ROWS - 1) + lane && jt >= (uint32_t)(TB_COLS - 1)) {
+            const uint32_t prow = it - (TB_ROWS - 1) - lane, pj = jt - (TB_COLS - 1);
+            const uint32_t pg0 = (pj >= (uint32_t)(TB_COLS - 1) ? pj - (TB_COLS - 1) : 0u) / G::CPL;
+#pragma unroll
+            for (int gi = 0; gi < T::NG; ++gi) {
+                const uint32_t gg = pg0 + gi;
+                if (gg * G::CPL <= pj) {
+                    const uint4* src = Hu + ((uint64_t)prow * NS + gg / 32u) * (G::UNITS * 32) + (gg & 31u);
+#pragma unroll
+                    for (int u = 0; u < G::UNITS; ++u) asm volatile("prefetch.global.L2 [%0];" :: "l"(src + u * 32));
+                }
+            }
+        }
         __syncwarp();
+        // stored value of cell (row it - a, column j) of the tile
+        auto cell = [&](uint32_t a, uint32_t j) -> int {
+            const uint32_t gi = j / G::CPL - g0, c = j % G::CPL;
+            const uint32_t w = tile[a * T::LDW + gi * NW + (P16 ? (c & (uint32_t)(NW - 1)) : c)];
+            if (P16) return (c >= (uint32_t)NW) ? (int)(int16_t)(w >> 16) : (int)(int16_t)(w & 0xFFFFu);
+            return (int)w;
+        };
         while (true) {
             if (ci == 0 && cj == 0) break;
             const uint32_t li = it - ci, lj = jt - cj;
-            if (li >= (uint32_t)TB_ROWS - 1 || lj >= (uint32_t)TB_COLS - 1) break;     // reload the tile around (ci, cj)
-            // (1) a run of diagonal moves through rows whose only predecessor is the previous rank: SPOA tries the
-            //     diagonal of the first predecessor first, so every lane can test "its" step of the run independently
-            {
-                const uint32_t a_ = li + lane, b_ = lj + lane;
-                bool cond = a_ + 1 < (uint32_t)TB_ROWS && b_ + 1 < (uint32_t)TB_COLS && ci > (uint32_t)lane && cj > (uint32_t)lane;
-                if (cond) {
-                    const uint32_t m0 = tm0[a_];
-                    const int dsc = (tseq[b_] == (m0 & 3u)) ? sc.sm : sc.sx;
-                    cond = (m0 & META_FAST) != 0 && tile[a_ * TB_LD + b_] == tile[(a_ + 1) * TB_LD + b_ + 1] + dsc;
-                }
-                const unsigned fm = __ballot_sync(FULL, !cond);
-                const uint32_t run = fm ? (uint32_t)(__ffs(fm) - 1) : 32u;
-                if (run > 0) {
-                    if ((uint64_t)n_out + run > gv.ncap) { bad = true; break; }
-                    if ((uint32_t)lane < run) {
-                        gv.aln_rank[n_out + lane] = (int32_t)(ci - lane - 1);
-                        gv.aln_pos[n_out + lane] = (int32_t)(cj - lane - 1);
+            // ---- every lane decides the move of cell (ci - lane, cj - lane)
+            //      kind: 0 diagonal to the previous rank, 1 another move (di rows up, dj columns left), 2 needs the generic step,
+            //            3 reload the tile here, 4 no move reproduces the cell (cannot happen), 5 the walk is complete
+            int kind = 3; uint32_t di = 0, dj = 0;
+            if ((uint32_t)lane <= ci && (uint32_t)lane <= cj) {
+                const uint32_t i = ci - lane, j = cj - lane, a_ = li + lane, b_ = lj + lane;
+                if (i == 0 && j == 0) kind = 5;
+                else if (a_ + 1 < (uint32_t)TB_ROWS && b_ + 1 < (uint32_t)TB_COLS) {
+                    const int val = cell(a_, j);
+                    if (i == 0) { kind = 1; di = 0; dj = 1; }              // row 0: only horizontal moves are left
+                    else {
+                        const uint32_t m0 = tm0[a_];
+                        const uint32_t npc = (m0 >> 3) & 3u;
+                        if (npc == 3) kind = 2;
+                        else {
+                            const uint32_t np = npc == 0 ? 1u : npc;
+                            const uint32_t d0 = npc == 0 ? i : meta_d0(m0), d1 = meta_d1(m0);
+                            const uint32_t far = (a_ + d0 >= (uint32_t)TB_ROWS) || (np == 2 && a_ + d1 >= (uint32_t)TB_ROWS);
+                            if (far) kind = a_ == 0 ? 2 : 3;                // a predecessor row is outside the tile
+                            else {
+                                kind = 4;
+                                if (j != 0) {
+                                    const int dsc = (tseq[b_] == (m0 & 3u)) ? sc.sm : sc.sx;
+                                    if (val == cell(a_ + d0, j - 1) + dsc) { kind = d0 == 1 ? 0 : 1; di = d0; dj = 1; }
+                                    else if (np == 2 && val == cell(a_ + d1, j - 1) + dsc) { kind = d1 == 1 ? 0 : 1; di = d1; dj = 1; }
+                                }
+                                if (kind == 4) {
+                                    if (val == cell(a_ + d0, j) + g) { kind = 1; di = d0; dj = 0; }
+                                    else if (np == 2 && val == cell(a_ + d1, j) + g) { kind = 1; di = d1; dj = 0; }
+                                    else if (j != 0 && val == cell(a_, j - 1)) { kind = 1; di = 0; dj = 1; }
+                                }
+                            }
+                        }
                     }
-                    n_out += run; ci -= run; cj -= run;
-                    continue;
                 }
             }
-            // (2) one generic step in SPOA's preference order: diagonal over predecessors (in-edge order), vertical, horizontal
+            const unsigned fm = __ballot_sync(FULL, kind != 0);           // never 0: the tile's edge cells say "reload"
+            const uint32_t run = (uint32_t)(__ffs(fm) - 1);
+            const int kr = __shfl_sync(FULL, kind, run);
+            const uint32_t extra = kr == 1 ? 1u : 0u;
+            if ((uint64_t)n_out + run + extra > gv.ncap) { bad = true; break; }
+            if ((uint32_t)lane < run) {
+                gv.aln_rank[n_out + lane] = (int32_t)(ci - lane - 1);
+                gv.aln_pos[n_out + lane] = (int32_t)(cj - lane - 1);
+            } else if ((uint32_t)lane == run && extra) {
+                gv.aln_rank[n_out + run] = di == 0 ? -1 : (int32_t)(ci - run - 1);
+                gv.aln_pos[n_out + run] = dj == 0 ? -1 : (int32_t)(cj - run - 1);
+            }
+            const uint32_t xdi = __shfl_sync(FULL, di, run), xdj = __shfl_sync(FULL, dj, run);
+            n_out += run + extra; ci -= run; cj -= run;
+            if (extra) { ci -= xdi; cj -= xdj; continue; }
+            if (kr == 3) break;                                           // reload the tile around (ci, cj)
+            if (kr == 5) continue;                                        // (0, 0) reached: the loop head ends the walk
+            if (kr == 4) { bad = true; break; }
+            // ---- kr == 2: one generic step on one lane (three or more predecessors, or predecessor rows outside the tile)
             if (lane == 0) {
                 const uint32_t i = ci, j = cj;
                 auto getH = [&](uint32_t ii, uint32_t jj) -> int {
-                    uint32_t a_ = it - ii, b_ = jt - jj;   // ii <= it, jj <= jt always hold on a walk up/left
-                    if (a_ < (uint32_t)TB_ROWS && b_ < (uint32_t)TB_COLS) return tile[a_ * TB_LD + b_];
+                    const uint32_t a_ = it - ii, b_ = jt - jj;   // ii <= it, jj <= jt always hold on a walk up/left
+                    if (a_ < (uint32_t)TB_ROWS && b_ < (uint32_t)TB_COLS) return cell(a_, jj);
                     return sv.load(ii, jj);
                 };
-                const int val = tile[li * TB_LD + lj];
+                const int val = getH(i, j);
                 uint32_t pi = i, pj = j;
                 bool found = false;
                 if (i != 0) {
-                    const uint32_t m0 = tm0[li];
+                    const uint32_t m0 = gv.meta0[i - 1];
                     const uint32_t code = m0 & 3u, npc = (m0 >> 3) & 3u, d0 = meta_d0(m0), m1 = meta_d1(m0);
                     uint32_t np = npc, cs = 0;
                     if (npc == 0) np = 1;
                     if (npc == 3) { cs = gv.pred_off[i - 1]; np = gv.pred_off[i] - cs; }
                     if (j != 0) {
-                        const int dsc = (tseq[lj] == code) ? sc.sm : sc.sx;
+                        const int dsc = ((uint32_t)base_code(seq[j - 1]) == code) ? sc.sm : sc.sx;
                         for (uint32_t x = 0; x < np && !found; ++x) {
                             uint32_t prow = npc == 0 ? 0 : npc == 3 ? gv.pred_rank[cs + x] + 1 : i - (x == 0 ? d0 : m1);
                             if (val == getH(prow, j - 1) + dsc) { pi = prow; pj = j - 1; found = true; }
@@ -964,6 +1044,7 @@ __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8
             n_out = __shfl_sync(FULL, n_out, 0);
             bad = __shfl_sync(FULL, (int)bad, 0) != 0;
             if (bad) break;
+            if (it - ci >= (uint32_t)TB_ROWS - 1 || jt - cj >= (uint32_t)TB_COLS - 1) break;     // left the tile: reload
         }
     }
     if (lane == 0) *gv.aln_len = bad ? 0 : n_out;
@@ -1266,6 +1347,113 @@ __device__ __noinline__ int w_toposort(GraphView& g, uint8_t* wsm, int lane) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// w_consensus_scores: the rank-order pass of SPOA's heaviest bundle (g_consensus_scores), 32 ranks at a time.
+// The serial version is a chain of dependent global loads per node (rank -> node -> in-list -> edge -> score of the
+// tail node): ~5 memory round trips per node on one lane. Here every lane loads the in-list of one rank of the batch
+// (all round trips overlap), then the 32 nodes are resolved in rank order with the scores of in-batch predecessors
+// passed through shuffles. Scores are kept as int32 (path weight <= 2 * reads * nodes) and stored as SPOA's int64.
+// Same score[] / pred[] arrays and the same maximal node as the serial code; branch completion and the backtrack stay
+// on one lane (g_consensus_finish).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __noinline__ uint32_t w_consensus_scores(GraphView& g, GraphScratch& s, int lane) {
+    const uint32_t N = *g.n_nodes;
+    constexpr int K = 4;                                                  // in-edges held in registers; longer lists walk memory
+    uint32_t max_id = 0; int max_sc = -1;
+    for (uint32_t r0 = 0; r0 < N; r0 += 32) {
+        const uint32_t r = r0 + lane;
+        const bool valid = r < N;
+        uint32_t u = 0, eb[K], ew[K], rk[K]; int sb[K];
+        int deg = 0; bool more = false;
+        if (valid) {
+            u = g.rank2node[r];
+            uint32_t x = g.in_head[u];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                eb[k] = 0; ew[k] = 0; rk[k] = 0; sb[k] = -1;
+                if (x != NIL) { eb[k] = g.e_begin[x]; ew[k] = g.e_w[x]; x = g.e_next_in[x]; deg = k + 1; }
+            }
+            more = x != NIL;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (k < deg) {
+                    rk[k] = g.node2rank[eb[k]];
+                    if (rk[k] < r0) sb[k] = (int)s.score[eb[k]];         // resolved in an earlier batch
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) { eb[k] = 0; ew[k] = 0; rk[k] = 0; sb[k] = -1; }
+        }
+        const int maxdeg = __reduce_max_sync(FULL, deg);
+        int myscore = -1; int32_t mypred = -1;
+        const int nb = (N - r0) < 32u ? (int)(N - r0) : 32;
+        for (int q = 0; q < nb; ++q) {
+            int v[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) v[k] = (k < maxdeg) ? __shfl_sync(FULL, myscore, (int)((rk[k] - r0) & 31u)) : -1;
+            if (lane == q) {
+                int cur = -1, ps = -1; int32_t cp = -1;
+                if (!more) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        if (k < deg) {
+                            const int sbk = rk[k] >= r0 ? v[k] : sb[k];
+                            const int w = (int)ew[k];
+                            if (cur < w || (cur == w && ps <= sbk)) { cur = w; cp = (int32_t)eb[k]; ps = sbk; }
+                        }
+                    }
+                } else {                                                  // long in-list: scores of earlier ranks are in memory by now
+                    for (uint32_t y = g.in_head[u]; y != NIL; y = g.e_next_in[y]) {
+                        const uint32_t b = g.e_begin[y];
+                        const int w = (int)g.e_w[y];
+                        const int sbk = (int)s.score[b];
+                        if (cur < w || (cur == w && ps <= sbk)) { cur = w; cp = (int32_t)b; ps = sbk; }
+                    }
+                }
+                if (cp != -1) cur += ps;
+                myscore = cur; mypred = cp;
+                s.score[u] = (int64_t)cur; s.pred[u] = cp;
+            }
+            __syncwarp();
+        }
+        if (valid) s.stack[r] = mypred == -1 ? NIL : g.node2rank[mypred];   // the chosen predecessor by rank, for the backtrack
+        // first strict maximum in rank order
+        const int bm = __reduce_max_sync(FULL, valid ? myscore : INT32_MIN);
+        if (bm > max_sc) {
+            const int src = __ffs(__ballot_sync(FULL, valid && myscore == bm)) - 1;
+            max_id = __shfl_sync(FULL, u, src);
+            max_sc = bm;
+        }
+    }
+    return max_id;
+}
+
+// Backtrack of the consensus path from node max_id (a sink, so no branch completion ran) along the predecessor ranks
+// that w_consensus_scores left in s.stack. A path runs down the ranks, mostly to the previous one: 32 ranks are
+// loaded at a time and the hops inside the batch go through shuffles instead of dependent global loads. Node ids
+// land in `out` in path order; returns the path length.
+__device__ __noinline__ uint32_t w_consensus_backtrack(GraphView& g, GraphScratch& s, uint32_t max_id, uint32_t* out, int lane) {
+    uint32_t cur = g.node2rank[max_id], n = 0;
+    while (cur != NIL) {
+        const uint32_t rb = cur & ~31u;
+        uint32_t pr = NIL, nd = 0;
+        if (rb + lane <= cur) { pr = s.stack[rb + lane]; nd = g.rank2node[rb + lane]; }
+        uint32_t vis = 0, pos = cur;
+        while (pos != NIL && pos >= rb) {
+            vis |= 1u << (pos - rb);
+            pos = __shfl_sync(FULL, pr, (int)(pos - rb));
+        }
+        if ((vis >> lane) & 1u) out[n + __popc(vis >> lane) - 1] = nd;   // descending ranks for now
+        n += __popc(vis);
+        cur = pos;
+    }
+    __syncwarp();
+    for (uint32_t a = lane; a < n / 2; a += 32) { const uint32_t t = out[a]; out[a] = out[n - 1 - a]; out[n - 1 - a] = t; }
+    __syncwarp();
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // k_poa_edges: the persistent per-edge kernel.
 // ---------------------------------------------------------------------------------------------------------
 #ifndef HGPU_MINBLOCKS
@@ -1358,7 +1546,11 @@ __global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, HGPU_MINBLOCKS) k_poa
             if (a.stop_round != 0xFFFFFFFFu) debug_stop = true;
             // heaviest-bundle consensus; node ids land in aln_rank
             if (st == ST_OK && !debug_stop) {
-                if (lane == 0) n_cons = g_consensus(gv, gs, reinterpret_cast<uint32_t*>(gv.aln_rank));
+                if (*gv.n_nodes <= (1u << 20)) {                          // int32 path scores hold
+                    const uint32_t max_id = w_consensus_scores(gv, gs, lane);
+                    if (gv.out_head[max_id] == NIL) n_cons = w_consensus_backtrack(gv, gs, max_id, reinterpret_cast<uint32_t*>(gv.aln_rank), lane);
+                    else if (lane == 0) n_cons = g_consensus_finish(gv, gs, max_id, reinterpret_cast<uint32_t*>(gv.aln_rank));   // branch completion: serial
+                } else if (lane == 0) n_cons = g_consensus(gv, gs, reinterpret_cast<uint32_t*>(gv.aln_rank));
                 n_cons = __shfl_sync(FULL, n_cons, 0);
                 __syncwarp();
             }
@@ -1483,7 +1675,11 @@ __global__ void __launch_bounds__(32 * TEAM, 768 / (32 * TEAM)) k_poa_edges_team
             }
             if (a.stop_round != 0xFFFFFFFFu) debug_stop = true;
             if (st == ST_OK && !debug_stop && lead) {
-                if (lane == 0) n_cons = g_consensus(gv, gs, reinterpret_cast<uint32_t*>(gv.aln_rank));
+                if (*gv.n_nodes <= (1u << 20)) {                          // int32 path scores hold
+                    const uint32_t max_id = w_consensus_scores(gv, gs, lane);
+                    if (gv.out_head[max_id] == NIL) n_cons = w_consensus_backtrack(gv, gs, max_id, reinterpret_cast<uint32_t*>(gv.aln_rank), lane);
+                    else if (lane == 0) n_cons = g_consensus_finish(gv, gs, max_id, reinterpret_cast<uint32_t*>(gv.aln_rank));   // branch completion: serial
+                } else if (lane == 0) n_cons = g_consensus(gv, gs, reinterpret_cast<uint32_t*>(gv.aln_rank));
                 n_cons = __shfl_sync(FULL, n_cons, 0);
                 __syncwarp();
             }

@@ -278,9 +278,10 @@ HGPU_HD uint32_t g_branch_completion(GraphView& g, GraphScratch& s, uint32_t ran
     return max_id;
 }
 
-HGPU_HD uint32_t g_consensus(GraphView& g, GraphScratch& s, uint32_t* out) {
+// first half of SPOA's traverse_heaviest_bundle: best in-edge / path score of every node in rank order; returns the
+// first node (rank order) with the maximal score
+HGPU_HD uint32_t g_consensus_scores(GraphView& g, GraphScratch& s) {
     const uint32_t N = *g.n_nodes;
-    if (N == 0) return 0;
     for (uint32_t i = 0; i < N; ++i) { s.score[i] = -1; s.pred[i] = -1; }
     uint32_t max_id = 0;
     for (uint32_t r = 0; r < N; ++r) {
@@ -293,12 +294,22 @@ HGPU_HD uint32_t g_consensus(GraphView& g, GraphScratch& s, uint32_t* out) {
         if (s.pred[u] != -1) s.score[u] += s.score[s.pred[u]];
         if (s.score[max_id] < s.score[u]) max_id = u;
     }
+    return max_id;
+}
+
+// second half: branch completion until the path ends in a sink, then the backtrack; node ids of the path land in `out`
+HGPU_HD uint32_t g_consensus_finish(GraphView& g, GraphScratch& s, uint32_t max_id, uint32_t* out) {
     while (g.out_head[max_id] != NIL) max_id = g_branch_completion(g, s, g.node2rank[max_id]);
     uint32_t n = 0;
     while (s.pred[max_id] != -1) { out[n++] = max_id; max_id = (uint32_t)s.pred[max_id]; }
     out[n++] = max_id;
     for (uint32_t a = 0, b = n - 1; a < b; ++a, --b) { uint32_t t = out[a]; out[a] = out[b]; out[b] = t; }
     return n;
+}
+
+HGPU_HD uint32_t g_consensus(GraphView& g, GraphScratch& s, uint32_t* out) {
+    if (*g.n_nodes == 0) return 0;
+    return g_consensus_finish(g, s, g_consensus_scores(g, s), out);
 }
 
 }  // namespace hgpu
