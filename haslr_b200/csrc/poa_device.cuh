@@ -1286,32 +1286,45 @@ __device__ __noinline__ int w_toposort(GraphView& g, uint8_t* wsm, int lane) {
             nr += __popc(em);
             __syncwarp();
             if (f >= 32) break;
-            // SPOA's DFS from root i0+f, verbatim, on one lane
+            // SPOA's DFS from root i0+f on one lane: same visits and the same emission order as the serial code, with
+            // two changes that only remove memory round trips: (1) the loads of a visit are issued before their first
+            // use (node record and aligned triple together, both words of an edge together); (2) a node that pushed
+            // children is flagged on the stack - when the walk returns to it every child is emitted (a child is only
+            // popped once permanent), so it is finalised on the spot instead of walking its lists a second time.
             if (lane == 0) {
+                constexpr uint32_t EXPANDED = 0x80000000u, HAS_ALIGNED = 0x40000000u, IDMASK = 0x3FFFFFFFu;
                 uint32_t sp = 0, guard = 0;
                 const uint32_t limit = 16u * (N + *g.n_edges) + 1024u;
                 stk[sp++] = i0 + f;
                 while (sp > 0) {
                     if (++guard > limit) { okflag = 0; break; }
-                    const uint32_t v = stk[sp - 1];
+                    const uint32_t self = sp - 1;
+                    const uint32_t top = stk[self];
+                    const uint32_t v = top & IDMASK;
+                    if (is_perm(v)) { --sp; continue; }
+                    const bool chk = !((nochk[v >> 5] >> (v & 31)) & 1u);
+                    uint32_t al[3] = {NIL, NIL, NIL};
                     bool vvalid = true;
-                    if (!is_perm(v)) {
-                        const bool chk = !((nochk[v >> 5] >> (v & 31)) & 1u);
-                        for (uint32_t x = g.in_head[v]; x != NIL; x = g.e_next_in[x]) {
-                            const uint32_t b = g.e_begin[x];
+                    if (top & EXPANDED) {
+                        if (chk && (top & HAS_ALIGNED)) { al[0] = g.aligned[3 * v]; al[1] = g.aligned[3 * v + 1]; al[2] = g.aligned[3 * v + 2]; }
+                    } else {
+                        uint32_t x = g.in_head[v];
+                        const uint32_t a0 = g.aligned[3 * v], a1 = g.aligned[3 * v + 1], a2 = g.aligned[3 * v + 2];
+                        while (x != NIL) {
+                            const uint32_t b = g.e_begin[x], nx = g.e_next_in[x];
                             if (!is_perm(b)) {
                                 if (sp >= TOPO_STACK) { okflag = 0; break; }
                                 stk[sp++] = b; vvalid = false;
                             }
+                            x = nx;
                         }
                         if (!okflag) break;
-                        uint32_t al[3] = {NIL, NIL, NIL};
                         if (chk) {
+                            al[0] = a0; al[1] = a0 == NIL ? NIL : a1; al[2] = (a0 == NIL || a1 == NIL) ? NIL : a2;
 #pragma unroll
                             for (int q = 0; q < 3; ++q) {
-                                const uint32_t o = g.aligned[3 * v + q];
+                                const uint32_t o = al[q];
                                 if (o == NIL) break;
-                                al[q] = o;
                                 if (!is_perm(o)) {
                                     if (sp >= TOPO_STACK) { okflag = 0; break; }
                                     stk[sp++] = o; nochk[o >> 5] |= 1u << (o & 31); vvalid = false;
@@ -1319,19 +1332,20 @@ __device__ __noinline__ int w_toposort(GraphView& g, uint8_t* wsm, int lane) {
                             }
                             if (!okflag) break;
                         }
-                        if (vvalid) {
-                            perm[v >> 5] |= 1u << (v & 31);
-                            if (chk) {
-                                g.rank2node[nr] = v; g.node2rank[v] = nr; ++nr;
+                        if (!vvalid) stk[self] = v | EXPANDED | (a0 != NIL ? HAS_ALIGNED : 0u);   // children first; finalised on return
+                    }
+                    if (vvalid) {
+                        perm[v >> 5] |= 1u << (v & 31);
+                        if (chk) {
+                            g.rank2node[nr] = v; g.node2rank[v] = nr; ++nr;
 #pragma unroll
-                                for (int q = 0; q < 3; ++q) {
-                                    if (al[q] == NIL) break;
-                                    g.rank2node[nr] = al[q]; g.node2rank[al[q]] = nr; ++nr;
-                                }
+                            for (int q = 0; q < 3; ++q) {
+                                if (al[q] == NIL) break;
+                                g.rank2node[nr] = al[q]; g.node2rank[al[q]] = nr; ++nr;
                             }
                         }
+                        --sp;
                     }
-                    if (vvalid) --sp;
                 }
             }
             nr = __shfl_sync(FULL, nr, 0);
@@ -1457,7 +1471,7 @@ __device__ __noinline__ uint32_t w_consensus_backtrack(GraphView& g, GraphScratc
 // k_poa_edges: the persistent per-edge kernel.
 // ---------------------------------------------------------------------------------------------------------
 #ifndef HGPU_MINBLOCKS
-#define HGPU_MINBLOCKS 8
+#define HGPU_MINBLOCKS 7
 #endif
 __device__ __forceinline__ int lane_id() {       // read once, never rematerialised from S2R inside the hot loops
     const int l = (int)(threadIdx.x & 31u);
