@@ -546,16 +546,16 @@ struct Fill16 {
     using G = Geo<DP_NW16, true>;
     static constexpr uint32_t NEG2 = ((uint32_t)(G::NEGV & 0xFFFF)) * 0x10001u;
 
-    // t[k] := max(t[k], diagonal from src shifted one column, vertical from src); hs0 = the word left of src[0]
-    __device__ __forceinline__ static void acc(uint32_t (&t)[8], const uint32_t (&src)[8], uint32_t hs0, uint32_t pf, uint32_t g2) {
-        t[0] = __vimax3_s16x2(t[0], __vadd2(hs0, lds_off<0>(pf)), __vadd2(src[0], g2));
-        t[1] = __vimax3_s16x2(t[1], __vadd2(src[0], lds_off<128>(pf)), __vadd2(src[1], g2));
-        t[2] = __vimax3_s16x2(t[2], __vadd2(src[1], lds_off<256>(pf)), __vadd2(src[2], g2));
-        t[3] = __vimax3_s16x2(t[3], __vadd2(src[2], lds_off<384>(pf)), __vadd2(src[3], g2));
-        t[4] = __vimax3_s16x2(t[4], __vadd2(src[3], lds_off<512>(pf)), __vadd2(src[4], g2));
-        t[5] = __vimax3_s16x2(t[5], __vadd2(src[4], lds_off<640>(pf)), __vadd2(src[5], g2));
-        t[6] = __vimax3_s16x2(t[6], __vadd2(src[5], lds_off<768>(pf)), __vadd2(src[6], g2));
-        t[7] = __vimax3_s16x2(t[7], __vadd2(src[6], lds_off<896>(pf)), __vadd2(src[7], g2));
+    // A[k] := max(A[k], diagonal from src shifted one column, vertical from src); hs0 = the word left of src[0]
+    __device__ __forceinline__ static void acc(uint32_t (&A)[8], const uint4 s0, const uint4 s1, uint32_t hs0, const uint4 p0, const uint4 p1, uint32_t g2) {
+        A[7] = __vimax3_s16x2(A[7], __vadd2(s1.z, p1.w), __vadd2(s1.w, g2));
+        A[6] = __vimax3_s16x2(A[6], __vadd2(s1.y, p1.z), __vadd2(s1.z, g2));
+        A[5] = __vimax3_s16x2(A[5], __vadd2(s1.x, p1.y), __vadd2(s1.y, g2));
+        A[4] = __vimax3_s16x2(A[4], __vadd2(s0.w, p1.x), __vadd2(s1.x, g2));
+        A[3] = __vimax3_s16x2(A[3], __vadd2(s0.z, p0.w), __vadd2(s0.w, g2));
+        A[2] = __vimax3_s16x2(A[2], __vadd2(s0.y, p0.z), __vadd2(s0.z, g2));
+        A[1] = __vimax3_s16x2(A[1], __vadd2(s0.x, p0.y), __vadd2(s0.y, g2));
+        A[0] = __vimax3_s16x2(A[0], __vadd2(hs0, p0.x), __vadd2(s0.x, g2));
     }
     // the word "one column to the left" of src[0]: low half = column 15 of the lane to the left (or the stripe
     // boundary value for lane 0), high half = this lane's column 7
@@ -596,8 +596,8 @@ __device__ __forceinline__ uint32_t ldg_u32(unsigned long long base, uint32_t in
 // registers. The body is one small code path on purpose: the kernel is instruction-cache bound otherwise, and a spill
 // reload in this loop costs an L2 round trip.
 struct Row16State {
-    uint32_t pf_lane;        // shared address of prof[0][0][lane]
-    uint32_t frame;          // shared address of the FillFrame16; parked row r is at frame + 128 + (r & 1) * 1024 + lane * 4, word k at + k * 128
+    uint32_t pf_lane;        // shared address of this lane's 16 bytes of prof[0][0]: prof[code][half][lane][4 words]
+    uint32_t frame;          // shared address of the FillFrame16; parked row r is at frame + 128 + (r & 1) * 1024 as [half][lane][4 words]
     uint32_t g2;             // packed gap
     uint32_t row_bytes;      // distance between consecutive rows of the stripe in the slot
     uint64_t dst;            // slot address of this lane's first unit of row i
@@ -607,8 +607,13 @@ struct Row16State {
 };
 static constexpr uint32_t FILL16_PARKED = 128;      // byte offset of the parked rows behind the frame
 
-__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
-    asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
 }
 
 __device__ __forceinline__ void row16(uint32_t (&A)[8], Row16State& S, uint32_t m0, int q, uint32_t i,
@@ -617,7 +622,7 @@ __device__ __forceinline__ void row16(uint32_t (&A)[8], Row16State& S, uint32_t 
     const int lane = S.lane;
     const uint32_t g2 = S.g2;
     const uint32_t pf = S.pf_lane + (m0 & 3u) * (uint32_t)(F::NW * 32 * 4);
-    const uint32_t parked = S.frame + FILL16_PARKED + (uint32_t)lane * 4u;
+    const uint32_t parked = S.frame + FILL16_PARKED + (uint32_t)lane * 16u;
     const uint32_t npc = (m0 >> 3) & 3u;
     const bool fast = (m0 & META_FAST) != 0;
     // ---- predecessor list; is row i-1 one of them?
@@ -633,19 +638,20 @@ __device__ __forceinline__ void row16(uint32_t (&A)[8], Row16State& S, uint32_t 
     }
     const uint32_t hs0 = F::left_word(A, diag_in, lane);
     if (save) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) sts_u32(parked + ((i - 1) & 1u) * 1024u + k * 128, A[k]);
+        sts_v4(parked + ((i - 1) & 1u) * 1024u, A[0], A[1], A[2], A[3]);
+        sts_v4(parked + ((i - 1) & 1u) * 1024u + 512u, A[4], A[5], A[6], A[7]);
     }
+    const uint4 p0 = lds_v4(pf), p1 = lds_v4(pf + 512u);           // the row's profile: scores of the node base against the lane's 16 columns
     // ---- row i-1 (registers): diagonal and vertical moves, in place
     if (has1) {
-        A[7] = __viaddmax_s16x2(A[7], g2, __vadd2(A[6], lds_off<896>(pf)));
-        A[6] = __viaddmax_s16x2(A[6], g2, __vadd2(A[5], lds_off<768>(pf)));
-        A[5] = __viaddmax_s16x2(A[5], g2, __vadd2(A[4], lds_off<640>(pf)));
-        A[4] = __viaddmax_s16x2(A[4], g2, __vadd2(A[3], lds_off<512>(pf)));
-        A[3] = __viaddmax_s16x2(A[3], g2, __vadd2(A[2], lds_off<384>(pf)));
-        A[2] = __viaddmax_s16x2(A[2], g2, __vadd2(A[1], lds_off<256>(pf)));
-        A[1] = __viaddmax_s16x2(A[1], g2, __vadd2(A[0], lds_off<128>(pf)));
-        A[0] = __viaddmax_s16x2(A[0], g2, __vadd2(hs0, lds_off<0>(pf)));
+        A[7] = __viaddmax_s16x2(A[7], g2, __vadd2(A[6], p1.w));
+        A[6] = __viaddmax_s16x2(A[6], g2, __vadd2(A[5], p1.z));
+        A[5] = __viaddmax_s16x2(A[5], g2, __vadd2(A[4], p1.y));
+        A[4] = __viaddmax_s16x2(A[4], g2, __vadd2(A[3], p1.x));
+        A[3] = __viaddmax_s16x2(A[3], g2, __vadd2(A[2], p0.w));
+        A[2] = __viaddmax_s16x2(A[2], g2, __vadd2(A[1], p0.z));
+        A[1] = __viaddmax_s16x2(A[1], g2, __vadd2(A[0], p0.y));
+        A[0] = __viaddmax_s16x2(A[0], g2, __vadd2(hs0, p0.x));
     } else {
 #pragma unroll
         for (int k = 0; k < 8; ++k) A[k] = F::NEG2;
@@ -665,19 +671,16 @@ __device__ __forceinline__ void row16(uint32_t (&A)[8], Row16State& S, uint32_t 
                 bl = ql >= 0 ? __shfl_sync(FULL, (int)S.bcx, ql & 31) : (int)ldg_u32(lds_u64(S.frame + FRAME16(bc_prev)), i - dist);
             }
             const bool near = dist == 2;
-            const uint32_t psrc = parked + (i & 1u) * 1024u;        // parked row i-2
-            const uint64_t src = S.dst - (uint64_t)dist * S.row_bytes;
-            uint32_t hi = near ? lds_u32v(psrc + 7 * 128) : ldg_w(src, 512 + 12);
-            uint32_t left = __shfl_up_sync(FULL, hi, 1);
-            if (lane == 0) left = (uint32_t)bl << 16;
-            const uint32_t h0 = __byte_perm(left, hi, 0x5432);
-#pragma unroll
-            for (int k = 7; k >= 1; --k) {
-                const uint32_t lo = near ? lds_u32v(psrc + (k - 1) * 128) : ldg_w(src, ((k - 1) >> 2) * 512 + ((k - 1) & 3) * 4);
-                A[k] = __vimax3_s16x2(A[k], __vadd2(lo, lds_u32v(pf + k * 128)), __vadd2(hi, g2));
-                hi = lo;
+            uint4 s0, s1;
+            if (near) {                                             // parked row i-2
+                s0 = lds_v4(parked + (i & 1u) * 1024u); s1 = lds_v4(parked + (i & 1u) * 1024u + 512u);
+            } else {                                                // a far row (3.6 % of rows): back from the slot
+                const uint64_t src = S.dst - (uint64_t)dist * S.row_bytes;
+                s0 = ldg_v4(src, 0); s1 = ldg_v4(src, 1);
             }
-            A[0] = __vimax3_s16x2(A[0], __vadd2(h0, lds_u32v(pf)), __vadd2(hi, g2));
+            uint32_t left = __shfl_up_sync(FULL, s1.w, 1);
+            if (lane == 0) left = (uint32_t)bl << 16;
+            F::acc(A, s0, s1, __byte_perm(left, s1.w, 0x5432), p0, p1, g2);
         }
     }
     // horizontal gaps = prefix maximum in hat space. In the lane: one chain scans columns 0..7 (low halves) and 8..15
@@ -727,7 +730,7 @@ __device__ __forceinline__ bool meta_reads_two_back(uint32_t m0) {
     return npc == 3 || meta_d0(m0) == 2 || (npc == 2 && meta_d1(m0) == 2);
 }
 
-// sequence profile of stripe s: prof[code][k][lane] = hat scores of the lane's k-th word (columns k, k+8)
+// sequence profile of stripe s: prof[code][k / 4][lane][k % 4] = hat scores of the lane's k-th word (columns k, k+8)
 __device__ __noinline__ void fill16_profile(uint32_t* prof, const FillFrame16* frame, uint32_t s, int lane) {
     constexpr int NW = DP_NW16;
     using G = Geo<NW, true>;
@@ -744,7 +747,7 @@ __device__ __noinline__ void fill16_profile(uint32_t* prof, const FillFrame16* f
         for (int c = 0; c < 4; ++c) {
             const int va = ca < 0 ? 0 : (ca == c ? sm : sx);
             const int vb = cb < 0 ? 0 : (cb == c ? sm : sx);
-            prof[(c * NW + k) * 32 + lane] = ((uint32_t)va & 0xFFFFu) | ((uint32_t)vb << 16);
+            prof[((c * 2 + (k >> 2)) * 32 + lane) * 4 + (k & 3)] = ((uint32_t)va & 0xFFFFu) | ((uint32_t)vb << 16);
         }
     }
 }
@@ -774,7 +777,7 @@ __device__ __noinline__ bool dp_fill16(const uint32_t* meta0, const uint32_t* pr
     Row16State S;
     S.lane = lane;
     S.g2 = pack2(gap);
-    S.pf_lane = (uint32_t)__cvta_generic_to_shared(prof + lane);
+    S.pf_lane = (uint32_t)__cvta_generic_to_shared(prof + lane * 4);
     S.frame = (uint32_t)__cvta_generic_to_shared(frame);
     S.row_bytes = NS * (uint32_t)(G::UNITS * 32 * 16);
     S.bcx = 0; S.bco = 0;

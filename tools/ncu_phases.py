@@ -13,18 +13,21 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MARKS = [  # (substring that starts a region, phase name), looked up per file in source order
-    ("struct SlotView", "slotview(load: traceback reads)"), ("struct RowOps", "fill32.rowops"), ("void team_publish", "team"),
-    ("bool dp_fill(", "fill32"), ("struct Fill16", "fill16.acc(slow rows)"), ("void row16(", "fill16.row_hdr"),
-    ("if ((m0 & META_FAST) != 0) {                                    // single predecessor", "fill16.fast"),
-    ("const uint32_t npc = (m0 >> 3) & 3u;\n        uint32_t t[8];", "fill16.slow"),
-    ("// horizontal gaps = prefix maximum in hat space. In the lane", "fill16.scan"),
-    ("// stream the row out; its last cell", "fill16.store"), ("bool meta_reads_two_back", "fill16.batch"),
-    ("bool dp_fill16(", "fill16.setup+batch"), ("bool dp_traceback(", "tb.endcell"), ("// tile of the stored matrix", "tb.tile"),
-    ("// (1) a run of diagonal moves", "tb.diagrun"), ("// (2) one generic step", "tb.generic"), ("bool dp_align(", "dp_align"),
+    ("struct SlotView", "slotview(load: end cell, generic step)"), ("struct RowOps", "fill32.rowops"), ("void team_publish", "team"),
+    ("bool dp_fill(", "fill32"), ("struct Fill16", "fill16.helpers"), ("void row16(", "fill16.row:predecessors"),
+    ("// ---- row i-1 (registers): diagonal and vertical moves, in place", "fill16.row:from_row_i-1"),
+    ("// ---- every other predecessor row streams through two registers", "fill16.row:other_predecessor_rows"),
+    ("// horizontal gaps = prefix maximum in hat space. In the lane", "fill16.row:prefix_max"),
+    ("// stream the row out; its last cell", "fill16.row:store"), ("bool meta_reads_two_back", "fill16.batch"),
+    ("void fill16_profile(", "fill16.profile"), ("bool dp_fill16(", "fill16.setup+batch_loop"),
+    ("struct TbTile", "tb.endcell"), ("// ---- tile with (ci, cj) in its corner", "tb.tile_load+prefetch"),
+    ("// ---- every lane decides the move of cell", "tb.lane_decisions"), ("// ---- kr == 2: one generic step", "tb.generic"),
+    ("bool dp_align(", "dp_align"),
     ("void w_init_chain(", "init_chain"), ("void w_build_meta(", "build_meta"), ("uint32_t w_add_alignment(", "add_alignment"),
     ("int w_toposort(", "topo.batch"), ("// SPOA's DFS from root", "topo.dfs"), ("nr = __shfl_sync(FULL, nr, 0);", "topo.batch"),
+    ("uint32_t w_consensus_scores(", "consensus.scores"), ("uint32_t w_consensus_backtrack(", "consensus.backtrack"),
     ("int lane_id()", "kernel.main"), ("void k_poa_edges(", "kernel.main"), ("void k_poa_edges_team(", "kernel.team"),
-    ("uint32_t g_branch_completion(", "graph.consensus"), ("bool g_add_alignment(", "graph.serial_add"), ("bool g_toposort(", "graph.serial_topo"),
+    ("uint32_t g_branch_completion(", "graph.consensus_serial"), ("bool g_add_alignment(", "graph.serial_add"), ("bool g_toposort(", "graph.serial_topo"),
 ]
 
 
