@@ -155,7 +155,7 @@ def reference_arm(args):
     dt = time.perf_counter() - t
     v = nb / dt / 1e6
     sample = f"{n} of {N_EDGES} cfg3 edges per step ({DEPTH} x {GAP_LEN} bp), restated SPOA 1.1.3 int16 SSE4.1, one edge per queue grab"
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16",
         "data": "synthetic", "config": {"workload": f"cfg3 batched-POA stress: {N_EDGES} edges x {DEPTH} x {GAP_LEN} bp (bounded sample per step)",
@@ -164,6 +164,15 @@ def reference_arm(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+def emit(obj):
+    """The one JSON line goes to the real stdout; everything else a library prints (NCCL banners ...) was sent to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():
@@ -310,7 +319,7 @@ def main():
         cpu = {"value": nb / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port", "gcups": ccells / dt / 1e9,
                "sample": f"first {n} of {n_edges} edges of rank 0's shard ({nb / 1e6:.1f} Mbases, {dt:.1f} s), restated SPOA 1.1.3 int16 SSE4.1, {cores} threads"}
 
-    print(json.dumps({
+    emit(({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int16", "data": "synthetic",

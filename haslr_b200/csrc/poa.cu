@@ -141,7 +141,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
     HGPU_CUDA(ctx, S->e_seg_off.ensure(n_edges + 1)); HGPU_CUDA(ctx, S->items.ensure(n_edges + 1));
     HGPU_CUDA(ctx, S->status.ensure(n_edges + 1)); HGPU_CUDA(ctx, S->cons_len.ensure(n_edges + 1));
     HGPU_CUDA(ctx, S->cons_pos.ensure(n_edges + 1)); HGPU_CUDA(ctx, S->out_nodes.ensure(n_edges + 1));
-    HGPU_CUDA(ctx, S->stats.ensure(8)); HGPU_CUDA(ctx, S->pool_cursor.ensure(1)); HGPU_CUDA(ctx, S->counters.ensure(256));
+    HGPU_CUDA(ctx, S->stats.ensure(32)); HGPU_CUDA(ctx, S->pool_cursor.ensure(1)); HGPU_CUDA(ctx, S->counters.ensure(256));
     if (n_seg) {
         HGPU_CUDA(ctx, cudaMemcpyAsync(S->seg_ptr.p, seg_ptr.data(), n_seg * 8, cudaMemcpyHostToDevice, st));
         HGPU_CUDA(ctx, cudaMemcpyAsync(S->seg_len.p, seg_len.data(), n_seg * 4, cudaMemcpyHostToDevice, st));
@@ -319,6 +319,10 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
             a.ws = S->ws.p; a.wl = c.wl; a.arena = S->arena.p; a.slot_bytes = c.slot;
             S->last_wl = c.wl; S->last_slot = c.slot;
             a.sc = sc; a.stats = S->stats.p; a.stop_round = opt.stop_round; a.force_i32 = opt.force_i32;
+#if HGPU_PHASE_CLOCKS
+            HGPU_CUDA(ctx, cudaMemsetAsync(S->stats.p + 8, 0, 16 * sizeof(unsigned long long), st));
+            a.phase_clk = S->stats.p + 8;
+#endif
             if (const char* e = getenv("HGPU_PROBE")) { a.probe = (uint32_t)atoi(e); a.probe_round = 1; }
             if (const char* e = getenv("HGPU_PROBE_ROUND")) a.probe_round = (uint32_t)atoi(e);
             k_poa_edges<<<blocks, 32 * DP_WARPS_PER_BLOCK, smem, st>>>(a);
@@ -349,6 +353,17 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
     unsigned long long sth[8];
     HGPU_CUDA(ctx, cudaMemcpyAsync(sth, S->stats.p, sizeof sth, cudaMemcpyDeviceToHost, st));
     HGPU_CUDA(ctx, cudaStreamSynchronize(st));
+#if HGPU_PHASE_CLOCKS
+    {
+        unsigned long long pc[16];
+        HGPU_CUDA(ctx, cudaMemcpy(pc, S->stats.p + 8, sizeof pc, cudaMemcpyDeviceToHost));
+        static const char* nm[9] = {"queue", "init", "fill", "traceback", "add_alignment", "toposort", "dp_records", "consensus", "publish"};
+        double tot = 0; for (int i = 0; i < 9; ++i) tot += (double)pc[i];
+        fprintf(stderr, "[phase clocks, warp-cycles of the last class]");
+        for (int i = 0; i < 9; ++i) fprintf(stderr, " %s %.1f%%", nm[i], 100.0 * (double)pc[i] / (tot > 0 ? tot : 1));
+        fprintf(stderr, "\n");
+    }
+#endif
     S->st.cells = sth[0]; S->st.cells_padded = sth[1]; S->st.alignments = sth[2]; S->st.alignments_i32 = sth[3]; S->st.bases_in = sth[4];
     return HGPU_OK;
 }

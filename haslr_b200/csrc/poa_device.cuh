@@ -49,7 +49,7 @@ struct DpScores {
 struct WsLayout {
     uint32_t ncap, ecap, scap;
     uint64_t o_hdr, o_code, o_in_head, o_in_tail, o_out_head, o_aligned, o_e_begin, o_e_end, o_e_w, o_e_next_in, o_e_next_out,
-        o_rank2node, o_node2rank, o_meta0, o_pred_off, o_pred_rank, o_aln_rank, o_aln_pos, o_mark, o_check, o_stack,
+        o_rank2node, o_node2rank, o_meta0, o_pred_off, o_pred_rank, o_sinks, o_aln_rank, o_aln_pos, o_mark, o_check, o_stack,
         o_score, o_pred;
     uint64_t bytes;
 };
@@ -67,7 +67,7 @@ __host__ __device__ inline WsLayout ws_layout(uint32_t ncap, uint32_t ecap) {
     w.o_e_begin = take(4 * e); w.o_e_end = take(4 * e); w.o_e_w = take(4 * e); w.o_e_next_in = take(4 * e); w.o_e_next_out = take(4 * e);
     w.o_rank2node = take(4 * n); w.o_node2rank = take(4 * n);
     w.o_meta0 = take(4 * n);
-    w.o_pred_off = take(4 * (n + 1)); w.o_pred_rank = take(4 * e);
+    w.o_pred_off = take(4 * (n + 1)); w.o_pred_rank = take(4 * e); w.o_sinks = take(4 * n);
     w.o_aln_rank = take(4 * n); w.o_aln_pos = take(4 * n);
     w.o_mark = take(n); w.o_check = take(n);
     w.o_stack = take(4 * (uint64_t)w.scap);
@@ -77,13 +77,13 @@ __host__ __device__ inline WsLayout ws_layout(uint32_t ncap, uint32_t ecap) {
 }
 
 // header words of a workspace
-enum : int { HDR_N_NODES = 0, HDR_N_EDGES = 1, HDR_ALN_LEN = 2, HDR_LAST_P16 = 3, HDR_LAST_V = 4, HDR_LAST_L = 5, HDR_LAST_BIAS = 6 };
+enum : int { HDR_N_NODES = 0, HDR_N_EDGES = 1, HDR_ALN_LEN = 2, HDR_LAST_P16 = 3, HDR_LAST_V = 4, HDR_LAST_L = 5, HDR_LAST_BIAS = 6, HDR_N_SINKS = 7 };
 
 __host__ __device__ inline GraphView bind_graph(uint8_t* base, const WsLayout& w) {
     GraphView g;
     g.ncap = w.ncap; g.ecap = w.ecap;
     uint32_t* hdr = reinterpret_cast<uint32_t*>(base + w.o_hdr);
-    g.n_nodes = hdr + HDR_N_NODES; g.n_edges = hdr + HDR_N_EDGES; g.aln_len = hdr + HDR_ALN_LEN;
+    g.n_nodes = hdr + HDR_N_NODES; g.n_edges = hdr + HDR_N_EDGES; g.aln_len = hdr + HDR_ALN_LEN; g.n_sinks = hdr + HDR_N_SINKS;
     g.code = base + w.o_code;
     g.in_head = reinterpret_cast<uint32_t*>(base + w.o_in_head);
     g.in_tail = reinterpret_cast<uint32_t*>(base + w.o_in_tail);
@@ -99,6 +99,7 @@ __host__ __device__ inline GraphView bind_graph(uint8_t* base, const WsLayout& w
     g.meta0 = reinterpret_cast<uint32_t*>(base + w.o_meta0);
     g.pred_off = reinterpret_cast<uint32_t*>(base + w.o_pred_off);
     g.pred_rank = reinterpret_cast<uint32_t*>(base + w.o_pred_rank);
+    g.sinks = reinterpret_cast<uint32_t*>(base + w.o_sinks);
     g.aln_rank = reinterpret_cast<int32_t*>(base + w.o_aln_rank);
     g.aln_pos = reinterpret_cast<int32_t*>(base + w.o_aln_pos);
     return g;
@@ -188,6 +189,7 @@ struct PoaArgs {
     unsigned long long* stats;   // [0] cells [1] cells computed incl. padding [2] alignments [3] int32 alignments [4] bases in
     uint32_t stop_round;         // debug: stop after the fill+traceback of this round (0xFFFFFFFF = run to consensus)
     int force_i32;
+    unsigned long long* phase_clk; // developer build (-DHGPU_PHASE_CLOCKS=1): per-phase SM cycles summed over warps, [16]
     uint32_t probe, probe_round; // developer timing probes (HGPU_PROBE=phase, HGPU_PROBE_ROUND=k): the edge ends in round k after 1 fill, 2 traceback,
                                  // 3 add_alignment, 4 topological sort, 5 DP records; results are invalid
 };
@@ -887,11 +889,11 @@ __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8
     sv.bind(slot, V, L);
     // end cell: best Hhat[i][L] over sink nodes, first maximum in rank order (SPOA kNW)
     int best = INT32_MIN; uint32_t best_i = 0;
-    for (uint32_t r = lane; r < V; r += 32) {
-        if (gv.meta0[r] & META_SINK) {
-            int v = sv.load(r + 1, L);
-            if (v > best) { best = v; best_i = r + 1; }
-        }
+    const uint32_t n_sinks = *gv.n_sinks;
+    for (uint32_t x = lane; x < n_sinks; x += 32) {                      // the sink list is built with the DP records
+        const uint32_t r = gv.sinks[x];
+        const int v = sv.load(r + 1, L);
+        if (v > best) { best = v; best_i = r + 1; }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -1083,44 +1085,72 @@ __device__ __forceinline__ void w_init_chain(GraphView& g, const uint8_t* seq, u
     if (lane == 0) {
         g.pred_off[L] = L - 1;
         *g.n_nodes = L; *g.n_edges = L - 1; *g.aln_len = 0;
+        g.sinks[0] = L - 1; *g.n_sinks = 1;
     }
     __syncwarp();
 }
 
 // per-rank DP records (meta0 / pred CSR) from rank2node/node2rank + in-lists; same content as g_build_meta
-__device__ __forceinline__ void w_build_meta(GraphView& g, int lane) {
+// Every access below is a dependent global load (rank -> node -> in-list -> edge -> rank of its tail), so one rank per
+// lane leaves the warp waiting on ~6 round trips per 32 ranks. Each lane therefore carries four ranks (128 per
+// iteration) through the same stages together: the round trips of the four overlap.
+__device__ __noinline__ void w_build_meta(GraphView& g, int lane) {
     const uint32_t N = *g.n_nodes;
-    uint32_t running = 0;
-    for (uint32_t r0 = 0; r0 < N; r0 += 32) {
-        const uint32_t r = r0 + lane;
-        uint32_t deg = 0, v = 0;
-        if (r < N) {
-            v = g.rank2node[r];
-            for (uint32_t x = g.in_head[v]; x != NIL; x = g.e_next_in[x]) ++deg;
-        }
-        uint32_t incl = deg;
+    constexpr int K = 4;
+    uint32_t running = 0, n_sinks = 0;
+    for (uint32_t r0 = 0; r0 < N; r0 += 32 * K) {
+        uint32_t v[K], ih[K], cd[K], oh[K], b0[K], b1[K], n1[K], n2[K], q0[K], q1[K], deg[K];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t o = __shfl_up_sync(FULL, incl, d);
-            if (lane >= d) incl += o;
+        for (int k = 0; k < K; ++k) { const uint32_t r = r0 + k * 32 + lane; v[k] = r < N ? g.rank2node[r] : NIL; }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            ih[k] = NIL; cd[k] = 0; oh[k] = NIL;
+            if (v[k] != NIL) { ih[k] = g.in_head[v[k]]; cd[k] = g.code[v[k]]; oh[k] = g.out_head[v[k]]; }
         }
-        const uint32_t off = running + incl - deg;
-        if (r < N) {
-            const uint32_t base = g.code[v] | (g.out_head[v] == NIL ? META_SINK : 0u);
-            g.pred_off[r] = off;
-            uint32_t np = 0, d0 = 0, d1 = 0;
-            for (uint32_t x = g.in_head[v]; x != NIL; x = g.e_next_in[x]) {
-                uint32_t pr = g.node2rank[g.e_begin[x]];
-                g.pred_rank[off + np] = pr;
-                if (np == 0) d0 = r - pr;
-                if (np == 1) d1 = r - pr;
-                ++np;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { b0[k] = NIL; n1[k] = NIL; if (ih[k] != NIL) { b0[k] = g.e_begin[ih[k]]; n1[k] = g.e_next_in[ih[k]]; } }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            q0[k] = 0; b1[k] = NIL; n2[k] = NIL;
+            if (b0[k] != NIL) q0[k] = g.node2rank[b0[k]];
+            if (n1[k] != NIL) { b1[k] = g.e_begin[n1[k]]; n2[k] = g.e_next_in[n1[k]]; }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            q1[k] = 0;
+            if (b1[k] != NIL) q1[k] = g.node2rank[b1[k]];
+            deg[k] = (ih[k] != NIL) + (n1[k] != NIL);
+            for (uint32_t x = n2[k]; x != NIL; x = g.e_next_in[x]) ++deg[k];       // three or more in-edges: rare
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const uint32_t r = r0 + k * 32 + lane;
+            uint32_t incl = deg[k];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += o;
             }
-            g.meta0[r] = meta_pack(base, r, np, d0, d1);
+            const uint32_t off = running + incl - deg[k];
+            bool is_sink = false;
+            if (v[k] != NIL) {
+                const uint32_t base = cd[k] | (oh[k] == NIL ? META_SINK : 0u);
+                g.pred_off[r] = off;
+                uint32_t d0 = 0, d1 = 0;
+                if (deg[k] >= 1) { g.pred_rank[off] = q0[k]; d0 = r - q0[k]; }
+                if (deg[k] >= 2) { g.pred_rank[off + 1] = q1[k]; d1 = r - q1[k]; }
+                uint32_t np = 2;
+                for (uint32_t x = n2[k]; x != NIL; x = g.e_next_in[x]) g.pred_rank[off + np++] = g.node2rank[g.e_begin[x]];
+                g.meta0[r] = meta_pack(base, r, deg[k], d0, d1);
+                is_sink = (base & META_SINK) != 0;
+            }
+            const unsigned sm_ = __ballot_sync(FULL, is_sink);
+            if (is_sink) g.sinks[n_sinks + __popc(sm_ & ((1u << lane) - 1))] = r;
+            n_sinks += __popc(sm_);
+            running += __shfl_sync(FULL, incl, 31);
         }
-        running += __shfl_sync(FULL, incl, 31);
     }
-    if (lane == 0) g.pred_off[N] = running;
+    if (lane == 0) { g.pred_off[N] = running; *g.n_sinks = n_sinks; }
     __syncwarp();
 }
 
@@ -1149,35 +1179,52 @@ __device__ __noinline__ uint32_t w_add_alignment(GraphView& g, GraphScratch& s, 
         if (pos != -1) by_j[pos] = (uint32_t)g.aln_rank[t];     // rank, or 0xFFFFFFFF for an insertion
     }
     __syncwarp();
-    // (A)+(B): node of every position; new nodes numbered in alignment order
+    // (A)+(B): node of every position; new nodes numbered in alignment order. Four positions per lane (j0 + 32k + lane)
+    // go through the dependent loads (rank -> node -> base / aligned triple -> bases of the aligned nodes) together.
     uint32_t n_new = 0;
     bool full = true;
-    for (uint32_t j0 = 0; j0 < L; j0 += 32) {
-        const uint32_t j = j0 + lane;
-        bool isnew = false; uint32_t node = NIL, al = NIL;
-        if (j < L) {
-            const uint32_t rk = by_j[j];
-            const uint32_t c = base_code(seq[j]);
-            if (rk == ABSENT) full = false;
-            else if (rk == 0xFFFFFFFFu) isnew = true;
-            else {
-                const uint32_t a = g.rank2node[rk];
-                if (g.code[a] == c) node = a;
-                else {
+    constexpr int K = 4;
+    for (uint32_t j0 = 0; j0 < L; j0 += 32 * K) {
+        uint32_t rk[K], c[K], an[K], o0[K], o1[K], o2[K], ca[K];
 #pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        const uint32_t o = g.aligned[3 * a + q];
-                        if (o == NIL) break;
-                        if (g.code[o] == c) { node = o; break; }
-                    }
-                    if (node == NIL) { isnew = true; al = a; }
-                }
-            }
+        for (int k = 0; k < K; ++k) {
+            const uint32_t j = j0 + k * 32 + lane;
+            rk[k] = ABSENT; c[k] = 0;
+            if (j < L) { rk[k] = by_j[j]; c[k] = base_code(seq[j]); if (rk[k] == ABSENT) full = false; }
         }
-        const unsigned m = __ballot_sync(FULL, isnew);
-        if (isnew) node = N0 + n_new + __popc(m & ((1u << lane) - 1));
-        n_new += __popc(m);
-        if (j < L) { nid[j] = node; alto[j] = al; }
+#pragma unroll
+        for (int k = 0; k < K; ++k) an[k] = (rk[k] < 0xFFFFFFFEu) ? g.rank2node[rk[k]] : NIL;      // neither ABSENT nor an insertion
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            ca[k] = 0; o0[k] = NIL; o1[k] = NIL; o2[k] = NIL;
+            if (an[k] != NIL) { ca[k] = g.code[an[k]]; o0[k] = g.aligned[3 * an[k]]; o1[k] = g.aligned[3 * an[k] + 1]; o2[k] = g.aligned[3 * an[k] + 2]; }
+        }
+        uint32_t c0[K], c1[K], c2[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (o0[k] == NIL) { o1[k] = NIL; o2[k] = NIL; } else if (o1[k] == NIL) o2[k] = NIL;
+            const bool look = an[k] != NIL && ca[k] != c[k];                                            // the aligned nodes matter only on a mismatch
+            c0[k] = (look && o0[k] != NIL) ? g.code[o0[k]] : 4u;
+            c1[k] = (look && o1[k] != NIL) ? g.code[o1[k]] : 4u;
+            c2[k] = (look && o2[k] != NIL) ? g.code[o2[k]] : 4u;
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const uint32_t j = j0 + k * 32 + lane;
+            bool isnew = false; uint32_t node = NIL, al = NIL;
+            if (j < L && rk[k] != ABSENT) {
+                if (rk[k] == 0xFFFFFFFFu) isnew = true;
+                else if (ca[k] == c[k]) node = an[k];
+                else if (c0[k] == c[k]) node = o0[k];
+                else if (c1[k] == c[k]) node = o1[k];
+                else if (c2[k] == c[k]) node = o2[k];
+                else { isnew = true; al = an[k]; }
+            }
+            const unsigned m = __ballot_sync(FULL, isnew);
+            if (isnew) node = N0 + n_new + __popc(m & ((1u << lane) - 1));
+            n_new += __popc(m);
+            if (j < L) { nid[j] = node; alto[j] = al; }
+        }
     }
     if (__any_sync(FULL, !full)) return 0xFFFFFFFFu;             // nothing modified yet
     __syncwarp();
@@ -1203,29 +1250,53 @@ __device__ __noinline__ uint32_t w_add_alignment(GraphView& g, GraphScratch& s, 
         g.aligned[3 * v] = a3[0]; g.aligned[3 * v + 1] = a3[1]; g.aligned[3 * v + 2] = a3[2];
     }
     __syncwarp();
-    // (C): edges between consecutive positions, weight 2 (both bases contribute 1)
+    // (C): edges between consecutive positions, weight 2 (both bases contribute 1); four positions per lane again
     uint32_t e_new = 0;
-    for (uint32_t j0 = 1; j0 < L; j0 += 32) {
-        const uint32_t j = j0 + lane;
-        bool need = false; uint32_t b = NIL, e = NIL;
-        if (j < L) {
-            b = nid[j - 1]; e = nid[j];
-            need = true;
-            for (uint32_t x = g.out_head[b]; x != NIL; x = g.e_next_out[x])
-                if (g.e_end[x] == e) { g.e_w[x] += 2; need = false; break; }
+    for (uint32_t j0 = 1; j0 < L; j0 += 32 * K) {
+        uint32_t b[K], e[K], x[K], xe[K], xn[K], tl[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const uint32_t j = j0 + k * 32 + lane;
+            b[k] = NIL; e[k] = NIL;
+            if (j < L) { b[k] = nid[j - 1]; e[k] = nid[j]; }
         }
-        const unsigned m = __ballot_sync(FULL, need);
-        if (need) {
-            const uint32_t x = E0 + e_new + __popc(m & ((1u << lane) - 1));
-            g.e_begin[x] = b; g.e_end[x] = e; g.e_w[x] = 2;
-            g.e_next_in[x] = NIL;
-            g.e_next_out[x] = g.out_head[b];
-            g.out_head[b] = x;
-            const uint32_t tl = g.in_tail[e];
-            if (tl == NIL) g.in_head[e] = x; else g.e_next_in[tl] = x;
-            g.in_tail[e] = x;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { x[k] = NIL; tl[k] = NIL; if (b[k] != NIL) { x[k] = g.out_head[b[k]]; tl[k] = g.in_tail[e[k]]; } }
+        const uint32_t oh0 = x[0], oh1 = x[1], oh2 = x[2], oh3 = x[3];
+        const uint32_t oh[K] = {oh0, oh1, oh2, oh3};
+        bool hit[K] = {false, false, false, false};
+        // walk the out-lists of the four tails in step: first two edges with overlapped loads, longer lists one by one
+#pragma unroll
+        for (int step = 0; step < 2; ++step) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) { xe[k] = NIL; xn[k] = NIL; if (x[k] != NIL && !hit[k]) { xe[k] = g.e_end[x[k]]; xn[k] = g.e_next_out[x[k]]; } }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (x[k] != NIL && !hit[k]) {
+                    if (xe[k] == e[k]) hit[k] = true; else x[k] = xn[k];
+                }
+            }
         }
-        e_new += __popc(m);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            while (x[k] != NIL && !hit[k]) { if (g.e_end[x[k]] == e[k]) hit[k] = true; else x[k] = g.e_next_out[x[k]]; }
+            if (hit[k]) g.e_w[x[k]] += 2;
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const bool need = b[k] != NIL && !hit[k];
+            const unsigned m = __ballot_sync(FULL, need);
+            if (need) {
+                const uint32_t nx = E0 + e_new + __popc(m & ((1u << lane) - 1));
+                g.e_begin[nx] = b[k]; g.e_end[nx] = e[k]; g.e_w[nx] = 2;
+                g.e_next_in[nx] = NIL;
+                g.e_next_out[nx] = oh[k];
+                g.out_head[b[k]] = nx;
+                if (tl[k] == NIL) g.in_head[e[k]] = nx; else g.e_next_in[tl[k]] = nx;
+                g.in_tail[e[k]] = nx;
+            }
+            e_new += __popc(m);
+        }
     }
     if (lane == 0) { *g.n_nodes = N0 + n_new; *g.n_edges = E0 + e_new; }
     __syncwarp();
@@ -1243,7 +1314,7 @@ __device__ __noinline__ uint32_t w_add_alignment(GraphView& g, GraphScratch& s, 
 // Returns 1 ok, 0 failed (stack overflow / step guard): the caller falls back to the serial g_toposort.
 // ---------------------------------------------------------------------------------------------------------
 static constexpr uint32_t TOPO_BM_WORDS = HGPU_RING ? 576 : 400;     // nodes per bitmap = 32x
-static constexpr uint32_t TOPO_STACK = (DP_SMEM_PER_WARP - 2 * TOPO_BM_WORDS * 4) / 4;   // 384 entries
+static constexpr uint32_t TOPO_STACK = (DP_SMEM_PER_WARP - 2 * TOPO_BM_WORDS * 4) / 4;
 
 __device__ __noinline__ int w_toposort(GraphView& g, uint8_t* wsm, int lane) {
     const uint32_t N = *g.n_nodes;
@@ -1476,6 +1547,20 @@ __device__ __noinline__ uint32_t w_consensus_backtrack(GraphView& g, GraphScratc
 #ifndef HGPU_MINBLOCKS
 #define HGPU_MINBLOCKS 7
 #endif
+#ifndef HGPU_PHASE_CLOCKS
+#define HGPU_PHASE_CLOCKS 0
+#endif
+#if HGPU_PHASE_CLOCKS
+#define PHASE_CLK_DECL long long pc_t = clock64(); unsigned long long pc_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define PHASE_CLK(idx) { const long long pc_n = clock64(); pc_acc[idx] += (unsigned long long)(pc_n - pc_t); pc_t = pc_n; }
+#define PHASE_CLK_FLUSH(a) if (lane == 0 && (a).phase_clk) { for (int pc_i = 0; pc_i < 10; ++pc_i) atomicAdd((a).phase_clk + pc_i, pc_acc[pc_i]); }
+#else
+#define PHASE_CLK_DECL
+#define PHASE_CLK(idx)
+#define PHASE_CLK_FLUSH(a)
+#endif
+enum : int { PC_QUEUE = 0, PC_INIT = 1, PC_FILL = 2, PC_TRACEBACK = 3, PC_ADD = 4, PC_TOPO = 5, PC_META = 6, PC_CONSENSUS = 7, PC_PUBLISH = 8 };
+
 __device__ __forceinline__ int lane_id() {       // read once, never rematerialised from S2R inside the hot loops
     const int l = (int)(threadIdx.x & 31u);
     return __shfl_sync(FULL, l, l);                 // a shuffle result is opaque to ptxas, S2R is not
@@ -1493,6 +1578,7 @@ __global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, HGPU_MINBLOCKS) k_poa
     GraphScratch gs = bind_scratch(wsb, a.wl);
     uint32_t* hdr = reinterpret_cast<uint32_t*>(wsb + a.wl.o_hdr);
     unsigned long long st_cells = 0, st_padded = 0, st_aln = 0, st_aln32 = 0, st_bases = 0;
+    PHASE_CLK_DECL
 
     while (true) {
         uint32_t item = 0;
@@ -1500,6 +1586,7 @@ __global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, HGPU_MINBLOCKS) k_poa
         item = __shfl_sync(FULL, item, 0);
         if (item >= a.n_items) break;
         const uint32_t e = a.items[item];
+        PHASE_CLK(PC_QUEUE)
         const uint32_t s0 = a.e_seg_off[e];
         const uint32_t R = a.e_seg_off[e + 1] - s0;
         uint32_t st = ST_OK;
@@ -1512,6 +1599,7 @@ __global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, HGPU_MINBLOCKS) k_poa
             const uint32_t L0 = a.seg_len[s0];
             if (L0 > gv.ncap || L0 > gv.ecap) st = ST_CAPACITY;
             else { w_init_chain(gv, a.bases + a.seg_ptr[s0], L0, lane); e_bases += L0; }
+            PHASE_CLK(PC_INIT)
             for (uint32_t k = 1; k < R && st == ST_OK; ++k) {
                 const uint32_t V = *gv.n_nodes;
                 const uint32_t NE = *gv.n_edges;
@@ -1526,8 +1614,17 @@ __global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, HGPU_MINBLOCKS) k_poa
                     e_cells += (unsigned long long)(V + 1) * (L + 1);
                     debug_stop = true; break;
                 }
-                bool ok = p16 ? dp_align<DP_NW16, true>(gv, slot, wsm, seq, V, L, a.sc, lane)
-                              : dp_align<DP_NW32, false>(gv, slot, wsm, seq, V, L, a.sc, lane);
+                bool ok;
+                if (p16) {
+                    dp_fill16<false>(gv.meta0, gv.pred_off, gv.pred_rank, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, Geo<DP_NW16, true>::bias(V, a.sc), lane, 0, 1, nullptr);
+                    PHASE_CLK(PC_FILL)
+                    ok = dp_traceback<DP_NW16, true>(gv, slot, wsm, seq, V, L, a.sc, lane);
+                } else {
+                    dp_fill<DP_NW32, false>(gv, slot, wsm, seq, V, L, a.sc, lane, 0, 1, nullptr);
+                    PHASE_CLK(PC_FILL)
+                    ok = dp_traceback<DP_NW32, false>(gv, slot, wsm, seq, V, L, a.sc, lane);
+                }
+                PHASE_CLK(PC_TRACEBACK)
                 if (probe == 2) { e_cells += (unsigned long long)(V + 1) * (L + 1); debug_stop = true; break; }
                 if (lane == 0) {
                     hdr[HDR_LAST_P16] = p16 ? 1u : 0u; hdr[HDR_LAST_V] = V; hdr[HDR_LAST_L] = L;
@@ -1548,6 +1645,7 @@ __global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, HGPU_MINBLOCKS) k_poa
                     __syncwarp();
                 }
                 if (ust != ST_OK) { st = ust; break; }
+                PHASE_CLK(PC_ADD)
                 if (probe == 3) { debug_stop = true; break; }
                 if (!w_toposort(gv, wsm, lane)) {          // too large for the shared-memory bitmaps / deep DFS: serial
                     ust = ST_OK;
@@ -1556,8 +1654,10 @@ __global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, HGPU_MINBLOCKS) k_poa
                     __syncwarp();
                     if (ust != ST_OK) { st = ust; break; }
                 }
+                PHASE_CLK(PC_TOPO)
                 if (probe == 4) { debug_stop = true; break; }
                 w_build_meta(gv, lane);
+                PHASE_CLK(PC_META)
                 if (probe == 5) { debug_stop = true; break; }
             }
             if (a.stop_round != 0xFFFFFFFFu) debug_stop = true;
@@ -1572,6 +1672,7 @@ __global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, HGPU_MINBLOCKS) k_poa
                 __syncwarp();
             }
         }
+        PHASE_CLK(PC_CONSENSUS)
         // publish
         unsigned long long pos = 0;
         if (lane == 0 && n_cons > 0) {
@@ -1592,7 +1693,9 @@ __global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, HGPU_MINBLOCKS) k_poa
             if (a.out_nodes) a.out_nodes[e] = *gv.n_nodes;
         }
         __syncwarp();
+        PHASE_CLK(PC_PUBLISH)
     }
+    PHASE_CLK_FLUSH(a)
     if (lane == 0 && a.stats) {
         atomicAdd(a.stats + 0, st_cells); atomicAdd(a.stats + 1, st_padded); atomicAdd(a.stats + 2, st_aln);
         atomicAdd(a.stats + 3, st_aln32); atomicAdd(a.stats + 4, st_bases);

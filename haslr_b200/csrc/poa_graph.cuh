@@ -60,6 +60,8 @@ struct GraphView {
     uint32_t* meta0;      // [ncap] by rank
     uint32_t* pred_off;   // [ncap+1] by rank, CSR into pred_rank
     uint32_t* pred_rank;  // [ecap]
+    uint32_t* sinks;      // [ncap] ranks of the nodes without out-edges, ascending (the traceback's end-cell candidates)
+    uint32_t* n_sinks;
     int32_t* aln_rank;    // [ncap] alignment, traceback order (last pair first): rank or -1
     int32_t* aln_pos;     // [ncap] sequence position or -1
     uint32_t* n_nodes;    // scalars of this edge
@@ -233,7 +235,7 @@ HGPU_HD bool g_toposort(GraphView& g, GraphScratch& s) {
 // Per-rank records for the DP kernel: code, sink flag, predecessor ranks in in-edge order.
 HGPU_HD void g_build_meta(GraphView& g) {
     const uint32_t N = *g.n_nodes;
-    uint32_t pe = 0;
+    uint32_t pe = 0, ns = 0;
     for (uint32_t r = 0; r < N; ++r) {
         uint32_t v = g.rank2node[r];
         const uint32_t base = g.code[v] | (g.out_head[v] == NIL ? META_SINK : 0u);
@@ -247,8 +249,10 @@ HGPU_HD void g_build_meta(GraphView& g) {
             ++np;
         }
         g.meta0[r] = meta_pack(base, r, np, d0, d1);
+        if (base & META_SINK) g.sinks[ns++] = r;
     }
     g.pred_off[N] = pe;
+    *g.n_sinks = ns;
 }
 
 // SPOA Graph::traverse_heaviest_bundle + branch_completion. Writes node ids of the consensus path into `out`

@@ -16,10 +16,10 @@ namespace {
 struct Store {
     std::vector<uint8_t> code, mark, check;
     std::vector<uint32_t> in_head, in_tail, out_head, aligned, e_begin, e_end, e_w, e_next_in, e_next_out, rank2node, node2rank,
-        meta0, pred_off, pred_rank, stack;
+        meta0, pred_off, pred_rank, stack, sinks;
     std::vector<int32_t> aln_rank, aln_pos, pred;
     std::vector<int64_t> score;
-    uint32_t n_nodes = 0, n_edges = 0, aln_len = 0;
+    uint32_t n_nodes = 0, n_edges = 0, aln_len = 0, n_sinks = 0;
     GraphView g; GraphScratch s;
     Store(uint32_t ncap, uint32_t ecap) {
         code.resize(ncap); mark.resize(ncap); check.resize(ncap);
@@ -34,7 +34,7 @@ struct Store {
         g.e_next_in = e_next_in.data(); g.e_next_out = e_next_out.data(); g.rank2node = rank2node.data();
         g.node2rank = node2rank.data(); g.meta0 = meta0.data(); g.pred_off = pred_off.data();
         g.pred_rank = pred_rank.data(); g.aln_rank = aln_rank.data(); g.aln_pos = aln_pos.data();
-        g.n_nodes = &n_nodes; g.n_edges = &n_edges; g.aln_len = &aln_len;
+        g.n_nodes = &n_nodes; g.n_edges = &n_edges; g.aln_len = &aln_len; sinks.resize(ncap); g.sinks = sinks.data(); g.n_sinks = &n_sinks;
         s.mark = mark.data(); s.check = check.data(); s.stack = stack.data(); s.stack_cap = (uint32_t)stack.size();
         s.score = score.data(); s.pred = pred.data();
     }
