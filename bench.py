@@ -31,6 +31,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 METRIC = "long_read_Mbases_per_s_through_backbone_POA"
 UNIT = "Mbases/s"
 N_EDGES, DEPTH, GAP_LEN = 200_000, 6, 1500
+DEEP_EDGES, DEEP_DEPTH, DEEP_GAP = 592, 28, 2500   # second shape: 4 edges per SM of BASELINE config 2's median edge
 ERR = (0.04, 0.03, 0.02)  # ins, del, sub
 SCORES = (5, -4, -8)       # Assemble.cpp:8-11
 
@@ -43,9 +44,11 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def gen_cfg3_torch(n_edges, seed, device, chunk=8192):
+def gen_cfg3_torch(n_edges, seed, device, chunk=8192, DEPTH=None, GAP_LEN=None):
     """Seeded cfg3 input generated on the GPU: per edge a random 1.5 kb truth and DEPTH noisy copies.
     Returns (bases uint8 cuda tensor, seg_off uint64 numpy, edge_seg_off uint32 numpy)."""
+    DEPTH = globals()["DEPTH"] if DEPTH is None else DEPTH
+    GAP_LEN = globals()["GAP_LEN"] if GAP_LEN is None else GAP_LEN
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(seed)
@@ -183,6 +186,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--edges", type=int, default=N_EDGES, help="edges per GPU (default: the cfg3 size; smaller values are for debugging only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-deep", action="store_true", help="skip the deep-edge (config 2 shape) leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -310,6 +314,35 @@ def main():
                 "kernel_ms_per_launch": kernel_ms / max(1, args.steps * klaunch), "launches_per_step": klaunch,
                 "algorithmic_bytes_per_launch": alg_bytes / max(1, args.steps * klaunch)}
 
+    # ---- second shape, reported beside the headline: deep edges as a real 25x dataset produces them (BASELINE config 2:
+    #      median 28 supporting reads over a 2.5 kb gap, graphs of ~10^4 nodes, most cells outside the plain int16 range)
+    deep = None
+    if world == 1 and not args.no_deep:
+        dd, dso, deo = gen_cfg3_torch(DEEP_EDGES, 77, dev, chunk=64, DEPTH=DEEP_DEPTH, GAP_LEN=DEEP_GAP)
+        dn = int(dso[-1])
+        dout = torch.empty(dn // DEEP_DEPTH * 2 + 4096, dtype=torch.uint8, device=dev)
+        for _ in range(2):
+            doff, dstat = ctx.poa_batch_dev(dd.data_ptr(), dso, deo, dout.data_ptr(), dout.numel(), *SCORES)
+        assert (dstat == 0).all(), f"deep edges: status {np.unique(dstat)}"
+        torch.cuda.synchronize()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for _ in range(2):
+            ctx.poa_batch_dev(dd.data_ptr(), dso, deo, dout.data_ptr(), dout.numel(), *SCORES)
+        d1.record(); torch.cuda.synchronize()
+        dst = ctx.poa_stats()
+        dms = d0.elapsed_time(d1) / 2
+        dchk = None
+        if not args.no_cpu:
+            rc, roff, _, _, _ = run_oracle_sample(dd.cpu().numpy(), dso, deo, 4, os.cpu_count() or 1)
+            assert np.array_equal(doff[:5], roff) and dout[: int(doff[4])].cpu().numpy().tobytes() == rc.tobytes(), "deep edges: consensus differs from the oracle"
+            dchk = "first 4 edges bit-exact vs oracle"
+        deep = {"workload": f"{DEEP_EDGES} edges x {DEEP_DEPTH} supporting reads x {DEEP_GAP} bp gap (BASELINE config 2 edge shape)",
+                "value": dn / (dms / 1e3) / 1e6, "unit": UNIT, "ms_per_step": dms, "gcups": dst["cells"] / (dms / 1e3) / 1e9,
+                "alignments": dst["alignments"], "alignments_rel16": dst["alignments_rel16"], "alignments_i32": dst["alignments_i32"],
+                "kernels": "k_poa_edges_deep (+ k_poa_edges_team for the largest)", "check": dchk}
+        del dd, dout
+
     # ---- CPU baseline: the oracle on a bounded sample of the same edges, all host cores
     cpu = None
     if not args.no_cpu:
@@ -331,7 +364,7 @@ def main():
                    "check": check},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
-        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "deep_edges": deep,
     }))
     if world > 1:
         dist.destroy_process_group()

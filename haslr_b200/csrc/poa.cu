@@ -4,6 +4,7 @@
 // instead of T threads pulling one edge each from a mutex-guarded cursor and calling SPOA, all edges of a call
 // are queued on the device and pulled by the warps of one persistent kernel (poa_device.cuh).
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -36,8 +37,17 @@ struct PoaState {
     bool have_result = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t stream2 = nullptr;   // the team kernel (few huge edges) runs beside the warp-per-edge kernel
+    static constexpr int NCS = 4;     // size classes whose arenas fit the budget together run side by side on these
+    cudaStream_t cstream[NCS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t cev[NCS] = {nullptr, nullptr, nullptr, nullptr};
     uint32_t cfg_team = 8;            // 0 disables the team kernel
     double cfg_team_min_cells = 2.0e8;
+    uint32_t cfg_teams_per_sm = 2;    // resident teams per SM (HGPU_TEAMS_PER_SM); the rest of the SM runs warp-per-edge blocks
+    double cfg_budget_frac = 0.88;    // share of the free device memory the arenas may take (HGPU_BUDGET_FRAC)
+    double cfg_team_div = 3000.0;     // an edge goes to the team kernel when it holds more than 1/cfg_team_div of the batch's cells (HGPU_TEAM_DIV)
+    uint32_t cfg_deep_min_reads = 10; // edges with at least this many supporting reads run in k_poa_edges_deep (HGPU_DEEP_MIN_READS)
+    int cfg_force = 0;                // HGPU_FORCE_MODE: 1 = every alignment in int32, 2 = every alignment in REL16 (tests)
+    int verbose = 0;                  // HGPU_VERBOSE=1: pass / class plan and per-launch device time on stderr
 };
 
 void poa_state_destroy(PoaState* s) {
@@ -47,6 +57,7 @@ void poa_state_destroy(PoaState* s) {
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->stream2) cudaStreamDestroy(s->stream2);
+    for (int i = 0; i < PoaState::NCS; ++i) { if (s->cstream[i]) cudaStreamDestroy(s->cstream[i]); if (s->cev[i]) cudaEventDestroy(s->cev[i]); }
     delete s;
 }
 
@@ -56,6 +67,12 @@ static PoaState* poa_state(hgpu_t* ctx) {
         // developer knobs (tests force the team kernel onto small inputs with these)
         if (const char* e = getenv("HGPU_TEAM")) ctx->poa->cfg_team = (uint32_t)atoi(e);
         if (const char* e = getenv("HGPU_TEAM_MIN_CELLS")) ctx->poa->cfg_team_min_cells = atof(e);
+        if (const char* e = getenv("HGPU_VERBOSE")) ctx->poa->verbose = atoi(e);
+        if (const char* e = getenv("HGPU_TEAM_DIV")) ctx->poa->cfg_team_div = std::max(1.0, atof(e));
+        if (const char* e = getenv("HGPU_TEAMS_PER_SM")) ctx->poa->cfg_teams_per_sm = (uint32_t)std::max(1, std::min(2, atoi(e)));
+        if (const char* e = getenv("HGPU_BUDGET_FRAC")) ctx->poa->cfg_budget_frac = std::max(0.1, std::min(0.92, atof(e)));
+        if (const char* e = getenv("HGPU_FORCE_MODE")) ctx->poa->cfg_force = atoi(e);
+        if (const char* e = getenv("HGPU_DEEP_MIN_READS")) ctx->poa->cfg_deep_min_reads = (uint32_t)atoi(e);
     }
     return ctx->poa;
 }
@@ -81,18 +98,18 @@ struct EdgeEst {
     uint64_t slot;       // score-matrix bytes needed (estimate)
     double cells;        // DP cells (estimate)
     uint32_t lmax;       // longest segment
+    bool deep;           // many supporting reads: the graph gets several times wider than the gap (k_poa_edges_deep)
 };
 
 // Node-count growth model: every later segment adds about `growth` new nodes per base (SURVEY.md §8(d):
 // |V| grows ~ L * (ins + sub) per read). growth >= 1 means the worst case (every base a new node).
-void estimate_edge(const uint32_t* len, uint32_t R, double growth, const DpScores& sc, bool force_i32, EdgeEst* out) {
+void estimate_edge(const uint32_t* len, uint32_t R, double growth, const DpScores& sc, int force, EdgeEst* out) {
     double V = len[0], cells = 0;
     uint64_t slot = 0;
     uint32_t lmax = len[0];
     for (uint32_t k = 1; k < R; ++k) {
         uint32_t Vi = (uint32_t)std::min<double>(V + 1.0, 4.0e9);
-        bool p16 = !force_i32 && dp_fits16(Vi, len[k], sc);
-        slot = std::max(slot, dp_slot_bytes(Vi, len[k], p16));
+        slot = std::max(slot, dp_slot_bytes(Vi, len[k], dp_mode(Vi, len[k], sc, force)));
         cells += (V + 1.0) * (len[k] + 1.0);
         // overhang beyond the graph's current span also becomes new nodes
         double over = len[k] > V ? (double)len[k] - V : 0.0;
@@ -164,13 +181,20 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
     if (S->cfg_max_warps) max_warps = std::min(max_warps, S->cfg_max_warps);
     if (opt.max_warps) max_warps = std::min(max_warps, opt.max_warps);
     max_warps = std::max<uint32_t>(DP_WARPS_PER_BLOCK, max_warps / DP_WARPS_PER_BLOCK * DP_WARPS_PER_BLOCK);
+    // the deep-edge kernel: a ring of parked rows per warp, fewer resident warps
+    int blocks_per_sm_deep = 0;
+    const size_t smem_deep = (size_t)DP_WARPS_PER_BLOCK * DP_SMEM_PER_WARP_DEEP;
+    HGPU_CUDA(ctx, cudaFuncSetAttribute(k_poa_edges_deep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_deep));
+    HGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm_deep, k_poa_edges_deep, 32 * DP_WARPS_PER_BLOCK, smem_deep));
+    if (blocks_per_sm_deep < 1) HGPU_FAIL(ctx, HGPU_E_INTERNAL, "k_poa_edges_deep cannot be resident");
+    uint32_t max_warps_deep = std::min<uint32_t>(max_warps, (uint32_t)ctx->sm_count * blocks_per_sm_deep * DP_WARPS_PER_BLOCK);
     uint64_t budget = S->cfg_arena_bytes;
     if (!budget) {
         size_t fr = 0, tot = 0;
         HGPU_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
         fr += S->arena.n + S->ws.n;   // what we already hold can be reused
-        budget = (uint64_t)(fr * 0.80);
-        budget = std::min<uint64_t>(budget, 96ull << 30);
+        budget = (uint64_t)(fr * S->cfg_budget_frac);
+        budget = std::min<uint64_t>(budget, 165ull << 30);
     }
 
     std::vector<uint32_t> pending(n_edges);
@@ -188,19 +212,21 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
             uint32_t e = pending[i];
             uint32_t R = e_off[e + 1] - e_off[e];
             est[i].edge = e;
+            est[i].deep = R >= S->cfg_deep_min_reads;
             if (R == 0) { est[i].ncap = 64; est[i].slot = 4096; est[i].cells = 0; est[i].lmax = 0; continue; }
-            estimate_edge(seg_len.data() + e_off[e], R, growth, sc, opt.force_i32 != 0, &est[i]);
+            estimate_edge(seg_len.data() + e_off[e], R, growth, sc, opt.force_i32, &est[i]);
             uint64_t sum = 0; uint32_t lmax = 0;
             for (uint32_t k = 0; k < R; ++k) { sum += seg_len[e_off[e] + k]; lmax = std::max(lmax, seg_len[e_off[e] + k]); }
             pool_cap += growth >= 1.0 ? sum : std::min<uint64_t>(sum, (uint64_t)(2.0 * lmax * (1.0 + growth)) + 256);
         }
         // ---- edges so large that one warp would be the tail of the whole pass go to the team kernel (a block per edge):
-        //      a lone warp fills ~2.4 G cells/s against ~1 T cells/s for the device, so "large" = more than 1/400 of the work
+        //      a lone warp on a deep graph sustains ~0.4 G cells/s (one dependent instruction stream, IPC 0.15: profiles/r1i_*)
+        //      against ~1 T cells/s for the device, so "large" = more than 1/3000 of the work (swept on BASELINE config 2)
         std::vector<EdgeEst> team;
         if (S->cfg_team >= 2 && opt.stop_round == 0xFFFFFFFFu) {
             double total = 0;
             for (const EdgeEst& x : est) total += x.cells;
-            const double thr = std::max(total / 400.0, S->cfg_team_min_cells);
+            const double thr = std::max(total / S->cfg_team_div, S->cfg_team_min_cells);
             std::vector<EdgeEst> rest;
             for (const EdgeEst& x : est) {
                 const bool wide = x.lmax >= 2u * (uint32_t)Geo<DP_NW16, true>::SW - 1;     // at least 3 stripes to spread
@@ -208,7 +234,8 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
             }
             est.swap(rest);
         }
-        auto by_size = [](const EdgeEst& a, const EdgeEst& b) {
+        auto by_size = [](const EdgeEst& a, const EdgeEst& b) {      // deep edges first, then by slot size, largest first
+            if (a.deep != b.deep) return a.deep;
             if (a.slot != b.slot) return a.slot > b.slot;
             return a.edge < b.edge;
         };
@@ -233,7 +260,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
             tslot = (tslot + 127) / 128 * 128;
             const WsLayout twl = ws_layout(nc, nc + nc / 4 + 64);
             const uint64_t tbudget = budget / 2;              // the other half stays with the warp-per-edge kernel
-            uint32_t teams = (uint32_t)std::min<uint64_t>({(uint64_t)team.size(), (uint64_t)ctx->sm_count * 3, tbudget / (tslot + twl.bytes)});
+            uint32_t teams = (uint32_t)std::min<uint64_t>({(uint64_t)team.size(), (uint64_t)ctx->sm_count * S->cfg_teams_per_sm, tbudget / (tslot + twl.bytes)});
             if (teams == 0) {
                 for (const EdgeEst& x : team) est.push_back(x);          // does not fit even once: let the classes report it
                 std::sort(est.begin(), est.end(), by_size);
@@ -251,7 +278,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
                 a.pool = pass->pool.p; a.pool_cap = pass->pool.n; a.pool_cursor = S->pool_cursor.p;
                 a.ws = S->ws_team.p; a.wl = twl; a.arena = S->arena_team.p; a.slot_bytes = tslot;
                 a.sc = sc; a.stats = S->stats.p; a.stop_round = opt.stop_round; a.force_i32 = opt.force_i32;
-                const size_t tsmem = (size_t)TEAM * DP_SMEM_PER_WARP + (TEAM + 4) * 4;
+                const size_t tsmem = (size_t)TEAM * DP_SMEM_PER_WARP_DEEP + (TEAM + 4) * 4;
                 HGPU_CUDA(ctx, cudaFuncSetAttribute(k_poa_edges_team<TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
                 HGPU_CUDA(ctx, cudaEventRecord(S->ev_fork, st));          // uploads and memsets above are on `st`
                 HGPU_CUDA(ctx, cudaStreamWaitEvent(S->stream2, S->ev_fork, 0));
@@ -260,15 +287,25 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
                 HGPU_CUDA(ctx, cudaEventRecord(S->ev_join, S->stream2));
                 ctx->launches++; S->st.dp_launches++;
                 team_launched = true;
+                if (S->verbose) {
+                    double tc = 0; for (const EdgeEst& x : team) tc += x.cells;
+                    fprintf(stderr, "[poa] attempt %d growth %.2f: team kernel %zu edges on %u teams, slot %.1f MB, ncap %u, %.3e cells (largest %.3e)\n",
+                            attempt, growth, team.size(), teams, tslot / 1048576.0, nc, tc, team[0].cells);
+                }
             }
         }
 
         // ---- size classes: a class ends where the slot estimate has halved, unless memory is no constraint
-        struct Cls { size_t a, b; uint64_t slot; WsLayout wl; uint32_t warps; };
+        struct Cls { size_t a, b; uint64_t slot; WsLayout wl; uint32_t warps; bool deep; };
         std::vector<Cls> classes;
+        size_t n_deep = 0;
+        while (n_deep < est.size() && est[n_deep].deep) ++n_deep;
         size_t i = 0;
         while (i < est.size()) {
-            Cls c; c.a = i; c.slot = (est[i].slot + 127) / 128 * 128;
+            const bool deep = i < n_deep;
+            const size_t end = deep ? n_deep : est.size();           // a class never mixes the two kernels
+            const uint32_t mw = deep ? max_warps_deep : max_warps;
+            Cls c; c.a = i; c.slot = (est[i].slot + 127) / 128 * 128; c.deep = deep;
             auto plan = [&](size_t a, size_t b, Cls& cc) {
                 uint32_t nc = 64;
                 for (size_t q = a; q < b; ++q) nc = std::max(nc, est[q].ncap);
@@ -276,13 +313,13 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
                 cc.wl = ws_layout(nc, ec);
                 uint64_t per = cc.slot + cc.wl.bytes;
                 uint64_t w = budget / per;
-                cc.warps = (uint32_t)std::min<uint64_t>(w, max_warps);
+                cc.warps = (uint32_t)std::min<uint64_t>(w, mw);
             };
-            plan(i, est.size(), c);
-            size_t j = est.size();
-            if (c.warps < max_warps) {
+            plan(i, end, c);
+            size_t j = end;
+            if (c.warps < mw) {
                 j = i + 1;
-                while (j < est.size() && est[j].slot * 2 > c.slot) ++j;
+                while (j < end && est[j].slot * 2 > c.slot) ++j;
                 plan(i, j, c);
             }
             c.b = j;
@@ -291,6 +328,12 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
         }
         if (classes.size() > 256) HGPU_FAIL(ctx, HGPU_E_INTERNAL, "too many size classes (%zu)", classes.size());
 
+        // ---- launches. A class is one persistent kernel with its own slots and workspaces; consecutive classes whose
+        //      memory fits the budget together form a wave and run side by side (each on its own stream), so a class of a
+        //      few huge edges does not hold the device alone. Waves follow each other on `st`.
+        struct Launch { size_t ci; uint32_t warps, blocks; uint64_t arena_off, ws_off; };
+        std::vector<std::vector<Launch>> waves(1);
+        uint64_t wave_a = 0, wave_w = 0, arena_need = 0, ws_need = 0;
         for (size_t ci = 0; ci < classes.size(); ++ci) {
             Cls& c = classes[ci];
             const uint32_t n_items = (uint32_t)(c.b - c.a);
@@ -302,34 +345,79 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
                 HGPU_CUDA(ctx, cudaStreamSynchronize(st));
                 continue;
             }
-            uint32_t warps = std::min<uint32_t>(c.warps, (n_items + 0) ? n_items : 1);
+            uint32_t warps = std::min<uint32_t>(c.warps, n_items ? n_items : 1);
             uint32_t blocks = (warps + DP_WARPS_PER_BLOCK - 1) / DP_WARPS_PER_BLOCK;
             warps = blocks * DP_WARPS_PER_BLOCK;
             if ((uint64_t)warps > c.warps && c.warps >= (uint32_t)DP_WARPS_PER_BLOCK) { blocks = c.warps / DP_WARPS_PER_BLOCK; warps = blocks * DP_WARPS_PER_BLOCK; }
-            HGPU_CUDA(ctx, S->arena.ensure((size_t)warps * c.slot));
-            HGPU_CUDA(ctx, S->ws.ensure((size_t)warps * c.wl.bytes));
-            S->st.arena_bytes = std::max<uint64_t>(S->st.arena_bytes, (uint64_t)warps * c.slot);
-            if (opt.stop_round != 0xFFFFFFFFu)   // debug inspection looks for the one workspace that holds a graph
-                HGPU_CUDA(ctx, cudaMemsetAsync(S->ws.p, 0, (size_t)warps * c.wl.bytes, st));
-            PoaArgs a{};
-            a.bases = d_bases; a.seg_ptr = S->seg_ptr.p; a.seg_len = S->seg_len.p; a.e_seg_off = S->e_seg_off.p;
-            a.items = S->items.p + c.a; a.n_items = n_items; a.counter = S->counters.p + ci;
-            a.status = S->status.p; a.cons_len = S->cons_len.p; a.cons_pos = S->cons_pos.p; a.out_nodes = S->out_nodes.p;
-            a.pool = pass->pool.p; a.pool_cap = pass->pool.n; a.pool_cursor = S->pool_cursor.p;
-            a.ws = S->ws.p; a.wl = c.wl; a.arena = S->arena.p; a.slot_bytes = c.slot;
-            S->last_wl = c.wl; S->last_slot = c.slot;
-            a.sc = sc; a.stats = S->stats.p; a.stop_round = opt.stop_round; a.force_i32 = opt.force_i32;
-#if HGPU_PHASE_CLOCKS
-            HGPU_CUDA(ctx, cudaMemsetAsync(S->stats.p + 8, 0, 16 * sizeof(unsigned long long), st));
-            a.phase_clk = S->stats.p + 8;
-#endif
-            if (const char* e = getenv("HGPU_PROBE")) { a.probe = (uint32_t)atoi(e); a.probe_round = 1; }
-            if (const char* e = getenv("HGPU_PROBE_ROUND")) a.probe_round = (uint32_t)atoi(e);
-            k_poa_edges<<<blocks, 32 * DP_WARPS_PER_BLOCK, smem, st>>>(a);
-            HGPU_CUDA(ctx, cudaGetLastError());
-            ctx->launches++; S->st.dp_launches++;
+            const uint64_t na = (uint64_t)warps * c.slot, nw = (uint64_t)warps * c.wl.bytes;
+            if (!waves.back().empty() && (wave_a + wave_w + na + nw > budget || waves.back().size() >= (size_t)PoaState::NCS)) {
+                waves.emplace_back(); wave_a = 0; wave_w = 0;
+            }
+            waves.back().push_back({ci, warps, blocks, wave_a, wave_w});
+            wave_a += na; wave_w += nw;
+            arena_need = std::max(arena_need, wave_a); ws_need = std::max(ws_need, wave_w);
         }
-        if (team_launched) HGPU_CUDA(ctx, cudaStreamWaitEvent(st, S->ev_join, 0));
+        HGPU_CUDA(ctx, S->arena.ensure(arena_need));
+        HGPU_CUDA(ctx, S->ws.ensure(ws_need));
+        S->st.arena_bytes = std::max<uint64_t>(S->st.arena_bytes, arena_need);
+        for (size_t wi = 0; wi < waves.size(); ++wi) {
+            const std::vector<Launch>& wave = waves[wi];
+            if (wave.empty()) continue;
+            const bool side_by_side = wave.size() > 1;
+            cudaEvent_t vb = nullptr, ve = nullptr;
+            if (S->verbose) { cudaEventCreate(&vb); cudaEventCreate(&ve); cudaEventRecord(vb, st); }
+            if (side_by_side) HGPU_CUDA(ctx, cudaEventRecord(S->ev_fork, st));
+            for (size_t li = 0; li < wave.size(); ++li) {
+                const Launch& ln = wave[li];
+                Cls& c = classes[ln.ci];
+                const uint32_t n_items = (uint32_t)(c.b - c.a);
+                cudaStream_t ls = side_by_side ? S->cstream[li] : st;
+                if (side_by_side) HGPU_CUDA(ctx, cudaStreamWaitEvent(ls, S->ev_fork, 0));
+                if (opt.stop_round != 0xFFFFFFFFu)   // debug inspection looks for the one workspace that holds a graph
+                    HGPU_CUDA(ctx, cudaMemsetAsync(S->ws.p + ln.ws_off, 0, (size_t)ln.warps * c.wl.bytes, ls));
+                PoaArgs a{};
+                a.bases = d_bases; a.seg_ptr = S->seg_ptr.p; a.seg_len = S->seg_len.p; a.e_seg_off = S->e_seg_off.p;
+                a.items = S->items.p + c.a; a.n_items = n_items; a.counter = S->counters.p + ln.ci;
+                a.status = S->status.p; a.cons_len = S->cons_len.p; a.cons_pos = S->cons_pos.p; a.out_nodes = S->out_nodes.p;
+                a.pool = pass->pool.p; a.pool_cap = pass->pool.n; a.pool_cursor = S->pool_cursor.p;
+                a.ws = S->ws.p + ln.ws_off; a.wl = c.wl; a.arena = S->arena.p + ln.arena_off; a.slot_bytes = c.slot;
+                S->last_wl = c.wl; S->last_slot = c.slot;
+                a.sc = sc; a.stats = S->stats.p; a.stop_round = opt.stop_round; a.force_i32 = opt.force_i32;
+#if HGPU_PHASE_CLOCKS
+                HGPU_CUDA(ctx, cudaMemsetAsync(S->stats.p + 8, 0, 16 * sizeof(unsigned long long), ls));
+                a.phase_clk = S->stats.p + 8;
+#endif
+                if (const char* e = getenv("HGPU_PROBE")) { a.probe = (uint32_t)atoi(e); a.probe_round = 1; }
+                if (const char* e = getenv("HGPU_PROBE_ROUND")) a.probe_round = (uint32_t)atoi(e);
+                if (c.deep) k_poa_edges_deep<<<ln.blocks, 32 * DP_WARPS_PER_BLOCK, smem_deep, ls>>>(a);
+                else k_poa_edges<<<ln.blocks, 32 * DP_WARPS_PER_BLOCK, smem, ls>>>(a);
+                HGPU_CUDA(ctx, cudaGetLastError());
+                ctx->launches++; S->st.dp_launches++;
+                if (side_by_side) {
+                    HGPU_CUDA(ctx, cudaEventRecord(S->cev[li], ls));
+                    HGPU_CUDA(ctx, cudaStreamWaitEvent(st, S->cev[li], 0));
+                }
+                if (S->verbose) {
+                    double cc = 0, cmax = 0; for (size_t q = c.a; q < c.b; ++q) { cc += est[q].cells; cmax = std::max(cmax, est[q].cells); }
+                    fprintf(stderr, "[poa] attempt %d growth %.2f wave %zu/%zu class %zu/%zu%s: %u edges on %u warps, slot %.1f MB, ws %.1f MB, %.3e cells (largest edge %.3e)\n",
+                            attempt, growth, wi, waves.size(), ln.ci, classes.size(), c.deep ? " (deep)" : "", n_items, ln.warps, c.slot / 1048576.0, c.wl.bytes / 1048576.0, cc, cmax);
+                }
+            }
+            if (S->verbose) {
+                cudaEventRecord(ve, st); cudaEventSynchronize(ve);
+                float ms = 0; cudaEventElapsedTime(&ms, vb, ve);
+                fprintf(stderr, "[poa] wave %zu: %.1f ms\n", wi, ms);
+                cudaEventDestroy(vb); cudaEventDestroy(ve);
+            }
+        }
+        if (team_launched) {
+            HGPU_CUDA(ctx, cudaStreamWaitEvent(st, S->ev_join, 0));
+            if (S->verbose) {
+                const auto t0 = std::chrono::steady_clock::now();
+                cudaStreamSynchronize(st);
+                fprintf(stderr, "[poa] team kernel outlasted the classes by %.1f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+            }
+        }
         if (S->timing) {
             HGPU_CUDA(ctx, cudaEventRecord(S->ev1, st));
             HGPU_CUDA(ctx, cudaEventSynchronize(S->ev1));
@@ -364,7 +452,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
         fprintf(stderr, "\n");
     }
 #endif
-    S->st.cells = sth[0]; S->st.cells_padded = sth[1]; S->st.alignments = sth[2]; S->st.alignments_i32 = sth[3]; S->st.bases_in = sth[4];
+    S->st.cells = sth[0]; S->st.cells_padded = sth[1]; S->st.alignments = sth[2]; S->st.alignments_i32 = sth[3] & 0xFFFFFFFFull; S->st.alignments_rel16 = sth[3] >> 32; S->st.bases_in = sth[4];
     return HGPU_OK;
 }
 
@@ -402,6 +490,10 @@ static int poa_prepare(hgpu_t* ctx, const uint64_t* seg_off, const uint32_t* edg
         HGPU_CUDA(ctx, cudaEventCreate(&S->ev0)); HGPU_CUDA(ctx, cudaEventCreate(&S->ev1));
         HGPU_CUDA(ctx, cudaEventCreateWithFlags(&S->ev_fork, cudaEventDisableTiming)); HGPU_CUDA(ctx, cudaEventCreateWithFlags(&S->ev_join, cudaEventDisableTiming));
         HGPU_CUDA(ctx, cudaStreamCreateWithFlags(&S->stream2, cudaStreamNonBlocking));
+        for (int i = 0; i < PoaState::NCS; ++i) {
+            HGPU_CUDA(ctx, cudaStreamCreateWithFlags(&S->cstream[i], cudaStreamNonBlocking));
+            HGPU_CUDA(ctx, cudaEventCreateWithFlags(&S->cev[i], cudaEventDisableTiming));
+        }
     }
     return HGPU_OK;
 }
@@ -414,7 +506,8 @@ extern "C" int hgpu_poa_batch_dev(hgpu_t* ctx, const uint8_t* d_bases, const uin
     PoaState* S = poa_state(ctx);
     DpScores sc; make_scores(ctx, match, mismatch, gap, &sc);
     std::vector<uint32_t> status_h, len_h;
-    rc = poa_run(ctx, d_bases, seg_off, edge_seg_off, n_edges, sc, PoaRunOpts(), status_h, len_h);
+    PoaRunOpts ropt; ropt.force_i32 = S->cfg_force;
+    rc = poa_run(ctx, d_bases, seg_off, edge_seg_off, n_edges, sc, ropt, status_h, len_h);
     if (rc) return rc;
     for (uint32_t e = 0; e < n_edges; ++e) out_status[e] = status_h[e];
     uint64_t total = 0;
@@ -561,7 +654,7 @@ extern "C" int hgpu_poa_debug(hgpu_t* ctx, const uint8_t* bases, const uint64_t*
     if (node_code) for (uint32_t i = 0; i < N; ++i) node_code[i] = (uint8_t)"ACGT"[g.code[i]];
     if (lens.size() <= n_prior) return HGPU_OK;      // graph only
     const uint32_t V = hdr[HDR_LAST_V], L = hdr[HDR_LAST_L];
-    const bool p16 = hdr[HDR_LAST_P16] != 0;
+    const int mode = (int)hdr[HDR_LAST_P16];
     const int bias = (int)hdr[HDR_LAST_BIAS];
     sizes->L = L;
     const uint32_t n = *g.aln_len;
@@ -580,7 +673,8 @@ extern "C" int hgpu_poa_debug(hgpu_t* ctx, const uint8_t* bases, const uint64_t*
         DevBuf<int32_t> dH;
         HGPU_CUDA(ctx, dH.alloc(cells));
         uint8_t* slot_p = S->arena.p + (uint64_t)w * slot;
-        if (p16) k_poa_dump_H<DP_NW16, true><<<ctx->sm_count * 4, 256, 0, st>>>(slot_p, V, L, bias, sc.g, dH.p);
+        if (mode == DPM_ABS16) k_poa_dump_H<DP_NW16, true><<<ctx->sm_count * 4, 256, 0, st>>>(slot_p, V, L, bias, sc.g, dH.p);
+        else if (mode == DPM_REL16) k_poa_dump_H<DP_NW16, true, true><<<ctx->sm_count * 4, 256, 0, st>>>(slot_p, V, L, 0, sc.g, dH.p);
         else k_poa_dump_H<DP_NW32, false><<<ctx->sm_count * 4, 256, 0, st>>>(slot_p, V, L, bias, sc.g, dH.p);
         HGPU_CUDA(ctx, cudaGetLastError());
         ctx->launches++;

@@ -160,10 +160,34 @@ static constexpr int DP_NW32 = 8;   // int32 kernel:  8 columns per lane, 256-co
 #define HGPU_RING 0
 #endif
 static constexpr int DP_SMEM_PER_WARP = 6272;  // int16 fill: profile 4 KB + frame 128 B + two parked rows 2 KB; reused by the traceback tile (4384 B) and the sort bitmaps
+// Deep edges (tens of supporting reads) have graphs several times wider than the gap: most ranks read predecessor rows 2-8
+// ranks back. Their kernel (k_poa_edges_deep, and the team kernel) parks EVERY row in a ring of DP_RING_DEEP rows in shared
+// memory, so those reads never leave the SM; a lone warp otherwise waits a full L2 round trip per predecessor row.
+static constexpr int DP_RING_DEEP = 8;
+static constexpr int DP_SMEM_PER_WARP_DEEP = 4096 + 128 + DP_RING_DEEP * 1024;
 static constexpr int DP_WARPS_PER_BLOCK = 4;
 
-__host__ __device__ inline uint64_t dp_slot_bytes(uint32_t V, uint32_t L, bool p16) {
-    return p16 ? Geo<DP_NW16, true>::slot_bytes(V, L) : Geo<DP_NW32, false>::slot_bytes(V, L);
+// Cell encodings of a stored score matrix. ABS16: int16 Hhat + bias, when the whole range 13(L+1) + 8(V+2) fits.
+// REL16: int16 relative to the row's own value at the left edge of the stripe (kept as int32 in the boundary-column
+// arrays) - Hhat never decreases along a row, so the in-stripe range is [0, hi_step * 512] whatever V and L are; rows
+// are re-based by (base of predecessor row - base of this row) <= -gap when they are combined. I32: plain int32, for
+// scores the packed arithmetic cannot hold (and on request, for tests).
+enum : int { DPM_I32 = 0, DPM_ABS16 = 1, DPM_REL16 = 2 };
+static constexpr int REL_CLAMP = -16000;             // a re-base below this can never win against the row's own cells (>= 0)
+__host__ __device__ inline bool dp_rel_ok(const DpScores& sc) {
+    return sc.hi_step < (1 << 19) && (int64_t)sc.hi_step * (32 * 2 * DP_NW16) + (int64_t)sc.lo_step + 1024 < -(int64_t)REL_CLAMP;
+}
+// force: 0 = pick, 1 = int32, 2 = REL16 even where ABS16 would fit (tests)
+__host__ __device__ inline int dp_mode(uint32_t V, uint32_t L, const DpScores& sc, int force) {
+    if (force == 1 || sc.hi_step >= (1 << 19)) return DPM_I32;
+    if (force == 2 && dp_rel_ok(sc)) return DPM_REL16;
+    if (dp_fits16(V, L, sc)) return DPM_ABS16;
+    return dp_rel_ok(sc) ? DPM_REL16 : DPM_I32;
+}
+__host__ __device__ inline uint64_t dp_slot_bytes(uint32_t V, uint32_t L, int mode) {
+    if (mode == DPM_I32) return Geo<DP_NW32, false>::slot_bytes(V, L);
+    // REL16 keeps one more boundary array: the bases of stripe 0 (column 0 of every row)
+    return Geo<DP_NW16, true>::slot_bytes(V, L) + (mode == DPM_REL16 ? ((uint64_t)(V + 1) * 4 + 15) / 16 * 16 : 0);
 }
 
 struct PoaArgs {
@@ -198,11 +222,11 @@ struct PoaArgs {
 
 __device__ __forceinline__ uint32_t pack2(int v) { return ((uint32_t)v & 0xFFFFu) * 0x10001u; }
 
-template <int NW, bool P16>
+template <int NW, bool P16, bool REL = false>
 struct SlotView {
     using G = Geo<NW, P16>;
     uint32_t* H;       // score words
-    int32_t* bcol;     // [NS][V+1] last column of each stripe (stored space)
+    int32_t* bcol;     // [NS][V+1] last column of each stripe (stored space); REL: [NS+1][V+1] row bases per stripe (Hhat, int32)
     uint32_t V, L, NS;
     __device__ __forceinline__ void bind(uint8_t* slot, uint32_t V_, uint32_t L_) {
         V = V_; L = L_; NS = G::stripes(L_);
@@ -217,7 +241,7 @@ struct SlotView {
         uint32_t s = j / G::SW, jj = j - s * G::SW, ln = jj / G::CPL, c = jj - ln * G::CPL;
         uint32_t k = P16 ? (c & (uint32_t)(NW - 1)) : c;      // P16: word k = columns k (low half) and k+NW (high half)
         uint32_t w = H[(((uint64_t)i * NS + s) * G::UNITS + (k >> 2)) * 128 + ln * 4 + (k & 3)];
-        if (P16) return (c >= (uint32_t)NW) ? (int)(int16_t)(w >> 16) : (int)(int16_t)(w & 0xFFFFu);
+        if (P16) return ((c >= (uint32_t)NW) ? (int)(int16_t)(w >> 16) : (int)(int16_t)(w & 0xFFFFu)) + (REL ? bcol[(uint64_t)s * (V + 1) + i] : 0);
         return (int)w;
     }
 };
@@ -605,6 +629,8 @@ struct Row16State {
     uint64_t dst;            // slot address of this lane's first unit of row i
     uint32_t bcx;            // batch register: lane q holds the boundary value of row r0+q+1 in the stripe to the left
     uint32_t bco;            // batch register: lane q collects the last cell of row r0+q+1 (boundary for the next stripe)
+    uint32_t npk, pk0, pk1;  // RING > 2, batch registers: lane q holds the predecessor count (0xFF: walk the CSR) and up to four rank
+                             // distances (16 bits each) of a row r0+q+1 whose record says "walk the CSR", fetched for 32 rows at once
     int lane; bool has_prev, has_next;
 };
 static constexpr uint32_t FILL16_PARKED = 128;      // byte offset of the parked rows behind the frame
@@ -618,6 +644,11 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
     return v;
 }
 
+// REL (DPM_REL16): cells are relative to the row's own base; diag_in / carry_in then carry the BASES (int32 Hhat) of
+// row i-1 and row i, predecessor rows are re-based on the fly and the left boundary of a row is its re-base itself.
+// RING: rows parked in shared memory. 2 = rows i-1 / i-2 by parity, parked only when `save` says a later row needs them;
+// more = a ring of the last RING rows, every row parked.
+template <bool REL, int RING>
 __device__ __forceinline__ void row16(uint32_t (&A)[8], Row16State& S, uint32_t m0, int q, uint32_t i,
                                       int diag_in, int carry_in, bool save) {
     using F = Fill16;
@@ -631,17 +662,64 @@ __device__ __forceinline__ void row16(uint32_t (&A)[8], Row16State& S, uint32_t 
     uint32_t np = npc == 0 ? 1u : npc, cs = 0;
     unsigned long long prank = 0;
     bool has1 = fast || (npc != 3 && npc != 0 && (meta_d0(m0) == 1 || (npc == 2 && meta_d1(m0) == 1)));
+    uint32_t pd01 = 0, pd23 = 0;
+    bool packed = false;                                            // RING > 2: the row's CSR distances came with the batch
     if (npc == 3) {
-        const unsigned long long poff = lds_u64(S.frame + FRAME16(pred_off));
-        prank = lds_u64(S.frame + FRAME16(pred_rank));
-        cs = ldg_u32(poff, i - 1);
-        np = ldg_u32(poff, i) - cs;
-        for (uint32_t x = 0; x < np; ++x) has1 = has1 || ldg_u32(prank, cs + x) + 2 == i;
+        if (RING > 2) {
+            const uint32_t k = __shfl_sync(FULL, S.npk, q);
+            if (k != 0xFFu) {
+                packed = true; np = k;
+                pd01 = __shfl_sync(FULL, S.pk0, q); pd23 = __shfl_sync(FULL, S.pk1, q);
+                has1 = (pd01 & 0xFFFFu) == 1u || (np > 1 && (pd01 >> 16) == 1u) || (np > 2 && (pd23 & 0xFFFFu) == 1u) || (np > 3 && (pd23 >> 16) == 1u);
+            }
+        }
+        if (!packed) {
+            const unsigned long long poff = lds_u64(S.frame + FRAME16(pred_off));
+            prank = lds_u64(S.frame + FRAME16(pred_rank));
+            cs = ldg_u32(poff, i - 1);
+            np = ldg_u32(poff, i) - cs;
+            for (uint32_t x = 0; x < np; ++x) has1 = has1 || ldg_u32(prank, cs + x) + 2 == i;
+        }
     }
-    const uint32_t hs0 = F::left_word(A, diag_in, lane);
-    if (save) {
-        sts_v4(parked + ((i - 1) & 1u) * 1024u, A[0], A[1], A[2], A[3]);
-        sts_v4(parked + ((i - 1) & 1u) * 1024u + 512u, A[4], A[5], A[6], A[7]);
+    auto dist_of = [&](uint32_t x) -> uint32_t {                    // rank distance to the x-th predecessor row
+        if (npc == 3) {
+            if (RING > 2 && packed) return ((x < 2 ? pd01 : pd23) >> ((x & 1u) * 16u)) & 0xFFFFu;
+            return i - (ldg_u32(prank, cs + x) + 1);
+        }
+        if (npc == 0) return i;                                     // no predecessor: the virtual row 0
+        return x == 0 ? meta_d0(m0) : meta_d1(m0);
+    };
+    if (REL && !S.has_prev) {
+        // stripe 0: the row's base is its own column 0, Hhat[i][0] = gap + max over the predecessors' bases; it is laid down
+        // here, row by row (lane q of bcx keeps it for the rows of this batch, the batch end stores it for later ones)
+        int best = diag_in;
+        if (!fast) {
+            best = INT32_MIN;
+            for (uint32_t x = 0; x < np; ++x) {
+                const uint32_t dist = dist_of(x);
+                int b = diag_in;
+                if (dist != 1) {
+                    const int ql = q - (int)dist;
+                    b = ql >= 0 ? __shfl_sync(FULL, (int)S.bcx, ql & 31) : (int)ldg_u32(lds_u64(S.frame + FRAME16(bc_prev)), i - dist);
+                }
+                best = max(best, b);
+            }
+        }
+        carry_in = best + (int)(int16_t)(g2 & 0xFFFFu);
+        if (lane == q) S.bcx = (uint32_t)carry_in;
+    }
+    uint32_t hs0 = 0;
+    if (!REL) hs0 = F::left_word(A, diag_in, lane);
+    if (RING > 2 || save) {
+        sts_v4(parked + ((i - 1) & (uint32_t)(RING - 1)) * 1024u, A[0], A[1], A[2], A[3]);
+        sts_v4(parked + ((i - 1) & (uint32_t)(RING - 1)) * 1024u + 512u, A[4], A[5], A[6], A[7]);
+    }
+    if (REL && has1) {                                              // row i-1 into this row's frame
+        const int d1 = max(diag_in - carry_in, REL_CLAMP);
+        const uint32_t d2 = pack2(d1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) A[k] = __vadd2(A[k], d2);
+        hs0 = F::left_word(A, S.has_prev ? d1 : F::G::NEGV, lane);
     }
     const uint4 p0 = lds_v4(pf), p1 = lds_v4(pf + 512u);           // the row's profile: scores of the node base against the lane's 16 columns
     // ---- row i-1 (registers): diagonal and vertical moves, in place
@@ -662,23 +740,28 @@ __device__ __forceinline__ void row16(uint32_t (&A)[8], Row16State& S, uint32_t 
     if (!fast) {
 #pragma unroll 1
         for (uint32_t x = 0; x < np; ++x) {
-            uint32_t dist;                                          // rank distance to this predecessor row
-            if (npc == 3) dist = i - (ldg_u32(prank, cs + x) + 1);
-            else if (npc == 0) dist = i;                            // no predecessor: the virtual row 0
-            else dist = x == 0 ? meta_d0(m0) : meta_d1(m0);
+            const uint32_t dist = dist_of(x);
             if (dist == 1) continue;
             int bl = F::G::NEGV;                                    // Hhat[i - dist][first column of the stripe - 1]
-            if (S.has_prev) {
+            if (REL || S.has_prev) {
                 const int ql = q - (int)dist;                       // bcx lane that holds row i - dist
                 bl = ql >= 0 ? __shfl_sync(FULL, (int)S.bcx, ql & 31) : (int)ldg_u32(lds_u64(S.frame + FRAME16(bc_prev)), i - dist);
             }
-            const bool near = dist == 2;
+            const bool near = RING > 2 ? dist <= (uint32_t)RING : dist == 2;
             uint4 s0, s1;
-            if (near) {                                             // parked row i-2
-                s0 = lds_v4(parked + (i & 1u) * 1024u); s1 = lds_v4(parked + (i & 1u) * 1024u + 512u);
+            if (near) {                                             // a parked row (RING 2: row i-2)
+                const uint32_t pa = parked + ((i - dist) & (uint32_t)(RING - 1)) * 1024u;
+                s0 = lds_v4(pa); s1 = lds_v4(pa + 512u);
             } else {                                                // a far row (3.6 % of rows): back from the slot
                 const uint64_t src = S.dst - (uint64_t)dist * S.row_bytes;
                 s0 = ldg_v4(src, 0); s1 = ldg_v4(src, 1);
+            }
+            if (REL) {                                              // bl is that row's base: re-base its cells, its boundary is the re-base
+                const int dp = max(bl - carry_in, REL_CLAMP);
+                const uint32_t d2 = pack2(dp);
+                s0.x = __vadd2(s0.x, d2); s0.y = __vadd2(s0.y, d2); s0.z = __vadd2(s0.z, d2); s0.w = __vadd2(s0.w, d2);
+                s1.x = __vadd2(s1.x, d2); s1.y = __vadd2(s1.y, d2); s1.z = __vadd2(s1.z, d2); s1.w = __vadd2(s1.w, d2);
+                bl = S.has_prev ? dp : F::G::NEGV;
             }
             uint32_t left = __shfl_up_sync(FULL, s1.w, 1);
             if (lane == 0) left = (uint32_t)bl << 16;
@@ -694,6 +777,8 @@ __device__ __forceinline__ void row16(uint32_t (&A)[8], Row16State& S, uint32_t 
     // Across lanes the exclusive prefix is needed. Lane totals almost always rise up to the lane holding the row
     // maximum and everything right of it inherits that maximum, so: neighbour total (1 SHFL) + row maximum (1 REDUX)
     // + two ballots decide the common case exactly; any violation falls back to the 5-step scan.
+    const int row_base = carry_in;                                  // REL only
+    if (REL) carry_in = S.has_prev ? 0 : F::G::NEGV;                // the cell left of the stripe is the base itself
     const int nbv = __shfl_up_sync(FULL, tot, 1);
     const int rowmax = __reduce_max_sync(FULL, tot);
     const int prevv = (lane == 0) ? carry_in : nbv;
@@ -721,7 +806,7 @@ __device__ __forceinline__ void row16(uint32_t (&A)[8], Row16State& S, uint32_t 
     S.dst += S.row_bytes;
     if (S.has_next) {
         const uint32_t last = __shfl_sync(FULL, A[7], 31);
-        if (lane == q) S.bco = (uint32_t)((int32_t)last >> 16);
+        if (lane == q) S.bco = (uint32_t)(((int32_t)last >> 16) + (REL ? row_base : 0));
     }
 }
 
@@ -756,7 +841,7 @@ __device__ __noinline__ void fill16_profile(uint32_t* prof, const FillFrame16* f
 
 // The fill of one alignment. Everything that is not needed row by row (graph arrays, slot geometry, the sequence, the
 // scores) is parked in the shared-memory frame first, so the row loop keeps its working set in registers.
-template <bool TEAM>
+template <bool TEAM, bool REL = false, int RING = 2>
 __device__ __noinline__ bool dp_fill16(const uint32_t* meta0, const uint32_t* pred_off, const uint32_t* pred_rank, uint8_t* slot, uint8_t* wsm,
                                        const uint8_t* seq, uint32_t V, uint32_t L, int sm, int sx, int gap, int bias, int lane,
                                        uint32_t trank, uint32_t tsize, volatile uint32_t* vprog) {
@@ -792,8 +877,13 @@ __device__ __noinline__ bool dp_fill16(const uint32_t* meta0, const uint32_t* pr
         {
             const unsigned long long bcol = lds_u64(S.frame + FRAME16(bcol));
             if (lane == 0) {
-                frame->bc_prev = s > 0 ? bcol + 4ull * (s - 1) * (Vs + 1) : 0ull;
-                frame->bc_cur = bcol + 4ull * s * (Vs + 1);
+                if (REL) {                                          // array s = bases of stripe s, array s+1 = bases of the next one
+                    frame->bc_prev = bcol + 4ull * s * (Vs + 1);
+                    frame->bc_cur = bcol + 4ull * (s + 1) * (Vs + 1);
+                } else {
+                    frame->bc_prev = s > 0 ? bcol + 4ull * (s - 1) * (Vs + 1) : 0ull;
+                    frame->bc_cur = bcol + 4ull * s * (Vs + 1);
+                }
             }
         }
         __syncwarp();
@@ -812,6 +902,7 @@ __device__ __noinline__ bool dp_fill16(const uint32_t* meta0, const uint32_t* pr
             stg_cs_v4_512(S.dst, b2, b2, b2, b2);
             S.dst += S.row_bytes;
             if (lane == 31) asm volatile("st.global.u32 [%0], %1;" :: "l"(lds_u64(S.frame + FRAME16(bc_cur))), "r"(lds_u32v(S.frame + FRAME16(bias))) : "memory");
+            if (REL && s == 0 && lane == 0) asm volatile("st.global.u32 [%0], %1;" :: "l"(lds_u64(S.frame + FRAME16(bc_prev))), "r"(0) : "memory");   // base of row 0
         }
         if (TEAM) team_publish(vprog, trank, s * (Vs + 1) + 1, lane);
 
@@ -822,6 +913,7 @@ __device__ __noinline__ bool dp_fill16(const uint32_t* meta0, const uint32_t* pr
             if (TEAM && !team_wait(vprog, (trank + tsize - 1) % tsize, (s - 1) * (Vs + 1) + 1, lane)) sync_ok = false;
             diag = (int)ldg_u32(lds_u64(S.frame + FRAME16(bc_prev)), 0);
         }
+        if (REL) diag = 0;                                            // base of row 0
 #pragma unroll 1
         for (uint32_t r0 = 0; r0 < Vs; r0 += 32) {
             const uint32_t rr = r0 + lane;
@@ -833,20 +925,40 @@ __device__ __noinline__ bool dp_fill16(const uint32_t* meta0, const uint32_t* pr
                     if (!team_wait(vprog, (trank + tsize - 1) % tsize, (s - 1) * (Vs + 1) + need_rows, lane)) sync_ok = false;
                 }
                 S.bcx = (rr < Vs) ? ldg_u32(lds_u64(S.frame + FRAME16(bc_prev)), rr + 1) : 0u;
+            } else if (REL) {
+                S.bcx = 0u;                 // stripe 0: the bases are produced by the rows themselves
+            }
+            if (RING > 2) {                 // rows that "walk the CSR": count and distances of up to four predecessors, 32 rows at once
+                S.npk = 0xFFu; S.pk0 = 0u; S.pk1 = 0u;
+                if (rr < Vs && ((mm0 >> 3) & 3u) == 3u) {
+                    const unsigned long long poff = lds_u64(S.frame + FRAME16(pred_off)), prk = lds_u64(S.frame + FRAME16(pred_rank));
+                    const uint32_t c0 = ldg_u32(poff, rr), n = ldg_u32(poff, rr + 1) - c0;
+                    if (n <= 4u) {
+                        uint32_t d[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                        for (uint32_t x = 0; x < 4u; ++x) if (x < n) d[x] = rr - ldg_u32(prk, c0 + x);
+                        if ((d[0] | d[1] | d[2] | d[3]) <= 0xFFFFu) { S.npk = n; S.pk0 = d[0] | (d[1] << 16); S.pk1 = d[2] | (d[3] << 16); }
+                    }
+                }
             }
             const int nb = (Vs - r0) < 32u ? (int)(Vs - r0) : 32;
             // bit q of save_mask: row r0+q+1 parks row r0+q in B before overwriting it, because row r0+q+2 reads two ranks back
-            const uint32_t save_mask = __ballot_sync(FULL, meta_reads_two_back(mm0)) >> 1;
+            const uint32_t save_mask = RING == 2 ? __ballot_sync(FULL, meta_reads_two_back(mm0)) >> 1 : 0u;
 #pragma unroll 1
             for (int q = 0; q < nb; ++q) {
                 const uint32_t m0 = __shfl_sync(FULL, mm0, q);
                 int carry = G::NEGV;
-                if (S.has_prev) carry = __shfl_sync(FULL, (int)S.bcx, q);
+                if (REL || S.has_prev) carry = __shfl_sync(FULL, (int)S.bcx, q);
                 bool save = ((save_mask >> q) & 1u) != 0;
-                if (q == 31) save = (__ballot_sync(FULL, rr + 32 < Vs && meta_reads_two_back(nm0)) & 1u) != 0;   // first row of the next batch
-                row16(A, S, m0, q, r0 + q + 1, diag, carry, save);
-                diag = carry;
+                if (RING == 2 && q == 31) save = (__ballot_sync(FULL, rr + 32 < Vs && meta_reads_two_back(nm0)) & 1u) != 0;   // first row of the next batch
+                row16<REL, RING>(A, S, m0, q, r0 + q + 1, diag, carry, save);
+                diag = (REL && !S.has_prev) ? __shfl_sync(FULL, (int)S.bcx, q) : carry;      // base of the row just done
             }
+            if (REL && !S.has_prev && lane < nb) {
+                const unsigned long long bp = lds_u64(S.frame + FRAME16(bc_prev));
+                asm volatile("st.global.u32 [%0], %1;" :: "l"(bp + 4ull * (rr + 1)), "r"(S.bcx) : "memory");
+            }
+            if (REL && !S.has_prev) __syncwarp();                     // later rows read these through other lanes' loads
             if (S.has_next && lane < nb) {
                 const unsigned long long bc = lds_u64(S.frame + FRAME16(bc_cur));
                 asm volatile("st.global.u32 [%0], %1;" :: "l"(bc + 4ull * (rr + 1)), "r"(S.bco) : "memory");
@@ -870,22 +982,22 @@ __device__ __noinline__ bool dp_fill16(const uint32_t* meta0, const uint32_t* pr
 // plus the first move of another kind. Only rows with three or more predecessors, or predecessors outside the
 // tile, take the one-lane generic step.
 // ---------------------------------------------------------------------------------------------------------
-template <int NW, bool P16>
+template <int NW, bool P16, bool REL = false>
 struct TbTile {
     using G = Geo<NW, P16>;
     static constexpr int NG = (TB_COLS + G::CPL - 2) / G::CPL + 1;        // column groups a 32-column window can touch (3 / 5)
     static constexpr int LDW = NG * NW + 4;                               // row stride in words (16-byte multiple, spreads banks)
-    static constexpr int BYTES = TB_ROWS * LDW * 4 + TB_ROWS * 4 + TB_COLS;
+    static constexpr int BYTES = TB_ROWS * LDW * 4 + TB_ROWS * 4 + TB_COLS + (REL ? 2 * TB_ROWS * 4 : 0);   // REL: row bases of the (at most two) stripes a tile touches
     static_assert(BYTES <= DP_SMEM_PER_WARP, "traceback tile does not fit the warp's shared memory");
 };
 
-template <int NW, bool P16>
+template <int NW, bool P16, bool REL = false>
 __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8_t* wsm, const uint8_t* seq,
                                        uint32_t V, uint32_t L, const DpScores sc, int lane) {
     using G = Geo<NW, P16>;
-    using T = TbTile<NW, P16>;
+    using T = TbTile<NW, P16, REL>;
     const int g = sc.g;
-    SlotView<NW, P16> sv;
+    SlotView<NW, P16, REL> sv;
     sv.bind(slot, V, L);
     // end cell: best Hhat[i][L] over sink nodes, first maximum in rank order (SPOA kNW)
     int best = INT32_MIN; uint32_t best_i = 0;
@@ -904,6 +1016,7 @@ __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8
     uint32_t* tile = reinterpret_cast<uint32_t*>(wsm);                    // [TB_ROWS][LDW] raw words: row it - a, groups g0 ..
     uint32_t* tm0 = tile + TB_ROWS * T::LDW;
     uint8_t* tseq = reinterpret_cast<uint8_t*>(tm0 + TB_ROWS);
+    int32_t* tbase = reinterpret_cast<int32_t*>(tseq + TB_COLS);         // REL: [2][TB_ROWS] bases of the tile's rows in its first / second stripe
     const uint4* Hu = reinterpret_cast<const uint4*>(sv.H);
     const uint32_t NS = sv.NS;
     uint32_t ci = best_i, cj = L, n_out = 0;
@@ -926,6 +1039,11 @@ __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8
                 }
             }
             if (row >= 1) tm0[lane] = gv.meta0[row - 1];
+            if (REL) {
+                const uint32_t sA = g0 / 32u;
+                tbase[lane] = sv.bcol[(uint64_t)sA * (V + 1) + row];
+                tbase[TB_ROWS + lane] = sv.bcol[(uint64_t)(sA + 1) * (V + 1) + row];
+            }
         }
         if (jt >= (uint32_t)lane + 1) tseq[lane] = (uint8_t)base_code(seq[jt - lane - 1]);
         // prefetch what the walk will most likely read next: the rows above the tile, one tile to the left
@@ -947,7 +1065,8 @@ __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8
         auto cell = [&](uint32_t a, uint32_t j) -> int {
             const uint32_t gi = j / G::CPL - g0, c = j % G::CPL;
             const uint32_t w = tile[a * T::LDW + gi * NW + (P16 ? (c & (uint32_t)(NW - 1)) : c)];
-            if (P16) return (c >= (uint32_t)NW) ? (int)(int16_t)(w >> 16) : (int)(int16_t)(w & 0xFFFFu);
+            if (P16) return ((c >= (uint32_t)NW) ? (int)(int16_t)(w >> 16) : (int)(int16_t)(w & 0xFFFFu))
+                            + (REL ? tbase[((gi + g0) / 32u - g0 / 32u) * TB_ROWS + a] : 0);
             return (int)w;
         };
         while (true) {
@@ -1566,12 +1685,13 @@ __device__ __forceinline__ int lane_id() {       // read once, never remateriali
     return __shfl_sync(FULL, l, l);                 // a shuffle result is opaque to ptxas, S2R is not
 }
 
-__global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, HGPU_MINBLOCKS) k_poa_edges(PoaArgs a) {
+template <int RING>
+__device__ __forceinline__ void poa_edges_body(const PoaArgs& a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = lane_id();
     const int wib = threadIdx.x >> 5;
     const uint32_t gw = blockIdx.x * DP_WARPS_PER_BLOCK + wib;
-    uint8_t* wsm = smem_raw + (size_t)wib * DP_SMEM_PER_WARP;
+    uint8_t* wsm = smem_raw + (size_t)wib * (RING > 2 ? DP_SMEM_PER_WARP_DEEP : DP_SMEM_PER_WARP);
     uint8_t* slot = a.arena + (uint64_t)gw * a.slot_bytes;
     uint8_t* wsb = a.ws + (uint64_t)gw * a.wl.bytes;
     GraphView gv = bind_graph(wsb, a.wl);
@@ -1605,20 +1725,25 @@ __global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, HGPU_MINBLOCKS) k_poa
                 const uint32_t NE = *gv.n_edges;
                 const uint32_t L = a.seg_len[s0 + k];
                 const uint8_t* seq = a.bases + a.seg_ptr[s0 + k];
-                const bool p16 = !a.force_i32 && dp_fits16(V, L, a.sc);
+                const int mode = dp_mode(V, L, a.sc, a.force_i32);
+                const bool p16 = mode != DPM_I32;
                 if ((uint64_t)V + L > gv.ncap || (uint64_t)NE + L + 1 > gv.ecap) { st = ST_CAPACITY; break; }
-                if (dp_slot_bytes(V, L, p16) > a.slot_bytes) { st = ST_TOO_LARGE; break; }
+                if (dp_slot_bytes(V, L, mode) > a.slot_bytes) { st = ST_TOO_LARGE; break; }
                 const uint32_t probe = (k == a.probe_round) ? a.probe : 0u;
                 if (probe == 1) {
-                    if (p16) dp_fill16<false>(gv.meta0, gv.pred_off, gv.pred_rank, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, Geo<DP_NW16, true>::bias(V, a.sc), lane, 0, 1, nullptr);
+                    if (mode == DPM_ABS16) dp_fill16<false, false, RING>(gv.meta0, gv.pred_off, gv.pred_rank, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, Geo<DP_NW16, true>::bias(V, a.sc), lane, 0, 1, nullptr);
                     e_cells += (unsigned long long)(V + 1) * (L + 1);
                     debug_stop = true; break;
                 }
                 bool ok;
-                if (p16) {
-                    dp_fill16<false>(gv.meta0, gv.pred_off, gv.pred_rank, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, Geo<DP_NW16, true>::bias(V, a.sc), lane, 0, 1, nullptr);
+                if (mode == DPM_ABS16) {
+                    dp_fill16<false, false, RING>(gv.meta0, gv.pred_off, gv.pred_rank, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, Geo<DP_NW16, true>::bias(V, a.sc), lane, 0, 1, nullptr);
                     PHASE_CLK(PC_FILL)
                     ok = dp_traceback<DP_NW16, true>(gv, slot, wsm, seq, V, L, a.sc, lane);
+                } else if (mode == DPM_REL16) {
+                    dp_fill16<false, true, RING>(gv.meta0, gv.pred_off, gv.pred_rank, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, 0, lane, 0, 1, nullptr);
+                    PHASE_CLK(PC_FILL)
+                    ok = dp_traceback<DP_NW16, true, true>(gv, slot, wsm, seq, V, L, a.sc, lane);
                 } else {
                     dp_fill<DP_NW32, false>(gv, slot, wsm, seq, V, L, a.sc, lane, 0, 1, nullptr);
                     PHASE_CLK(PC_FILL)
@@ -1627,13 +1752,13 @@ __global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, HGPU_MINBLOCKS) k_poa
                 PHASE_CLK(PC_TRACEBACK)
                 if (probe == 2) { e_cells += (unsigned long long)(V + 1) * (L + 1); debug_stop = true; break; }
                 if (lane == 0) {
-                    hdr[HDR_LAST_P16] = p16 ? 1u : 0u; hdr[HDR_LAST_V] = V; hdr[HDR_LAST_L] = L;
-                    hdr[HDR_LAST_BIAS] = (uint32_t)(p16 ? Geo<DP_NW16, true>::bias(V, a.sc) : 0);
+                    hdr[HDR_LAST_P16] = (uint32_t)mode; hdr[HDR_LAST_V] = V; hdr[HDR_LAST_L] = L;
+                    hdr[HDR_LAST_BIAS] = (uint32_t)(mode == DPM_ABS16 ? Geo<DP_NW16, true>::bias(V, a.sc) : 0);
                 }
                 e_cells += (unsigned long long)(V + 1) * (L + 1);
                 e_padded += (unsigned long long)(V + 1) *
                              (p16 ? Geo<DP_NW16, true>::stripes(L) * Geo<DP_NW16, true>::SW : Geo<DP_NW32, false>::stripes(L) * Geo<DP_NW32, false>::SW);
-                e_aln += 1; e_aln32 += p16 ? 0 : 1; e_bases += L;
+                e_aln += 1; e_aln32 += mode == DPM_I32 ? 1ull : (mode == DPM_REL16 ? (1ull << 32) : 0ull);   /* low word int32, high word REL16 */ e_bases += L;
                 if (!ok) { st = ST_TRACEBACK; break; }
                 if (k == a.stop_round) { debug_stop = true; break; }
                 // fold the alignment into the graph, re-sort, rebuild the DP records (same results as SPOA's serial code)
@@ -1702,6 +1827,11 @@ __global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, HGPU_MINBLOCKS) k_poa
     }
 }
 
+// shallow edges (a handful of supporting reads): as many resident warps as possible, two parked rows per warp
+__global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, HGPU_MINBLOCKS) k_poa_edges(PoaArgs a) { poa_edges_body<2>(a); }
+// deep edges: a ring of parked rows per warp (4 blocks of 4 warps per SM by shared memory)
+__global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, 4) k_poa_edges_deep(PoaArgs a) { poa_edges_body<DP_RING_DEEP>(a); }
+
 // ---------------------------------------------------------------------------------------------------------
 // k_poa_edges_team<TEAM>: one BLOCK of TEAM warps per backbone edge, for edges whose score matrices are so large
 // that a single warp would become the tail of the whole batch (deep coverage x long gap). The fill of one
@@ -1709,13 +1839,13 @@ __global__ void __launch_bounds__(32 * DP_WARPS_PER_BLOCK, HGPU_MINBLOCKS) k_poa
 // traceback, graph update and consensus run on warp 0 exactly as in k_poa_edges, so results are identical.
 // ---------------------------------------------------------------------------------------------------------
 template <int TEAM>
-__global__ void __launch_bounds__(32 * TEAM, 768 / (32 * TEAM)) k_poa_edges_team(PoaArgs a) {
+__global__ void __launch_bounds__(32 * TEAM, 512 / (32 * TEAM)) k_poa_edges_team(PoaArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = lane_id();
     const uint32_t wib = threadIdx.x >> 5;                  // = rank in the team
     const uint32_t gw = blockIdx.x;                          // one slot / workspace per team
-    uint8_t* wsm = smem_raw + (size_t)wib * DP_SMEM_PER_WARP;
-    volatile uint32_t* vprog = reinterpret_cast<volatile uint32_t*>(smem_raw + (size_t)TEAM * DP_SMEM_PER_WARP);   // [TEAM]
+    uint8_t* wsm = smem_raw + (size_t)wib * DP_SMEM_PER_WARP_DEEP;
+    volatile uint32_t* vprog = reinterpret_cast<volatile uint32_t*>(smem_raw + (size_t)TEAM * DP_SMEM_PER_WARP_DEEP);   // [TEAM]
     volatile uint32_t* bcast = vprog + TEAM;                 // [4]: item, status, flag, spare
     uint8_t* slot = a.arena + (uint64_t)gw * a.slot_bytes;
     uint8_t* wsb = a.ws + (uint64_t)gw * a.wl.bytes;
@@ -1750,25 +1880,28 @@ __global__ void __launch_bounds__(32 * TEAM, 768 / (32 * TEAM)) k_poa_edges_team
                 const uint32_t NE = *gv.n_edges;
                 const uint32_t L = a.seg_len[s0 + k];
                 const uint8_t* seq = a.bases + a.seg_ptr[s0 + k];
-                const bool p16 = !a.force_i32 && dp_fits16(V, L, a.sc);
+                const int mode = dp_mode(V, L, a.sc, a.force_i32);
+                const bool p16 = mode != DPM_I32;
                 if ((uint64_t)V + L > gv.ncap || (uint64_t)NE + L + 1 > gv.ecap) { st = ST_CAPACITY; break; }
-                if (dp_slot_bytes(V, L, p16) > a.slot_bytes) { st = ST_TOO_LARGE; break; }
-                const bool fill_ok = p16 ? dp_fill16<true>(gv.meta0, gv.pred_off, gv.pred_rank, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, Geo<DP_NW16, true>::bias(V, a.sc), lane, wib, TEAM, vprog)
+                if (dp_slot_bytes(V, L, mode) > a.slot_bytes) { st = ST_TOO_LARGE; break; }
+                const bool fill_ok = mode == DPM_ABS16 ? dp_fill16<true, false, DP_RING_DEEP>(gv.meta0, gv.pred_off, gv.pred_rank, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, Geo<DP_NW16, true>::bias(V, a.sc), lane, wib, TEAM, vprog)
+                                   : mode == DPM_REL16 ? dp_fill16<true, true, DP_RING_DEEP>(gv.meta0, gv.pred_off, gv.pred_rank, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, 0, lane, wib, TEAM, vprog)
                                          : dp_fill<DP_NW32, false>(gv, slot, wsm, seq, V, L, a.sc, lane, wib, TEAM, vprog);
                 const int all_ok = __syncthreads_and(fill_ok ? 1 : 0);    // every stripe stored (and no wait gave up)
                 if (!all_ok) { st = ST_SYNC; break; }
                 uint32_t rst = ST_OK;
                 if (lead) {
-                    bool ok = p16 ? dp_traceback<DP_NW16, true>(gv, slot, wsm, seq, V, L, a.sc, lane)
+                    bool ok = mode == DPM_ABS16 ? dp_traceback<DP_NW16, true>(gv, slot, wsm, seq, V, L, a.sc, lane)
+                            : mode == DPM_REL16 ? dp_traceback<DP_NW16, true, true>(gv, slot, wsm, seq, V, L, a.sc, lane)
                                   : dp_traceback<DP_NW32, false>(gv, slot, wsm, seq, V, L, a.sc, lane);
                     if (lane == 0) {
-                        hdr[HDR_LAST_P16] = p16 ? 1u : 0u; hdr[HDR_LAST_V] = V; hdr[HDR_LAST_L] = L;
-                        hdr[HDR_LAST_BIAS] = (uint32_t)(p16 ? Geo<DP_NW16, true>::bias(V, a.sc) : 0);
+                        hdr[HDR_LAST_P16] = (uint32_t)mode; hdr[HDR_LAST_V] = V; hdr[HDR_LAST_L] = L;
+                        hdr[HDR_LAST_BIAS] = (uint32_t)(mode == DPM_ABS16 ? Geo<DP_NW16, true>::bias(V, a.sc) : 0);
                     }
                     e_cells += (unsigned long long)(V + 1) * (L + 1);
                     e_padded += (unsigned long long)(V + 1) *
                                  (p16 ? Geo<DP_NW16, true>::stripes(L) * Geo<DP_NW16, true>::SW : Geo<DP_NW32, false>::stripes(L) * Geo<DP_NW32, false>::SW);
-                    e_aln += 1; e_aln32 += p16 ? 0 : 1; e_bases += L;
+                    e_aln += 1; e_aln32 += mode == DPM_I32 ? 1ull : (mode == DPM_REL16 ? (1ull << 32) : 0ull);   /* low word int32, high word REL16 */ e_bases += L;
                     if (!ok) rst = ST_TRACEBACK;
                     else if (k != a.stop_round) {
                         uint32_t ust = w_add_alignment(gv, gs, seq, L, lane);
@@ -1844,9 +1977,9 @@ __global__ void __launch_bounds__(256) k_poa_gather(const uint64_t* cons_pos, co
 }
 
 // Debug: export the score matrix of warp 0's last alignment in the reference's H space (row-major (V+1)*(L+1) int32).
-template <int NW, bool P16>
+template <int NW, bool P16, bool REL = false>
 __global__ void k_poa_dump_H(uint8_t* slot, uint32_t V, uint32_t L, int bias, int gap, int32_t* H) {
-    SlotView<NW, P16> sv;
+    SlotView<NW, P16, REL> sv;
     sv.bind(slot, V, L);
     const uint64_t total = (uint64_t)(V + 1) * (L + 1);
     for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total; idx += (uint64_t)gridDim.x * blockDim.x) {

@@ -38,7 +38,8 @@ class PoaStats(C.Structure):
     _fields_ = [("cells", C.c_uint64), ("cells_padded", C.c_uint64), ("alignments", C.c_uint64),
                 ("alignments_i32", C.c_uint64), ("bases_in", C.c_uint64), ("bases_out", C.c_uint64),
                 ("dp_launches", C.c_uint64), ("update_launches", C.c_uint64), ("other_launches", C.c_uint64),
-                ("ms_dp", C.c_float), ("ms_update", C.c_float), ("ms_other", C.c_float), ("arena_bytes", C.c_uint64)]
+                ("ms_dp", C.c_float), ("ms_update", C.c_float), ("ms_other", C.c_float), ("arena_bytes", C.c_uint64),
+                ("alignments_rel16", C.c_uint64)]
 
 
 class DbgSizes(C.Structure):
@@ -171,8 +172,9 @@ class Context:
     def poa_configure(self, arena_bytes=0, max_warps=0):
         self._check(self.L.hgpu_poa_configure(self.h, arena_bytes, max_warps))
 
-    def poa_debug(self, bases, seg_off, n_prior, match=5, mismatch=-4, gap=-8, force_i32=False, want_H=True):
-        """Graph after n_prior segments (rank order) + score matrix / alignment of the next one; same dict as the oracle's."""
+    def poa_debug(self, bases, seg_off, n_prior, match=5, mismatch=-4, gap=-8, force_i32=0, want_H=True):
+        """force_i32: 0 = the cell encoding the batch path picks, 1 = int32, 2 = row-relative int16 (REL16).
+        Graph after n_prior segments (rank order) + score matrix / alignment of the next one; same dict as the oracle's."""
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         seg_off = np.ascontiguousarray(seg_off, dtype=np.uint64)
         n_segs = len(seg_off) - 1

@@ -261,8 +261,8 @@ int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& 
         if (r != HGPU_OK) { fprintf(stderr, "[ERROR] hgpu_poa_batch (gpu %zu): %s\n", gi, hgpu_last_error(ctxs[gi])); rc[gi] = r; return; }
         hgpu_poa_stats st;
         if (hgpu_poa_get_stats(ctxs[gi], &st) == HGPU_OK)
-            fprintf(stderr, "       gpu %zu: %zu edges, %llu alignments (%llu int32), %.1f Mbases in, %.3e DP cells, kernel %.1f ms (%.0f GCUPS), %llu launches\n",
-                    gi, my.size(), (unsigned long long)st.alignments, (unsigned long long)st.alignments_i32, st.bases_in / 1e6, (double)st.cells,
+            fprintf(stderr, "       gpu %zu: %zu edges, %llu alignments (%llu rel16, %llu int32), %.1f Mbases in, %.3e DP cells, kernel %.1f ms (%.0f GCUPS), %llu launches\n",
+                    gi, my.size(), (unsigned long long)st.alignments, (unsigned long long)st.alignments_rel16, (unsigned long long)st.alignments_i32, st.bases_in / 1e6, (double)st.cells,
                     st.ms_dp, st.ms_dp > 0 ? st.cells / (st.ms_dp * 1e6) : 0.0, (unsigned long long)st.dp_launches);
         for (size_t k = 0; k < my.size(); ++k) {
             if (status[k] != 0) { fprintf(stderr, "[ERROR] POA failed for edge %u with status %u\n", my[k], status[k]); rc[gi] = HGPU_E_INTERNAL; }

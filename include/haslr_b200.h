@@ -117,12 +117,13 @@ typedef struct {
     uint64_t cells;            /* sum over alignments of (|V|+1)*(L+1): the algorithmic DP cells */
     uint64_t cells_padded;     /* cells actually computed (stripe padding included) */
     uint64_t alignments;       /* graph-NW alignments run */
-    uint64_t alignments_i32;   /* of which in the int32 kernel (score range too wide for int16) */
+    uint64_t alignments_i32;   /* of which in the int32 kernel (scores the packed int16 arithmetic cannot hold) */
     uint64_t bases_in;         /* segment bases consumed */
     uint64_t bases_out;        /* consensus bases produced */
     uint64_t dp_launches, update_launches, other_launches;
     float    ms_dp, ms_update, ms_other;   /* CUDA-event time per kernel family, only if timing enabled */
     uint64_t arena_bytes;      /* score-matrix arena size used */
+    uint64_t alignments_rel16; /* alignments whose range exceeds plain int16 and ran in row-relative int16 cells */
 } hgpu_poa_stats;
 int hgpu_poa_get_stats(const hgpu_t* ctx, hgpu_poa_stats* out);
 /* Per-kernel-family CUDA-event timing (serialises the families; leave off when measuring whole-job throughput). */
@@ -132,7 +133,7 @@ int hgpu_poa_configure(hgpu_t* ctx, uint64_t arena_bytes, uint32_t max_batch_edg
 
 /* Debug/inspection (used by the parity tests): graph after the first n_prior non-empty segments of ONE edge, in
  * rank order, plus the score matrix and alignment of the next segment. H is written in the reference's H space
- * (row-major (V+1)*(L+1) int32). force_i32 != 0 runs the int32 kernel; force_nw selects the stripe width
+ * (row-major (V+1)*(L+1) int32). force_i32: 0 = the encoding the batch path would pick, 1 = int32 cells, 2 = int16 cells relative to the row base (REL16); force_nw selects the stripe width
  * (words per lane: 8/16/24/32, 0 = auto). Any output may be NULL. */
 typedef struct { uint32_t n_nodes, n_edges, aln_len, L; } hgpu_poa_dbg_sizes;
 int hgpu_poa_debug(hgpu_t* ctx, const uint8_t* bases, const uint64_t* seg_off, uint32_t n_segs, uint32_t n_prior,

@@ -21,9 +21,10 @@ def check_batch(ctx, oracle, bases, seg_off, eso, scores=(5, -4, -8)):
 
 
 @pytest.mark.parametrize("n_prior", [1, 2, 5])
-@pytest.mark.parametrize("force_i32", [False, True])
+@pytest.mark.parametrize("force_i32", [0, 1, 2])
 def test_score_matrix_and_alignment_match_oracle(ctx, oracle, n_prior, force_i32):
-    """The whole DP matrix (in the reference's H space), the alignment and the graph it is computed on."""
+    """The whole DP matrix (in the reference's H space), the alignment and the graph it is computed on, in each of the
+    three cell encodings (0 = picked: plain int16 here, 1 = int32, 2 = row-relative int16)."""
     bases, seg_off, eso, _ = synth.poa_batch(7, 1, depth=7, length=700, length_jitter=0.0)
     ref = oracle.poa_debug(bases, seg_off, n_prior)
     got = ctx.poa_debug(bases, seg_off, n_prior, force_i32=force_i32)
@@ -38,7 +39,7 @@ def test_score_matrix_and_alignment_match_oracle(ctx, oracle, n_prior, force_i32
 def test_score_matrix_multi_stripe(ctx, oracle):
     """L > 512 columns: several stripes, boundary-column hand-off between them."""
     bases, seg_off, eso, _ = synth.poa_batch(11, 1, depth=4, length=1500)
-    for force in (False, True):
+    for force in (0, 1, 2):
         ref = oracle.poa_debug(bases, seg_off, 3)
         got = ctx.poa_debug(bases, seg_off, 3, force_i32=force)
         assert np.array_equal(got["H"], ref["H"])
@@ -62,11 +63,49 @@ def test_consensus_high_error_and_depth(ctx, oracle):
     check_batch(ctx, oracle, bases, seg_off, eso)
 
 
-def test_consensus_int32_range(ctx, oracle):
-    """Segments long enough that the int16 score range does not hold (SPOA switches to int32 lanes too)."""
+def test_consensus_wide_range(ctx, oracle):
+    """Segments long enough that the plain int16 score range does not hold (SPOA switches to int32 lanes there): these
+    alignments run in row-relative int16 cells, and in int32 cells when that is forced."""
     bases, seg_off, eso, _ = synth.poa_batch(13, 3, depth=3, length=4000)
     st = check_batch(ctx, oracle, bases, seg_off, eso)
-    assert st["alignments_i32"] > 0
+    assert st["alignments_rel16"] > 0 and st["alignments_i32"] == 0
+
+
+def test_score_matrix_wide_range_rel16(ctx, oracle):
+    """A matrix whose range needs the row-relative encoding (13 (L+1) + 8 (V+2) > 64000), cell by cell."""
+    bases, seg_off, eso, _ = synth.poa_batch(17, 1, depth=4, length=3300)
+    ref = oracle.poa_debug(bases, seg_off, 3)
+    got = ctx.poa_debug(bases, seg_off, 3)
+    assert np.array_equal(got["H"], ref["H"])
+    assert np.array_equal(got["aln_node"], ref["aln_node"]) and np.array_equal(got["aln_pos"], ref["aln_pos"])
+
+
+def test_consensus_deep_long_edges_rel16(ctx, oracle):
+    """BASELINE config 2 shape: 25x coverage over 2-3 kb gaps, graphs of several thousand nodes."""
+    bases, seg_off, eso, _ = synth.poa_batch(19, 6, depth=14, length=2600, length_jitter=0.2)
+    st = check_batch(ctx, oracle, bases, seg_off, eso)
+    assert st["alignments_rel16"] > 0
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_forced_encodings_whole_batches(oracle, monkeypatch, mode):
+    """Every alignment of a batch forced into int32 (1) / row-relative int16 (2) cells: same consensus as the oracle."""
+    import haslr_b200
+    monkeypatch.setenv("HGPU_FORCE_MODE", str(mode))
+    c = haslr_b200.Context(0)
+    try:
+        b, so, eo, _ = synth.poa_batch(3, 64, depth=6, length=400, length_jitter=0.3)
+        st = check_batch(c, oracle, b, so, eo)
+        assert st["alignments_rel16" if mode == 2 else "alignments_i32"] == st["alignments"]
+        b, so, eo, _ = synth.poa_batch(9, 32, depth=24, length=300, err=(0.08, 0.06, 0.04), length_jitter=0.3, depth_jitter=6)
+        check_batch(c, oracle, b, so, eo)
+        b, so, eo, _ = synth.poa_batch(5, 24, depth=6, length=1500)
+        check_batch(c, oracle, b, so, eo)
+        rng = np.random.default_rng(23)               # unrelated segments: many predecessor-free ranks and far predecessors
+        b, so, eo = synth.from_strings([[bytes(synth.ACGT[rng.integers(0, 4, 700)]) for _ in range(6)] for _ in range(4)])
+        check_batch(c, oracle, b, so, eo)
+    finally:
+        c.close()
 
 
 def test_edge_cases(ctx, oracle):
@@ -124,6 +163,30 @@ def test_roundtrip_property_large(ctx):
         assert cons[int(off[e]): int(off[e + 1])].tobytes() == t.tobytes()
 
 
+@pytest.mark.parametrize("force_i32", [0, 1, 2])
+def test_deep_kernel_score_matrix_and_batches(oracle, monkeypatch, force_i32):
+    """k_poa_edges_deep (every row parked in a shared-memory ring; normally edges with >= 10 supporting reads), forced
+    onto small inputs: score matrix and alignment cell by cell in each encoding, then whole batches."""
+    import haslr_b200
+    monkeypatch.setenv("HGPU_DEEP_MIN_READS", "2")
+    if force_i32:
+        monkeypatch.setenv("HGPU_FORCE_MODE", str(force_i32))
+    c = haslr_b200.Context(0)
+    try:
+        bases, seg_off, eso, _ = synth.poa_batch(7, 1, depth=7, length=700)
+        for n_prior in (1, 4, 6):
+            ref = oracle.poa_debug(bases, seg_off, n_prior)
+            got = c.poa_debug(bases, seg_off, n_prior, force_i32=force_i32)
+            assert np.array_equal(got["H"], ref["H"])
+            assert np.array_equal(got["aln_node"], ref["aln_node"]) and np.array_equal(got["aln_pos"], ref["aln_pos"])
+        b, so, eo, _ = synth.poa_batch(9, 32, depth=24, length=300, err=(0.08, 0.06, 0.04), length_jitter=0.3, depth_jitter=6)
+        check_batch(c, oracle, b, so, eo)
+        b, so, eo, _ = synth.poa_batch(5, 24, depth=6, length=1500)
+        check_batch(c, oracle, b, so, eo)
+    finally:
+        c.close()
+
+
 def test_team_kernel_matches_oracle(oracle, monkeypatch):
     """Edges large enough for the block-per-edge kernel (forced here with a low threshold): multi-stripe score matrices
     filled by 8 warps in a pipeline must give the same consensus as the warp-per-edge kernel and the oracle."""
@@ -141,5 +204,6 @@ def test_team_kernel_matches_oracle(oracle, monkeypatch):
         eso = np.concatenate((es1, es2[1:] + es1[-1], es3[1:] + es1[-1] + es2[-1])).astype(np.uint32)
         st = check_batch(c, oracle, bases, seg_off, eso)
         assert st["dp_launches"] >= 2          # team kernel + warp-per-edge kernel
+        assert st["alignments_rel16"] > 0      # the long gaps run in row-relative int16 cells, stripes pipelined over the team
     finally:
         c.close()

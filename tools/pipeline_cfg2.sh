@@ -6,9 +6,9 @@ T=${1:-/tmp/cfg2}; mkdir -p $T; cd $T
 NT=$(nproc)
 ARGS="-c contigs.fa -l reads.fa -m map.paf --aln-block 500 --aln-sim 0.85 --edge-sup 3"
 rm -rf ref new
-( time /root/repo/oracle/_ref/haslr_assemble_ref -t $NT $ARGS -d ref > ref.out 2> ref.err ) 2> ref.time
+[ -n "$SKIP_REF" ] || ( time /root/repo/oracle/_ref/haslr_assemble_ref -t $NT $ARGS -d ref > ref.out 2> ref.err ) 2> ref.time
 ( time /root/repo/bin/haslr_assemble -t $NT $ARGS -d new > new.out 2> new.err ) 2> new.time
-echo "== reference ($NT threads)"; grep -E "^\[NOTE\]|elapsed" ref.err | paste - - | sed 's/\[NOTE\] //' | cut -c1-150; cat ref.time
+[ -n "$SKIP_REF" ] || echo "== reference ($NT threads)"; [ -n "$SKIP_REF" ] || grep -E "^\[NOTE\]|elapsed" ref.err | paste - - | sed 's/\[NOTE\] //' | cut -c1-150; [ -n "$SKIP_REF" ] || cat ref.time
 echo "== haslr_b200"; grep -E "^\[NOTE\]|elapsed" new.err | paste - - | sed 's/\[NOTE\] //' | cut -c1-150; cat new.time
 for f in compact_uniq.txt backbone.01.init.gfa backbone.02.weakEdge.gfa backbone.06.smallbubble.gfa asm.final.fa asm.final.ann; do cmp -s ref/$f new/$f && echo "same $f" || echo "DIFF $f"; done
-grep -c ">" new/asm.final.fa; grep -h "segments\|Mbases" new.err | head
+grep -c ">" new/asm.final.fa; grep -h "segments\|Mbases\|^\[poa\]" new.err | head -60
