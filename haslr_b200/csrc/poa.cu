@@ -26,6 +26,7 @@ struct PoaState {
     DevBuf<uint32_t> seg_len, e_seg_off, items, status, cons_len, out_nodes, counters;
     DevBuf<unsigned long long> stats, pool_cursor;
     std::vector<std::unique_ptr<PoaPass>> passes;
+    std::vector<std::unique_ptr<PoaPass>> spare;   // consensus pools of earlier calls, reused (a cudaMalloc/cudaFree pair per call costs tens of ms)
     hgpu_poa_stats st{};
     bool timing = false;
     uint64_t cfg_arena_bytes = 0;
@@ -44,7 +45,7 @@ struct PoaState {
     double cfg_team_min_cells = 2.0e8;
     uint32_t cfg_teams_per_sm = 2;    // resident teams per SM (HGPU_TEAMS_PER_SM); the rest of the SM runs warp-per-edge blocks
     double cfg_budget_frac = 0.88;    // share of the free device memory the arenas may take (HGPU_BUDGET_FRAC)
-    double cfg_team_div = 3000.0;     // an edge goes to the team kernel when it holds more than 1/cfg_team_div of the batch's cells (HGPU_TEAM_DIV)
+    double cfg_team_alpha = 1.5;      // an edge goes to the team kernel when it holds more than alpha x (batch cells / busy warps) (HGPU_TEAM_ALPHA)
     uint32_t cfg_deep_min_reads = 10; // edges with at least this many supporting reads run in k_poa_edges_deep (HGPU_DEEP_MIN_READS)
     int cfg_force = 0;                // HGPU_FORCE_MODE: 1 = every alignment in int32, 2 = every alignment in REL16 (tests)
     int verbose = 0;                  // HGPU_VERBOSE=1: pass / class plan and per-launch device time on stderr
@@ -68,7 +69,7 @@ static PoaState* poa_state(hgpu_t* ctx) {
         if (const char* e = getenv("HGPU_TEAM")) ctx->poa->cfg_team = (uint32_t)atoi(e);
         if (const char* e = getenv("HGPU_TEAM_MIN_CELLS")) ctx->poa->cfg_team_min_cells = atof(e);
         if (const char* e = getenv("HGPU_VERBOSE")) ctx->poa->verbose = atoi(e);
-        if (const char* e = getenv("HGPU_TEAM_DIV")) ctx->poa->cfg_team_div = std::max(1.0, atof(e));
+        if (const char* e = getenv("HGPU_TEAM_ALPHA")) ctx->poa->cfg_team_alpha = std::max(0.01, atof(e));
         if (const char* e = getenv("HGPU_TEAMS_PER_SM")) ctx->poa->cfg_teams_per_sm = (uint32_t)std::max(1, std::min(2, atoi(e)));
         if (const char* e = getenv("HGPU_BUDGET_FRAC")) ctx->poa->cfg_budget_frac = std::max(0.1, std::min(0.92, atof(e)));
         if (const char* e = getenv("HGPU_FORCE_MODE")) ctx->poa->cfg_force = atoi(e);
@@ -109,7 +110,9 @@ void estimate_edge(const uint32_t* len, uint32_t R, double growth, const DpScore
     uint32_t lmax = len[0];
     for (uint32_t k = 1; k < R; ++k) {
         uint32_t Vi = (uint32_t)std::min<double>(V + 1.0, 4.0e9);
-        slot = std::max(slot, dp_slot_bytes(Vi, len[k], dp_mode(Vi, len[k], sc, force)));
+        const int mode = dp_mode(Vi, len[k], sc, force);
+        if (mode == DPM_REL16) out->deep = true;                     // only k_poa_edges_deep carries the REL16 code
+        slot = std::max(slot, dp_slot_bytes(Vi, len[k], mode));
         cells += (V + 1.0) * (len[k] + 1.0);
         // overhang beyond the graph's current span also becomes new nodes
         double over = len[k] > V ? (double)len[k] - V : 0.0;
@@ -136,6 +139,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
                    const DpScores& sc, const PoaRunOpts& opt, std::vector<uint32_t>& status_h, std::vector<uint32_t>& len_h) {
     PoaState* S = poa_state(ctx);
     cudaStream_t st = ctx->stream;
+    for (auto& p : S->passes) if (S->spare.size() < 4) S->spare.push_back(std::move(p));
     S->passes.clear();
     S->have_result = false;
     memset(&S->st, 0, sizeof S->st);
@@ -199,7 +203,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
 
     std::vector<uint32_t> pending(n_edges);
     std::iota(pending.begin(), pending.end(), 0u);
-    double growth = 0.15;
+    double growth = 0.10;             // new nodes per base per read, first guess (measured 0.05-0.07 at 9 % read error); retried x2.5 when an edge outgrows it
     std::vector<EdgeEst> est;
     std::vector<uint32_t> items_h;
     const uint64_t budget_total = budget;
@@ -221,12 +225,17 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
         }
         // ---- edges so large that one warp would be the tail of the whole pass go to the team kernel (a block per edge):
         //      a lone warp on a deep graph sustains ~0.4 G cells/s (one dependent instruction stream, IPC 0.15: profiles/r1i_*)
-        //      against ~1 T cells/s for the device, so "large" = more than 1/3000 of the work (swept on BASELINE config 2)
+        //      against ~1 T cells/s for the device
         std::vector<EdgeEst> team;
         if (S->cfg_team >= 2 && opt.stop_round == 0xFFFFFFFFu) {
             double total = 0;
             for (const EdgeEst& x : est) total += x.cells;
-            const double thr = std::max(total / S->cfg_team_div, S->cfg_team_min_cells);
+            // (a) fewer edges than resident teams: the device is mostly empty, every wide edge gets a team (3.3x faster per edge);
+            // (b) otherwise only the tail: with W warps busy an edge is "tail" when it holds more than cfg_team_alpha times the
+            //     average share of a warp, total / W (alpha 1.5 ~ 1/3000 of the batch on BASELINE config 2, the swept optimum)
+            const bool few = est.size() <= (size_t)ctx->sm_count * S->cfg_teams_per_sm;
+            const double share = total / (double)std::max<size_t>(1, std::min<size_t>(est.size(), max_warps));
+            const double thr = few ? S->cfg_team_min_cells / 8.0 : std::max(S->cfg_team_alpha * share, S->cfg_team_min_cells);
             std::vector<EdgeEst> rest;
             for (const EdgeEst& x : est) {
                 const bool wide = x.lmax >= 2u * (uint32_t)Geo<DP_NW16, true>::SW - 1;     // at least 3 stripes to spread
@@ -246,8 +255,12 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
         for (size_t i = 0; i < team.size(); ++i) items_h[est.size() + i] = team[i].edge;
         HGPU_CUDA(ctx, cudaMemcpyAsync(S->items.p, items_h.data(), items_h.size() * 4, cudaMemcpyHostToDevice, st));
 
-        std::unique_ptr<PoaPass> pass(new PoaPass());
-        HGPU_CUDA(ctx, pass->pool.alloc(pool_cap + 256));
+        std::unique_ptr<PoaPass> pass;
+        for (size_t q = 0; q < S->spare.size(); ++q)
+            if (S->spare[q]->pool.n >= pool_cap + 256 && S->spare[q]->pool.n <= 2 * (pool_cap + 256) + (1u << 20)) {
+                pass = std::move(S->spare[q]); S->spare.erase(S->spare.begin() + q); break;
+            }
+        if (!pass) { pass.reset(new PoaPass()); HGPU_CUDA(ctx, pass->pool.alloc(pool_cap + 256)); }
         HGPU_CUDA(ctx, cudaMemsetAsync(S->pool_cursor.p, 0, sizeof(unsigned long long), st));
         HGPU_CUDA(ctx, cudaMemsetAsync(S->counters.p, 0, 256 * 4, st));
 

@@ -1725,7 +1725,10 @@ __device__ __forceinline__ void poa_edges_body(const PoaArgs& a) {
                 const uint32_t NE = *gv.n_edges;
                 const uint32_t L = a.seg_len[s0 + k];
                 const uint8_t* seq = a.bases + a.seg_ptr[s0 + k];
-                const int mode = dp_mode(V, L, a.sc, a.force_i32);
+                int mode = dp_mode(V, L, a.sc, a.force_i32);
+                // the shallow kernel carries no REL16 code (it is instruction-cache bound): the host sends every edge it expects
+                // to leave the plain int16 range to the deep kernel; one that does so unexpectedly runs in int32 cells here
+                if (RING == 2 && mode == DPM_REL16) mode = DPM_I32;
                 const bool p16 = mode != DPM_I32;
                 if ((uint64_t)V + L > gv.ncap || (uint64_t)NE + L + 1 > gv.ecap) { st = ST_CAPACITY; break; }
                 if (dp_slot_bytes(V, L, mode) > a.slot_bytes) { st = ST_TOO_LARGE; break; }
@@ -1740,7 +1743,7 @@ __device__ __forceinline__ void poa_edges_body(const PoaArgs& a) {
                     dp_fill16<false, false, RING>(gv.meta0, gv.pred_off, gv.pred_rank, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, Geo<DP_NW16, true>::bias(V, a.sc), lane, 0, 1, nullptr);
                     PHASE_CLK(PC_FILL)
                     ok = dp_traceback<DP_NW16, true>(gv, slot, wsm, seq, V, L, a.sc, lane);
-                } else if (mode == DPM_REL16) {
+                } else if (RING > 2 && mode == DPM_REL16) {
                     dp_fill16<false, true, RING>(gv.meta0, gv.pred_off, gv.pred_rank, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, 0, lane, 0, 1, nullptr);
                     PHASE_CLK(PC_FILL)
                     ok = dp_traceback<DP_NW16, true, true>(gv, slot, wsm, seq, V, L, a.sc, lane);

@@ -5,6 +5,7 @@
 // a read position (:129-155,253-338), the per-edge consensus call (:479-560 — here ONE batched hgpu_poa_batch call
 // instead of a SPOA engine per edge per thread) and the simple-path stitching (:607-810,1045-1077).
 #include <algorithm>
+#include <cstring>
 #include <deque>
 #include <iterator>
 #include <set>
@@ -179,21 +180,24 @@ void calc_edge_coordinates(Graph& g, const std::vector<EdgeRef>& edges, const Co
 // ---------------------------------------------------------------------------------------------------------
 // consensus: gather every edge's segments, ONE batched POA call per GPU, scatter the strings back
 // ---------------------------------------------------------------------------------------------------------
-static void append_segment(const SeqStore& reads, const CnsSupp& s, std::string& out) {
-    // substr(spos, epos - spos + 1) on the read (strand 0) or its reverse complement (strand 1), uint32 arithmetic
-    // as in Assemble.cpp:529-532 (quirk Q7: a wrapped length takes the tail)
+// substr(spos, epos - spos + 1) on the read (strand 0) or its reverse complement (strand 1), uint32 arithmetic
+// as in Assemble.cpp:529-532 (quirk Q7: a wrapped length takes the tail)
+static uint32_t segment_length(const SeqStore& reads, const CnsSupp& s) {
     const uint32_t len = reads.len(s.lr_id);
     if (s.spos > len) { fprintf(stderr, "[ERROR] segment start %u beyond read %u of length %u\n", s.spos, s.lr_id, len); exit(EXIT_FAILURE); }
     const uint32_t want = s.epos - s.spos + 1;
-    const uint32_t cnt = std::min<uint32_t>(want, len - s.spos);
+    return std::min<uint32_t>(want, len - s.spos);
+}
+static void write_segment(const SeqStore& reads, const CnsSupp& s, uint32_t cnt, char* out) {
+    const uint32_t len = reads.len(s.lr_id);
     const char* r = reads.data(s.lr_id);
     if (s.lr_strand == 0) {
-        out.append(r + s.spos, cnt);
+        memcpy(out, r + s.spos, cnt);
     } else {
         // revcomp(read)[spos .. spos+cnt) = complement of read[len-1-spos], read[len-2-spos], ...
         for (uint32_t k = 0; k < cnt; ++k) {
             const char c = r[len - 1 - s.spos - k];
-            out.push_back(c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : 'A');
+            out[k] = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : 'A';
         }
     }
 }
@@ -201,19 +205,33 @@ static void append_segment(const SeqStore& reads, const CnsSupp& s, std::string&
 static double now_s() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + t.tv_nsec * 1e-9; }
 
 int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& reads, const std::vector<hgpu_t*>& ctxs,
-                   const std::string& logpath, bool write_log) {
+                   const std::string& logpath, bool write_log, unsigned threads) {
     const size_t n = edges.size();
     const double t0 = now_s();
     std::string bases;
     std::vector<uint64_t> seg_off{0};
     std::vector<uint32_t> edge_seg_off{0};
     std::vector<Edge*> e1(n), e2(n);
+    std::vector<const CnsSupp*> seg_src;
     for (size_t e = 0; e < n; ++e) {
         const EdgeRef& er = edges[e];
         e1[e] = &g[er.node1].edges[er.rev1][(er.node2 << 1) | er.rev2];
         e2[e] = &g[er.node2].edges[1 - er.rev2][(er.node1 << 1) | (1 - er.rev1)];
-        for (const CnsSupp& s : e1[e]->cns_supp) { append_segment(reads, s, bases); seg_off.push_back(bases.size()); }
+        for (const CnsSupp& s : e1[e]->cns_supp) { seg_src.push_back(&s); seg_off.push_back(seg_off.back() + segment_length(reads, s)); }
         edge_seg_off.push_back((uint32_t)(seg_off.size() - 1));
+    }
+    bases.resize(seg_off.back());
+    {   // the copies (and reverse complements) are independent: all host threads
+        const size_t n_seg = seg_src.size();
+        const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(threads, n_seg / 256 + 1));
+        auto work = [&](unsigned t) {
+            for (size_t q = n_seg * t / nt; q < n_seg * (t + 1) / nt; ++q)
+                write_segment(reads, *seg_src[q], (uint32_t)(seg_off[q + 1] - seg_off[q]), &bases[seg_off[q]]);
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
     }
     // shard: edges dealt to GPUs by estimated DP cost (sum of len^2-ish), largest first; one host thread per GPU
     const size_t G = std::max<size_t>(1, ctxs.size());

@@ -99,7 +99,7 @@ void enumerate_edges(Graph& g, uint32_t flag, std::vector<EdgeRef>& out);
 void calc_edge_coordinates(Graph& g, const std::vector<EdgeRef>& edges, const ContigStore& contigs, const SeqStore& reads,
                            const CompactReads& cl, const PafTable& paf, const std::string& logpath);
 int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& reads, const std::vector<hgpu_t*>& ctxs,
-                   const std::string& logpath, bool write_log);
+                   const std::string& logpath, bool write_log, unsigned threads);
 void write_assembly(Graph& g, const ContigStore& contigs, const std::string& out_dir);
 
 }  // namespace haslr

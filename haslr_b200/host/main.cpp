@@ -93,13 +93,21 @@ int main(int argc, char** argv) {
     auto lap = [&]() { fprintf(stderr, "       elapsed time %.2lf CPU seconds (%.2lf real seconds)\n\n", cpu_time() - c0, real_time() - r0); };
     const std::string& d = opt.out_dir;
 
-    std::vector<hgpu_t*> ctxs;
-    for (int i = 0; i < opt.gpus; ++i) {
-        hgpu_t* h = nullptr;
-        int rc = hgpu_create(opt.gpus == 1 ? -1 : i, &h);
-        if (rc != HGPU_OK) { fprintf(stderr, "[ERROR] hgpu_create(device %d): %s — this build needs a B200-class GPU\n", i, hgpu_strerror(rc)); return EXIT_FAILURE; }
-        ctxs.push_back(h);
-    }
+    // the CUDA contexts (seconds of driver start-up on a cold process) come up while the input files are read
+    std::vector<hgpu_t*> ctxs((size_t)opt.gpus, nullptr);
+    std::vector<int> ctx_rc((size_t)opt.gpus, HGPU_OK);
+    std::thread ctx_thread([&]() {
+        for (int i = 0; i < opt.gpus; ++i) ctx_rc[i] = hgpu_create(opt.gpus == 1 ? -1 : i, &ctxs[i]);
+    });
+    auto join_contexts = [&]() -> bool {
+        if (ctx_thread.joinable()) ctx_thread.join();
+        for (int i = 0; i < opt.gpus; ++i)
+            if (ctx_rc[i] != HGPU_OK) {
+                fprintf(stderr, "[ERROR] hgpu_create(device %d): %s — this build needs a B200-class GPU\n", i, hgpu_strerror(ctx_rc[i]));
+                return false;
+            }
+        return true;
+    };
     fprintf(stderr, "[NOTE] number of threads: %d, GPUs: %d\n\n", opt.num_threads, opt.gpus);
 
     fprintf(stderr, "[NOTE] loading contig sequences...\n");
@@ -134,6 +142,7 @@ int main(int argc, char** argv) {
 
     // (i) filters + per-read sort + overlap fix + chaining, on the GPU
     fprintf(stderr, "[NOTE] fixing overlapping alignments and building compact long reads (GPU)...\n");
+    if (!join_contexts()) return EXIT_FAILURE;       // no CPU path: without the device the run ends here
     CompactReads cl;
     {
         hgpu_hits_t h{(uint32_t)paf.size(), paf.q_start.data(), paf.q_end.data(), paf.t_id.data(), paf.t_len.data(), paf.t_start.data(),
@@ -210,7 +219,7 @@ int main(int argc, char** argv) {
     // (iii) all edges in one batched POA call per GPU
     fprintf(stderr, "[NOTE] calling consensus sequence between anchors (GPU, %zu edges)...\n", edges.size());
     enumerate_edges(g, 12, edges);
-    if (!edges.empty() && call_consensus(g, edges, reads, ctxs, d + "/log_consensus.txt", logs) != 0) return EXIT_FAILURE;
+    if (!edges.empty() && call_consensus(g, edges, reads, ctxs, d + "/log_consensus.txt", logs, opt.num_threads) != 0) return EXIT_FAILURE;
     lap();
 
     fprintf(stderr, "[NOTE] generating the assembly from the cleaned backbone graph...\n");
