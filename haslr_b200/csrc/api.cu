@@ -42,6 +42,7 @@ extern "C" void hgpu_destroy(hgpu_t* ctx) {
     cudaDeviceSynchronize();
     poa_state_destroy(ctx->poa);
     k12_state_destroy(ctx->k12);
+    coord_state_destroy(ctx->coords);
     delete ctx;
 }
 

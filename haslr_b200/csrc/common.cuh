@@ -10,6 +10,7 @@
 
 struct PoaState;  // poa.cu
 struct K12State;  // k12.cu
+struct CoordState;  // coords.cu
 
 struct hgpu_ctx {
     int device = 0;
@@ -20,6 +21,7 @@ struct hgpu_ctx {
     uint64_t launches = 0;
     PoaState* poa = nullptr;
     K12State* k12 = nullptr;
+    CoordState* coords = nullptr;
 };
 
 #define HGPU_CUDA(ctx, expr)                                                                         \
@@ -63,3 +65,4 @@ struct DevBuf {
 
 void poa_state_destroy(PoaState* s);
 void k12_state_destroy(K12State* s);
+void coord_state_destroy(CoordState* s);

@@ -13,7 +13,7 @@ HGPU_OK, HGPU_E_INVALID, HGPU_E_CUDA, HGPU_E_NOMEM, HGPU_E_NOSPACE, HGPU_E_UNSUP
 EXPORTS = (
     "hgpu_create", "hgpu_destroy", "hgpu_set_stream", "hgpu_strerror", "hgpu_last_error", "hgpu_abi_version",
     "hgpu_launch_count", "hgpu_compact_lr", "hgpu_backbone_edges", "hgpu_poa_batch", "hgpu_poa_batch_dev",
-    "hgpu_poa_fetch", "hgpu_poa_get_stats", "hgpu_poa_set_timing", "hgpu_poa_configure", "hgpu_poa_debug",
+    "hgpu_poa_fetch", "hgpu_poa_get_stats", "hgpu_poa_set_timing", "hgpu_poa_configure", "hgpu_poa_debug", "hgpu_edge_coords",
 )
 
 
@@ -49,6 +49,8 @@ class DbgSizes(C.Structure):
 CL_ELEM = np.dtype([(n, "<u4") for n in ("hit", "q_start", "q_end", "t_start", "t_end", "n_match", "n_block",
                                          "cg_lo", "cg_lo_len", "cg_hi", "cg_hi_len")])
 EDGE_SUPP = np.dtype([("lr_id_strand", "<u4"), ("cmp_head", "<u4"), ("cmp_tail", "<u4")])
+EDGE_COORD = np.dtype([(n, "<u4") for n in ("int1_lo", "int1_hi", "int2_lo", "int2_hi", "c1", "c2", "n_best", "n_cns")])
+SUPP_COORD = np.dtype([("lr_start", "<i8"), ("lr_end", "<i8"), ("lr_strand", "<u4"), ("in_best", "<u4")])
 
 
 def lib_path():
@@ -249,3 +251,28 @@ def _backbone_edges(self, cl_tid, cl_rev, cl_read_off, min_edge_sup=3):
 
 Context.compact_lr = _compact_lr
 Context.backbone_edges = _backbone_edges
+
+
+def _edge_coords(self, edge_rev, supp_off, supp, elems, cl_read_off, read_len, hits):
+    """hgpu_edge_coords: per edge (rev1 | rev2 << 1) and its supports -> (EDGE_COORD[n_edges], SUPP_COORD[n_supp])."""
+    edge_rev = np.ascontiguousarray(edge_rev, dtype=np.uint8)
+    supp_off = np.ascontiguousarray(supp_off, dtype=np.uint32)
+    supp = np.ascontiguousarray(supp, dtype=EDGE_SUPP)
+    elems = np.ascontiguousarray(elems, dtype=CL_ELEM)
+    cl_read_off = np.ascontiguousarray(cl_read_off, dtype=np.uint32)
+    read_len = np.ascontiguousarray(read_len, dtype=np.uint32)
+    is_rev = np.ascontiguousarray(hits["is_rev"], dtype=np.uint8)
+    cg_off = np.ascontiguousarray(hits["cg_off"], dtype=np.uint32)
+    cg_ops = np.ascontiguousarray(hits["cg_ops"], dtype=np.uint32)
+    n = len(edge_rev)
+    oe = np.zeros(max(n, 1), dtype=EDGE_COORD); os_ = np.zeros(max(len(supp), 1), dtype=SUPP_COORD)
+    self.L.hgpu_edge_coords.restype = C.c_int
+    self.L.hgpu_edge_coords.argtypes = [C.c_void_p, C.c_uint32, u8p, u32p, C.c_void_p, C.c_void_p, u32p, C.c_uint32, u32p, u8p, u32p, u32p,
+                                        C.c_uint32, C.c_void_p, C.c_void_p]
+    self._check(self.L.hgpu_edge_coords(self.h, n, _p(edge_rev, u8p), _p(supp_off, u32p), supp.ctypes.data, elems.ctypes.data,
+                                        _p(cl_read_off, u32p), len(cl_read_off) - 1, _p(read_len, u32p), _p(is_rev, u8p), _p(cg_off, u32p),
+                                        _p(cg_ops, u32p), len(is_rev), oe.ctypes.data, os_.ctypes.data))
+    return oe[:n], os_[: len(supp)]
+
+
+Context.edge_coords = _edge_coords

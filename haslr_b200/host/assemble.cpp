@@ -1,9 +1,10 @@
 // Edge coordinates, consensus calling (GPU) and stitching.
 //
 // Restates the behaviour of the reference's src/haslr_assemble/src/Assemble.cpp: the canonical edge enumeration
-// (:365-434), the best-supported-interval sweeps (:24-126), the eight CIGAR-walk cases that map a contig position to
-// a read position (:129-155,253-338), the per-edge consensus call (:479-560 — here ONE batched hgpu_poa_batch call
-// instead of a SPOA engine per edge per thread) and the simple-path stitching (:607-810,1045-1077).
+// (:365-434), the edge coordinates (:24-363 — the interval sweeps and CIGAR walks run on the GPU, one hgpu_edge_coords
+// call for all edges; this file turns the answer into cns_supp lists and the reference's log), the per-edge consensus
+// call (:479-560 — here ONE batched hgpu_poa_batch call instead of a SPOA engine per edge per thread) and the
+// simple-path stitching (:607-810,1045-1077).
 #include <algorithm>
 #include <cstring>
 #include <deque>
@@ -35,127 +36,71 @@ void enumerate_edges(Graph& g, uint32_t flag, std::vector<EdgeRef>& out) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// best supported interval on one anchor contig: sweep over sorted begin/end lists (Assemble.cpp:24-126).
-// ge = true for the head contig (a later interval of equal depth wins), false for the tail contig.
+// edge coordinates: one hgpu_edge_coords call for all edges (best supported intervals on both anchors, the reads in
+// both best sets, the CIGAR walks to the anchor positions — Assemble.cpp:24-363); the host fills the graph's
+// cns_supp / head_end / tail_beg from the answer and writes the reference's log_coordinate.txt from it.
 // ---------------------------------------------------------------------------------------------------------
-static void best_interval(std::vector<std::pair<uint32_t, uint32_t>>& beg, std::vector<std::pair<uint32_t, uint32_t>>& end, bool ge,
-                          std::pair<uint32_t, uint32_t>& best, std::set<uint32_t>& best_lrs) {
-    std::sort(beg.begin(), beg.end());
-    std::sort(end.begin(), end.end());
-    int cur = 0, top = 0, i = 0, j = 0;
-    const int len = (int)beg.size();
-    uint32_t lo = 0, hi = 0;
-    bool open = false;
-    std::set<uint32_t> cur_lrs;
-    while (i < len && j < len) {
-        if (beg[i].first < end[j].first) {
-            ++cur;
-            cur_lrs.insert(beg[i].second);
-            if (ge ? cur >= top : cur > top) { top = cur; lo = beg[i].first; best_lrs = cur_lrs; open = true; }
-            ++i;
-        } else {
-            if (open) { hi = end[j].first; open = false; }
-            --cur;
-            cur_lrs.erase(end[j].second);
-            ++j;
-        }
+int calc_edge_coordinates(Graph& g, const std::vector<EdgeRef>& edges, const ContigStore& contigs, const SeqStore& reads,
+                          const CompactReads& cl, const PafTable& paf, hgpu_t* ctx, const std::string& logpath) {
+    if (edges.empty()) return 0;           // the reference returns before opening the log (quirk Q12)
+    const size_t n = edges.size();
+    std::vector<uint8_t> edge_rev(n);
+    std::vector<uint32_t> supp_off(n + 1, 0), read_len(reads.size());
+    std::vector<hgpu_edge_supp> supp;
+    std::vector<Edge*> e1(n), e2(n);
+    for (size_t e = 0; e < n; ++e) {
+        const EdgeRef& er = edges[e];
+        e1[e] = &g[er.node1].edges[er.rev1][(er.node2 << 1) | er.rev2];
+        e2[e] = &g[er.node2].edges[1 - er.rev2][(er.node1 << 1) | (1 - er.rev1)];
+        edge_rev[e] = (uint8_t)(er.rev1 | (er.rev2 << 1));
+        for (const EdgeSupp& s : e1[e]->edge_supp) supp.push_back({s.lr_id, s.cmp_head_id, s.cmp_tail_id});
+        supp_off[e + 1] = (uint32_t)supp.size();
     }
-    if (open) hi = end[j].first;
-    best = {lo, hi};
-}
+    for (size_t r = 0; r < reads.size(); ++r) read_len[r] = reads.len(r);
+    std::vector<hgpu_edge_coord> oe(n);
+    std::vector<hgpu_supp_coord> os(supp.size() + 1);
+    const int rc = hgpu_edge_coords(ctx, (uint32_t)n, edge_rev.data(), supp_off.data(), supp.data(), cl.elems.data(), cl.off.data(),
+                                    (uint32_t)reads.size(), read_len.data(), paf.is_rev.data(), paf.cg_off.data(),
+                                    paf.cg_ops.empty() ? paf.cg_off.data() : paf.cg_ops.data(), (uint32_t)paf.size(), oe.data(), os.data());
+    if (rc != HGPU_OK) { fprintf(stderr, "[ERROR] hgpu_edge_coords: %s\n", hgpu_last_error(ctx)); return rc; }
 
-// The kept part of a compact element's CIGAR as a run list: runs cg_lo..cg_hi of the hit, first/last clipped.
-struct RunView {
-    const uint32_t* ops; uint32_t lo, hi, lo_len, hi_len;
-    uint32_t n() const { return hi - lo + 1; }
-    // k-th run in forward order
-    void get(uint32_t k, uint32_t& op, uint32_t& len) const {
-        const uint32_t r = lo + k;
-        op = ops[r] & 3u;
-        len = (r == lo) ? lo_len : (r == hi ? hi_len : ops[r] >> 2);
-    }
-};
-static RunView run_view(const PafTable& paf, const hgpu_cl_elem& e) {
-    if (paf.cg_off[e.hit + 1] == paf.cg_off[e.hit]) return RunView{paf.cg_ops.data(), 1, 0, 0, 0};   // row without cg:Z: — no ops to walk
-    return RunView{paf.cg_ops.data() + paf.cg_off[e.hit], e.cg_lo, e.cg_hi, e.cg_lo_len, e.cg_hi_len};
-}
-
-// asm_find_lr_pos (Assemble.cpp:129-155) on runs: walk until the contig coordinate reaches `contig_pos`
-static long long find_lr_pos(const RunView& cg, bool reversed, uint32_t lr_curr, uint32_t c_curr, int lr_step, int c_step, uint32_t contig_pos) {
-    if ((c_step > 0 && c_curr > contig_pos) || (c_step < 0 && c_curr < contig_pos)) return -1;
-    uint32_t dist = c_step > 0 ? contig_pos - c_curr : c_curr - contig_pos;     // contig steps still to go
-    const uint32_t n = cg.n();
-    for (uint32_t k = 0; k < n && dist > 0; ++k) {
-        uint32_t op, len;
-        cg.get(reversed ? n - 1 - k : k, op, len);
-        if (op == 0) {                     // M: both move
-            const uint32_t take = std::min(len, dist);
-            lr_curr += (uint32_t)lr_step * take; dist -= take;
-        } else if (op == 1) {              // I: only the read moves
-            lr_curr += (uint32_t)lr_step * len;
-        } else {                           // D / anything else: only the contig moves
-            dist -= std::min(len, dist);
-        }
-    }
-    return lr_curr;
-}
-
-void calc_edge_coordinates(Graph& g, const std::vector<EdgeRef>& edges, const ContigStore& contigs, const SeqStore& reads,
-                           const CompactReads& cl, const PafTable& paf, const std::string& logpath) {
-    if (edges.empty()) return;             // the reference returns before opening the log (quirk Q12)
     FILE* fp = logpath.empty() ? nullptr : open_write(logpath);
 #define LOG(...) do { if (fp) fprintf(fp, __VA_ARGS__); } while (0)
     auto elem = [&](uint32_t rid, uint32_t cmp) -> const hgpu_cl_elem& { return cl.elems[cl.off[rid] + cmp]; };
-    for (const EdgeRef& er : edges) {
-        const uint32_t node1 = er.node1, rev1 = er.rev1, node2 = er.node2, rev2 = er.rev2;
+    for (size_t e = 0; e < n; ++e) {
+        const uint32_t node1 = edges[e].node1, rev1 = edges[e].rev1, node2 = edges[e].node2, rev2 = edges[e].rev2;
+        Edge& edge1 = *e1[e];
+        Edge& edge2 = *e2[e];
+        const std::vector<EdgeSupp>& es = edge1.edge_supp;
+        const hgpu_edge_coord& c = oe[e];
+        const hgpu_supp_coord* sc = os.data() + supp_off[e];
         LOG("calc_coords th_id:%d %u:%c -> %u:%c\n", 0, node1, sgn(rev1), node2, sgn(rev2));
-        Edge& edge1 = g[node1].edges[rev1][(node2 << 1) | rev2];
-        Edge& edge2 = g[node2].edges[1 - rev2][(node1 << 1) | (1 - rev1)];
         LOG("edge      %u:%c -> %u:%c\n", node1, sgn(rev1), node2, sgn(rev2));
         LOG("edge_twin %u:%c -> %u:%c\n", node2, sgn(1 - rev2), node1, sgn(1 - rev1));
-        const std::vector<EdgeSupp>& es = edge1.edge_supp;
         LOG("\tedge_supp size:%zu\n", es.size());
-        std::vector<std::pair<uint32_t, uint32_t>> beg1, end1, beg2, end2;
-        for (uint32_t i = 0; i < es.size(); ++i) {
+        if (fp) for (uint32_t i = 0; i < es.size(); ++i) {
             const hgpu_cl_elem& h = elem(es[i].lr_id, es[i].cmp_head_id);
             const hgpu_cl_elem& t = elem(es[i].lr_id, es[i].cmp_tail_id);
             LOG("\tsupp_detail head\t%u\t%u\t%c\ttail\t%u\t%u\t%c\n", h.t_start, h.t_end, sgn(paf.is_rev[h.hit]), t.t_start, t.t_end, sgn(paf.is_rev[t.hit]));
-            beg1.push_back({h.t_start, i}); end1.push_back({h.t_end, i});
-            beg2.push_back({t.t_start, i}); end2.push_back({t.t_end, i});
         }
-        std::pair<uint32_t, uint32_t> int1, int2;
-        std::set<uint32_t> lrs1, lrs2;
-        best_interval(beg1, end1, true, int1, lrs1);
-        LOG("    @@@ best interval contig1 %u %u\n", int1.first, int1.second);
-        best_interval(beg2, end2, false, int2, lrs2);
-        LOG("    @@@ best_interval contig2 %u %u\n", int2.first, int2.second);
-        const uint32_t c1 = rev1 == 0 ? int1.second - 1 : int1.first;      // last shared base on the head contig
-        const uint32_t c2 = rev2 == 0 ? int2.first : int2.second - 1;      // first shared base on the tail contig
-        std::vector<uint32_t> best;
-        std::set_intersection(lrs1.begin(), lrs1.end(), lrs2.begin(), lrs2.end(), std::back_inserter(best));
-        LOG("coordinates contig1_pos: %u\tcontig2_pos: %u\n", c1, c2);
-        LOG("supproting_lr: %lu\n", (unsigned long)best.size());
+        LOG("    @@@ best interval contig1 %u %u\n", c.int1_lo, c.int1_hi);
+        LOG("    @@@ best_interval contig2 %u %u\n", c.int2_lo, c.int2_hi);
+        LOG("coordinates contig1_pos: %u\tcontig2_pos: %u\n", c.c1, c.c2);
+        LOG("supproting_lr: %lu\n", (unsigned long)c.n_best);
         auto no_support = [&]() {
             edge1.cns_supp.clear(); edge2.cns_supp.clear();
             edge1.head_end = edge2.tail_beg = (rev1 == 0 ? contigs.len(node1) - 1 : 0);
             edge1.tail_beg = edge2.head_end = (rev2 == 0 ? 0 : contigs.len(node2) - 1);
         };
-        if (best.empty()) { no_support(); continue; }
-        for (uint32_t bi : best) {
-            const uint32_t rid = es[bi].lr_id, rlen = reads.len(rid);
-            const hgpu_cl_elem& a1 = elem(rid, es[bi].cmp_head_id);
-            const hgpu_cl_elem& a2 = elem(rid, es[bi].cmp_tail_id);
-            const uint32_t rstrand = (rev1 == paf.is_rev[a1.hit]) ? 0 : 1;
+        if (c.n_best == 0) { no_support(); continue; }           // the reference returns here, without the blank line
+        edge1.cns_supp.clear(); edge2.cns_supp.clear();
+        for (uint32_t i = 0; i < es.size(); ++i) {
+            if (!sc[i].in_best) continue;
+            const uint32_t rid = es[i].lr_id, rlen = reads.len(rid), rstrand = sc[i].lr_strand;
             LOG("    +++ lr:%u len:%u strand:%c\n", rid, rlen, sgn(rstrand));
-            const RunView cg1 = run_view(paf, a1), cg2 = run_view(paf, a2);
-            long long lr_start, lr_end;
-            // head anchor: where on the (oriented) read does contig position c1 fall; cases 1/2 and 5/6 differ only in q0
-            const uint32_t q0h = rstrand == 0 ? a1.q_start : rlen - a1.q_end;
-            const uint32_t q0t = rstrand == 0 ? a2.q_end - 1 : rlen - a2.q_start - 1;
-            if (rev1 == 0) { LOG("        case %d\n", rstrand ? 5 : 1); lr_start = find_lr_pos(cg1, false, q0h, a1.t_start, +1, +1, c1); }
-            else           { LOG("        case %d\n", rstrand ? 6 : 2); lr_start = find_lr_pos(cg1, true, q0h, a1.t_end - 1, +1, -1, c1); }
-            if (rev2 == 0) { LOG("        case %d\n", rstrand ? 7 : 3); lr_end = find_lr_pos(cg2, true, q0t, a2.t_end - 1, -1, -1, c2); }
-            else           { LOG("        case %d\n", rstrand ? 8 : 4); lr_end = find_lr_pos(cg2, false, q0t, a2.t_start, -1, +1, c2); }
+            LOG("        case %d\n", rev1 == 0 ? (rstrand ? 5 : 1) : (rstrand ? 6 : 2));
+            LOG("        case %d\n", rev2 == 0 ? (rstrand ? 7 : 3) : (rstrand ? 8 : 4));
+            const long long lr_start = sc[i].lr_start, lr_end = sc[i].lr_end;
             if (lr_start != -1 && lr_end != -1) {
                 LOG("        [coordinate] subseq_len:%lld lr_start:%lld lr_end:%lld\n", lr_end - lr_start - 1, lr_start + 1, lr_end - 1);
                 edge1.cns_supp.push_back({rid, rstrand, uint32_t(lr_start + 1), uint32_t(lr_end - 1)});
@@ -165,8 +110,8 @@ void calc_edge_coordinates(Graph& g, const std::vector<EdgeRef>& edges, const Co
             }
         }
         if (!edge1.cns_supp.empty()) {
-            edge1.head_end = edge2.tail_beg = c1;
-            edge1.tail_beg = edge2.head_end = c2;
+            edge1.head_end = edge2.tail_beg = c.c1;
+            edge1.tail_beg = edge2.head_end = c.c2;
         } else {
             no_support();
         }
@@ -175,6 +120,7 @@ void calc_edge_coordinates(Graph& g, const std::vector<EdgeRef>& edges, const Co
 #undef LOG
     // (the reference never closes this file; it is flushed at exit — same bytes)
     if (fp) fclose(fp);
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------

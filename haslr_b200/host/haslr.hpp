@@ -96,8 +96,8 @@ void report_branching(const Graph& g, const std::string& logpath);
 // assemble.cpp
 struct EdgeRef { uint32_t node1, rev1, node2, rev2; };
 void enumerate_edges(Graph& g, uint32_t flag, std::vector<EdgeRef>& out);
-void calc_edge_coordinates(Graph& g, const std::vector<EdgeRef>& edges, const ContigStore& contigs, const SeqStore& reads,
-                           const CompactReads& cl, const PafTable& paf, const std::string& logpath);
+int calc_edge_coordinates(Graph& g, const std::vector<EdgeRef>& edges, const ContigStore& contigs, const SeqStore& reads,
+                          const CompactReads& cl, const PafTable& paf, hgpu_t* ctx, const std::string& logpath);
 int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& reads, const std::vector<hgpu_t*>& ctxs,
                    const std::string& logpath, bool write_log, unsigned threads);
 void write_assembly(Graph& g, const ContigStore& contigs, const std::string& out_dir);

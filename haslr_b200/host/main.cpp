@@ -210,10 +210,10 @@ int main(int argc, char** argv) {
     lap();
     report_branching(g, d + "/backbone.branching.log");
 
-    fprintf(stderr, "[NOTE] calculating long read coordinates between anchors...\n");
+    fprintf(stderr, "[NOTE] calculating long read coordinates between anchors (GPU)...\n");
     std::vector<EdgeRef> edges;
     enumerate_edges(g, 11, edges);
-    calc_edge_coordinates(g, edges, contigs, reads, cl, paf, logs ? d + "/log_coordinate.txt" : std::string());
+    if (calc_edge_coordinates(g, edges, contigs, reads, cl, paf, ctxs[0], logs ? d + "/log_coordinate.txt" : std::string()) != 0) return EXIT_FAILURE;
     lap();
 
     // (iii) all edges in one batched POA call per GPU

@@ -90,6 +90,34 @@ int hgpu_backbone_edges(hgpu_t* ctx, const uint32_t* cl_tid, const uint8_t* cl_r
                         uint64_t* out_key, uint32_t* out_supp_off, hgpu_edge_supp* out_supp, uint8_t* out_keep,
                         uint64_t* out_n_entries);
 
+/* ---- (iv) edge coordinates: the stretch of each supporting long read that spans an edge's gap -----------------
+ * (numbered after (iii) because it was added after it; in the pipeline it runs between (ii) + graph cleaning and (iii).)
+ * Replaces asm_calc_single_edge_coordinates with asm_best_supported_interval_contig1/2 and asm_find_lr_pos
+ * (Assemble.cpp:24-155,157-363) and the pthread edge queue of asm_calc_coordinates_MT around them (Assemble.cpp:436-477).
+ * Edge e: rev1 = edge_rev[e] & 1, rev2 = (edge_rev[e] >> 1) & 1 (strands of node1 / node2 as asm_get_next_edge yields
+ * them); its supports are supp[supp_off[e] .. supp_off[e+1]) in edge_supp order (the strand bit of lr_id_strand is
+ * ignored). elems / cl_read_off are hgpu_compact_lr's outputs, read_len the long-read lengths, hit_is_rev / cg_off /
+ * cg_ops the hit table the elements point into (hgpu_hits_t). Outputs are aligned with the inputs: one
+ * hgpu_edge_coord per edge and one hgpu_supp_coord per support. A support yields a cns_supp entry
+ * {lr_id, lr_strand, spos = lr_start + 1, epos = lr_end - 1} (Assemble.cpp:322-325) iff in_best and both lr_start and
+ * lr_end are != -1; an edge with n_cns == 0 keeps no consensus support (Assemble.cpp:244-251,354-361). */
+typedef struct {
+    uint32_t int1_lo, int1_hi;   /* best supported interval on the head contig (best_int1) */
+    uint32_t int2_lo, int2_hi;   /* ... on the tail contig (best_int2) */
+    uint32_t c1, c2;             /* contig1_pos, contig2_pos */
+    uint32_t n_best;             /* |best_lrs1 n best_lrs2| */
+    uint32_t n_cns;              /* of which both CIGAR walks succeeded = cns_supp.size() */
+} hgpu_edge_coord;
+typedef struct {
+    int64_t  lr_start, lr_end;   /* asm_find_lr_pos results (exclusive bounds), -1 = refused; meaningful iff in_best */
+    uint32_t lr_strand;          /* strand of the read relative to the edge */
+    uint32_t in_best;            /* 1 iff the support is in both best sets */
+} hgpu_supp_coord;
+int hgpu_edge_coords(hgpu_t* ctx, uint32_t n_edges, const uint8_t* edge_rev, const uint32_t* supp_off, const hgpu_edge_supp* supp,
+                     const hgpu_cl_elem* elems, const uint32_t* cl_read_off, uint32_t n_reads, const uint32_t* read_len,
+                     const uint8_t* hit_is_rev, const uint32_t* cg_off, const uint32_t* cg_ops, uint32_t n_hits,
+                     hgpu_edge_coord* out_edge, hgpu_supp_coord* out_supp);
+
 /* ---- (iii) batched POA consensus -------------------------------------------------------------------------
  * Replaces the body of asm_calc_single_cns_seq (Assemble.cpp:499-554), i.e. per backbone edge the five SPOA
  * calls createAlignmentEngine(kNW, match, mismatch, gap), createGraph(), align_sequence_with_graph(),

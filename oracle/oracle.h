@@ -4,8 +4,8 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this library.
  * The product library (haslr_b200/csrc) never includes or links anything in oracle/.
  *
- * K1/K2 (oracle_k12.cpp) restate Longread.cpp / Backbone_graph.cpp and are pinned against outputs of the
- * reference binary built by oracle/Makefile (tests/golden/). K3 (oracle_poa.cpp) wraps the restated SPOA
+ * K1/K2 (oracle_k12.cpp) and K4 (oracle_coords.cpp) restate Longread.cpp / Backbone_graph.cpp / the coordinate part
+ * of Assemble.cpp and are pinned against outputs of the reference binary built by oracle/Makefile (tests/golden/). K3 (oracle_poa.cpp) wraps the restated SPOA
  * 1.1.3 (spoa_restated/spoa.hpp): PARITY UNPINNED — see that header.
  */
 #ifndef HASLR_ORACLE_H
@@ -81,6 +81,20 @@ typedef struct { uint32_t lr_id_strand; /* lr_id | strand << 31 */ uint32_t cmp_
 int64_t oracle_backbone_edges(const uint32_t* cl_tid, const uint8_t* cl_rev, const uint32_t* cl_read_off, uint32_t n_reads,
                               uint32_t min_edge_sup,
                               uint64_t* out_key, uint32_t* out_supp_off, oracle_edge_supp* out_supp, uint8_t* out_keep);
+
+/* ---- K4: edge coordinates (Assemble.cpp:24-155,157-363) --------------------------------------------------- */
+/* edge e: rev1 = edge_rev[e] & 1, rev2 = edge_rev[e] >> 1 & 1; its supports are supp[supp_off[e] .. supp_off[e+1]) in
+ * edge_supp order (lr_id_strand's strand bit is ignored); elems / cl_read_off = the compact long reads;
+ * hit_is_rev / cg_off / cg_ops = the PAF hit table the elements point into. Outputs are aligned with the inputs:
+ * one oracle_edge_coord per edge, one oracle_supp_coord per support (in_best = 1 for members of best_lrs1 n best_lrs2;
+ * lr_start / lr_end as asm_find_lr_pos returns them, -1 = refused; a support yields a cns_supp entry iff in_best and
+ * both are != -1: {lr_id, lr_strand, lr_start + 1, lr_end - 1}). */
+typedef struct { uint32_t int1_lo, int1_hi, int2_lo, int2_hi, c1, c2, n_best, n_cns; } oracle_edge_coord;
+typedef struct { int64_t lr_start, lr_end; uint32_t lr_strand, in_best; } oracle_supp_coord;
+int oracle_edge_coords(uint32_t n_edges, const uint8_t* edge_rev, const uint32_t* supp_off, const oracle_edge_supp* supp,
+                       const oracle_cl_elem* elems, const uint32_t* cl_read_off, const uint32_t* read_len,
+                       const uint8_t* hit_is_rev, const uint32_t* cg_off, const uint32_t* cg_ops,
+                       oracle_edge_coord* out_edge, oracle_supp_coord* out_supp);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,10 @@
        syn200k_backbone0[12].stat  bbg_general_stats output
        syn200k_poa.txt.gz          log_consensus.txt reduced to: per edge the segments fed to SPOA and the consensus
                                    (the reference's own call sequence, Assemble.cpp:499-554, around the restated SPOA)
+       syn200k_coords.txt          log_coordinate.txt reduced to: per edge  E node1 rev1 node2 rev2 n_supp int1 int2 c1 c2 n_best,
+                                   per support  D head(t_start t_end strand) tail(...),  per best support  S lr len strand
+                                   spos epos | X   (asm_calc_single_edge_coordinates, Assemble.cpp:157-363)
+       syn200k_read_len.npy        long-read lengths (Longread_List_t::reads[i].len)
 """
 import gzip
 import os
@@ -64,6 +68,40 @@ def main():
                 elif want_seq:
                     g.write(want_seq + " " + line)
                     want_seq = False
+        # edge coordinates
+        sg = {"+": 0, "-": 1}
+        with open(os.path.join(out, "log_coordinate.txt")) as f, open(os.path.join(HERE, "syn200k_coords.txt"), "w") as g:
+            cur = None
+            def flush():
+                if cur:
+                    g.write("E %s %s\n" % (" ".join(map(str, cur["e"])), " ".join(map(str, cur["v"]))))
+                    g.write("".join(cur["lines"]))
+            for line in f:
+                t = line.split()
+                if line.startswith("edge "):
+                    flush()
+                    a, b = t[1].split(":"), t[3].split(":")
+                    cur = {"e": [int(a[0]), sg[a[1]], int(b[0]), sg[b[1]]], "v": [], "lines": []}
+                elif line.startswith("\tedge_supp size:"):
+                    cur["v"].append(int(line.split(":")[1]))
+                elif line.startswith("\tsupp_detail"):
+                    cur["lines"].append("D %s %s %d %s %s %d\n" % (t[2], t[3], sg[t[4]], t[6], t[7], sg[t[8]]))
+                elif "@@@" in line:
+                    cur["v"] += [int(t[-2]), int(t[-1])]
+                elif line.startswith("coordinates"):
+                    cur["v"] += [int(t[2]), int(t[4])]
+                elif line.startswith("supproting_lr"):
+                    cur["v"].append(int(t[1]))
+                elif "+++" in line:
+                    cur["pending"] = "S %s %s %d" % (t[1].split(":")[1], t[2].split(":")[1], sg[t[3].split(":")[1]])
+                elif "[coordinate]" in line:
+                    if "could not" in line:
+                        cur["lines"].append(cur["pending"] + " X\n")
+                    else:
+                        cur["lines"].append("%s %s %s\n" % (cur["pending"], t[2].split(":")[1], t[3].split(":")[1]))
+            flush()
+        reads = io_helpers.load_fasta(os.path.join(tmp, "reads.fa"))
+        np.save(os.path.join(HERE, "syn200k_read_len.npy"), np.array([len(r) for r in reads], dtype=np.uint32))
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     for n in sorted(os.listdir(HERE)):

@@ -33,3 +33,44 @@ def poa_edges():
             elif tag == "C":
                 out[-1][2] = rest.encode()
     return out
+
+
+def coords():
+    """[dict(edge=(node1, rev1, node2, rev2), n_supp, int1, int2, c1, c2, n_best, detail=[(hs, he, hrev, ts, te, trev)],
+    best=[(lr, len, strand, spos, epos) | (lr, len, strand, None, None)])] in the order the reference processed the edges."""
+    out = []
+    with open(os.path.join(GOLD, "syn200k_coords.txt")) as f:
+        for line in f:
+            t = line.split()
+            if t[0] == "E":
+                v = list(map(int, t[1:]))
+                out.append(dict(edge=tuple(v[0:4]), n_supp=v[4], int1=(v[5], v[6]), int2=(v[7], v[8]), c1=v[9], c2=v[10], n_best=v[11],
+                                detail=[], best=[]))
+            elif t[0] == "D":
+                out[-1]["detail"].append(tuple(map(int, t[1:])))
+            elif t[0] == "S":
+                out[-1]["best"].append((int(t[1]), int(t[2]), int(t[3])) + ((None, None) if t[4] == "X" else (int(t[4]), int(t[5]))))
+    return out
+
+
+def read_len():
+    return np.load(os.path.join(GOLD, "syn200k_read_len.npy"))
+
+
+def coord_inputs(oracle):
+    """Inputs of the edge-coordinate stage for the golden dataset: the edges the reference processed (after cleaning), with
+    their supports looked up in the oracle's K2 table of the oracle's K1 output (cleaning removes edges, never edits them)."""
+    g = inputs()
+    elems, off = oracle.compact_lr(g["hits"], g["read_off"], g["mean_kmer"], g["uniq_freq"])
+    key, soff, supp, _ = oracle.backbone_edges(g["hits"]["t_id"][elems["hit"]], g["hits"]["is_rev"][elems["hit"]], off, 3)
+    pos = {int(k): i for i, k in enumerate(key.tolist())}
+    gold = coords()
+    rev, so, parts = [], [0], []
+    for e in gold:
+        n1, r1, n2, r2 = e["edge"]
+        i = pos[(((n1 << 1) | r1) << 32) | ((n2 << 1) | r2)]
+        parts.append(supp[int(soff[i]): int(soff[i + 1])])
+        so.append(so[-1] + len(parts[-1]))
+        rev.append(r1 | (r2 << 1))
+    return dict(g=g, elems=elems, cl_off=off, edge_rev=np.array(rev, dtype=np.uint8), supp_off=np.array(so, dtype=np.uint32),
+                supp=np.concatenate(parts), read_len=read_len(), gold=gold)

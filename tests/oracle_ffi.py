@@ -154,3 +154,27 @@ def backbone_edges(cl_tid, cl_rev, cl_read_off, min_edge_sup=3):
     n = lib().oracle_backbone_edges(_p(cl_tid, u32p), _p(cl_rev, u8p), _p(cl_read_off, u32p), n_reads, min_edge_sup,
                                     _p(key, u64p), _p(soff, u32p), supp.ctypes.data, _p(keep, u8p))
     return key[:n].copy(), soff[: n + 1].copy(), supp[: int(soff[n])].copy(), keep[:n].copy()
+
+
+EDGE_COORD = np.dtype([(n, "<u4") for n in ("int1_lo", "int1_hi", "int2_lo", "int2_hi", "c1", "c2", "n_best", "n_cns")])
+SUPP_COORD = np.dtype([("lr_start", "<i8"), ("lr_end", "<i8"), ("lr_strand", "<u4"), ("in_best", "<u4")])
+
+
+def edge_coords(edge_rev, supp_off, supp, elems, cl_read_off, read_len, hits):
+    """K4 oracle: per edge (rev1 | rev2 << 1) and its supports -> (EDGE_COORD[n_edges], SUPP_COORD[n_supp])."""
+    edge_rev = np.ascontiguousarray(edge_rev, dtype=np.uint8)
+    supp_off = np.ascontiguousarray(supp_off, dtype=np.uint32)
+    supp = np.ascontiguousarray(supp, dtype=EDGE_SUPP)
+    elems = np.ascontiguousarray(elems, dtype=CL_ELEM)
+    cl_read_off = np.ascontiguousarray(cl_read_off, dtype=np.uint32)
+    read_len = np.ascontiguousarray(read_len, dtype=np.uint32)
+    n = len(edge_rev)
+    oe = np.zeros(max(n, 1), dtype=EDGE_COORD); os_ = np.zeros(max(len(supp), 1), dtype=SUPP_COORD)
+    L = lib()
+    L.oracle_edge_coords.restype = C.c_int
+    L.oracle_edge_coords.argtypes = [C.c_uint32, u8p, u32p, C.c_void_p, C.c_void_p, u32p, u32p, u8p, u32p, u32p, C.c_void_p, C.c_void_p]
+    rc = L.oracle_edge_coords(n, _p(edge_rev, u8p), _p(supp_off, u32p), supp.ctypes.data, elems.ctypes.data, _p(cl_read_off, u32p),
+                              _p(read_len, u32p), _p(hits["is_rev"], u8p), _p(hits["cg_off"], u32p), _p(hits["cg_ops"], u32p),
+                              oe.ctypes.data, os_.ctypes.data)
+    assert rc == 0
+    return oe[:n], os_[: len(supp)]
