@@ -1,6 +1,6 @@
 // (iv) edge coordinates: which stretch of every supporting long read spans the gap of a backbone edge — kernel + C ABI.
 //
-// hgpu_edge_coords replaces asm_calc_single_edge_coordinates and the pthread edge queue of asm_calc_coordinates_MT
+// hgpu_edge_coords replaces asm_calc_single_edge_coordinates and the pthread edge queue of asm_calc_edge_coordinates_MT
 // around it (reference src/haslr_assemble/src/Assemble.cpp:24-155,157-363,436-477). One warp per edge:
 //   1. lanes load the edge's supports and their head / tail compact-read elements (coalesced over the support list) and
 //      lay down four key lists (begin / end on each anchor contig), key = position << 32 | support index;

@@ -93,7 +93,7 @@ int hgpu_backbone_edges(hgpu_t* ctx, const uint32_t* cl_tid, const uint8_t* cl_r
 /* ---- (iv) edge coordinates: the stretch of each supporting long read that spans an edge's gap -----------------
  * (numbered after (iii) because it was added after it; in the pipeline it runs between (ii) + graph cleaning and (iii).)
  * Replaces asm_calc_single_edge_coordinates with asm_best_supported_interval_contig1/2 and asm_find_lr_pos
- * (Assemble.cpp:24-155,157-363) and the pthread edge queue of asm_calc_coordinates_MT around them (Assemble.cpp:436-477).
+ * (Assemble.cpp:24-155,157-363) and the pthread edge queue of asm_calc_edge_coordinates_MT around them (Assemble.cpp:436-477).
  * Edge e: rev1 = edge_rev[e] & 1, rev2 = (edge_rev[e] >> 1) & 1 (strands of node1 / node2 as asm_get_next_edge yields
  * them); its supports are supp[supp_off[e] .. supp_off[e+1]) in edge_supp order (the strand bit of lr_id_strand is
  * ignored). elems / cl_read_off are hgpu_compact_lr's outputs, read_len the long-read lengths, hit_is_rev / cg_off /
