@@ -5,7 +5,7 @@ NVFLAGS  := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-
 CSRC     := haslr_b200/csrc
 OBJDIR   := build/obj
 LIB      := haslr_b200/libhaslr_b200.so
-TUS      := api poa k12 coords
+TUS      := api poa k12 coords paf
 HDRS     := $(wildcard $(CSRC)/*.cuh) include/haslr_b200.h
 
 HOSTSRC  := $(wildcard haslr_b200/host/*.cpp)

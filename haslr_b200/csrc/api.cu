@@ -43,6 +43,7 @@ extern "C" void hgpu_destroy(hgpu_t* ctx) {
     poa_state_destroy(ctx->poa);
     k12_state_destroy(ctx->k12);
     coord_state_destroy(ctx->coords);
+    paf_state_destroy(ctx->paf);
     delete ctx;
 }
 

@@ -11,6 +11,7 @@
 struct PoaState;  // poa.cu
 struct K12State;  // k12.cu
 struct CoordState;  // coords.cu
+struct PafState;  // paf.cu
 
 struct hgpu_ctx {
     int device = 0;
@@ -22,6 +23,7 @@ struct hgpu_ctx {
     PoaState* poa = nullptr;
     K12State* k12 = nullptr;
     CoordState* coords = nullptr;
+    PafState* paf = nullptr;
 };
 
 #define HGPU_CUDA(ctx, expr)                                                                         \
@@ -66,3 +68,4 @@ struct DevBuf {
 void poa_state_destroy(PoaState* s);
 void k12_state_destroy(K12State* s);
 void coord_state_destroy(CoordState* s);
+void paf_state_destroy(PafState* s);

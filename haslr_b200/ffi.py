@@ -14,6 +14,7 @@ EXPORTS = (
     "hgpu_create", "hgpu_destroy", "hgpu_set_stream", "hgpu_strerror", "hgpu_last_error", "hgpu_abi_version",
     "hgpu_launch_count", "hgpu_compact_lr", "hgpu_backbone_edges", "hgpu_poa_batch", "hgpu_poa_batch_dev",
     "hgpu_poa_fetch", "hgpu_poa_get_stats", "hgpu_poa_set_timing", "hgpu_poa_configure", "hgpu_poa_debug", "hgpu_edge_coords",
+    "hgpu_paf_tokenize", "hgpu_paf_fetch",
 )
 
 
@@ -276,3 +277,30 @@ def _edge_coords(self, edge_rev, supp_off, supp, elems, cl_read_off, read_len, h
 
 
 Context.edge_coords = _edge_coords
+
+
+def _parse_paf(self, text):
+    """hgpu_paf_tokenize + hgpu_paf_fetch: PAF bytes -> hits dict (same keys as tests/io_helpers.parse_paf)."""
+    buf = np.frombuffer(bytes(text), dtype=np.uint8) if not isinstance(text, np.ndarray) else np.ascontiguousarray(text, dtype=np.uint8)
+    nr, no = C.c_uint64(0), C.c_uint64(0)
+    self.L.hgpu_paf_tokenize.restype = C.c_int
+    self.L.hgpu_paf_tokenize.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    self._check(self.L.hgpu_paf_tokenize(self.h, buf.ctypes.data if len(buf) else None, len(buf), C.byref(nr), C.byref(no)))
+    n, m = nr.value, no.value
+    names = ("q_id", "q_len", "q_start", "q_end", "t_id", "t_len", "t_start", "t_end", "n_match", "n_block")
+    h = {k: np.zeros(max(n, 1), dtype=np.uint32) for k in names}
+    h["is_rev"] = np.zeros(max(n, 1), dtype=np.uint8); h["mapq"] = np.zeros(max(n, 1), dtype=np.uint8)
+    h["cg_off"] = np.zeros(n + 1, dtype=np.uint32); h["cg_ops"] = np.zeros(max(m, 1), dtype=np.uint32)
+    self.L.hgpu_paf_fetch.restype = C.c_int
+    self.L.hgpu_paf_fetch.argtypes = [C.c_void_p] + [u32p] * 4 + [u8p] + [u32p] * 6 + [u8p, u32p, u32p]
+    self._check(self.L.hgpu_paf_fetch(self.h, _p(h["q_id"], u32p), _p(h["q_len"], u32p), _p(h["q_start"], u32p), _p(h["q_end"], u32p),
+                                      _p(h["is_rev"], u8p), _p(h["t_id"], u32p), _p(h["t_len"], u32p), _p(h["t_start"], u32p), _p(h["t_end"], u32p),
+                                      _p(h["n_match"], u32p), _p(h["n_block"], u32p), _p(h["mapq"], u8p), _p(h["cg_off"], u32p), _p(h["cg_ops"], u32p)))
+    for k in names + ("is_rev", "mapq"):
+        h[k] = h[k][:n]
+    if m == 0:
+        h["cg_ops"] = np.zeros(1, dtype=np.uint32)       # io_helpers.parse_paf keeps one dummy word so pointers stay valid
+    return h
+
+
+Context.parse_paf = _parse_paf

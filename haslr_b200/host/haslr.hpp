@@ -73,7 +73,7 @@ typedef std::vector<Node> Graph;
 // io.cpp
 void load_fasta(const std::string& path, SeqStore& out, ContigStore* contig_meta);
 void load_fofn(const std::string& path, std::vector<std::string>& files);
-void load_paf(const std::string& path, PafTable& paf);
+void load_paf(const std::string& path, PafTable& paf, hgpu_t* ctx);
 void finish_paf(PafTable& paf, size_t n_reads);
 double calc_uniq_freq(const ContigStore& c);
 std::string revcomp(const std::string& s);

@@ -1,4 +1,5 @@
 // Input side: FASTA/FASTQ (plain or gzip), PAF, plus the small shared helpers.
+#include <sys/stat.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -126,67 +127,44 @@ void load_fofn(const std::string& path, std::vector<std::string>& files) {
     while (getline(fin, line)) if (!line.empty()) files.push_back(line);
 }
 
-static inline uint32_t parse_u32(const char* b, const char* e) {
-    uint64_t v = 0;
-    for (; b < e && *b >= '0' && *b <= '9'; ++b) v = v * 10 + (uint64_t)(*b - '0');
-    return (uint32_t)v;
-}
-
 // minimap2 PAF with cg:Z: (Longread.cpp:234-302 reads columns 1-12 and the cg tag). All rows are kept: the load
-// filters run on the GPU. The file is mapped whole and tokenised by hand — no per-field string objects.
-void load_paf(const std::string& path, PafTable& paf) {
+// filters run in hgpu_compact_lr. The file is read whole and tokenised on the GPU (hgpu_paf_tokenize / hgpu_paf_fetch);
+// further files of a fofn are appended.
+void load_paf(const std::string& path, PafTable& paf, hgpu_t* ctx) {
     FILE* fp = fopen(path.c_str(), "rb");
     if (!fp) { fprintf(stderr, "[ERROR] (load_paf) could not open file: %s\n", path.c_str()); exit(EXIT_FAILURE); }
-    std::vector<char> buf(1 << 24);
-    std::string carry;
-    auto parse_line = [&](const char* b, const char* e) {
-        if (b == e) return;
-        const char* f[13]; int nf = 0;
-        f[nf++] = b;
-        for (const char* p = b; p < e && nf < 13; ++p) if (*p == '\t') f[nf++] = p + 1;
-        if (nf < 12) { fprintf(stderr, "[ERROR] (load_paf) line with %d columns\n", nf); exit(EXIT_FAILURE); }
-        auto fe = [&](int i) { return i + 1 < nf ? f[i + 1] - 1 : e; };
-        paf.q_id.push_back(parse_u32(f[0], fe(0))); paf.q_len.push_back(parse_u32(f[1], fe(1)));
-        paf.q_start.push_back(parse_u32(f[2], fe(2))); paf.q_end.push_back(parse_u32(f[3], fe(3)));
-        paf.is_rev.push_back(*f[4] == '-' ? 1 : 0);
-        paf.t_id.push_back(parse_u32(f[5], fe(5))); paf.t_len.push_back(parse_u32(f[6], fe(6)));
-        paf.t_start.push_back(parse_u32(f[7], fe(7))); paf.t_end.push_back(parse_u32(f[8], fe(8)));
-        paf.n_match.push_back(parse_u32(f[9], fe(9))); paf.n_block.push_back(parse_u32(f[10], fe(10)));
-        paf.mapq.push_back((uint8_t)parse_u32(f[11], fe(11)));
-        // first cg:Z: tag among the optional columns
-        const char* p = nf > 12 ? f[12] : e;
-        while (p < e) {
-            const char* t = (const char*)memchr(p, '\t', e - p);
-            const char* te = t ? t : e;
-            if (te - p >= 5 && memcmp(p, "cg:Z:", 5) == 0) {
-                const char* c = p + 5;
-                while (c < te) {
-                    uint32_t n = 0;
-                    while (c < te && *c >= '0' && *c <= '9') n = n * 10 + (uint32_t)(*c++ - '0');
-                    if (c >= te) break;
-                    const char op = *c++;
-                    paf.cg_ops.push_back((n << 2) | (op == 'M' ? 0u : op == 'I' ? 1u : 2u));
-                }
-                break;
-            }
-            p = te + 1;
+    std::vector<char> text;
+    {
+        struct stat sb;
+        size_t guess = (fstat(fileno(fp), &sb) == 0 && sb.st_size > 0) ? (size_t)sb.st_size : (size_t)(1 << 24);
+        text.resize(guess + 1);
+        size_t n = 0;
+        while (true) {
+            if (n == text.size()) text.resize(text.size() * 2);
+            const size_t got = fread(text.data() + n, 1, text.size() - n, fp);
+            if (got == 0) break;
+            n += got;
         }
-        paf.cg_off.push_back((uint32_t)paf.cg_ops.size());
-    };
-    while (true) {
-        size_t n = fread(buf.data(), 1, buf.size(), fp);
-        if (n == 0) break;
-        const char* b = buf.data(); const char* end = b + n;
-        while (b < end) {
-            const char* nl = (const char*)memchr(b, '\n', end - b);
-            if (!nl) { carry.append(b, end - b); break; }
-            if (!carry.empty()) { carry.append(b, nl - b); parse_line(carry.data(), carry.data() + carry.size()); carry.clear(); }
-            else parse_line(b, nl);
-            b = nl + 1;
-        }
+        text.resize(n);
     }
-    if (!carry.empty()) parse_line(carry.data(), carry.data() + carry.size());
     fclose(fp);
+    uint64_t rows = 0, ops = 0;
+    if (hgpu_paf_tokenize(ctx, text.data(), text.size(), &rows, &ops) != HGPU_OK) {
+        fprintf(stderr, "[ERROR] (load_paf) %s: %s\n", path.c_str(), hgpu_last_error(ctx)); exit(EXIT_FAILURE);
+    }
+    const size_t r0 = paf.size(), o0 = paf.cg_ops.size();
+    if ((uint64_t)o0 + ops > 0xFFFFFFFFull || (uint64_t)r0 + rows > 0xFFFFFFFEull) { fprintf(stderr, "[ERROR] (load_paf) hit table too large\n"); exit(EXIT_FAILURE); }
+    std::vector<uint32_t>* cols[10] = {&paf.q_id, &paf.q_len, &paf.q_start, &paf.q_end, &paf.t_id, &paf.t_len, &paf.t_start, &paf.t_end, &paf.n_match, &paf.n_block};
+    for (auto* c : cols) c->resize(r0 + rows);
+    paf.is_rev.resize(r0 + rows); paf.mapq.resize(r0 + rows);
+    paf.cg_off.resize(r0 + rows + 1); paf.cg_ops.resize(o0 + ops);
+    std::vector<uint32_t> off(rows + 1);
+    if (hgpu_paf_fetch(ctx, paf.q_id.data() + r0, paf.q_len.data() + r0, paf.q_start.data() + r0, paf.q_end.data() + r0, paf.is_rev.data() + r0,
+                       paf.t_id.data() + r0, paf.t_len.data() + r0, paf.t_start.data() + r0, paf.t_end.data() + r0, paf.n_match.data() + r0,
+                       paf.n_block.data() + r0, paf.mapq.data() + r0, off.data(), paf.cg_ops.data() + o0) != HGPU_OK) {
+        fprintf(stderr, "[ERROR] (load_paf) %s: %s\n", path.c_str(), hgpu_last_error(ctx)); exit(EXIT_FAILURE);
+    }
+    for (uint64_t i = 0; i <= rows; ++i) paf.cg_off[r0 + i] = (uint32_t)(o0 + off[i]);
 }
 
 // rows must be grouped by read with read ids ascending (the reference silently assumes it: update_longreads,

@@ -129,12 +129,13 @@ int main(int argc, char** argv) {
     }
     fprintf(stderr, "       loaded %zu long reads\n", reads.size());
     lap();
-    fprintf(stderr, "[NOTE] loading alignment between contigs and long reads...\n");
+    fprintf(stderr, "[NOTE] loading alignment between contigs and long reads (tokenised on the GPU)...\n");
+    if (!join_contexts()) return EXIT_FAILURE;       // no CPU path: without the device the run ends here
     PafTable paf;
     {
         std::vector<std::string> files;
         if (opt.mapping_fofn) load_fofn(opt.mapping_path, files); else files.push_back(opt.mapping_path);
-        for (const auto& f : files) load_paf(f, paf);
+        for (const auto& f : files) load_paf(f, paf, ctxs[0]);
         finish_paf(paf, reads.size());
     }
     fprintf(stderr, "       loaded %zu alignment rows\n", paf.size());

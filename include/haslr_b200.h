@@ -37,6 +37,20 @@ int         hgpu_abi_version(void);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t    hgpu_launch_count(const hgpu_t* ctx);
 
+/* ---- (0) PAF text -> hit table -----------------------------------------------------------------------------
+ * Replaces the text side of load_alignment (Longread.cpp:250-289): getline, str_split on tabs, str2type<uint32_t> on
+ * columns 1-4 and 6-12 (Common.hpp:126-133), the strand character of column 5, the first optional column that starts
+ * with "cg:Z:". Every row is kept (the load filters F1-F4 are part of hgpu_compact_lr); empty lines are skipped; a line
+ * with fewer than 12 columns fails the call with HGPU_E_INVALID (the reference would index past its fields vector).
+ * text: minimap2 PAF, n_bytes of it (whole lines; a final line without a line feed is accepted). The CIGAR payload
+ * becomes run-length operations (len << 2) | op, op 0 = M, 1 = I, 2 = anything else — the layout hgpu_hits_t takes.
+ * hgpu_paf_tokenize uploads and scans the text and reports the table's size; hgpu_paf_fetch then fills caller arrays of
+ * *out_n_rows entries (cg_off: *out_n_rows + 1, cg_ops: *out_n_ops). */
+int hgpu_paf_tokenize(hgpu_t* ctx, const char* text, uint64_t n_bytes, uint64_t* out_n_rows, uint64_t* out_n_ops);
+int hgpu_paf_fetch(hgpu_t* ctx, uint32_t* q_id, uint32_t* q_len, uint32_t* q_start, uint32_t* q_end, uint8_t* is_rev,
+                   uint32_t* t_id, uint32_t* t_len, uint32_t* t_start, uint32_t* t_end, uint32_t* n_match, uint32_t* n_block,
+                   uint8_t* mapq, uint32_t* cg_off, uint32_t* cg_ops);
+
 /* ---- (i) PAF hits -> compact long reads ------------------------------------------------------------------
  * Replaces, per long read: load_alignment's filters F1-F4 and per-read sort (Longread.cpp:234-302),
  * process_lr_alignment_group (Longread.cpp:182-232), fix_overlapping_alignments (Longread.cpp:430-512) and

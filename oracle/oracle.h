@@ -82,6 +82,14 @@ int64_t oracle_backbone_edges(const uint32_t* cl_tid, const uint8_t* cl_rev, con
                               uint32_t min_edge_sup,
                               uint64_t* out_key, uint32_t* out_supp_off, oracle_edge_supp* out_supp, uint8_t* out_keep);
 
+/* ---- K0: PAF text -> hit table (Longread.cpp:250-289, text side only; all rows kept) -------------------------- */
+/* Returns the number of rows, -1 if a capacity is too small, -2 for a line with fewer than 12 columns. Empty lines are
+ * skipped. cg_off has rows + 1 entries; *n_ops_out = cg_off[rows]. */
+int64_t oracle_parse_paf(const char* text, uint64_t n_bytes, uint64_t row_cap, uint64_t op_cap,
+                         uint32_t* q_id, uint32_t* q_len, uint32_t* q_start, uint32_t* q_end, uint8_t* is_rev,
+                         uint32_t* t_id, uint32_t* t_len, uint32_t* t_start, uint32_t* t_end, uint32_t* n_match,
+                         uint32_t* n_block, uint8_t* mapq, uint32_t* cg_off, uint32_t* cg_ops, uint64_t* n_ops_out);
+
 /* ---- K4: edge coordinates (Assemble.cpp:24-155,157-363) --------------------------------------------------- */
 /* edge e: rev1 = edge_rev[e] & 1, rev2 = edge_rev[e] >> 1 & 1; its supports are supp[supp_off[e] .. supp_off[e+1]) in
  * edge_supp order (lr_id_strand's strand bit is ignored); elems / cl_read_off = the compact long reads;

@@ -178,3 +178,34 @@ def edge_coords(edge_rev, supp_off, supp, elems, cl_read_off, read_len, hits):
                               oe.ctypes.data, os_.ctypes.data)
     assert rc == 0
     return oe[:n], os_[: len(supp)]
+
+
+PAF_COLS = ("q_id", "q_len", "q_start", "q_end", "t_id", "t_len", "t_start", "t_end", "n_match", "n_block")
+
+
+def parse_paf_with(fn, text):
+    """Calls a C parser with oracle_parse_paf's signature; returns the hits dict (None if it refused the text), rc."""
+    buf = np.frombuffer(bytes(text), dtype=np.uint8)
+    row_cap = int((buf == 10).sum()) + 2
+    op_cap = len(buf) // 2 + 2
+    h = {k: np.zeros(row_cap, dtype=np.uint32) for k in PAF_COLS}
+    h["is_rev"] = np.zeros(row_cap, dtype=np.uint8); h["mapq"] = np.zeros(row_cap, dtype=np.uint8)
+    h["cg_off"] = np.zeros(row_cap + 1, dtype=np.uint32); h["cg_ops"] = np.zeros(op_cap, dtype=np.uint32)
+    nops = C.c_uint64(0)
+    fn.restype = C.c_int64
+    fn.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64] + [u32p] * 4 + [u8p] + [u32p] * 6 + [u8p, u32p, u32p, C.POINTER(C.c_uint64)]
+    n = fn(buf.ctypes.data if len(buf) else None, len(buf), row_cap, op_cap, _p(h["q_id"], u32p), _p(h["q_len"], u32p), _p(h["q_start"], u32p),
+           _p(h["q_end"], u32p), _p(h["is_rev"], u8p), _p(h["t_id"], u32p), _p(h["t_len"], u32p), _p(h["t_start"], u32p), _p(h["t_end"], u32p),
+           _p(h["n_match"], u32p), _p(h["n_block"], u32p), _p(h["mapq"], u8p), _p(h["cg_off"], u32p), _p(h["cg_ops"], u32p), C.byref(nops))
+    if n < 0:
+        return None, n
+    for k in PAF_COLS + ("is_rev", "mapq"):
+        h[k] = h[k][:n].copy()
+    h["cg_off"] = h["cg_off"][: n + 1].copy()
+    h["cg_ops"] = h["cg_ops"][: max(nops.value, 1)].copy()
+    return h, n
+
+
+def parse_paf(text):
+    """K0 oracle (Longread.cpp:250-289, text side)."""
+    return parse_paf_with(lib().oracle_parse_paf, text)

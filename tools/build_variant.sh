@@ -3,7 +3,7 @@
 set -e
 name=$1; shift
 mkdir -p build/var/$name
-for t in api poa k12 coords; do
+for t in api poa k12 coords paf; do
   /usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-Wall,-Wno-unused-function "$@" -c haslr_b200/csrc/$t.cu -o build/var/$name/$t.o &
 done
 wait
