@@ -1176,14 +1176,6 @@ __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8
     return !bad;
 }
 
-template <int NW, bool P16>
-__device__ DP_INLINE bool dp_align(const GraphView& gv, uint8_t* slot, uint8_t* wsm, const uint8_t* seq,
-                                   uint32_t V, uint32_t L, const DpScores sc, int lane) {
-    if (P16) dp_fill16<false>(gv.meta0, gv.pred_off, gv.pred_rank, slot, wsm, seq, V, L, sc.sm, sc.sx, sc.g, Geo<DP_NW16, true>::bias(V, sc), lane, 0, 1, nullptr);
-    else dp_fill<NW, false>(gv, slot, wsm, seq, V, L, sc, lane, 0, 1, nullptr);
-    return dp_traceback<NW, P16>(gv, slot, wsm, seq, V, L, sc, lane);
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // Lane-parallel pieces of the graph update.
 // ---------------------------------------------------------------------------------------------------------

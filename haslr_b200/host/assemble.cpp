@@ -151,7 +151,7 @@ static void write_segment(const SeqStore& reads, const CnsSupp& s, uint32_t cnt,
 static double now_s() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + t.tv_nsec * 1e-9; }
 
 int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& reads, const std::vector<hgpu_t*>& ctxs,
-                   const std::string& logpath, bool write_log, unsigned threads) {
+                   const std::string& logpath, bool write_log, unsigned threads, uint64_t* bases_in) {
     const size_t n = edges.size();
     const double t0 = now_s();
     std::string bases;
@@ -167,6 +167,7 @@ int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& 
         edge_seg_off.push_back((uint32_t)(seg_off.size() - 1));
     }
     bases.resize(seg_off.back());
+    if (bases_in) *bases_in = seg_off.back();
     {   // the copies (and reverse complements) are independent: all host threads
         const size_t n_seg = seg_src.size();
         const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(threads, n_seg / 256 + 1));

@@ -99,7 +99,7 @@ void enumerate_edges(Graph& g, uint32_t flag, std::vector<EdgeRef>& out);
 int calc_edge_coordinates(Graph& g, const std::vector<EdgeRef>& edges, const ContigStore& contigs, const SeqStore& reads,
                           const CompactReads& cl, const PafTable& paf, hgpu_t* ctx, const std::string& logpath);
 int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& reads, const std::vector<hgpu_t*>& ctxs,
-                   const std::string& logpath, bool write_log, unsigned threads);
+                   const std::string& logpath, bool write_log, unsigned threads, uint64_t* bases_in);
 void write_assembly(Graph& g, const ContigStore& contigs, const std::string& out_dir);
 
 }  // namespace haslr

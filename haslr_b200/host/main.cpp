@@ -141,6 +141,7 @@ int main(int argc, char** argv) {
     fprintf(stderr, "       loaded %zu alignment rows\n", paf.size());
     lap();
 
+    const double path_t0 = real_time();              // the clock of the backbone+POA path starts with the hits in host memory
     // (i) filters + per-read sort + overlap fix + chaining, on the GPU
     fprintf(stderr, "[NOTE] fixing overlapping alignments and building compact long reads (GPU)...\n");
     if (!join_contexts()) return EXIT_FAILURE;       // no CPU path: without the device the run ends here
@@ -220,8 +221,14 @@ int main(int argc, char** argv) {
     // (iii) all edges in one batched POA call per GPU
     fprintf(stderr, "[NOTE] calling consensus sequence between anchors (GPU, %zu edges)...\n", edges.size());
     enumerate_edges(g, 12, edges);
-    if (!edges.empty() && call_consensus(g, edges, reads, ctxs, d + "/log_consensus.txt", logs, opt.num_threads) != 0) return EXIT_FAILURE;
+    uint64_t poa_bases = 0;
+    if (!edges.empty() && call_consensus(g, edges, reads, ctxs, d + "/log_consensus.txt", logs, opt.num_threads, &poa_bases) != 0) return EXIT_FAILURE;
     lap();
+    {
+        const double dt = real_time() - path_t0;
+        fprintf(stderr, "[NOTE] backbone + POA path (hits in host memory -> consensus in host memory): %.1f long-read Mbases in %.2f s = %.1f Mbases/s\n\n",
+                poa_bases / 1e6, dt, dt > 0 ? poa_bases / 1e6 / dt : 0.0);
+    }
 
     fprintf(stderr, "[NOTE] generating the assembly from the cleaned backbone graph...\n");
     write_assembly(g, contigs, d);
