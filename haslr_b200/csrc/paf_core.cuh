@@ -24,11 +24,21 @@ struct PafLine {
     uint32_t n_cols;     // tab-separated columns found among the first 12
 };
 
-// unsigned decimal prefix of [b, e), as istringstream >> uint32_t reads a well-formed column
+// A column as `istringstream >> uint32_t` (str2type<uint32_t>, Common.hpp:126-133) reads it: leading white space skipped,
+// an optional sign, decimal digits up to the first other character. No digits -> 0 (the reference returns an
+// uninitialised value there); a magnitude above 2^32 - 1 -> 4294967295; a '-' negates modulo 2^32 (libstdc++ num_get).
 PAF_HD uint32_t paf_u32(const char* b, const char* e) {
+    while (b < e && (*b == ' ' || (*b >= '\t' && *b <= '\r'))) ++b;
+    bool neg = false;
+    if (b < e && (*b == '+' || *b == '-')) { neg = *b == '-'; ++b; }
     uint64_t v = 0;
-    for (; b < e && *b >= '0' && *b <= '9'; ++b) v = v * 10 + (uint64_t)(*b - '0');
-    return (uint32_t)v;
+    bool over = false;
+    for (; b < e && *b >= '0' && *b <= '9'; ++b) {
+        v = v * 10 + (uint64_t)(*b - '0');
+        if (v > 0xFFFFFFFFull) { over = true; v = 0xFFFFFFFFull; }
+    }
+    if (over) return 0xFFFFFFFFu;
+    return neg ? (uint32_t)(0u - (uint32_t)v) : (uint32_t)v;
 }
 
 // Scans one line [b, e) (no terminator). Returns false for an empty line (skipped) — and with n_cols < 12 for a

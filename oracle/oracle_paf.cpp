@@ -13,19 +13,23 @@
 namespace {
 // str2type<uint32_t> (Common.hpp:126-133) is `istringstream >> n`. Restated without the stream: numeric extraction needs
 // the C++ locale facets, which are not initialised when this library is dlopen'ed into a C host process (python) — the
-// stream then fails and every column reads 0. What the extraction does on a PAF column: skip white space, an optional
-// '+', decimal digits up to the first other character; no digits -> 0; a value above 2^32 - 1 -> 4294967295.
+// stream then fails and every column reads 0. What libstdc++'s extraction does (checked against a stand-alone program,
+// tests/test_paf_host.py::test_oracle_number_reading lists the cases): skip white space, an optional sign, decimal
+// digits up to the first other character; no digits -> 0 here (uninitialised in the reference); a magnitude above
+// 2^32 - 1 -> 4294967295; '-' negates modulo 2^32.
 template <typename T> T str2type(const std::string& str) {
     size_t i = 0;
     while (i < str.size() && isspace((unsigned char)str[i])) ++i;
-    if (i < str.size() && str[i] == '+') ++i;
+    bool neg = false;
+    if (i < str.size() && (str[i] == '+' || str[i] == '-')) { neg = str[i] == '-'; ++i; }
     unsigned long long v = 0;
     bool over = false;
     for (; i < str.size() && isdigit((unsigned char)str[i]); ++i) {
         v = v * 10 + (unsigned long long)(str[i] - '0');
         if (v > 0xFFFFFFFFull) over = true, v = 0xFFFFFFFFull;
     }
-    return (T)(over ? 0xFFFFFFFFull : v);
+    if (over) return (T)0xFFFFFFFFull;
+    return (T)(neg ? (uint32_t)(0u - (uint32_t)v) : (uint32_t)v);
 }
 void str_split(const std::string& s, char delim, std::vector<std::string>& out) {
     out.clear();

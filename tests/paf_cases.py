@@ -26,3 +26,23 @@ def golden_paf():
 def same_hits(a, b):
     return all(a[k].tobytes() == b[k].tobytes() for k in oracle_ffi.PAF_COLS + ("is_rev", "mapq", "cg_off")) and \
         a["cg_ops"][: int(a["cg_off"][-1])].tobytes() == b["cg_ops"][: int(b["cg_off"][-1])].tobytes()
+
+
+def line_of(cols, tags=()):
+    return b"\t".join(list(cols) + list(tags))
+
+
+def fuzzed(seed, n_lines=4000):
+    """(text, lines): rows assembled from odd tokens — signs, blanks, overflow, empty columns, carriage returns, tags in any order."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    toks = [b"0", b"7", b"60", b"255", b"256", b"4294967295", b"4294967296", b"123456789012", b" 9", b"+9", b"-9", b"9x", b"x", b"", b"\r5", b"5\r", b"007", b"- 1"]
+    tags = [b"tp:A:P", b"cg:Z:5M", b"cg:Z:", b"cg:Z:3M2I\r", b"cg:Z:10", b"cg:Z:M", b"NM:i:3", b"cg:z:5M", b"xcg:Z:5M", b"cg:Z:4294967296M1I", b"", b"cg:Z:1=2X3N"]
+    lines = []
+    for _ in range(n_lines):
+        cols = [toks[i] for i in rng.integers(0, len(toks), 12)]
+        cols[4] = [b"+", b"-", b"", b"-+", b"*"][int(rng.integers(0, 5))]
+        lines.append(line_of(cols, [tags[i] for i in rng.integers(0, len(tags), int(rng.integers(0, 4)))]))
+        if rng.random() < 0.05:
+            lines.append(b"")
+    return b"\n".join(lines), lines

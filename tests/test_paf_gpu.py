@@ -58,6 +58,14 @@ def test_tokeniser_large_random(ctx, oracle):
     assert n == 20000 and paf_cases.same_hits(got, ref)
 
 
+def test_tokeniser_fuzzed_lines(ctx, oracle):
+    """Rows assembled from odd tokens (signs, blanks, overflow, empty columns, carriage returns, tags in any order)."""
+    text, _ = paf_cases.fuzzed(11)
+    ref, n = oracle.parse_paf(text)
+    got = ctx.parse_paf(text)
+    assert n == 4000 and len(got["q_id"]) == n and paf_cases.same_hits(got, ref)
+
+
 def test_short_line_is_refused(ctx):
     import haslr_b200
     with pytest.raises(haslr_b200.HgpuError) as ei:

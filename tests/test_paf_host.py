@@ -56,3 +56,29 @@ def test_short_line_is_refused(pafhost, oracle):
     bad = b"1\t2\t3\t4\t+\t5\t6\t7\t8\t9\t10\n"
     assert oracle.parse_paf(bad)[1] == -2
     assert oracle_ffi.parse_paf_with(pafhost.pafhost_parse, bad)[1] == -2
+
+
+line_of = paf_cases.line_of
+
+
+def test_oracle_number_reading(oracle):
+    """The column reader against what `istringstream >> uint32_t` returns in a stand-alone C++ program (libstdc++ 13)."""
+    cases = {b" 12": 12, b"+12": 12, b"-5": 4294967291, b"4294967295": 4294967295, b"4294967296": 4294967295, b"99999999999": 4294967295,
+             b"12abc": 12, b"abc": 0, b"\r12": 12, b"0012": 12, b"-0": 0, b"- 5": 0, b"+-5": 0, b"1e3": 1, b"0x10": 0,
+             b"-4294967295": 1, b"-4294967296": 4294967295}
+    for tok, want in cases.items():
+        cols = [b"1", tok, b"3", b"4", b"+", b"5", b"6", b"7", b"8", b"9", b"10", b"60"]
+        h, n = oracle.parse_paf(line_of(cols) + b"\n")
+        assert n == 1 and int(h["q_len"][0]) == want, tok
+
+
+def test_core_matches_oracle_on_fuzzed_lines(pafhost, oracle):
+    """Lines assembled from odd tokens: signs, blanks, overflow, empty columns, carriage returns, tags in any order."""
+    text, lines = paf_cases.fuzzed(11)
+    ref, n = oracle.parse_paf(text)
+    got, m = oracle_ffi.parse_paf_with(pafhost.pafhost_parse, text)
+    assert n == m == 4000
+    for k in oracle_ffi.PAF_COLS + ("is_rev", "mapq", "cg_off"):
+        bad = np.nonzero(got[k] != ref[k])[0]
+        assert len(bad) == 0, (k, bad[:3], lines[int(bad[0])] if k != "cg_off" else None)
+    assert paf_cases.same_hits(got, ref)
