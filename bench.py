@@ -332,15 +332,17 @@ def main():
         d1.record(); torch.cuda.synchronize()
         dst = ctx.poa_stats()
         dms = d0.elapsed_time(d1) / 2
-        dchk = None
+        dchk, dcpu = None, None
         if not args.no_cpu:
-            rc, roff, _, _, _ = run_oracle_sample(dd.cpu().numpy(), dso, deo, 4, os.cpu_count() or 1)
+            rc, roff, ccells, cdt, cnb = run_oracle_sample(dd.cpu().numpy(), dso, deo, 4, os.cpu_count() or 1)
             assert np.array_equal(doff[:5], roff) and dout[: int(doff[4])].cpu().numpy().tobytes() == rc.tobytes(), "deep edges: consensus differs from the oracle"
             dchk = "first 4 edges bit-exact vs oracle"
+            # the checker's own speed on those 4 edges (one edge per thread, so 4 host threads busy): context, not a baseline run
+            dcpu = {"edges": 4, "threads_busy": 4, "value": cnb / cdt / 1e6, "unit": UNIT, "gcups": ccells / cdt / 1e9}
         deep = {"workload": f"{DEEP_EDGES} edges x {DEEP_DEPTH} supporting reads x {DEEP_GAP} bp gap (BASELINE config 2 edge shape)",
                 "value": dn / (dms / 1e3) / 1e6, "unit": UNIT, "ms_per_step": dms, "gcups": dst["cells"] / (dms / 1e3) / 1e9,
                 "alignments": dst["alignments"], "alignments_rel16": dst["alignments_rel16"], "alignments_i32": dst["alignments_i32"],
-                "kernels": "k_poa_edges_deep (+ k_poa_edges_team for the largest)", "check": dchk}
+                "kernels": "k_poa_edges_deep (+ k_poa_edges_team for the largest)", "check": dchk, "cpu_oracle_on_check": dcpu}
         del dd, dout
 
     # ---- CPU baseline: the oracle on a bounded sample of the same edges, all host cores
