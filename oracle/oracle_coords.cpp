@@ -17,47 +17,48 @@ namespace {
 
 typedef std::pair<uint32_t, uint32_t> P;
 
-// Assemble.cpp:24-74 (ge = true, "curr_supp >= best_supp") and :76-126 (ge = false, ">")
-void best_interval(std::vector<P>& beg_list, std::vector<P>& end_list, bool ge, P& best_int, std::set<uint32_t>& best_lrs) {
-    std::sort(beg_list.begin(), beg_list.end());
-    std::sort(end_list.begin(), end_list.end());
-    int curr_supp = 0, best_supp = 0, i = 0, j = 0;
-    const int len = (int)beg_list.size();
-    uint32_t beg_best = 0, end_best = 0;          // uninitialised in the reference; every edge has >= 1 support
-    bool interval_started = false;
-    std::set<uint32_t> curr_lrs;
-    while (i < len && j < len) {
-        if (beg_list[i].first < end_list[j].first) {
-            curr_supp++;
-            curr_lrs.insert(beg_list[i].second);
-            if (ge ? curr_supp >= best_supp : curr_supp > best_supp) {
-                best_supp = curr_supp;
-                beg_best = beg_list[i].first;
-                best_lrs = curr_lrs;
-                interval_started = true;
-            }
-            i++;
+// Assemble.cpp:24-74 (later_wins = true: a later interval of EQUAL depth replaces the optimum, the `>=` of contig1) and
+// :76-126 (later_wins = false, the `>` of contig2). Two sorted event lists are merged; the set of reads currently
+// covering the sweep position is copied whenever a new optimum is reached; the optimum's interval closes at the next
+// end event.
+void best_interval(std::vector<P>& starts, std::vector<P>& stops, bool later_wins, P& interval, std::set<uint32_t>& members) {
+    std::sort(starts.begin(), starts.end());
+    std::sort(stops.begin(), stops.end());
+    const int n = (int)starts.size();
+    int depth = 0, top = 0, a = 0, z = 0;
+    uint32_t lo = 0, hi = 0;                      // uninitialised in the reference; every edge has >= 1 support
+    bool open = false;
+    std::set<uint32_t> covering;
+    while (a < n && z < n) {
+        const bool start_event = starts[a].first < stops[z].first;      // on a tie the stop is taken first
+        if (start_event) {
+            ++depth;
+            covering.insert(starts[a].second);
+            const bool better = later_wins ? depth >= top : depth > top;
+            if (better) { top = depth; lo = starts[a].first; members = covering; open = true; }
+            ++a;
         } else {
-            if (interval_started) { end_best = end_list[j].first; interval_started = false; }
-            curr_supp--;
-            curr_lrs.erase(end_list[j].second);
-            j++;
+            if (open) { hi = stops[z].first; open = false; }
+            --depth;
+            covering.erase(stops[z].second);
+            ++z;
         }
     }
-    if (interval_started) end_best = end_list[j].first;
-    best_int = P(beg_best, end_best);
+    if (open) hi = stops[z].first;
+    interval = P(lo, hi);
 }
 
-// Assemble.cpp:129-155, on the expanded CIGAR
-long long find_lr_pos(const std::string& cigar_str, uint32_t lr_curr, uint32_t c_curr, int lr_step, int c_step, uint32_t contig_pos) {
-    if ((c_step > 0 && c_curr > contig_pos) || (c_step < 0 && c_curr < contig_pos)) return -1;
-    for (size_t i = 0; i < cigar_str.size(); i++) {
-        if (c_curr == contig_pos) break;
-        if (cigar_str[i] == 'M') { c_curr += c_step; lr_curr += lr_step; }
-        else if (cigar_str[i] == 'I') { lr_curr += lr_step; }
-        else { c_curr += c_step; }
+// Assemble.cpp:129-155, on the expanded CIGAR: step through the operations until the contig coordinate arrives at
+// `target`; M moves both coordinates, I the read only, anything else the contig only. -1 if the start is already past it.
+long long find_lr_pos(const std::string& ops, uint32_t read_pos, uint32_t contig_at, int read_dir, int contig_dir, uint32_t target) {
+    const bool past = contig_dir > 0 ? contig_at > target : contig_at < target;
+    if (past) return -1;
+    for (size_t k = 0; k < ops.size() && contig_at != target; ++k) {
+        const char op = ops[k];
+        if (op != 'I') contig_at += contig_dir;
+        if (op == 'M' || op == 'I') read_pos += read_dir;
     }
-    return lr_curr;
+    return read_pos;
 }
 
 // the CIGAR an element carries after the overlap fix, one character per operation (expand_cigar, Common.cpp)
