@@ -17,6 +17,7 @@
                                    per support  D head(t_start t_end strand) tail(...),  per best support  S lr len strand
                                    spos epos | X   (asm_calc_single_edge_coordinates, Assemble.cpp:157-363)
        syn200k_read_len.npy        long-read lengths (Longread_List_t::reads[i].len)
+       syn200k_asm.final.fa.gz, .ann  the assembly and its annotation (stitching, Assemble.cpp:607-810,1045-1077)
 """
 import gzip
 import os
@@ -105,6 +106,10 @@ def main():
                     else:
                         cur["lines"].append("%s %s %s\n" % (cur["pending"], t[2].split(":")[1], t[3].split(":")[1]))
             flush()
+        # the assembly itself (stitching: Assemble.cpp:607-810,1045-1077)
+        with open(os.path.join(out, "asm.final.fa"), "rb") as f, gzip.open(os.path.join(HERE, "syn200k_asm.final.fa.gz"), "wb") as g:
+            g.write(f.read())
+        shutil.copy(os.path.join(out, "asm.final.ann"), os.path.join(HERE, "syn200k_asm.final.ann"))
         reads = io_helpers.load_fasta(os.path.join(tmp, "reads.fa"))
         np.save(os.path.join(HERE, "syn200k_read_len.npy"), np.array([len(r) for r in reads], dtype=np.uint32))
     finally:
