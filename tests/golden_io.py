@@ -74,3 +74,12 @@ def coord_inputs(oracle):
         rev.append(r1 | (r2 << 1))
     return dict(g=g, elems=elems, cl_off=off, edge_rev=np.array(rev, dtype=np.uint8), supp_off=np.array(so, dtype=np.uint32),
                 supp=np.concatenate(parts), read_len=read_len(), gold=gold)
+
+
+def k1_adversarial(seed):
+    """Adversarial K1/K2 fixture (tests/golden/make_k1_adversarial.py): PAF text, contig table, reference compact_uniq.txt / GFA links."""
+    z = np.load(os.path.join(GOLD, f"k1adv_{seed}.npz"))
+    with gzip.open(os.path.join(GOLD, f"k1adv_{seed}.paf.gz"), "rb") as f:
+        paf = f.read()
+    return dict(paf=paf, contig_len=z["contig_len"], mean_kmer=np.ascontiguousarray(z["mean_kmer"]), n_reads=int(z["n_reads"]),
+                compact=text(f"k1adv_{seed}.compact_uniq.txt"), links01=text(f"k1adv_{seed}.links01"), links02=text(f"k1adv_{seed}.links02"))

@@ -107,3 +107,20 @@ def test_compact_lr_and_backbone_fresh_synthetic(ctx, oracle):
     key, soff, supp, keep = ctx.backbone_edges(tid, rev, goff, 3)
     rkey, rsoff, rsupp, rkeep = oracle.backbone_edges(tid, rev, goff, 3)
     assert np.array_equal(key, rkey) and np.array_equal(soff, rsoff) and np.array_equal(keep, rkeep) and supp.tobytes() == rsupp.tobytes()
+
+
+@pytest.mark.xfail(strict=False, reason="added after round 1's GPU minutes were spent: the same fixtures pass through the oracle and the "
+                   "host/device-shared cores on the CPU (test_oracle_golden.py, test_k1_host.py); not yet run on a device — drop this marker once it has")
+@pytest.mark.parametrize("seed", [1, 2])
+def test_adversarial_hits_text_to_edge_table(ctx, oracle, seed):
+    """tests/golden/k1adv_*: PAF text -> hit table -> compact reads -> edge table, all on the GPU, against the reference
+    binary's compact_uniq.txt and GFA links (heavy overlaps, sort ties, repeated contigs, rows at the filter thresholds)."""
+    a = golden_io.k1_adversarial(seed)
+    hits = ctx.parse_paf(a["paf"])
+    read_off = np.searchsorted(hits["q_id"], np.arange(a["n_reads"] + 1), side="left").astype(np.uint32)
+    uf = io_helpers.calc_uniq_freq(a["contig_len"], a["mean_kmer"])
+    elems, off = ctx.compact_lr(hits, read_off, a["mean_kmer"], uf)
+    assert io_helpers.format_compact(elems, off, hits) == a["compact"]
+    key, soff, supp, keep = ctx.backbone_edges(hits["t_id"][elems["hit"]], hits["is_rev"][elems["hit"]], off, 3)
+    assert io_helpers.format_gfa_links(key) == a["links01"]
+    assert io_helpers.format_gfa_links(key[keep == 1]) == a["links02"]

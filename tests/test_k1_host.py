@@ -76,3 +76,16 @@ def test_restated_std_sort_matches_libstdcxx(k1, n):
         if n == 0:
             a = np.zeros(1, np.uint32)
         assert k1.k1host_sort_check(a.ctypes.data_as(u32p), a.ctypes.data_as(u32p), n, None) == 0
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_core_on_adversarial_hits(k1, oracle, seed):
+    """tests/golden/k1adv_*: heavy overlaps, sort ties, repeated contigs — the product core against the oracle and the reference text."""
+    a = golden_io.k1_adversarial(seed)
+    hits, _ = oracle.parse_paf(a["paf"])
+    read_off = np.searchsorted(hits["q_id"], np.arange(a["n_reads"] + 1), side="left").astype(np.uint32)
+    uf = io_helpers.calc_uniq_freq(a["contig_len"], a["mean_kmer"])
+    got, goff = run_k1(k1, hits, read_off, a["mean_kmer"], uf)
+    ref, roff = oracle.compact_lr(hits, read_off, a["mean_kmer"], uf)
+    assert np.array_equal(goff, roff) and got.tobytes() == ref.tobytes()
+    assert io_helpers.format_compact(got, goff, hits) == a["compact"]
