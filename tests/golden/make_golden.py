@@ -75,37 +75,8 @@ def main():
                     g.write(want_seq + " " + line)
                     want_seq = False
         # edge coordinates
-        sg = {"+": 0, "-": 1}
-        with open(os.path.join(out, "log_coordinate.txt")) as f, open(os.path.join(HERE, "syn200k_coords.txt"), "w") as g:
-            cur = None
-            def flush():
-                if cur:
-                    g.write("E %s %s\n" % (" ".join(map(str, cur["e"])), " ".join(map(str, cur["v"]))))
-                    g.write("".join(cur["lines"]))
-            for line in f:
-                t = line.split()
-                if line.startswith("edge "):
-                    flush()
-                    a, b = t[1].split(":"), t[3].split(":")
-                    cur = {"e": [int(a[0]), sg[a[1]], int(b[0]), sg[b[1]]], "v": [], "lines": []}
-                elif line.startswith("\tedge_supp size:"):
-                    cur["v"].append(int(line.split(":")[1]))
-                elif line.startswith("\tsupp_detail"):
-                    cur["lines"].append("D %s %s %d %s %s %d\n" % (t[2], t[3], sg[t[4]], t[6], t[7], sg[t[8]]))
-                elif "@@@" in line:
-                    cur["v"] += [int(t[-2]), int(t[-1])]
-                elif line.startswith("coordinates"):
-                    cur["v"] += [int(t[2]), int(t[4])]
-                elif line.startswith("supproting_lr"):
-                    cur["v"].append(int(t[1]))
-                elif "+++" in line:
-                    cur["pending"] = "S %s %s %d" % (t[1].split(":")[1], t[2].split(":")[1], sg[t[3].split(":")[1]])
-                elif "[coordinate]" in line:
-                    if "could not" in line:
-                        cur["lines"].append(cur["pending"] + " X\n")
-                    else:
-                        cur["lines"].append("%s %s %s\n" % (cur["pending"], t[2].split(":")[1], t[3].split(":")[1]))
-            flush()
+        with open(os.path.join(HERE, "syn200k_coords.txt"), "w") as g:
+            g.write(io_helpers.reduce_coordinate_log(os.path.join(out, "log_coordinate.txt")))
         # the assembly itself (stitching: Assemble.cpp:607-810,1045-1077)
         with open(os.path.join(out, "asm.final.fa"), "rb") as f, gzip.open(os.path.join(HERE, "syn200k_asm.final.fa.gz"), "wb") as g:
             g.write(f.read())

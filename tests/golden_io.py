@@ -83,3 +83,26 @@ def k1_adversarial(seed):
         paf = f.read()
     return dict(paf=paf, contig_len=z["contig_len"], mean_kmer=np.ascontiguousarray(z["mean_kmer"]), n_reads=int(z["n_reads"]),
                 compact=text(f"k1adv_{seed}.compact_uniq.txt"), links01=text(f"k1adv_{seed}.links01"), links02=text(f"k1adv_{seed}.links02"))
+
+
+def parse_coords_text(txt):
+    out = []
+    for line in txt.splitlines():
+        t = line.split()
+        if t[0] == "E":
+            v = list(map(int, t[1:]))
+            out.append(dict(edge=tuple(v[0:4]), n_supp=v[4], int1=(v[5], v[6]), int2=(v[7], v[8]), c1=v[9], c2=v[10], n_best=v[11], detail=[], best=[]))
+        elif t[0] == "D":
+            out[-1]["detail"].append(tuple(map(int, t[1:])))
+        elif t[0] == "S":
+            out[-1]["best"].append((int(t[1]), int(t[2]), int(t[3])) + ((None, None) if t[4] == "X" else (int(t[4]), int(t[5]))))
+    return out
+
+
+def k4_adversarial(seed):
+    """Adversarial K4 fixture (tests/golden/make_k4_adversarial.py): PAF text, contig / read tables, the reference's reduced log_coordinate.txt."""
+    z = np.load(os.path.join(GOLD, f"k4adv_{seed}.npz"))
+    with gzip.open(os.path.join(GOLD, f"k4adv_{seed}.paf.gz"), "rb") as f:
+        paf = f.read()
+    return dict(paf=paf, contig_len=z["contig_len"], mean_kmer=np.ascontiguousarray(z["mean_kmer"]), read_len=z["read_len"],
+                gold=parse_coords_text(text(f"k4adv_{seed}.coords.txt")))

@@ -119,3 +119,44 @@ def format_gfa_links(keys):
 def gfa_links_of_file(path):
     with open(path) as f:
         return "".join(l for l in f if l.startswith("L\t"))
+
+
+def reduce_coordinate_log(path):
+    """log_coordinate.txt of the reference (asm_calc_single_edge_coordinates, Assemble.cpp:157-363) reduced to:
+    per edge  E node1 rev1 node2 rev2 n_supp int1_lo int1_hi int2_lo int2_hi c1 c2 n_best,
+    per support  D head(t_start t_end strand) tail(t_start t_end strand),
+    per best support  S lr len strand spos epos | S lr len strand X."""
+    sg = {"+": 0, "-": 1}
+    out = []
+    cur = None
+
+    def flush():
+        if cur:
+            out.append("E %s %s\n" % (" ".join(map(str, cur["e"])), " ".join(map(str, cur["v"]))))
+            out.extend(cur["lines"])
+    with open(path) as f:
+        for line in f:
+            t = line.split()
+            if line.startswith("edge "):
+                flush()
+                a, b = t[1].split(":"), t[3].split(":")
+                cur = {"e": [int(a[0]), sg[a[1]], int(b[0]), sg[b[1]]], "v": [], "lines": []}
+            elif line.startswith("\tedge_supp size:"):
+                cur["v"].append(int(line.split(":")[1]))
+            elif line.startswith("\tsupp_detail"):
+                cur["lines"].append("D %s %s %d %s %s %d\n" % (t[2], t[3], sg[t[4]], t[6], t[7], sg[t[8]]))
+            elif "@@@" in line:
+                cur["v"] += [int(t[-2]), int(t[-1])]
+            elif line.startswith("coordinates"):
+                cur["v"] += [int(t[2]), int(t[4])]
+            elif line.startswith("supproting_lr"):
+                cur["v"].append(int(t[1]))
+            elif "+++" in line:
+                cur["pending"] = "S %s %s %d" % (t[1].split(":")[1], t[2].split(":")[1], sg[t[3].split(":")[1]])
+            elif "[coordinate]" in line:
+                if "could not" in line:
+                    cur["lines"].append(cur["pending"] + " X\n")
+                else:
+                    cur["lines"].append("%s %s %s\n" % (cur["pending"], t[2].split(":")[1], t[3].split(":")[1]))
+    flush()
+    return "".join(out)
