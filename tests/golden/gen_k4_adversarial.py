@@ -1,4 +1,6 @@
-import numpy as np, sys, os
+import sys
+
+import numpy as np
 seed=int(sys.argv[1]); out=sys.argv[2]; n_reads=int(sys.argv[3]) if len(sys.argv)>3 else 300
 rng=np.random.default_rng(seed)
 ACGT=np.frombuffer(b"ACGT",np.uint8)

@@ -4,7 +4,6 @@ import numpy as np
 import pytest
 
 import golden_io
-import oracle_ffi
 import paf_cases
 
 pytestmark = pytest.mark.gpu
