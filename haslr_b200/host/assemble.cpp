@@ -128,13 +128,13 @@ int calc_edge_coordinates(Graph& g, const std::vector<EdgeRef>& edges, const Con
 // ---------------------------------------------------------------------------------------------------------
 // substr(spos, epos - spos + 1) on the read (strand 0) or its reverse complement (strand 1), uint32 arithmetic
 // as in Assemble.cpp:529-532 (quirk Q7: a wrapped length takes the tail)
-static uint32_t segment_length(const SeqStore& reads, const CnsSupp& s) {
+uint32_t segment_length(const SeqStore& reads, const CnsSupp& s) {
     const uint32_t len = reads.len(s.lr_id);
     if (s.spos > len) { fprintf(stderr, "[ERROR] segment start %u beyond read %u of length %u\n", s.spos, s.lr_id, len); exit(EXIT_FAILURE); }
     const uint32_t want = s.epos - s.spos + 1;
     return std::min<uint32_t>(want, len - s.spos);
 }
-static void write_segment(const SeqStore& reads, const CnsSupp& s, uint32_t cnt, char* out) {
+void write_segment(const SeqStore& reads, const CnsSupp& s, uint32_t cnt, char* out) {
     const uint32_t len = reads.len(s.lr_id);
     const char* r = reads.data(s.lr_id);
     if (s.lr_strand == 0) {

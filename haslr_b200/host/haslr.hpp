@@ -98,6 +98,8 @@ struct EdgeRef { uint32_t node1, rev1, node2, rev2; };
 void enumerate_edges(Graph& g, uint32_t flag, std::vector<EdgeRef>& out);
 int calc_edge_coordinates(Graph& g, const std::vector<EdgeRef>& edges, const ContigStore& contigs, const SeqStore& reads,
                           const CompactReads& cl, const PafTable& paf, hgpu_t* ctx, const std::string& logpath);
+uint32_t segment_length(const SeqStore& reads, const CnsSupp& s);                     // Assemble.cpp:529-532 (uint32 arithmetic, quirk Q7)
+void write_segment(const SeqStore& reads, const CnsSupp& s, uint32_t cnt, char* out);   // the read, or its reverse complement, from spos
 int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& reads, const std::vector<hgpu_t*>& ctxs,
                    const std::string& logpath, bool write_log, unsigned threads, uint64_t* bases_in);
 void write_assembly(Graph& g, const ContigStore& contigs, const std::string& out_dir);

@@ -67,3 +67,22 @@ extern "C" int asmhost_finish(const uint32_t* head_end, const uint32_t* tail_beg
     write_assembly(G, CONTIGS, out_dir);
     return 0;
 }
+
+// the segments call_consensus would feed to the POA for cns_supp entries (lr_id, lr_strand, spos, epos), concatenated
+extern "C" long long asmhost_segments(const char* read_seq, const uint64_t* read_off, uint32_t n_reads, const uint32_t* cns4, uint32_t n_cns,
+                                      char* out, uint64_t out_cap, uint64_t* out_off) {
+    SeqStore reads;
+    reads.seq.assign(read_seq, read_seq + read_off[n_reads]);
+    reads.off.assign(read_off, read_off + n_reads + 1);
+    uint64_t at = 0;
+    out_off[0] = 0;
+    for (uint32_t i = 0; i < n_cns; ++i) {
+        const CnsSupp s{cns4[4 * i], cns4[4 * i + 1], cns4[4 * i + 2], cns4[4 * i + 3]};
+        const uint32_t cnt = segment_length(reads, s);
+        if (at + cnt > out_cap) return -1;
+        write_segment(reads, s, cnt, out + at);
+        at += cnt;
+        out_off[i + 1] = at;
+    }
+    return (long long)at;
+}

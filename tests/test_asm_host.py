@@ -70,3 +70,40 @@ def test_assembly_matches_reference(asm, oracle, tmp_path):
         assert f.read() == gz.read()
     with open(out / "asm.final.ann") as f:
         assert f.read() == golden_io.text("syn200k_asm.final.ann")
+
+
+def test_segments_match_what_the_reference_fed_to_spoa(asm, oracle):
+    """The product's segment extraction (read or reverse complement from spos, uint32 length arithmetic) on the cns_supp lists the
+    oracle's edge coordinates give, against the segments the reference binary logged for the golden dataset (log_consensus.txt)."""
+    g = golden_io.inputs()
+    with tempfile.TemporaryDirectory() as tmp:
+        subprocess.run([oracle_ffi.GEN_BIN, tmp, "200000", "600", "8000", "7"], check=True, stdout=subprocess.DEVNULL)
+        reads = [bytes(c if c in b"ACGT" else 65 for c in r.upper()) for r in io_helpers.load_fasta(os.path.join(tmp, "reads.fa"))]
+    assert [len(r) for r in reads] == list(golden_io.read_len())
+    ci = golden_io.coord_inputs(oracle)
+    oe, os_ = oracle.edge_coords(ci["edge_rev"], ci["supp_off"], ci["supp"], ci["elems"], ci["cl_off"], ci["read_len"], g["hits"])
+    want = golden_io.poa_edges()
+    assert len(want) == len(ci["gold"]) == 120
+    cns, per_edge = [], []
+    for e in range(120):
+        k = 0
+        for i in range(int(ci["supp_off"][e]), int(ci["supp_off"][e + 1])):
+            o = os_[i]
+            if o["in_best"] and o["lr_start"] != -1 and o["lr_end"] != -1:
+                cns.append((int(ci["supp"][i]["lr_id_strand"]) & 0x7FFFFFFF, int(o["lr_strand"]), int(o["lr_start"]) + 1, int(o["lr_end"]) - 1)); k += 1
+        per_edge.append(k)
+    cns4 = np.array(cns, dtype=np.uint32).reshape(-1)
+    roff = np.concatenate(([0], np.cumsum([len(r) for r in reads]))).astype(np.uint64)
+    cap = int(sum(len(s) for _, segs, _ in want for s in segs)) + 1024
+    out = C.create_string_buffer(cap); ooff = np.zeros(len(cns) + 1, dtype=np.uint64)
+    asm.asmhost_segments.restype = C.c_longlong
+    asm.asmhost_segments.argtypes = [C.c_char_p, u64p, C.c_uint32, u32p, C.c_uint32, C.c_char_p, C.c_uint64, u64p]
+    n = asm.asmhost_segments(b"".join(reads), roff.ctypes.data_as(u64p), len(reads), cns4.ctypes.data_as(u32p), len(cns), out, cap, ooff.ctypes.data_as(u64p))
+    assert n >= 0
+    k = 0
+    for e, (label, segs, _) in enumerate(want):
+        assert per_edge[e] == len(segs), label
+        for s in segs:
+            assert out.raw[int(ooff[k]): int(ooff[k + 1])] == s, (label, k)
+            k += 1
+    assert k == len(cns)
