@@ -1,7 +1,7 @@
 // Context management of the C ABI (include/haslr_b200.h).
 #include "common.cuh"
 
-extern "C" int hgpu_abi_version(void) { return 1; }
+extern "C" int hgpu_abi_version(void) { return 2; }   // 2: hgpu_poa_stats grew (alignments_rel16), hgpu_edge_coords, hgpu_paf_tokenize / hgpu_paf_fetch
 
 extern "C" const char* hgpu_strerror(int code) {
     switch (code) {

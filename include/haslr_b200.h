@@ -33,7 +33,7 @@ void        hgpu_destroy(hgpu_t* ctx);
 int         hgpu_set_stream(hgpu_t* ctx, void* cuda_stream /* cudaStream_t, NULL = default */);
 const char* hgpu_strerror(int code);
 const char* hgpu_last_error(const hgpu_t* ctx);
-int         hgpu_abi_version(void);
+int         hgpu_abi_version(void);   /* 2 since hgpu_poa_stats grew and (0) / (iv) were added */
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t    hgpu_launch_count(const hgpu_t* ctx);
 
