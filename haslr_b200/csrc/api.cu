@@ -1,7 +1,7 @@
 // Context management of the C ABI (include/haslr_b200.h).
 #include "common.cuh"
 
-extern "C" int hgpu_abi_version(void) { return 2; }   // 2: hgpu_poa_stats grew (alignments_rel16), hgpu_edge_coords, hgpu_paf_tokenize / hgpu_paf_fetch
+extern "C" int hgpu_abi_version(void) { return 3; }   // 3: device-resident stages (hgpu_hits_group, *_dev), hgpu_stage_stats / hgpu_set_timing
 
 extern "C" const char* hgpu_strerror(int code) {
     switch (code) {
@@ -56,3 +56,15 @@ extern "C" int hgpu_set_stream(hgpu_t* ctx, void* cuda_stream) {
 extern "C" const char* hgpu_last_error(const hgpu_t* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
 
 extern "C" uint64_t hgpu_launch_count(const hgpu_t* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int hgpu_get_stage_stats(const hgpu_t* ctx, hgpu_stage_stats* out) {
+    if (!ctx || !out) return HGPU_E_INVALID;
+    *out = ctx->stage;
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_set_timing(hgpu_t* ctx, int enabled) {
+    if (!ctx) return HGPU_E_INVALID;
+    ctx->timing = enabled != 0;
+    return hgpu_poa_set_timing(ctx, enabled);
+}

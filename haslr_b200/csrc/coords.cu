@@ -24,6 +24,7 @@ struct CoordState {
     DevBuf<uint64_t> keys;
     DevBuf<hgpu_edge_coord> out_edge;
     DevBuf<hgpu_supp_coord> out_supp;
+    DevBuf<unsigned long long> counters;     // [0] CIGAR runs in the windows walked, [1] first invalid support (min), [2] first invalid element (min)
 };
 void coord_state_destroy(CoordState* s) { delete s; }
 
@@ -32,12 +33,38 @@ static constexpr unsigned FULLM = 0xFFFFFFFFu;
 // keys: 8 lists of n_supp entries (4 unsorted, 4 sorted), edge e uses [supp_off[e], supp_off[e+1]) of each;
 // mask: 2 bitmasks per edge, words [2 * (supp_off[e] / 32 + e) ...) — ceil(n/32) words each, zeroed by the host
 __global__ void __launch_bounds__(128) k4_edge_coords(CoordIn in, uint32_t n_edges, const uint8_t* edge_rev, const uint32_t* supp_off,
-                                                      uint32_t n_supp, uint64_t* keys, uint32_t* mask,
-                                                      hgpu_edge_coord* out_edge, hgpu_supp_coord* out_supp) {
+                                                      uint32_t n_supp, uint32_t n_reads, uint32_t n_hits, uint64_t* keys, uint32_t* mask,
+                                                      hgpu_edge_coord* out_edge, hgpu_supp_coord* out_supp, unsigned long long* counters) {
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
+    unsigned long long runs = 0;
     for (uint32_t e = gw; e < n_edges; e += nw) {
-        const uint32_t b = supp_off[e], n = supp_off[e + 1] - b;
+        const uint32_t b = supp_off[e];
+        if (supp_off[e + 1] < b || supp_off[e + 1] > n_supp) { if (lane == 0) atomicMin(counters + 1, (unsigned long long)b); continue; }
+        const uint32_t n = supp_off[e + 1] - b;
+        // the reference indexes its containers unchecked; refuse (and skip the edge) instead of reading out of bounds
+        bool bad = false;
+        for (uint32_t k = lane; k < n; k += 32) {
+            const hgpu_edge_supp sp = in.supp[b + k];
+            const uint32_t rid = sp.lr_id_strand & 0x7FFFFFFFu;
+            bool sbad = rid >= n_reads;
+            if (!sbad) {
+                const uint32_t cnt = in.cl_read_off[rid + 1] - in.cl_read_off[rid];
+                sbad = sp.cmp_head >= cnt || sp.cmp_tail >= cnt;
+            }
+            if (sbad) { atomicMin(counters + 1, (unsigned long long)(b + k)); bad = true; continue; }
+            for (int side = 0; side < 2; ++side) {
+                const uint32_t j = in.cl_read_off[rid] + (side ? sp.cmp_tail : sp.cmp_head);
+                const hgpu_cl_elem& el = in.elems[j];
+                bool ebad = el.hit >= n_hits;
+                if (!ebad) {
+                    const uint32_t w = in.cg_off[el.hit + 1] - in.cg_off[el.hit];
+                    ebad = w && (el.cg_lo > el.cg_hi || el.cg_hi >= w);
+                }
+                if (ebad) { atomicMin(counters + 2, (unsigned long long)j); bad = true; }
+            }
+        }
+        if (__any_sync(FULLM, bad)) continue;
         const uint32_t rev1 = edge_rev[e] & 1u, rev2 = (edge_rev[e] >> 1) & 1u;
         const hgpu_edge_supp* es = in.supp + b;
         uint64_t* const raw = keys + b;                             // list l: raw + l * n_supp (unsorted), srt + l * n_supp (sorted)
@@ -85,7 +112,12 @@ __global__ void __launch_bounds__(128) k4_edge_coords(CoordIn in, uint32_t n_edg
                 best = ((m1[k >> 5] & m2[k >> 5]) >> (k & 31u)) & 1u;
                 hgpu_supp_coord o;
                 o.lr_start = -1; o.lr_end = -1; o.lr_strand = 0; o.in_best = 0;
-                if (best) { k4_walk(in, es[k], rev1, rev2, c1, c2, &o); ok = o.lr_start != -1 && o.lr_end != -1; }
+                if (best) {
+                    k4_walk(in, es[k], rev1, rev2, c1, c2, &o); ok = o.lr_start != -1 && o.lr_end != -1;
+                    const hgpu_cl_elem& h = k4_elem(in, es[k], true);
+                    const hgpu_cl_elem& t = k4_elem(in, es[k], false);
+                    runs += (h.cg_hi - h.cg_lo + 1) + (t.cg_hi - t.cg_lo + 1);
+                }
                 out_supp[b + k] = o;
             }
             n_best += __popc(__ballot_sync(FULLM, best));
@@ -98,6 +130,54 @@ __global__ void __launch_bounds__(128) k4_edge_coords(CoordIn in, uint32_t n_edg
         }
         __syncwarp();
     }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) runs += __shfl_xor_sync(FULLM, runs, d);
+    if (lane == 0 && runs) atomicAdd(counters, runs);
+}
+
+// K4 on device-resident compact reads and hit table; edges / supports / read lengths come from the host (they are made by
+// the host's graph cleaning)
+static int edge_coords_run(hgpu_t* ctx, uint32_t n_edges, const uint8_t* edge_rev, const uint32_t* supp_off, const hgpu_edge_supp* supp,
+                           const hgpu_cl_elem* d_elems, const uint32_t* d_cl_read_off, uint32_t n_reads, const uint32_t* read_len,
+                           const uint8_t* d_hit_is_rev, const uint32_t* d_cg_off, const uint32_t* d_cg_ops, uint32_t n_hits,
+                           hgpu_edge_coord* out_edge, hgpu_supp_coord* out_supp) {
+    CoordState* S = ctx->coords;
+    cudaStream_t st = ctx->stream;
+    const uint32_t n_supp = supp_off[n_edges];
+    ctx->stage.ms_k4 = 0; ctx->stage.launches_k4 = 0; ctx->stage.k4_edges = n_edges; ctx->stage.k4_supports = n_supp; ctx->stage.k4_runs = 0;
+    const size_t mask_words = 2 * ((size_t)n_supp / 32 + n_edges) + 2;
+    HGPU_CUDA(ctx, S->edge_rev.ensure(n_edges)); HGPU_CUDA(ctx, S->supp_off.ensure(n_edges + 1)); HGPU_CUDA(ctx, S->supp.ensure(n_supp));
+    HGPU_CUDA(ctx, S->read_len.ensure(n_reads));
+    HGPU_CUDA(ctx, S->keys.ensure(8 * (size_t)n_supp)); HGPU_CUDA(ctx, S->mask.ensure(mask_words));
+    HGPU_CUDA(ctx, S->out_edge.ensure(n_edges)); HGPU_CUDA(ctx, S->out_supp.ensure(n_supp)); HGPU_CUDA(ctx, S->counters.ensure(4));
+    HGPU_H2D(ctx, S->edge_rev.p, edge_rev, n_edges);
+    HGPU_H2D(ctx, S->supp_off.p, supp_off, (size_t)(n_edges + 1) * 4);
+    HGPU_H2D(ctx, S->supp.p, supp, (size_t)n_supp * sizeof(hgpu_edge_supp));
+    HGPU_H2D(ctx, S->read_len.p, read_len, (size_t)n_reads * 4);
+    HGPU_CUDA(ctx, cudaMemsetAsync(S->mask.p, 0, mask_words * 4, st));
+    HGPU_CUDA(ctx, cudaMemsetAsync(S->out_edge.p, 0, (size_t)n_edges * sizeof(hgpu_edge_coord), st));
+    HGPU_CUDA(ctx, cudaMemsetAsync(S->out_supp.p, 0, (size_t)n_supp * sizeof(hgpu_supp_coord), st));
+    const unsigned long long init[3] = {0ull, ~0ull, ~0ull};
+    HGPU_CUDA(ctx, cudaMemcpyAsync(S->counters.p, init, sizeof init, cudaMemcpyHostToDevice, st));
+
+    CoordIn in{S->supp.p, d_elems, d_cl_read_off, S->read_len.p, d_hit_is_rev, d_cg_off, d_cg_ops};
+    const uint32_t blocks = std::min<uint32_t>((n_edges + 3) / 4, (uint32_t)ctx->sm_count * 16);     // 16 blocks of 4 warps = every warp slot of an SM
+    stage_begin(ctx, ctx->ev_k4);
+    k4_edge_coords<<<blocks, 128, 0, st>>>(in, n_edges, S->edge_rev.p, S->supp_off.p, n_supp, n_reads, n_hits, S->keys.p, S->mask.p, S->out_edge.p,
+                                           S->out_supp.p, S->counters.p);
+    HGPU_CUDA(ctx, cudaGetLastError());
+    stage_end(ctx, ctx->ev_k4);
+    ctx->launches++; ctx->stage.launches_k4 = 1;
+    unsigned long long cnt[3];
+    HGPU_CUDA(ctx, cudaMemcpyAsync(cnt, S->counters.p, sizeof cnt, cudaMemcpyDeviceToHost, st));
+    HGPU_D2H(ctx, out_edge, S->out_edge.p, (size_t)n_edges * sizeof(hgpu_edge_coord));
+    HGPU_D2H(ctx, out_supp, S->out_supp.p, (size_t)n_supp * sizeof(hgpu_supp_coord));
+    HGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->stage.ms_k4 = stage_ms(ctx, ctx->ev_k4);
+    ctx->stage.k4_runs = cnt[0];
+    if (cnt[1] != ~0ull) HGPU_FAIL(ctx, HGPU_E_INVALID, "support %llu names a read or a compact-read element that does not exist (or supp_off is not monotone there)", cnt[1]);
+    if (cnt[2] != ~0ull) HGPU_FAIL(ctx, HGPU_E_INVALID, "compact-read element %llu names a hit or a CIGAR window that does not exist", cnt[2]);
+    return HGPU_OK;
 }
 
 extern "C" int hgpu_edge_coords(hgpu_t* ctx, uint32_t n_edges, const uint8_t* edge_rev, const uint32_t* supp_off, const hgpu_edge_supp* supp,
@@ -109,53 +189,33 @@ extern "C" int hgpu_edge_coords(hgpu_t* ctx, uint32_t n_edges, const uint8_t* ed
     if (!edge_rev || !supp_off || !cl_read_off || !read_len || !hit_is_rev || !cg_off || !out_edge) HGPU_FAIL(ctx, HGPU_E_INVALID, "null argument");
     const uint32_t n_supp = supp_off[n_edges];
     const uint32_t n_elems = cl_read_off[n_reads];
-    for (uint32_t e = 0; e < n_edges; ++e)
-        if (supp_off[e + 1] < supp_off[e]) HGPU_FAIL(ctx, HGPU_E_INVALID, "supp_off not monotone at edge %u", e);
     if (n_supp && (!supp || !elems || !out_supp)) HGPU_FAIL(ctx, HGPU_E_INVALID, "null argument");
-    // the reference indexes its containers unchecked; refuse instead of reading out of bounds on the device
-    for (uint32_t k = 0; k < n_supp; ++k) {
-        const uint32_t rid = supp[k].lr_id_strand & 0x7FFFFFFFu;
-        if (rid >= n_reads) HGPU_FAIL(ctx, HGPU_E_INVALID, "support %u names read %u >= n_reads %u", k, rid, n_reads);
-        const uint32_t cnt = cl_read_off[rid + 1] - cl_read_off[rid];
-        if (supp[k].cmp_head >= cnt || supp[k].cmp_tail >= cnt) HGPU_FAIL(ctx, HGPU_E_INVALID, "support %u indexes element %u/%u of a compact read with %u", k, supp[k].cmp_head, supp[k].cmp_tail, cnt);
-    }
     const uint32_t n_ops = n_hits ? cg_off[n_hits] : 0;
-    for (uint32_t j = 0; j < n_elems; ++j) {
-        const hgpu_cl_elem& el = elems[j];
-        if (el.hit >= n_hits) HGPU_FAIL(ctx, HGPU_E_INVALID, "element %u names hit %u >= n_hits %u", j, el.hit, n_hits);
-        const uint32_t w = cg_off[el.hit + 1] - cg_off[el.hit];
-        if (w && (el.cg_lo > el.cg_hi || el.cg_hi >= w)) HGPU_FAIL(ctx, HGPU_E_INVALID, "element %u: CIGAR window [%u, %u] outside its hit's %u runs", j, el.cg_lo, el.cg_hi, w);
-    }
     if (n_ops && !cg_ops) HGPU_FAIL(ctx, HGPU_E_INVALID, "null cg_ops");
     HGPU_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!ctx->coords) ctx->coords = new CoordState();
     CoordState* S = ctx->coords;
-    cudaStream_t st = ctx->stream;
-
-    const size_t mask_words = 2 * ((size_t)n_supp / 32 + n_edges) + 2;
-    HGPU_CUDA(ctx, S->edge_rev.ensure(n_edges)); HGPU_CUDA(ctx, S->supp_off.ensure(n_edges + 1)); HGPU_CUDA(ctx, S->supp.ensure(n_supp));
-    HGPU_CUDA(ctx, S->elems.ensure(n_elems)); HGPU_CUDA(ctx, S->cl_read_off.ensure(n_reads + 1)); HGPU_CUDA(ctx, S->read_len.ensure(n_reads));
+    HGPU_CUDA(ctx, S->elems.ensure(n_elems)); HGPU_CUDA(ctx, S->cl_read_off.ensure(n_reads + 1));
     HGPU_CUDA(ctx, S->hit_is_rev.ensure(n_hits)); HGPU_CUDA(ctx, S->cg_off.ensure(n_hits + 1)); HGPU_CUDA(ctx, S->cg_ops.ensure(n_ops));
-    HGPU_CUDA(ctx, S->keys.ensure(8 * (size_t)n_supp)); HGPU_CUDA(ctx, S->mask.ensure(mask_words));
-    HGPU_CUDA(ctx, S->out_edge.ensure(n_edges)); HGPU_CUDA(ctx, S->out_supp.ensure(n_supp));
-    HGPU_CUDA(ctx, cudaMemcpyAsync(S->edge_rev.p, edge_rev, n_edges, cudaMemcpyHostToDevice, st));
-    HGPU_CUDA(ctx, cudaMemcpyAsync(S->supp_off.p, supp_off, (size_t)(n_edges + 1) * 4, cudaMemcpyHostToDevice, st));
-    if (n_supp) HGPU_CUDA(ctx, cudaMemcpyAsync(S->supp.p, supp, (size_t)n_supp * sizeof(hgpu_edge_supp), cudaMemcpyHostToDevice, st));
-    if (n_elems) HGPU_CUDA(ctx, cudaMemcpyAsync(S->elems.p, elems, (size_t)n_elems * sizeof(hgpu_cl_elem), cudaMemcpyHostToDevice, st));
-    HGPU_CUDA(ctx, cudaMemcpyAsync(S->cl_read_off.p, cl_read_off, (size_t)(n_reads + 1) * 4, cudaMemcpyHostToDevice, st));
-    if (n_reads) HGPU_CUDA(ctx, cudaMemcpyAsync(S->read_len.p, read_len, (size_t)n_reads * 4, cudaMemcpyHostToDevice, st));
-    if (n_hits) HGPU_CUDA(ctx, cudaMemcpyAsync(S->hit_is_rev.p, hit_is_rev, n_hits, cudaMemcpyHostToDevice, st));
-    HGPU_CUDA(ctx, cudaMemcpyAsync(S->cg_off.p, cg_off, (size_t)(n_hits + 1) * 4, cudaMemcpyHostToDevice, st));
-    if (n_ops) HGPU_CUDA(ctx, cudaMemcpyAsync(S->cg_ops.p, cg_ops, (size_t)n_ops * 4, cudaMemcpyHostToDevice, st));
-    HGPU_CUDA(ctx, cudaMemsetAsync(S->mask.p, 0, mask_words * 4, st));
+    HGPU_H2D(ctx, S->elems.p, elems, (size_t)n_elems * sizeof(hgpu_cl_elem));
+    HGPU_H2D(ctx, S->cl_read_off.p, cl_read_off, (size_t)(n_reads + 1) * 4);
+    HGPU_H2D(ctx, S->hit_is_rev.p, hit_is_rev, n_hits);
+    HGPU_H2D(ctx, S->cg_off.p, cg_off, (size_t)(n_hits + 1) * 4);
+    HGPU_H2D(ctx, S->cg_ops.p, cg_ops, (size_t)n_ops * 4);
+    return edge_coords_run(ctx, n_edges, edge_rev, supp_off, supp, S->elems.p, S->cl_read_off.p, n_reads, read_len, S->hit_is_rev.p, S->cg_off.p,
+                           S->cg_ops.p, n_hits, out_edge, out_supp);
+}
 
-    CoordIn in{S->supp.p, S->elems.p, S->cl_read_off.p, S->read_len.p, S->hit_is_rev.p, S->cg_off.p, S->cg_ops.p};
-    const uint32_t blocks = std::min<uint32_t>((n_edges + 3) / 4, (uint32_t)ctx->sm_count * 16);     // 16 blocks of 4 warps = every warp slot of an SM
-    k4_edge_coords<<<blocks, 128, 0, st>>>(in, n_edges, S->edge_rev.p, S->supp_off.p, n_supp, S->keys.p, S->mask.p, S->out_edge.p, S->out_supp.p);
-    HGPU_CUDA(ctx, cudaGetLastError());
-    ctx->launches++;
-    HGPU_CUDA(ctx, cudaMemcpyAsync(out_edge, S->out_edge.p, (size_t)n_edges * sizeof(hgpu_edge_coord), cudaMemcpyDeviceToHost, st));
-    if (n_supp) HGPU_CUDA(ctx, cudaMemcpyAsync(out_supp, S->out_supp.p, (size_t)n_supp * sizeof(hgpu_supp_coord), cudaMemcpyDeviceToHost, st));
-    HGPU_CUDA(ctx, cudaStreamSynchronize(st));
-    return HGPU_OK;
+extern "C" int hgpu_edge_coords_dev(hgpu_t* ctx, uint32_t n_edges, const uint8_t* edge_rev, const uint32_t* supp_off, const hgpu_edge_supp* supp,
+                                    const uint32_t* read_len, uint32_t n_reads, hgpu_edge_coord* out_edge, hgpu_supp_coord* out_supp) {
+    if (!ctx) return HGPU_E_INVALID;
+    if (n_edges == 0) return HGPU_OK;
+    if (!edge_rev || !supp_off || !read_len || !out_edge) HGPU_FAIL(ctx, HGPU_E_INVALID, "null argument");
+    if (!ctx->hits.valid || !ctx->compact.valid || ctx->compact.n_reads != n_reads)
+        HGPU_FAIL(ctx, HGPU_E_INVALID, "hgpu_edge_coords_dev needs the hit table and the compact reads of %u reads resident on the device", n_reads);
+    if (supp_off[n_edges] && (!supp || !out_supp)) HGPU_FAIL(ctx, HGPU_E_INVALID, "null argument");
+    HGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->coords) ctx->coords = new CoordState();
+    return edge_coords_run(ctx, n_edges, edge_rev, supp_off, supp, ctx->compact.elems, ctx->compact.read_off, n_reads, read_len, ctx->hits.is_rev,
+                           ctx->hits.cg_off, ctx->hits.cg_ops, ctx->hits.n_hits, out_edge, out_supp);
 }

@@ -261,9 +261,11 @@ K1_HD void k1_cigar_window(const RleCigar& cg, uint32_t lo, uint32_t hi, ClElem&
 // Everything after the load filters for one read. `idx[0..n)` = rows of the read's hits that passed F1-F4,
 // in PAF order (it is permuted in place); `hit` = scratch for n K1Hit; `dp`/`prevc`/`cand` = scratch for n words
 // each; `take` = scratch for n bytes. Elements are written to `out` (capacity n). Returns their count.
+// `cg_total` (may be null): expanded CIGAR length of every row of `idx`, indexed by row, precomputed by the caller (the kernel
+// sums the runs lane-parallel); without it the runs are summed here.
 K1_HD uint32_t k1_process_read(const HitCols& h, const double* mean_kmer, const K1Params& p,
                                uint32_t* idx, uint32_t n, K1Hit* hit, uint32_t* dp, int32_t* prevc, uint32_t* cand,
-                               uint8_t* take, ClElem* out) {
+                               uint8_t* take, ClElem* out, const uint32_t* cg_total = nullptr) {
     const double uf = p.uniq_freq, dev = p.max_uniq_dev;
     // per-read sort by (q_end, q_start), Longread.cpp:256
     KeyLess lt{h.q_end, h.q_start};
@@ -290,7 +292,8 @@ K1_HD uint32_t k1_process_read(const HitCols& h, const double* mean_kmer, const 
         x.src = r; x.q_start = h.q_start[r]; x.q_end = h.q_end[r]; x.t_start = h.t_start[r]; x.t_end = h.t_end[r];
         x.n_match = h.n_match[r]; x.n_block = h.n_block[r]; x.is_rev = h.is_rev[r];
         uint32_t tot = 0;
-        for (uint32_t k = h.cg_off[r]; k < h.cg_off[r + 1]; ++k) tot += h.cg_ops[k] >> 2;
+        if (cg_total) tot = cg_total[r];
+        else for (uint32_t k = h.cg_off[r]; k < h.cg_off[r + 1]; ++k) tot += h.cg_ops[k] >> 2;
         x.lo = 0; x.hi = tot;
     }
     // overlap fix :430-512 on adjacent pairs, in place

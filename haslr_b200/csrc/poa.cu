@@ -70,7 +70,7 @@ static PoaState* poa_state(hgpu_t* ctx) {
         if (const char* e = getenv("HGPU_TEAM_MIN_CELLS")) ctx->poa->cfg_team_min_cells = atof(e);
         if (const char* e = getenv("HGPU_VERBOSE")) ctx->poa->verbose = atoi(e);
         if (const char* e = getenv("HGPU_TEAM_ALPHA")) ctx->poa->cfg_team_alpha = std::max(0.01, atof(e));
-        if (const char* e = getenv("HGPU_TEAMS_PER_SM")) ctx->poa->cfg_teams_per_sm = (uint32_t)std::max(1, std::min(2, atoi(e)));
+        if (const char* e = getenv("HGPU_TEAMS_PER_SM")) ctx->poa->cfg_teams_per_sm = (uint32_t)std::max(1, std::min(4, atoi(e)));
         if (const char* e = getenv("HGPU_BUDGET_FRAC")) ctx->poa->cfg_budget_frac = std::max(0.1, std::min(0.92, atof(e)));
         if (const char* e = getenv("HGPU_FORCE_MODE")) ctx->poa->cfg_force = atoi(e);
         if (const char* e = getenv("HGPU_DEEP_MIN_READS")) ctx->poa->cfg_deep_min_reads = (uint32_t)atoi(e);
@@ -267,13 +267,14 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
         if (S->timing) HGPU_CUDA(ctx, cudaEventRecord(S->ev0, st));
         bool team_launched = false;
         if (!team.empty()) {
-            constexpr int TEAM = 8;
+            const int TEAM = S->cfg_team >= 8 ? 8 : 4;
+            const uint32_t teams_per_sm = std::min<uint32_t>(S->cfg_teams_per_sm, TEAM == 8 ? 2u : 4u);
             uint64_t tslot = 0; uint32_t nc = 64;
             for (const EdgeEst& x : team) { tslot = std::max(tslot, x.slot); nc = std::max(nc, x.ncap); }
             tslot = (tslot + 127) / 128 * 128;
             const WsLayout twl = ws_layout(nc, nc + nc / 4 + 64);
             const uint64_t tbudget = budget / 2;              // the other half stays with the warp-per-edge kernel
-            uint32_t teams = (uint32_t)std::min<uint64_t>({(uint64_t)team.size(), (uint64_t)ctx->sm_count * S->cfg_teams_per_sm, tbudget / (tslot + twl.bytes)});
+            uint32_t teams = (uint32_t)std::min<uint64_t>({(uint64_t)team.size(), (uint64_t)ctx->sm_count * teams_per_sm, tbudget / (tslot + twl.bytes)});
             if (teams == 0) {
                 for (const EdgeEst& x : team) est.push_back(x);          // does not fit even once: let the classes report it
                 std::sort(est.begin(), est.end(), by_size);
@@ -292,10 +293,15 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
                 a.ws = S->ws_team.p; a.wl = twl; a.arena = S->arena_team.p; a.slot_bytes = tslot;
                 a.sc = sc; a.stats = S->stats.p; a.stop_round = opt.stop_round; a.force_i32 = opt.force_i32;
                 const size_t tsmem = (size_t)TEAM * DP_SMEM_PER_WARP_DEEP + (TEAM + 4) * 4;
-                HGPU_CUDA(ctx, cudaFuncSetAttribute(k_poa_edges_team<TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
                 HGPU_CUDA(ctx, cudaEventRecord(S->ev_fork, st));          // uploads and memsets above are on `st`
                 HGPU_CUDA(ctx, cudaStreamWaitEvent(S->stream2, S->ev_fork, 0));
-                k_poa_edges_team<TEAM><<<teams, 32 * TEAM, tsmem, S->stream2>>>(a);
+                if (TEAM == 8) {
+                    HGPU_CUDA(ctx, cudaFuncSetAttribute(k_poa_edges_team<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+                    k_poa_edges_team<8><<<teams, 32 * 8, tsmem, S->stream2>>>(a);
+                } else {
+                    HGPU_CUDA(ctx, cudaFuncSetAttribute(k_poa_edges_team<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+                    k_poa_edges_team<4><<<teams, 32 * 4, tsmem, S->stream2>>>(a);
+                }
                 HGPU_CUDA(ctx, cudaGetLastError());
                 HGPU_CUDA(ctx, cudaEventRecord(S->ev_join, S->stream2));
                 ctx->launches++; S->st.dp_launches++;

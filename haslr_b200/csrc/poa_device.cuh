@@ -50,7 +50,7 @@ struct WsLayout {
     uint32_t ncap, ecap, scap;
     uint64_t o_hdr, o_code, o_in_head, o_in_tail, o_out_head, o_aligned, o_e_begin, o_e_end, o_e_w, o_e_next_in, o_e_next_out,
         o_rank2node, o_node2rank, o_meta0, o_pred_off, o_pred_rank, o_sinks, o_aln_rank, o_aln_pos, o_mark, o_check, o_stack,
-        o_score, o_pred;
+        o_score, o_pred, o_plan_a, o_plan_b;
     uint64_t bytes;
 };
 
@@ -72,6 +72,7 @@ __host__ __device__ inline WsLayout ws_layout(uint32_t ncap, uint32_t ecap) {
     w.o_mark = take(n); w.o_check = take(n);
     w.o_stack = take(4 * (uint64_t)w.scap);
     w.o_score = take(8 * n); w.o_pred = take(4 * n);
+    w.o_plan_a = take(4 * n); w.o_plan_b = take(4 * n);      // deep kernels: per-rank predecessor plan (poa_fill_rel.cuh)
     w.bytes = (o + 127) / 128 * 128;
     return w;
 }
@@ -169,13 +170,15 @@ static constexpr int DP_WARPS_PER_BLOCK = 4;
 
 // Cell encodings of a stored score matrix. ABS16: int16 Hhat + bias, when the whole range 13(L+1) + 8(V+2) fits.
 // REL16: int16 relative to the row's own value at the left edge of the stripe (kept as int32 in the boundary-column
-// arrays) - Hhat never decreases along a row, so the in-stripe range is [0, hi_step * 512] whatever V and L are; rows
+// arrays) - Hhat never decreases along a row, so the in-stripe range is [0, (hi_step + lo_step) * 512] whatever V and L are; rows
 // are re-based by (base of predecessor row - base of this row) <= -gap when they are combined. I32: plain int32, for
 // scores the packed arithmetic cannot hold (and on request, for tests).
 enum : int { DPM_I32 = 0, DPM_ABS16 = 1, DPM_REL16 = 2 };
 static constexpr int REL_CLAMP = -16000;             // a re-base below this can never win against the row's own cells (>= 0)
 __host__ __device__ inline bool dp_rel_ok(const DpScores& sc) {
-    return sc.hi_step < (1 << 19) && (int64_t)sc.hi_step * (32 * 2 * DP_NW16) + (int64_t)sc.lo_step + 1024 < -(int64_t)REL_CLAMP;
+    // a row spans at most (hi_step + lo_step) per column inside a stripe: its left-edge cell may sit a vertical gap per
+    // column below the cells further right (e.g. Hhat[i][0] = -8 i against Hhat[i][i] = 13 i)
+    return sc.hi_step < (1 << 19) && ((int64_t)sc.hi_step + sc.lo_step) * (32 * 2 * DP_NW16) + (int64_t)sc.hi_step + 1024 < -(int64_t)REL_CLAMP;
 }
 // force: 0 = pick, 1 = int32, 2 = REL16 even where ABS16 would fit (tests)
 __host__ __device__ inline int dp_mode(uint32_t V, uint32_t L, const DpScores& sc, int force) {
@@ -183,6 +186,10 @@ __host__ __device__ inline int dp_mode(uint32_t V, uint32_t L, const DpScores& s
     if (force == 2 && dp_rel_ok(sc)) return DPM_REL16;
     if (dp_fits16(V, L, sc)) return DPM_ABS16;
     return dp_rel_ok(sc) ? DPM_REL16 : DPM_I32;
+}
+// the deep kernels run every alignment in REL16 (one row body, poa_fill_rel.cuh); int32 only for scores it cannot hold
+__host__ __device__ inline int dp_mode_deep(const DpScores& sc, int force) {
+    return (force == 1 || sc.hi_step >= (1 << 19) || !dp_rel_ok(sc)) ? DPM_I32 : DPM_REL16;
 }
 __host__ __device__ inline uint64_t dp_slot_bytes(uint32_t V, uint32_t L, int mode) {
     if (mode == DPM_I32) return Geo<DP_NW32, false>::slot_bytes(V, L);
@@ -972,6 +979,10 @@ __device__ __noinline__ bool dp_fill16(const uint32_t* meta0, const uint32_t* pr
     return sync_ok;
 }
 
+}  // namespace hgpu
+#include "poa_fill_rel.cuh"
+namespace hgpu {
+
 // ---------------------------------------------------------------------------------------------------------
 // Traceback. The stored matrix is read in tiles of 32 rows x 32 columns with the current cell in the corner. A
 // tile is kept as the raw 16-byte units of the slot (6 or 10 coalesced LDG.128 + STS.128 per lane, no unpacking),
@@ -1689,6 +1700,8 @@ __device__ __forceinline__ void poa_edges_body(const PoaArgs& a) {
     GraphView gv = bind_graph(wsb, a.wl);
     GraphScratch gs = bind_scratch(wsb, a.wl);
     uint32_t* hdr = reinterpret_cast<uint32_t*>(wsb + a.wl.o_hdr);
+    uint32_t* plan_a = reinterpret_cast<uint32_t*>(wsb + a.wl.o_plan_a);
+    uint32_t* plan_b = reinterpret_cast<uint32_t*>(wsb + a.wl.o_plan_b);
     unsigned long long st_cells = 0, st_padded = 0, st_aln = 0, st_aln32 = 0, st_bases = 0;
     PHASE_CLK_DECL
 
@@ -1710,14 +1723,14 @@ __device__ __forceinline__ void poa_edges_body(const PoaArgs& a) {
         } else {
             const uint32_t L0 = a.seg_len[s0];
             if (L0 > gv.ncap || L0 > gv.ecap) st = ST_CAPACITY;
-            else { w_init_chain(gv, a.bases + a.seg_ptr[s0], L0, lane); e_bases += L0; }
+            else { w_init_chain(gv, a.bases + a.seg_ptr[s0], L0, lane); e_bases += L0; if (RING > 2) w_build_plan(gv, plan_a, plan_b, lane); }
             PHASE_CLK(PC_INIT)
             for (uint32_t k = 1; k < R && st == ST_OK; ++k) {
                 const uint32_t V = *gv.n_nodes;
                 const uint32_t NE = *gv.n_edges;
                 const uint32_t L = a.seg_len[s0 + k];
                 const uint8_t* seq = a.bases + a.seg_ptr[s0 + k];
-                int mode = dp_mode(V, L, a.sc, a.force_i32);
+                int mode = RING > 2 ? dp_mode_deep(a.sc, a.force_i32) : dp_mode(V, L, a.sc, a.force_i32);
                 // the shallow kernel carries no REL16 code (it is instruction-cache bound): the host sends every edge it expects
                 // to leave the plain int16 range to the deep kernel; one that does so unexpectedly runs in int32 cells here
                 if (RING == 2 && mode == DPM_REL16) mode = DPM_I32;
@@ -1726,17 +1739,18 @@ __device__ __forceinline__ void poa_edges_body(const PoaArgs& a) {
                 if (dp_slot_bytes(V, L, mode) > a.slot_bytes) { st = ST_TOO_LARGE; break; }
                 const uint32_t probe = (k == a.probe_round) ? a.probe : 0u;
                 if (probe == 1) {
-                    if (mode == DPM_ABS16) dp_fill16<false, false, RING>(gv.meta0, gv.pred_off, gv.pred_rank, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, Geo<DP_NW16, true>::bias(V, a.sc), lane, 0, 1, nullptr);
+                    if (RING > 2 && mode == DPM_REL16) dp_fill_rel<false>(gv, plan_a, plan_b, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, lane, 0, 1, nullptr);
+                    else if (mode == DPM_ABS16) dp_fill16<false, false, 2>(gv.meta0, gv.pred_off, gv.pred_rank, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, Geo<DP_NW16, true>::bias(V, a.sc), lane, 0, 1, nullptr);
                     e_cells += (unsigned long long)(V + 1) * (L + 1);
                     debug_stop = true; break;
                 }
                 bool ok;
-                if (mode == DPM_ABS16) {
-                    dp_fill16<false, false, RING>(gv.meta0, gv.pred_off, gv.pred_rank, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, Geo<DP_NW16, true>::bias(V, a.sc), lane, 0, 1, nullptr);
+                if (RING == 2 && mode == DPM_ABS16) {
+                    dp_fill16<false, false, 2>(gv.meta0, gv.pred_off, gv.pred_rank, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, Geo<DP_NW16, true>::bias(V, a.sc), lane, 0, 1, nullptr);
                     PHASE_CLK(PC_FILL)
                     ok = dp_traceback<DP_NW16, true>(gv, slot, wsm, seq, V, L, a.sc, lane);
                 } else if (RING > 2 && mode == DPM_REL16) {
-                    dp_fill16<false, true, RING>(gv.meta0, gv.pred_off, gv.pred_rank, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, 0, lane, 0, 1, nullptr);
+                    dp_fill_rel<false>(gv, plan_a, plan_b, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, lane, 0, 1, nullptr);
                     PHASE_CLK(PC_FILL)
                     ok = dp_traceback<DP_NW16, true, true>(gv, slot, wsm, seq, V, L, a.sc, lane);
                 } else {
@@ -1777,6 +1791,7 @@ __device__ __forceinline__ void poa_edges_body(const PoaArgs& a) {
                 PHASE_CLK(PC_TOPO)
                 if (probe == 4) { debug_stop = true; break; }
                 w_build_meta(gv, lane);
+                if (RING > 2) w_build_plan(gv, plan_a, plan_b, lane);
                 PHASE_CLK(PC_META)
                 if (probe == 5) { debug_stop = true; break; }
             }
@@ -1847,6 +1862,8 @@ __global__ void __launch_bounds__(32 * TEAM, 512 / (32 * TEAM)) k_poa_edges_team
     GraphView gv = bind_graph(wsb, a.wl);
     GraphScratch gs = bind_scratch(wsb, a.wl);
     uint32_t* hdr = reinterpret_cast<uint32_t*>(wsb + a.wl.o_hdr);
+    uint32_t* plan_a = reinterpret_cast<uint32_t*>(wsb + a.wl.o_plan_a);
+    uint32_t* plan_b = reinterpret_cast<uint32_t*>(wsb + a.wl.o_plan_b);
     unsigned long long st_cells = 0, st_padded = 0, st_aln = 0, st_aln32 = 0, st_bases = 0;
     const bool lead = wib == 0;
 
@@ -1867,7 +1884,7 @@ __global__ void __launch_bounds__(32 * TEAM, 512 / (32 * TEAM)) k_poa_edges_team
         } else {
             const uint32_t L0 = a.seg_len[s0];
             if (L0 > gv.ncap || L0 > gv.ecap) st = ST_CAPACITY;
-            else if (lead) { w_init_chain(gv, a.bases + a.seg_ptr[s0], L0, lane); e_bases += L0; }
+            else if (lead) { w_init_chain(gv, a.bases + a.seg_ptr[s0], L0, lane); e_bases += L0; w_build_plan(gv, plan_a, plan_b, lane); }
             for (uint32_t k = 1; k < R && st == ST_OK; ++k) {
                 if (threadIdx.x < TEAM) vprog[threadIdx.x] = 0;
                 __syncthreads();                              // graph of round k-1 complete, progress words cleared
@@ -1875,20 +1892,18 @@ __global__ void __launch_bounds__(32 * TEAM, 512 / (32 * TEAM)) k_poa_edges_team
                 const uint32_t NE = *gv.n_edges;
                 const uint32_t L = a.seg_len[s0 + k];
                 const uint8_t* seq = a.bases + a.seg_ptr[s0 + k];
-                const int mode = dp_mode(V, L, a.sc, a.force_i32);
+                const int mode = dp_mode_deep(a.sc, a.force_i32);
                 const bool p16 = mode != DPM_I32;
                 if ((uint64_t)V + L > gv.ncap || (uint64_t)NE + L + 1 > gv.ecap) { st = ST_CAPACITY; break; }
                 if (dp_slot_bytes(V, L, mode) > a.slot_bytes) { st = ST_TOO_LARGE; break; }
-                const bool fill_ok = mode == DPM_ABS16 ? dp_fill16<true, false, DP_RING_DEEP>(gv.meta0, gv.pred_off, gv.pred_rank, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, Geo<DP_NW16, true>::bias(V, a.sc), lane, wib, TEAM, vprog)
-                                   : mode == DPM_REL16 ? dp_fill16<true, true, DP_RING_DEEP>(gv.meta0, gv.pred_off, gv.pred_rank, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, 0, lane, wib, TEAM, vprog)
-                                         : dp_fill<DP_NW32, false>(gv, slot, wsm, seq, V, L, a.sc, lane, wib, TEAM, vprog);
+                const bool fill_ok = mode == DPM_REL16 ? dp_fill_rel<true>(gv, plan_a, plan_b, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, lane, wib, TEAM, vprog)
+                                                       : dp_fill<DP_NW32, false>(gv, slot, wsm, seq, V, L, a.sc, lane, wib, TEAM, vprog);
                 const int all_ok = __syncthreads_and(fill_ok ? 1 : 0);    // every stripe stored (and no wait gave up)
                 if (!all_ok) { st = ST_SYNC; break; }
                 uint32_t rst = ST_OK;
                 if (lead) {
-                    bool ok = mode == DPM_ABS16 ? dp_traceback<DP_NW16, true>(gv, slot, wsm, seq, V, L, a.sc, lane)
-                            : mode == DPM_REL16 ? dp_traceback<DP_NW16, true, true>(gv, slot, wsm, seq, V, L, a.sc, lane)
-                                  : dp_traceback<DP_NW32, false>(gv, slot, wsm, seq, V, L, a.sc, lane);
+                    bool ok = mode == DPM_REL16 ? dp_traceback<DP_NW16, true, true>(gv, slot, wsm, seq, V, L, a.sc, lane)
+                                                : dp_traceback<DP_NW32, false>(gv, slot, wsm, seq, V, L, a.sc, lane);
                     if (lane == 0) {
                         hdr[HDR_LAST_P16] = (uint32_t)mode; hdr[HDR_LAST_V] = V; hdr[HDR_LAST_L] = L;
                         hdr[HDR_LAST_BIAS] = (uint32_t)(mode == DPM_ABS16 ? Geo<DP_NW16, true>::bias(V, a.sc) : 0);
@@ -1911,7 +1926,7 @@ __global__ void __launch_bounds__(32 * TEAM, 512 / (32 * TEAM)) k_poa_edges_team
                             ust = __shfl_sync(FULL, ust, 0);
                             __syncwarp();
                         }
-                        if (ust == ST_OK) w_build_meta(gv, lane);
+                        if (ust == ST_OK) { w_build_meta(gv, lane); w_build_plan(gv, plan_a, plan_b, lane); }
                         rst = ust;
                     }
                     if (lane == 0) bcast[1] = rst;

@@ -14,7 +14,8 @@ EXPORTS = (
     "hgpu_create", "hgpu_destroy", "hgpu_set_stream", "hgpu_strerror", "hgpu_last_error", "hgpu_abi_version",
     "hgpu_launch_count", "hgpu_compact_lr", "hgpu_backbone_edges", "hgpu_poa_batch", "hgpu_poa_batch_dev",
     "hgpu_poa_fetch", "hgpu_poa_get_stats", "hgpu_poa_set_timing", "hgpu_poa_configure", "hgpu_poa_debug", "hgpu_edge_coords",
-    "hgpu_paf_tokenize", "hgpu_paf_fetch",
+    "hgpu_paf_tokenize", "hgpu_paf_fetch", "hgpu_hits_group", "hgpu_compact_lr_dev", "hgpu_backbone_edges_dev", "hgpu_edge_coords_dev",
+    "hgpu_get_stage_stats", "hgpu_set_timing",
 )
 
 
@@ -41,6 +42,13 @@ class PoaStats(C.Structure):
                 ("dp_launches", C.c_uint64), ("update_launches", C.c_uint64), ("other_launches", C.c_uint64),
                 ("ms_dp", C.c_float), ("ms_update", C.c_float), ("ms_other", C.c_float), ("arena_bytes", C.c_uint64),
                 ("alignments_rel16", C.c_uint64)]
+
+
+class StageStats(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("ms_k0", "ms_k1", "ms_k2", "ms_k4")] + \
+               [(n, C.c_uint32) for n in ("launches_k0", "launches_k1", "launches_k2", "launches_k4")] + \
+               [(n, C.c_uint64) for n in ("k0_text_bytes", "k0_rows", "k0_ops", "k1_hits", "k1_reads", "k1_elems", "k2_pairs", "k2_entries",
+                                          "k4_edges", "k4_supports", "k4_runs", "h2d_bytes", "d2h_bytes")]
 
 
 class DbgSizes(C.Structure):
@@ -304,3 +312,87 @@ def _parse_paf(self, text):
 
 
 Context.parse_paf = _parse_paf
+
+
+# ---- device-resident stages: the hit table hgpu_paf_tokenize made stays on the device -------------------------------
+def _tokenize(self, text):
+    """hgpu_paf_tokenize only: the hit table stays on the device. Returns (n_rows, n_ops)."""
+    buf = np.frombuffer(bytes(text), dtype=np.uint8) if not isinstance(text, np.ndarray) else np.ascontiguousarray(text, dtype=np.uint8)
+    nr, no = C.c_uint64(0), C.c_uint64(0)
+    self.L.hgpu_paf_tokenize.restype = C.c_int
+    self.L.hgpu_paf_tokenize.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    self._check(self.L.hgpu_paf_tokenize(self.h, buf.ctypes.data if len(buf) else None, len(buf), C.byref(nr), C.byref(no)))
+    return nr.value, no.value
+
+
+def _hits_group(self, n_reads):
+    off = np.zeros(n_reads + 1, dtype=np.uint32)
+    self.L.hgpu_hits_group.restype = C.c_int
+    self.L.hgpu_hits_group.argtypes = [C.c_void_p, C.c_uint32, u32p]
+    self._check(self.L.hgpu_hits_group(self.h, n_reads, _p(off, u32p)))
+    return off
+
+
+def _compact_lr_dev(self, n_reads, n_hits, mean_kmer, uniq_freq, min_aln_block=500, min_aln_sim=0.85, min_aln_mapq=55, max_uniq_dev=0.15):
+    """Returns (elems CL_ELEM[], tid uint32[], rev uint8[], read_off uint32[n_reads+1]); the elements also stay on the device."""
+    mean_kmer = np.ascontiguousarray(mean_kmer, dtype=np.float64)
+    prm = K1Params(min_aln_sim, uniq_freq, max_uniq_dev, min_aln_block, min_aln_mapq)
+    elems = np.zeros(max(n_hits, 1), dtype=CL_ELEM); tid = np.zeros(max(n_hits, 1), dtype=np.uint32); rev = np.zeros(max(n_hits, 1), dtype=np.uint8)
+    out_off = np.zeros(n_reads + 1, dtype=np.uint32)
+    n = C.c_uint64(0)
+    self.L.hgpu_compact_lr_dev.restype = C.c_int
+    self.L.hgpu_compact_lr_dev.argtypes = [C.c_void_p, C.c_uint32, f64p, C.c_uint32, C.POINTER(K1Params), C.c_void_p, u32p, u8p, u32p, u64p]
+    self._check(self.L.hgpu_compact_lr_dev(self.h, n_reads, _p(mean_kmer, f64p), len(mean_kmer), C.byref(prm), elems.ctypes.data, _p(tid, u32p),
+                                           _p(rev, u8p), _p(out_off, u32p), C.byref(n)))
+    n = n.value
+    return elems[:n].copy(), tid[:n].copy(), rev[:n].copy(), out_off
+
+
+def _backbone_edges_dev(self, cl_read_off, min_edge_sup=3):
+    cnt = np.diff(np.asarray(cl_read_off).astype(np.int64))
+    cap = max(2 * int(np.maximum(cnt - 1, 0).sum()), 1)
+    key = np.zeros(cap, dtype=np.uint64); soff = np.zeros(cap + 1, dtype=np.uint32)
+    supp = np.zeros(cap, dtype=EDGE_SUPP); keep = np.zeros(cap, dtype=np.uint8)
+    n = C.c_uint64(0)
+    self.L.hgpu_backbone_edges_dev.restype = C.c_int
+    self.L.hgpu_backbone_edges_dev.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, u64p, u32p, C.c_void_p, u8p, u64p]
+    self._check(self.L.hgpu_backbone_edges_dev(self.h, min_edge_sup, cap, _p(key, u64p), _p(soff, u32p), supp.ctypes.data, _p(keep, u8p), C.byref(n)))
+    n = n.value
+    return key[:n].copy(), soff[: n + 1].copy(), supp[: int(soff[n])].copy(), keep[:n].copy()
+
+
+def _edge_coords_dev(self, edge_rev, supp_off, supp, read_len):
+    edge_rev = np.ascontiguousarray(edge_rev, dtype=np.uint8)
+    supp_off = np.ascontiguousarray(supp_off, dtype=np.uint32)
+    supp = np.ascontiguousarray(supp, dtype=EDGE_SUPP)
+    read_len = np.ascontiguousarray(read_len, dtype=np.uint32)
+    n = len(edge_rev)
+    oe = np.zeros(max(n, 1), dtype=EDGE_COORD); os_ = np.zeros(max(len(supp), 1), dtype=SUPP_COORD)
+    self.L.hgpu_edge_coords_dev.restype = C.c_int
+    self.L.hgpu_edge_coords_dev.argtypes = [C.c_void_p, C.c_uint32, u8p, u32p, C.c_void_p, u32p, C.c_uint32, C.c_void_p, C.c_void_p]
+    self._check(self.L.hgpu_edge_coords_dev(self.h, n, _p(edge_rev, u8p), _p(supp_off, u32p), supp.ctypes.data, _p(read_len, u32p), len(read_len),
+                                            oe.ctypes.data, os_.ctypes.data))
+    return oe[:n], os_[: len(supp)]
+
+
+def _stage_stats(self):
+    s = StageStats()
+    self.L.hgpu_get_stage_stats.restype = C.c_int
+    self.L.hgpu_get_stage_stats.argtypes = [C.c_void_p, C.POINTER(StageStats)]
+    self._check(self.L.hgpu_get_stage_stats(self.h, C.byref(s)))
+    return {k: getattr(s, k) for k, _ in StageStats._fields_}
+
+
+def _set_timing(self, on):
+    self.L.hgpu_set_timing.restype = C.c_int
+    self.L.hgpu_set_timing.argtypes = [C.c_void_p, C.c_int]
+    self._check(self.L.hgpu_set_timing(self.h, int(on)))
+
+
+Context.tokenize = _tokenize
+Context.hits_group = _hits_group
+Context.compact_lr_dev = _compact_lr_dev
+Context.backbone_edges_dev = _backbone_edges_dev
+Context.edge_coords_dev = _edge_coords_dev
+Context.stage_stats = _stage_stats
+Context.set_timing = _set_timing

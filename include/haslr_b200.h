@@ -33,9 +33,25 @@ void        hgpu_destroy(hgpu_t* ctx);
 int         hgpu_set_stream(hgpu_t* ctx, void* cuda_stream /* cudaStream_t, NULL = default */);
 const char* hgpu_strerror(int code);
 const char* hgpu_last_error(const hgpu_t* ctx);
-int         hgpu_abi_version(void);   /* 2 since hgpu_poa_stats grew and (0) / (iv) were added */
+int         hgpu_abi_version(void);   /* 3 since the device-resident stages (hgpu_hits_group, *_dev) and hgpu_stage_stats were added */
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t    hgpu_launch_count(const hgpu_t* ctx);
+
+/* Per-stage figures of the most recent call of each stage: CUDA-event time of the stage's kernels (copies excluded; only
+ * when timing is on, hgpu_set_timing), kernel launches, the units the stage processed (what the roofline figures of
+ * DESIGN.md are counted in) and the bytes this context has copied between host and device since it was created. */
+typedef struct {
+    float    ms_k0, ms_k1, ms_k2, ms_k4;
+    uint32_t launches_k0, launches_k1, launches_k2, launches_k4;
+    uint64_t k0_text_bytes, k0_rows, k0_ops;      /* PAF bytes scanned, rows and CIGAR runs emitted */
+    uint64_t k1_hits, k1_reads, k1_elems;         /* hit rows read, reads, compact elements written */
+    uint64_t k2_pairs, k2_entries;                /* adjacent pairs, directed edge entries */
+    uint64_t k4_edges, k4_supports, k4_runs;      /* edges, supports, CIGAR runs walked */
+    uint64_t h2d_bytes, d2h_bytes;
+} hgpu_stage_stats;
+int hgpu_get_stage_stats(const hgpu_t* ctx, hgpu_stage_stats* out);
+/* CUDA-event timing of the kernels of every stage (one event pair per call; also switches hgpu_poa_set_timing). */
+int hgpu_set_timing(hgpu_t* ctx, int enabled);
 
 /* ---- (0) PAF text -> hit table -----------------------------------------------------------------------------
  * Replaces the text side of load_alignment (Longread.cpp:250-289): getline, str_split on tabs, str2type<uint32_t> on
@@ -50,6 +66,12 @@ int hgpu_paf_tokenize(hgpu_t* ctx, const char* text, uint64_t n_bytes, uint64_t*
 int hgpu_paf_fetch(hgpu_t* ctx, uint32_t* q_id, uint32_t* q_len, uint32_t* q_start, uint32_t* q_end, uint8_t* is_rev,
                    uint32_t* t_id, uint32_t* t_len, uint32_t* t_start, uint32_t* t_end, uint32_t* n_match, uint32_t* n_block,
                    uint8_t* mapq, uint32_t* cg_off, uint32_t* cg_ops);
+
+/* The table hgpu_paf_tokenize made STAYS on the device (so does the one hgpu_compact_lr uploads): the *_dev entry points of
+ * (i), (ii) and (iv) read it there and nothing but results travels back. hgpu_hits_group slices it by read - rows must be
+ * grouped by ascending read id (Longread.cpp:57-84 assumes it silently; here a violation is HGPU_E_INVALID, as is a read id
+ * >= n_reads) - and optionally returns the n_reads + 1 offsets. */
+int hgpu_hits_group(hgpu_t* ctx, uint32_t n_reads, uint32_t* out_read_off /* may be NULL */);
 
 /* ---- (i) PAF hits -> compact long reads ------------------------------------------------------------------
  * Replaces, per long read: load_alignment's filters F1-F4 and per-read sort (Longread.cpp:234-302),
@@ -89,6 +111,11 @@ int hgpu_compact_lr(hgpu_t* ctx, const hgpu_hits_t* hits, const uint32_t* read_o
                     const double* mean_kmer, uint32_t n_contigs, const hgpu_k1_params* prm,
                     hgpu_cl_elem* out_elems, uint32_t* out_read_off, uint64_t* out_n);
 
+/* Same on the resident, grouped hit table; the elements also stay on the device for (ii) / (iv). out_elems, out_tid (contig
+ * of each element) and out_rev (its strand) may each be NULL when the host has no use for them. */
+int hgpu_compact_lr_dev(hgpu_t* ctx, uint32_t n_reads, const double* mean_kmer, uint32_t n_contigs, const hgpu_k1_params* prm,
+                        hgpu_cl_elem* out_elems, uint32_t* out_tid, uint8_t* out_rev, uint32_t* out_read_off, uint64_t* out_n);
+
 /* ---- (ii) compact long reads -> backbone edge table -----------------------------------------------------
  * Replaces bbg_build_graph + bbg_add_edge (Backbone_graph.cpp:148-171,10-25; Backbone_graph.hpp:60) and the
  * rule of bbg_remove_weak_edges (Backbone_graph.cpp:348-375; Backbone_graph.hpp:63).
@@ -103,6 +130,12 @@ int hgpu_backbone_edges(hgpu_t* ctx, const uint32_t* cl_tid, const uint8_t* cl_r
                         uint32_t n_reads, uint32_t min_edge_sup,
                         uint64_t* out_key, uint32_t* out_supp_off, hgpu_edge_supp* out_supp, uint8_t* out_keep,
                         uint64_t* out_n_entries);
+
+/* Same on the compact reads hgpu_compact_lr[_dev] left on the device. entry_cap = capacity of the output arrays in entries
+ * (out_supp_off: entry_cap + 1); HGPU_E_NOSPACE if 2 * pairs exceeds it. */
+int hgpu_backbone_edges_dev(hgpu_t* ctx, uint32_t min_edge_sup, uint64_t entry_cap,
+                            uint64_t* out_key, uint32_t* out_supp_off, hgpu_edge_supp* out_supp, uint8_t* out_keep,
+                            uint64_t* out_n_entries);
 
 /* ---- (iv) edge coordinates: the stretch of each supporting long read that spans an edge's gap -----------------
  * (numbered after (iii) because it was added after it; in the pipeline it runs between (ii) + graph cleaning and (iii).)
@@ -131,6 +164,10 @@ int hgpu_edge_coords(hgpu_t* ctx, uint32_t n_edges, const uint8_t* edge_rev, con
                      const hgpu_cl_elem* elems, const uint32_t* cl_read_off, uint32_t n_reads, const uint32_t* read_len,
                      const uint8_t* hit_is_rev, const uint32_t* cg_off, const uint32_t* cg_ops, uint32_t n_hits,
                      hgpu_edge_coord* out_edge, hgpu_supp_coord* out_supp);
+
+/* Same with the compact reads and the hit table resident on the device (only edges, supports and read lengths go up). */
+int hgpu_edge_coords_dev(hgpu_t* ctx, uint32_t n_edges, const uint8_t* edge_rev, const uint32_t* supp_off, const hgpu_edge_supp* supp,
+                         const uint32_t* read_len, uint32_t n_reads, hgpu_edge_coord* out_edge, hgpu_supp_coord* out_supp);
 
 /* ---- (iii) batched POA consensus -------------------------------------------------------------------------
  * Replaces the body of asm_calc_single_cns_seq (Assemble.cpp:499-554), i.e. per backbone edge the five SPOA
@@ -168,18 +205,19 @@ typedef struct {
     uint64_t alignments_rel16; /* alignments whose range exceeds plain int16 and ran in row-relative int16 cells */
 } hgpu_poa_stats;
 int hgpu_poa_get_stats(const hgpu_t* ctx, hgpu_poa_stats* out);
-/* Per-kernel-family CUDA-event timing (serialises the families; leave off when measuring whole-job throughput). */
+/* CUDA-event timing of the POA kernels: one event pair around the launches of a scheduling pass, read after the
+ * synchronisation the pass ends with anyway (ms_dp). */
 int hgpu_poa_set_timing(hgpu_t* ctx, int enabled);
-/* Tuning knobs: arena_bytes = score-matrix arena (0 = auto), max_batch_edges (0 = auto). */
-int hgpu_poa_configure(hgpu_t* ctx, uint64_t arena_bytes, uint32_t max_batch_edges);
+/* Tuning knobs: arena_bytes = score-matrix arena (0 = auto), max_warps = resident warps of the warp-per-edge kernels (0 = auto). */
+int hgpu_poa_configure(hgpu_t* ctx, uint64_t arena_bytes, uint32_t max_warps);
 
 /* Debug/inspection (used by the parity tests): graph after the first n_prior non-empty segments of ONE edge, in
  * rank order, plus the score matrix and alignment of the next segment. H is written in the reference's H space
- * (row-major (V+1)*(L+1) int32). force_i32: 0 = the encoding the batch path would pick, 1 = int32 cells, 2 = int16 cells relative to the row base (REL16); force_nw selects the stripe width
- * (words per lane: 8/16/24/32, 0 = auto). Any output may be NULL. */
+ * (row-major (V+1)*(L+1) int32). force_i32: 0 = the encoding the batch path would pick, 1 = int32 cells, 2 = int16 cells relative
+ * to the row base (REL16); `reserved` is ignored. Any output may be NULL. */
 typedef struct { uint32_t n_nodes, n_edges, aln_len, L; } hgpu_poa_dbg_sizes;
 int hgpu_poa_debug(hgpu_t* ctx, const uint8_t* bases, const uint64_t* seg_off, uint32_t n_segs, uint32_t n_prior,
-                   int8_t match, int8_t mismatch, int8_t gap, int force_i32, int force_nw,
+                   int8_t match, int8_t mismatch, int8_t gap, int force_i32, int reserved,
                    int32_t* H, uint64_t H_cap, int32_t* aln_node, int32_t* aln_pos, uint32_t aln_cap,
                    uint32_t* rank2node, uint8_t* node_code, uint32_t* pred_off, uint32_t* pred_node, uint32_t* pred_weight,
                    uint32_t node_cap, uint32_t edge_cap, hgpu_poa_dbg_sizes* sizes);

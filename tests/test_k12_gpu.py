@@ -109,8 +109,6 @@ def test_compact_lr_and_backbone_fresh_synthetic(ctx, oracle):
     assert np.array_equal(key, rkey) and np.array_equal(soff, rsoff) and np.array_equal(keep, rkeep) and supp.tobytes() == rsupp.tobytes()
 
 
-@pytest.mark.xfail(strict=False, reason="added after round 1's GPU minutes were spent: the same fixtures pass through the oracle and the "
-                   "host/device-shared cores on the CPU (test_oracle_golden.py, test_k1_host.py); not yet run on a device — drop this marker once it has")
 @pytest.mark.parametrize("seed", [1, 2])
 def test_adversarial_hits_text_to_edge_table(ctx, oracle, seed):
     """tests/golden/k1adv_*: PAF text -> hit table -> compact reads -> edge table, all on the GPU, against the reference
