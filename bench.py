@@ -44,43 +44,16 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def gen_cfg3_torch(n_edges, seed, device, chunk=8192, DEPTH=None, GAP_LEN=None):
-    """Seeded cfg3 input generated on the GPU: per edge a random 1.5 kb truth and DEPTH noisy copies.
-    Returns (bases uint8 cuda tensor, seg_off uint64 numpy, edge_seg_off uint32 numpy)."""
+def gen_cfg3_torch(n_edges, seed, device, chunk=4096, DEPTH=None, GAP_LEN=None):
+    """Seeded cfg3 input generated on the GPU by tests/synth.hashed_batch (counter-based: the numpy backend of the same function
+    gives the CPU arms the identical bytes). Returns (bases uint8 cuda tensor, seg_off uint64 numpy, edge_seg_off uint32 numpy)."""
+    import synth
     DEPTH = globals()["DEPTH"] if DEPTH is None else DEPTH
     GAP_LEN = globals()["GAP_LEN"] if GAP_LEN is None else GAP_LEN
-    import torch
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
-    p_ins, p_del, p_sub = ERR
-    parts, lens_all = [], []
-    for a in range(0, n_edges, chunk):
-        e = min(chunk, n_edges - a)
-        truth = torch.randint(0, 4, (e, 1, GAP_LEN), generator=g, device=device, dtype=torch.uint8).expand(e, DEPTH, GAP_LEN)
-        truth = truth.reshape(e * DEPTH, GAP_LEN)
-        u = torch.rand(truth.shape, generator=g, device=device)
-        keep = u >= p_del
-        sub = keep & (u < p_del + p_sub)
-        shift = torch.randint(1, 4, truth.shape, generator=g, device=device, dtype=torch.uint8)
-        code = torch.where(sub, (truth + shift) & 3, truth)
-        ins = torch.rand(truth.shape, generator=g, device=device) < p_ins
-        ins_code = torch.randint(0, 4, truth.shape, generator=g, device=device, dtype=torch.uint8)
-        cnt = keep.to(torch.int64) + ins.to(torch.int64)
-        lens = cnt.sum(1)
-        row_base = torch.cumsum(lens, 0) - lens
-        end = torch.cumsum(cnt, 1) + row_base[:, None]          # exclusive end of each truth position's output
-        out = torch.empty(int(lens.sum().item()), dtype=torch.uint8, device=device)
-        out[(end - cnt)[keep]] = acgt[code[keep].long()]
-        out[(end - 1)[ins]] = acgt[ins_code[ins].long()]
-        parts.append(out)
-        lens_all.append(lens.cpu().numpy())
-        del truth, u, keep, sub, shift, code, ins, ins_code, cnt, end
-    bases = torch.cat(parts)
-    lens = np.concatenate(lens_all).astype(np.uint64)
-    seg_off = np.concatenate(([0], np.cumsum(lens))).astype(np.uint64)
-    edge_seg_off = (np.arange(n_edges + 1, dtype=np.uint64) * DEPTH).astype(np.uint32)
-    return bases, seg_off, edge_seg_off
+    return synth.hashed_batch(n_edges, seed, depth=DEPTH, length=GAP_LEN, err=ERR, device=device, chunk=chunk)
+
+
+SHARD_SEED = 1000          # rank r's cfg3 shard is hashed_batch(seed SHARD_SEED + r); the reference arm samples rank 0's
 
 
 class ClockSampler:
@@ -147,7 +120,8 @@ def reference_arm(args):
     import synth
     cores = os.cpu_count() or 1
     n = cpu_sample_edges(cores) // 4 or 64     # per step; the run does warmup+steps of these
-    bases, seg_off, eso, _ = synth.poa_batch(12345, n, depth=DEPTH, length=GAP_LEN, err=ERR)
+    # the first n edges of rank 0's shard of the GPU arm: same generator, same seed, same bytes
+    bases, seg_off, eso = synth.hashed_batch(n, SHARD_SEED, depth=DEPTH, length=GAP_LEN, err=ERR)
     for _ in range(args.warmup):
         run_oracle_sample(bases, seg_off, eso, n, cores)
     t = time.perf_counter()
@@ -157,7 +131,11 @@ def reference_arm(args):
         nb += b
     dt = time.perf_counter() - t
     v = nb / dt / 1e6
-    sample = f"{n} of {N_EDGES} cfg3 edges per step ({DEPTH} x {GAP_LEN} bp), restated SPOA 1.1.3 int16 SSE4.1, one edge per queue grab"
+    sample = (f"first {n} of rank 0's {N_EDGES} cfg3 edges per step ({DEPTH} x {GAP_LEN} bp; the same bytes the GPU arm processes), "
+              "restated SPOA 1.1.3 int16 SSE4.1, one edge per queue grab")
+    wp = None
+    if not args.no_whole_path:
+        wp = reference_whole_path(cores)
     emit(({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16",
@@ -165,8 +143,139 @@ def reference_arm(args):
                                         "scores": list(SCORES)},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "whole_path": wp,
     }))
+
+
+CFG2 = dict(genome=10_000_000, reads=50_000, read_len=8000, seed=1)      # BASELINE config 2 (SURVEY 8d generator)
+
+
+def cfg2_dataset():
+    """BASELINE config 2 written by the seeded generator binary (tools/gen_synth.cpp) into a scratch directory."""
+    import tempfile
+    gen = next((p for p in (os.path.join(ROOT, "bin", "gen_synth"), os.path.join(ROOT, "oracle", "_ref", "gen_synth")) if os.path.exists(p)), None)
+    if gen is None:
+        return None
+    d = tempfile.mkdtemp(prefix="haslr_cfg2_")
+    subprocess.run([gen, d, str(CFG2["genome"]), str(CFG2["reads"]), str(CFG2["read_len"]), str(CFG2["seed"])], check=True, stdout=subprocess.DEVNULL)
+    return d
+
+
+def reference_whole_path(cores, d=None):
+    """The reference binary (oracle/_ref/haslr_assemble_ref: the unmodified reference sources + the restated SPOA) on config 2, all
+    host threads; stage times from its own log. Mbases = the long-read bases it fed to POA (the `>` records of log_consensus.txt)."""
+    import re
+    import shutil
+    ref = os.path.join(ROOT, "oracle", "_ref", "haslr_assemble_ref")
+    if not os.path.exists(ref):
+        return {"unavailable": "oracle/_ref/haslr_assemble_ref not built"}
+    own = d is None
+    d = d or cfg2_dataset()
+    if d is None:
+        return {"unavailable": "no generator binary"}
+    out = os.path.join(d, "ref")
+    t = time.perf_counter()
+    r = subprocess.run([ref, "-t", str(cores), "-c", "contigs.fa", "-l", "reads.fa", "-m", "map.paf", "--aln-block", "500", "--aln-sim", "0.85",
+                        "--edge-sup", "3", "-d", "ref"], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+    wall = time.perf_counter() - t
+    laps = [float(x) for x in re.findall(r"elapsed time [0-9.]+ CPU seconds \(([0-9.]+) real seconds\)", r.stderr)]
+    bases = 0
+    with open(os.path.join(out, "log_consensus.txt"), "rb") as f:
+        for ln in f:
+            if ln[:1] == b">" and ln[:2] != b">C":
+                bases += int(ln.split()[-1])
+    # laps: contigs, kmer freq, long reads, alignment loaded, overlaps fixed, compact reads, graph, weak, tips, 3 x bubbles, coordinates, consensus, ...
+    res = {"unavailable": "unexpected log"}
+    if r.returncode == 0 and len(laps) >= 14:
+        t_text, t_hits, t_cons = laps[2], laps[3], laps[13]
+        res = {"value": bases / 1e6 / (t_cons - t_text), "unit": UNIT, "cores": cores, "kind": "reference",
+               "Mbases": bases / 1e6, "s_from_paf_text": t_cons - t_text, "s_from_hits": t_cons - t_hits, "s_consensus_stage": laps[13] - laps[12],
+               "s_binary_wall": wall, "sample": "one run of oracle/_ref/haslr_assemble_ref on the whole config 2 dataset (restated SPOA linked in)"}
+    if own:
+        shutil.rmtree(d, ignore_errors=True)
+    return res
+
+
+def whole_path_leg(ctx, args, peak):
+    """BASELINE config 2 through libhaslr_path.so: PAF text + sequences in host memory -> consensus of every edge in host memory
+    (K0 tokenise, K1 compact reads, K2 edge table, host cleaning, K4 coordinates, segment gather, K3 POA), per-stage wall time and
+    per-kernel CUDA-event time against the algorithmic bytes of DESIGN.md."""
+    import ctypes as C
+    import shutil
+    lib_p = os.path.join(ROOT, "haslr_b200", "libhaslr_path.so")
+    d = cfg2_dataset()
+    if d is None or not os.path.exists(lib_p):
+        return {"unavailable": "generator binary or libhaslr_path.so not built"}
+
+    class Res(C.Structure):
+        _fields_ = [("n_rows", C.c_uint64), ("n_edges", C.c_uint64), ("poa_bases", C.c_uint64), ("cons_bytes", C.c_uint64), ("cons_crc", C.c_uint32),
+                    ("pad", C.c_uint32)] + [(n, C.c_double) for n in ("s_tokenize", "s_k1", "s_k2", "s_clean", "s_coords", "s_poa", "s_total")]
+    L = C.CDLL(lib_p)
+    L.haslr_path_open.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]
+    L.haslr_path_run.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.c_char_p, C.POINTER(Res)]
+    L.haslr_path_close.argtypes = [C.c_void_p]
+    L.haslr_path_sizes.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint64)] * 4
+    h = C.c_void_p()
+    j = lambda n: os.path.join(d, n).encode()
+    assert L.haslr_path_open(j("contigs.fa"), j("reads.fa"), j("map.paf"), C.byref(h)) == 0
+    sz = [C.c_uint64() for _ in range(4)]
+    L.haslr_path_sizes(h, *[C.byref(x) for x in sz])
+    ctxs = (C.c_void_p * 1)(ctx.h)
+    ctx.set_timing(True)
+    threads = os.cpu_count() or 1
+    res = Res()
+    runs = []
+    for it in range(1 + max(1, min(args.steps, 3))):               # one warm-up pass (sizes the device buffers), then the timed passes
+        s0 = ctx.stage_stats()
+        l0 = ctx.launch_count()
+        t = time.perf_counter()
+        rc = L.haslr_path_run(h, ctxs, 1, threads, None, C.byref(res))
+        dt = time.perf_counter() - t
+        assert rc == 0, ctx.L.hgpu_last_error(ctx.h).decode()
+        s1 = ctx.stage_stats()
+        runs.append((dt, {k: getattr(res, k) for k, _ in Res._fields_}, s1, ctx.poa_stats(), s1["h2d_bytes"] - s0["h2d_bytes"],
+                     s1["d2h_bytes"] - s0["d2h_bytes"], ctx.launch_count() - l0))
+    crcs = {r[1]["cons_crc"] for r in runs}
+    timed = runs[1:]
+    dt = sum(r[0] for r in timed) / len(timed)
+    _, rr, st, ps, h2d, d2h, launches = timed[-1]
+    mb = rr["poa_bases"] / 1e6
+    poa_h2d = rr["poa_bases"] + 8 * (ps["alignments"] + rr["n_edges"]) + 4 * rr["n_edges"]     # hgpu_poa_batch copies its own inputs (not counted by the stage counters)
+    kern = []
+
+    def k(name, ms, n_launch, alg_bytes, units):
+        kern.append({"kernel": name, "ms": ms, "launches": n_launch, "algorithmic_bytes": alg_bytes, "units": units,
+                     "achieved": (alg_bytes / (ms / 1e3) / 1e9) if ms > 0 else None, "unit": "GB/s",
+                     "frac": (alg_bytes / (ms / 1e3) / 1e9 / peak) if ms > 0 else None})
+    k("k0_* PAF tokeniser", st["ms_k0"], st["launches_k0"], 4 * st["k0_text_bytes"] + 42 * st["k0_rows"] + 4 * st["k0_ops"],
+      f"{st['k0_text_bytes']} text bytes x 4 passes + 42 B x {st['k0_rows']} rows + 4 B x {st['k0_ops']} CIGAR runs")
+    k("k1_compact_lr + k1_pack", st["ms_k1"], st["launches_k1"], 44 * st["k1_hits"] + 8 * int(sz[0].value),
+      f"44 B x {st['k1_hits']} hits + 8 B x {int(sz[0].value)} contigs (SURVEY 8d)")
+    k("k2_* edge table", st["ms_k2"], st["launches_k2"], 52 * st["k2_pairs"], f"52 B x {st['k2_pairs']} adjacent pairs (SURVEY 8d)")
+    k("k4_edge_coords", st["ms_k4"], st["launches_k4"], 124 * st["k4_supports"] + 4 * st["k4_runs"],
+      f"(24 out + 2 x 44 element + 12 in) B x {st['k4_supports']} supports + 4 B x {st['k4_runs']} CIGAR runs in the windows walked")
+    k("k_poa_* (deep / team / shallow classes side by side)", ps["ms_dp"], ps["dp_launches"], 4 * ps["cells"] + ps["bases_in"] + ps["bases_out"],
+      f"4 B x {ps['cells']} DP cells + bases in + consensus out (SURVEY 8d)")
+    kern[-1]["gcups"] = ps["cells"] / (ps["ms_dp"] / 1e3) / 1e9 if ps["ms_dp"] > 0 else None
+    out = {
+        "workload": f"BASELINE config 2: synthetic {CFG2['genome'] // 1_000_000} Mb genome, {int(sz[0].value)} SRC contigs, {int(sz[1].value)} long reads "
+                    f"({int(sz[2].value) / 1e6:.0f} Mbases), {int(sz[3].value) / 1e6:.0f} MB of PAF text ({rr['n_rows']} rows), seed {CFG2['seed']}",
+        "boundary": "haslr_path_run (libhaslr_path.so above the C ABI): inputs in HOST memory -> consensus strings in HOST memory",
+        "value": mb / dt, "unit": UNIT, "Mbases": mb, "s_per_pass": dt, "passes_timed": len(timed), "edges": rr["n_edges"],
+        "from_hits": {"value": mb / (dt - sum(r[1]["s_tokenize"] for r in timed) / len(timed)), "unit": UNIT,
+                      "note": "the same passes without the PAF tokenising stage (SURVEY 8d starts its clock with the hits parsed)"},
+        "stage_wall_s": {n[2:]: sum(r[1][n] for r in timed) / len(timed) for n in ("s_tokenize", "s_k1", "s_k2", "s_clean", "s_coords", "s_poa")},
+        "h2d_bytes_per_pass": h2d + poa_h2d, "d2h_bytes_per_pass": d2h + rr["cons_bytes"] + 12 * rr["n_edges"],
+        "cg_ops_uploads_per_pass": 0, "paf_text_uploads_per_pass": 1, "gpu_launches_per_pass": launches,
+        "kernels": kern, "deterministic": len(crcs) == 1, "consensus_crc32": "%08x" % rr["cons_crc"],
+        "check": "tests/test_drop_in_gpu.py::test_baseline_config2_full_size compares every output file of this dataset with the reference binary's",
+    }
+    if args.whole_path_ref:
+        out["cpu_reference"] = reference_whole_path(threads, d)
+    ctx.set_timing(False); ctx.poa_set_timing(True)
+    L.haslr_path_close(h)
+    shutil.rmtree(d, ignore_errors=True)
+    return out
 
 
 def emit(obj):
@@ -187,6 +296,8 @@ def main():
     ap.add_argument("--edges", type=int, default=N_EDGES, help="edges per GPU (default: the cfg3 size; smaller values are for debugging only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-deep", action="store_true", help="skip the deep-edge (config 2 shape) leg")
+    ap.add_argument("--no-whole-path", action="store_true", help="skip the whole-path leg (BASELINE config 2: PAF text -> consensus)")
+    ap.add_argument("--whole-path-ref", action="store_true", help="also time the reference binary on the whole-path dataset inside the native arm")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -210,7 +321,7 @@ def main():
     n_edges = args.edges
 
     # ---- synthetic cfg3 shard of this rank, resident in HBM and mirrored in pinned host memory
-    d_bases, seg_off, eso = gen_cfg3_torch(n_edges, 1000 + rank, dev)
+    d_bases, seg_off, eso = gen_cfg3_torch(n_edges, SHARD_SEED + rank, dev)
     n_bases = int(seg_off[-1])
     h_bases = torch.empty(n_bases, dtype=torch.uint8, pin_memory=True)
     h_bases.copy_(d_bases)
@@ -345,6 +456,11 @@ def main():
                 "kernels": "k_poa_edges_deep (+ k_poa_edges_team for the largest)", "check": dchk, "cpu_oracle_on_check": dcpu}
         del dd, dout
 
+    # ---- the whole path (BASELINE config 2) through the path library
+    whole = None
+    if world == 1 and not args.no_whole_path:
+        whole = whole_path_leg(ctx, args, peak)
+
     # ---- CPU baseline: the oracle on a bounded sample of the same edges, all host cores
     cpu = None
     if not args.no_cpu:
@@ -366,7 +482,7 @@ def main():
                    "check": check},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
-        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "deep_edges": deep,
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "deep_edges": deep, "whole_path": whole,
     }))
     if world > 1:
         dist.destroy_process_group()

@@ -5,6 +5,7 @@
 // are queued on the device and pulled by the warps of one persistent kernel (poa_device.cuh).
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -48,6 +49,8 @@ struct PoaState {
     double cfg_team_alpha = 1.5;      // an edge goes to the team kernel when it holds more than alpha x (batch cells / busy warps) (HGPU_TEAM_ALPHA)
     uint32_t cfg_deep_min_reads = 10; // edges with at least this many supporting reads run in k_poa_edges_deep (HGPU_DEEP_MIN_READS)
     int cfg_force = 0;                // HGPU_FORCE_MODE: 1 = every alignment in int32, 2 = every alignment in REL16 (tests)
+    int cfg_pool = 1;                 // HGPU_POOL=0: deep edges in the warp-per-edge / block-per-edge kernels instead of k_poa_pool (A/B runs, tests)
+    uint32_t cfg_pool_ctx = 0;        // HGPU_POOL_CTX: contexts (edges in flight) per pool block, 0 = by the stripes per alignment of the class
     int verbose = 0;                  // HGPU_VERBOSE=1: pass / class plan and per-launch device time on stderr
 };
 
@@ -74,6 +77,8 @@ static PoaState* poa_state(hgpu_t* ctx) {
         if (const char* e = getenv("HGPU_BUDGET_FRAC")) ctx->poa->cfg_budget_frac = std::max(0.1, std::min(0.92, atof(e)));
         if (const char* e = getenv("HGPU_FORCE_MODE")) ctx->poa->cfg_force = atoi(e);
         if (const char* e = getenv("HGPU_DEEP_MIN_READS")) ctx->poa->cfg_deep_min_reads = (uint32_t)atoi(e);
+        if (const char* e = getenv("HGPU_POOL")) ctx->poa->cfg_pool = atoi(e);
+        if (const char* e = getenv("HGPU_POOL_CTX")) ctx->poa->cfg_pool_ctx = (uint32_t)std::max(0, std::min((int)POOL_MAX_CTX, atoi(e)));
     }
     return ctx->poa;
 }
@@ -226,8 +231,18 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
         // ---- edges so large that one warp would be the tail of the whole pass go to the team kernel (a block per edge):
         //      a lone warp on a deep graph sustains ~0.4 G cells/s (one dependent instruction stream, IPC 0.15: profiles/r1i_*)
         //      against ~1 T cells/s for the device
+        const bool use_pool = S->cfg_pool != 0 && opt.stop_round == 0xFFFFFFFFu;
         std::vector<EdgeEst> team;
-        if (S->cfg_team >= 2 && opt.stop_round == 0xFFFFFFFFu) {
+        if (use_pool) {
+            // the pool kernel spreads the stripes of an alignment over the warps of its block: an edge that would be the tail of the
+            // warp-per-edge kernel (more than alpha x the average share of a warp, several stripes wide) goes there whatever its depth
+            double total = 0;
+            for (const EdgeEst& x : est) total += x.cells;
+            const double share = total / (double)std::max<size_t>(1, std::min<size_t>(est.size(), max_warps));
+            const double thr = std::max(S->cfg_team_alpha * share, S->cfg_team_min_cells);
+            for (EdgeEst& x : est)
+                if (!x.deep && x.lmax >= 2u * (uint32_t)Geo<DP_NW16, true>::SW - 1 && x.cells > thr) x.deep = true;
+        } else if (S->cfg_team >= 2 && opt.stop_round == 0xFFFFFFFFu) {
             double total = 0;
             for (const EdgeEst& x : est) total += x.cells;
             // (a) fewer edges than resident teams: the device is mostly empty, every wide edge gets a team (3.3x faster per edge);
@@ -315,7 +330,8 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
         }
 
         // ---- size classes: a class ends where the slot estimate has halved, unless memory is no constraint
-        struct Cls { size_t a, b; uint64_t slot; WsLayout wl; uint32_t warps; bool deep; };
+        struct Cls { size_t a, b; uint64_t slot; WsLayout wl; uint32_t warps; bool deep; bool pool; uint32_t ctx_per_block; };
+        const uint32_t pool_blocks_max = 2u * (uint32_t)ctx->sm_count;              // k_poa_pool: two blocks of 8 warps per SM
         std::vector<Cls> classes;
         size_t n_deep = 0;
         while (n_deep < est.size() && est[n_deep].deep) ++n_deep;
@@ -323,8 +339,9 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
         while (i < est.size()) {
             const bool deep = i < n_deep;
             const size_t end = deep ? n_deep : est.size();           // a class never mixes the two kernels
-            const uint32_t mw = deep ? max_warps_deep : max_warps;
-            Cls c; c.a = i; c.slot = (est[i].slot + 127) / 128 * 128; c.deep = deep;
+            const bool pool = deep && use_pool;
+            const uint32_t mw = pool ? pool_blocks_max * (uint32_t)POOL_MAX_CTX : deep ? max_warps_deep : max_warps;   // pool: slots = contexts
+            Cls c; c.a = i; c.slot = (est[i].slot + 127) / 128 * 128; c.deep = deep; c.pool = pool; c.ctx_per_block = 0;
             auto plan = [&](size_t a, size_t b, Cls& cc) {
                 uint32_t nc = 64;
                 for (size_t q = a; q < b; ++q) nc = std::max(nc, est[q].ncap);
@@ -364,10 +381,37 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
                 HGPU_CUDA(ctx, cudaStreamSynchronize(st));
                 continue;
             }
-            uint32_t warps = std::min<uint32_t>(c.warps, n_items ? n_items : 1);
-            uint32_t blocks = (warps + DP_WARPS_PER_BLOCK - 1) / DP_WARPS_PER_BLOCK;
-            warps = blocks * DP_WARPS_PER_BLOCK;
-            if ((uint64_t)warps > c.warps && c.warps >= (uint32_t)DP_WARPS_PER_BLOCK) { blocks = c.warps / DP_WARPS_PER_BLOCK; warps = blocks * DP_WARPS_PER_BLOCK; }
+            uint32_t warps, blocks;
+            if (c.pool) {
+                // contexts per block: enough edges in flight that 8 warps find a task (an edge offers its stripes while it fills and one
+                // task while its graph is updated, ~30 % of a lone warp's time), never more than the class can fill all blocks with
+                double ns = 0;
+                for (size_t q = c.a; q < c.b; ++q) ns += (double)Geo<DP_NW16, true>::stripes(est[q].lmax);
+                ns /= (double)std::max<size_t>(1, c.b - c.a);
+                uint32_t E = S->cfg_pool_ctx ? S->cfg_pool_ctx : (uint32_t)std::lround(POOL_WARPS / (0.3 + 0.7 * ns));
+                E = std::max<uint32_t>(2, std::min<uint32_t>(E, (uint32_t)POOL_MAX_CTX));
+                blocks = std::min<uint32_t>(pool_blocks_max, (n_items + E - 1) / E);
+                blocks = std::max<uint32_t>(1, std::min<uint32_t>(blocks, c.warps / E));
+                if (!S->cfg_pool_ctx) E = std::max<uint32_t>(1, std::min<uint32_t>(E, (n_items + blocks - 1) / blocks));
+                if ((uint64_t)blocks * E > c.warps) E = std::max<uint32_t>(1, c.warps / blocks);
+                c.ctx_per_block = E;
+                warps = blocks * E;                                            // = slots / workspaces of this class
+            } else {
+                warps = std::min<uint32_t>(c.warps, n_items ? n_items : 1);
+                blocks = (warps + DP_WARPS_PER_BLOCK - 1) / DP_WARPS_PER_BLOCK;
+                warps = blocks * DP_WARPS_PER_BLOCK;
+                if ((uint64_t)warps > c.warps) {
+                    if (c.warps >= (uint32_t)DP_WARPS_PER_BLOCK) { blocks = c.warps / DP_WARPS_PER_BLOCK; warps = blocks * DP_WARPS_PER_BLOCK; }
+                    else {
+                        // the budget admits fewer slots than one block has warps: report per edge instead of allocating past the budget
+                        std::vector<uint32_t> code(1, ST_TOO_LARGE);
+                        for (size_t q = c.a; q < c.b; ++q)
+                            HGPU_CUDA(ctx, cudaMemcpyAsync(S->status.p + est[q].edge, code.data(), 4, cudaMemcpyHostToDevice, st));
+                        HGPU_CUDA(ctx, cudaStreamSynchronize(st));
+                        continue;
+                    }
+                }
+            }
             const uint64_t na = (uint64_t)warps * c.slot, nw = (uint64_t)warps * c.wl.bytes;
             if (!waves.back().empty() && (wave_a + wave_w + na + nw > budget || waves.back().size() >= (size_t)PoaState::NCS)) {
                 waves.emplace_back(); wave_a = 0; wave_w = 0;
@@ -408,7 +452,11 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
 #endif
                 if (const char* e = getenv("HGPU_PROBE")) { a.probe = (uint32_t)atoi(e); a.probe_round = 1; }
                 if (const char* e = getenv("HGPU_PROBE_ROUND")) a.probe_round = (uint32_t)atoi(e);
-                if (c.deep) k_poa_edges_deep<<<ln.blocks, 32 * DP_WARPS_PER_BLOCK, smem_deep, ls>>>(a);
+                if (c.pool) {
+                    const size_t psmem = (size_t)POOL_WARPS * DP_SMEM_PER_WARP_DEEP + sizeof(PoolShared);
+                    HGPU_CUDA(ctx, cudaFuncSetAttribute(k_poa_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+                    k_poa_pool<<<ln.blocks, 32 * POOL_WARPS, psmem, ls>>>(a, c.ctx_per_block);
+                } else if (c.deep) k_poa_edges_deep<<<ln.blocks, 32 * DP_WARPS_PER_BLOCK, smem_deep, ls>>>(a);
                 else k_poa_edges<<<ln.blocks, 32 * DP_WARPS_PER_BLOCK, smem, ls>>>(a);
                 HGPU_CUDA(ctx, cudaGetLastError());
                 ctx->launches++; S->st.dp_launches++;
@@ -419,7 +467,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
                 if (S->verbose) {
                     double cc = 0, cmax = 0; for (size_t q = c.a; q < c.b; ++q) { cc += est[q].cells; cmax = std::max(cmax, est[q].cells); }
                     fprintf(stderr, "[poa] attempt %d growth %.2f wave %zu/%zu class %zu/%zu%s: %u edges on %u warps, slot %.1f MB, ws %.1f MB, %.3e cells (largest edge %.3e)\n",
-                            attempt, growth, wi, waves.size(), ln.ci, classes.size(), c.deep ? " (deep)" : "", n_items, ln.warps, c.slot / 1048576.0, c.wl.bytes / 1048576.0, cc, cmax);
+                            attempt, growth, wi, waves.size(), ln.ci, classes.size(), c.pool ? " (pool)" : c.deep ? " (deep)" : "", n_items, ln.warps, c.slot / 1048576.0, c.wl.bytes / 1048576.0, cc, cmax);
                 }
             }
             if (S->verbose) {
@@ -471,6 +519,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
         fprintf(stderr, "\n");
     }
 #endif
+    if (sth[7]) HGPU_FAIL(ctx, HGPU_E_INTERNAL, "k_poa_pool: a block ran out of tasks while edges were still open");
     S->st.cells = sth[0]; S->st.cells_padded = sth[1]; S->st.alignments = sth[2]; S->st.alignments_i32 = sth[3] & 0xFFFFFFFFull; S->st.alignments_rel16 = sth[3] >> 32; S->st.bases_in = sth[4];
     return HGPU_OK;
 }

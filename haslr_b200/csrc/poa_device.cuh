@@ -50,7 +50,7 @@ struct WsLayout {
     uint32_t ncap, ecap, scap;
     uint64_t o_hdr, o_code, o_in_head, o_in_tail, o_out_head, o_aligned, o_e_begin, o_e_end, o_e_w, o_e_next_in, o_e_next_out,
         o_rank2node, o_node2rank, o_meta0, o_pred_off, o_pred_rank, o_sinks, o_aln_rank, o_aln_pos, o_mark, o_check, o_stack,
-        o_score, o_pred, o_plan_a, o_plan_b;
+        o_score, o_pred, o_plan_a, o_plan_b, o_trec;
     uint64_t bytes;
 };
 
@@ -73,6 +73,7 @@ __host__ __device__ inline WsLayout ws_layout(uint32_t ncap, uint32_t ecap) {
     w.o_stack = take(4 * (uint64_t)w.scap);
     w.o_score = take(8 * n); w.o_pred = take(4 * n);
     w.o_plan_a = take(4 * n); w.o_plan_b = take(4 * n);      // deep kernels: per-rank predecessor plan (poa_fill_rel.cuh)
+    w.o_trec = take(32 * n);                                  // per-node record of the topological sort (w_build_trec)
     w.bytes = (o + 127) / 128 * 128;
     return w;
 }
@@ -1438,7 +1439,52 @@ __device__ __noinline__ uint32_t w_add_alignment(GraphView& g, GraphScratch& s, 
 static constexpr uint32_t TOPO_BM_WORDS = HGPU_RING ? 576 : 400;     // nodes per bitmap = 32x
 static constexpr uint32_t TOPO_STACK = (DP_SMEM_PER_WARP - 2 * TOPO_BM_WORDS * 4) / 4;
 
-__device__ __noinline__ int w_toposort(GraphView& g, uint8_t* wsm, int lane) {
+// Per-node record of the sort: everything a DFS visit needs in two 16-byte loads issued together, instead of the chain
+// in_head -> e_begin / e_next_in -> ... -> aligned (4-6 dependent round trips per node, which is what the serial part of
+// the sort spent its time on: 24-28 % of the warp-cycles of a deep edge, profiles/r2c_*).
+//   p[0..3] = tails of the first four in-edges in in-edge order (NIL-padded), a[0..2] = aligned nodes, more = id of the fifth in-edge
+struct __align__(16) TopoRec { uint32_t p[4]; uint32_t a[3]; uint32_t more; };
+static_assert(sizeof(TopoRec) == 32, "record layout");
+
+// all records, lane-parallel, four nodes per lane in flight (the chain of an in-list is still dependent loads, but 128 of them overlap)
+__device__ __noinline__ void w_build_trec(const GraphView& g, TopoRec* rec, int lane) {
+    const uint32_t N = *g.n_nodes;
+    constexpr int K = 4;
+    for (uint32_t v0 = 0; v0 < N; v0 += 32 * K) {
+        uint32_t x[K];
+        TopoRec r[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const uint32_t v = v0 + k * 32 + lane;
+            x[k] = NIL;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) r[k].p[q] = NIL;
+            r[k].a[0] = r[k].a[1] = r[k].a[2] = NIL; r[k].more = NIL;
+            if (v < N) { x[k] = g.in_head[v]; r[k].a[0] = g.aligned[3 * v]; r[k].a[1] = g.aligned[3 * v + 1]; r[k].a[2] = g.aligned[3 * v + 2]; }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (x[k] != NIL) { r[k].p[q] = g.e_begin[x[k]]; x[k] = g.e_next_in[x[k]]; }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const uint32_t v = v0 + k * 32 + lane;
+            if (v < N) {
+                if (r[k].a[0] == NIL) { r[k].a[1] = NIL; r[k].a[2] = NIL; } else if (r[k].a[1] == NIL) r[k].a[2] = NIL;
+                r[k].more = x[k];
+                uint4* dst = reinterpret_cast<uint4*>(rec + v);
+                dst[0] = make_uint4(r[k].p[0], r[k].p[1], r[k].p[2], r[k].p[3]);
+                dst[1] = make_uint4(r[k].a[0], r[k].a[1], r[k].a[2], r[k].more);
+            }
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __noinline__ int w_toposort(GraphView& g, const TopoRec* rec, uint8_t* wsm, int lane) {
     const uint32_t N = *g.n_nodes;
     if (N > TOPO_BM_WORDS * 32) return 0;
     uint32_t* perm = reinterpret_cast<uint32_t*>(wsm);
@@ -1447,6 +1493,7 @@ __device__ __noinline__ int w_toposort(GraphView& g, uint8_t* wsm, int lane) {
     for (uint32_t w = lane; w < (N + 31) / 32; w += 32) { perm[w] = 0; nochk[w] = 0; }
     __syncwarp();
     auto is_perm = [&](uint32_t v) -> bool { return (perm[v >> 5] >> (v & 31)) & 1u; };
+    const uint4* rec4 = reinterpret_cast<const uint4*>(rec);
     uint32_t nr = 0;
     int okflag = 1;
     for (uint32_t i0 = 0; i0 < N && okflag; i0 += 32) {
@@ -1455,13 +1502,12 @@ __device__ __noinline__ int w_toposort(GraphView& g, uint8_t* wsm, int lane) {
         uint32_t np = 0, p0 = NIL, p1 = NIL;
         bool slow = false;                                        // aligned nodes or more than two predecessors
         if (valid) {
-            uint32_t x = g.in_head[i];
-            if (x != NIL) {
-                p0 = g.e_begin[x]; np = 1; x = g.e_next_in[x];
-                if (x != NIL) { p1 = g.e_begin[x]; np = 2; if (g.e_next_in[x] != NIL) slow = true; }
-            }
-            if (g.aligned[3 * i] != NIL) slow = true;
+            const uint4 ra = rec4[2 * i], rb = rec4[2 * i + 1];
+            p0 = ra.x; p1 = ra.y;
+            np = (p0 != NIL) + (p1 != NIL);
+            slow = ra.z != NIL || rb.x != NIL;
         }
+        if (i + 32 < N) asm volatile("prefetch.global.L1 [%0];" :: "l"(rec4 + 2 * (i + 32)));   // the next batch's roots
         uint32_t pos = 0;
         while (true) {
             const uint32_t lo = i0 + pos;
@@ -1482,13 +1528,11 @@ __device__ __noinline__ int w_toposort(GraphView& g, uint8_t* wsm, int lane) {
             nr += __popc(em);
             __syncwarp();
             if (f >= 32) break;
-            // SPOA's DFS from root i0+f on one lane: same visits and the same emission order as the serial code, with
-            // two changes that only remove memory round trips: (1) the loads of a visit are issued before their first
-            // use (node record and aligned triple together, both words of an edge together); (2) a node that pushed
-            // children is flagged on the stack - when the walk returns to it every child is emitted (a child is only
-            // popped once permanent), so it is finalised on the spot instead of walking its lists a second time.
+            // SPOA's DFS from root i0+f on one lane: same visits and the same emission order as the serial code. A visit reads the
+            // node's record (two loads in flight together); a node that pushed children is flagged on the stack - when the walk
+            // returns to it every child is emitted (a child is only popped once permanent), so it is finalised on the spot.
             if (lane == 0) {
-                constexpr uint32_t EXPANDED = 0x80000000u, HAS_ALIGNED = 0x40000000u, IDMASK = 0x3FFFFFFFu;
+                constexpr uint32_t EXPANDED = 0x80000000u, IDMASK = 0x3FFFFFFFu;
                 uint32_t sp = 0, guard = 0;
                 const uint32_t limit = 16u * (N + *g.n_edges) + 1024u;
                 stk[sp++] = i0 + f;
@@ -1499,14 +1543,21 @@ __device__ __noinline__ int w_toposort(GraphView& g, uint8_t* wsm, int lane) {
                     const uint32_t v = top & IDMASK;
                     if (is_perm(v)) { --sp; continue; }
                     const bool chk = !((nochk[v >> 5] >> (v & 31)) & 1u);
-                    uint32_t al[3] = {NIL, NIL, NIL};
                     bool vvalid = true;
-                    if (top & EXPANDED) {
-                        if (chk && (top & HAS_ALIGNED)) { al[0] = g.aligned[3 * v]; al[1] = g.aligned[3 * v + 1]; al[2] = g.aligned[3 * v + 2]; }
-                    } else {
-                        uint32_t x = g.in_head[v];
-                        const uint32_t a0 = g.aligned[3 * v], a1 = g.aligned[3 * v + 1], a2 = g.aligned[3 * v + 2];
-                        while (x != NIL) {
+                    const uint4 rb = rec4[2 * v + 1];
+                    if (!(top & EXPANDED)) {
+                        const uint4 ra = rec4[2 * v];
+                        const uint32_t pp[4] = {ra.x, ra.y, ra.z, ra.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t b = pp[q];
+                            if (b == NIL) break;
+                            if (!is_perm(b)) {
+                                if (sp >= TOPO_STACK) { okflag = 0; break; }
+                                stk[sp++] = b; vvalid = false;
+                            }
+                        }
+                        for (uint32_t x = rb.w; x != NIL && okflag; ) {          // fifth in-edge onwards: walk the list (2 % of the nodes of a deep graph)
                             const uint32_t b = g.e_begin[x], nx = g.e_next_in[x];
                             if (!is_perm(b)) {
                                 if (sp >= TOPO_STACK) { okflag = 0; break; }
@@ -1516,7 +1567,7 @@ __device__ __noinline__ int w_toposort(GraphView& g, uint8_t* wsm, int lane) {
                         }
                         if (!okflag) break;
                         if (chk) {
-                            al[0] = a0; al[1] = a0 == NIL ? NIL : a1; al[2] = (a0 == NIL || a1 == NIL) ? NIL : a2;
+                            const uint32_t al[3] = {rb.x, rb.y, rb.z};
 #pragma unroll
                             for (int q = 0; q < 3; ++q) {
                                 const uint32_t o = al[q];
@@ -1528,12 +1579,13 @@ __device__ __noinline__ int w_toposort(GraphView& g, uint8_t* wsm, int lane) {
                             }
                             if (!okflag) break;
                         }
-                        if (!vvalid) stk[self] = v | EXPANDED | (a0 != NIL ? HAS_ALIGNED : 0u);   // children first; finalised on return
+                        if (!vvalid) stk[self] = v | EXPANDED;               // children first; finalised on return
                     }
                     if (vvalid) {
                         perm[v >> 5] |= 1u << (v & 31);
                         if (chk) {
                             g.rank2node[nr] = v; g.node2rank[v] = nr; ++nr;
+                            const uint32_t al[3] = {rb.x, rb.y, rb.z};
 #pragma unroll
                             for (int q = 0; q < 3; ++q) {
                                 if (al[q] == NIL) break;
@@ -1702,6 +1754,7 @@ __device__ __forceinline__ void poa_edges_body(const PoaArgs& a) {
     uint32_t* hdr = reinterpret_cast<uint32_t*>(wsb + a.wl.o_hdr);
     uint32_t* plan_a = reinterpret_cast<uint32_t*>(wsb + a.wl.o_plan_a);
     uint32_t* plan_b = reinterpret_cast<uint32_t*>(wsb + a.wl.o_plan_b);
+    TopoRec* trec = reinterpret_cast<TopoRec*>(wsb + a.wl.o_trec);
     unsigned long long st_cells = 0, st_padded = 0, st_aln = 0, st_aln32 = 0, st_bases = 0;
     PHASE_CLK_DECL
 
@@ -1781,7 +1834,8 @@ __device__ __forceinline__ void poa_edges_body(const PoaArgs& a) {
                 if (ust != ST_OK) { st = ust; break; }
                 PHASE_CLK(PC_ADD)
                 if (probe == 3) { debug_stop = true; break; }
-                if (!w_toposort(gv, wsm, lane)) {          // too large for the shared-memory bitmaps / deep DFS: serial
+                w_build_trec(gv, trec, lane);
+                if (!w_toposort(gv, trec, wsm, lane)) {    // too large for the shared-memory bitmaps / deep DFS: serial
                     ust = ST_OK;
                     if (lane == 0 && !g_toposort(gv, gs)) ust = ST_TOPOSORT;
                     ust = __shfl_sync(FULL, ust, 0);
@@ -1864,6 +1918,7 @@ __global__ void __launch_bounds__(32 * TEAM, 512 / (32 * TEAM)) k_poa_edges_team
     uint32_t* hdr = reinterpret_cast<uint32_t*>(wsb + a.wl.o_hdr);
     uint32_t* plan_a = reinterpret_cast<uint32_t*>(wsb + a.wl.o_plan_a);
     uint32_t* plan_b = reinterpret_cast<uint32_t*>(wsb + a.wl.o_plan_b);
+    TopoRec* trec = reinterpret_cast<TopoRec*>(wsb + a.wl.o_trec);
     unsigned long long st_cells = 0, st_padded = 0, st_aln = 0, st_aln32 = 0, st_bases = 0;
     const bool lead = wib == 0;
 
@@ -1921,7 +1976,8 @@ __global__ void __launch_bounds__(32 * TEAM, 512 / (32 * TEAM)) k_poa_edges_team
                             ust = __shfl_sync(FULL, ust, 0);
                             __syncwarp();
                         }
-                        if (ust == ST_OK && !w_toposort(gv, wsm, lane)) {
+                        if (ust == ST_OK) w_build_trec(gv, trec, lane);
+                        if (ust == ST_OK && !w_toposort(gv, trec, wsm, lane)) {
                             if (lane == 0 && !g_toposort(gv, gs)) ust = ST_TOPOSORT;
                             ust = __shfl_sync(FULL, ust, 0);
                             __syncwarp();
@@ -1974,6 +2030,10 @@ __global__ void __launch_bounds__(32 * TEAM, 512 / (32 * TEAM)) k_poa_edges_team
         atomicAdd(a.stats + 3, st_aln32); atomicAdd(a.stats + 4, st_bases);
     }
 }
+
+}  // namespace hgpu
+#include "poa_pool.cuh"
+namespace hgpu {
 
 // out[off[e] .. off[e]+len[e]) = consensus bytes of edge e
 __global__ void __launch_bounds__(256) k_poa_gather(const uint64_t* cons_pos, const uint32_t* cons_len,

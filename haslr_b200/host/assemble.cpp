@@ -41,7 +41,7 @@ void enumerate_edges(Graph& g, uint32_t flag, std::vector<EdgeRef>& out) {
 // cns_supp / head_end / tail_beg from the answer and writes the reference's log_coordinate.txt from it.
 // ---------------------------------------------------------------------------------------------------------
 int calc_edge_coordinates(Graph& g, const std::vector<EdgeRef>& edges, const ContigStore& contigs, const SeqStore& reads,
-                          const CompactReads& cl, const PafTable& paf, hgpu_t* ctx, const std::string& logpath) {
+                          const CompactReads& cl, hgpu_t* ctx, const std::string& logpath) {
     if (edges.empty()) return 0;           // the reference returns before opening the log (quirk Q12)
     const size_t n = edges.size();
     std::vector<uint8_t> edge_rev(n);
@@ -59,14 +59,15 @@ int calc_edge_coordinates(Graph& g, const std::vector<EdgeRef>& edges, const Con
     for (size_t r = 0; r < reads.size(); ++r) read_len[r] = reads.len(r);
     std::vector<hgpu_edge_coord> oe(n);
     std::vector<hgpu_supp_coord> os(supp.size() + 1);
-    const int rc = hgpu_edge_coords(ctx, (uint32_t)n, edge_rev.data(), supp_off.data(), supp.data(), cl.elems.data(), cl.off.data(),
-                                    (uint32_t)reads.size(), read_len.data(), paf.is_rev.data(), paf.cg_off.data(),
-                                    paf.cg_ops.empty() ? paf.cg_off.data() : paf.cg_ops.data(), (uint32_t)paf.size(), oe.data(), os.data());
-    if (rc != HGPU_OK) { fprintf(stderr, "[ERROR] hgpu_edge_coords: %s\n", hgpu_last_error(ctx)); return rc; }
+    // compact reads and the hit table (strands, run-length CIGARs) are still on the device: only edges and supports go up
+    const int rc = hgpu_edge_coords_dev(ctx, (uint32_t)n, edge_rev.data(), supp_off.data(), supp.data(), read_len.data(), (uint32_t)reads.size(),
+                                        oe.data(), os.data());
+    if (rc != HGPU_OK) { fprintf(stderr, "[ERROR] hgpu_edge_coords_dev: %s\n", hgpu_last_error(ctx)); return rc; }
 
     FILE* fp = logpath.empty() ? nullptr : open_write(logpath);
 #define LOG(...) do { if (fp) fprintf(fp, __VA_ARGS__); } while (0)
     auto elem = [&](uint32_t rid, uint32_t cmp) -> const hgpu_cl_elem& { return cl.elems[cl.off[rid] + cmp]; };
+    auto erev = [&](uint32_t rid, uint32_t cmp) -> uint32_t { return cl.rev[cl.off[rid] + cmp]; };
     for (size_t e = 0; e < n; ++e) {
         const uint32_t node1 = edges[e].node1, rev1 = edges[e].rev1, node2 = edges[e].node2, rev2 = edges[e].rev2;
         Edge& edge1 = *e1[e];
@@ -81,7 +82,8 @@ int calc_edge_coordinates(Graph& g, const std::vector<EdgeRef>& edges, const Con
         if (fp) for (uint32_t i = 0; i < es.size(); ++i) {
             const hgpu_cl_elem& h = elem(es[i].lr_id, es[i].cmp_head_id);
             const hgpu_cl_elem& t = elem(es[i].lr_id, es[i].cmp_tail_id);
-            LOG("\tsupp_detail head\t%u\t%u\t%c\ttail\t%u\t%u\t%c\n", h.t_start, h.t_end, sgn(paf.is_rev[h.hit]), t.t_start, t.t_end, sgn(paf.is_rev[t.hit]));
+            LOG("\tsupp_detail head\t%u\t%u\t%c\ttail\t%u\t%u\t%c\n", h.t_start, h.t_end, sgn(erev(es[i].lr_id, es[i].cmp_head_id)), t.t_start, t.t_end,
+                sgn(erev(es[i].lr_id, es[i].cmp_tail_id)));
         }
         LOG("    @@@ best interval contig1 %u %u\n", c.int1_lo, c.int1_hi);
         LOG("    @@@ best_interval contig2 %u %u\n", c.int2_lo, c.int2_hi);
@@ -154,8 +156,7 @@ int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& 
                    const std::string& logpath, bool write_log, unsigned threads, uint64_t* bases_in) {
     const size_t n = edges.size();
     const double t0 = now_s();
-    std::string bases;
-    std::vector<uint64_t> seg_off{0};
+    std::vector<uint64_t> seg_off{0};            // global segment offsets (lengths only: the bases go straight into the per-GPU buffers)
     std::vector<uint32_t> edge_seg_off{0};
     std::vector<Edge*> e1(n), e2(n);
     std::vector<const CnsSupp*> seg_src;
@@ -166,24 +167,14 @@ int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& 
         for (const CnsSupp& s : e1[e]->cns_supp) { seg_src.push_back(&s); seg_off.push_back(seg_off.back() + segment_length(reads, s)); }
         edge_seg_off.push_back((uint32_t)(seg_off.size() - 1));
     }
-    bases.resize(seg_off.back());
     if (bases_in) *bases_in = seg_off.back();
-    {   // the copies (and reverse complements) are independent: all host threads
-        const size_t n_seg = seg_src.size();
-        const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(threads, n_seg / 256 + 1));
-        auto work = [&](unsigned t) {
-            for (size_t q = n_seg * t / nt; q < n_seg * (t + 1) / nt; ++q)
-                write_segment(reads, *seg_src[q], (uint32_t)(seg_off[q + 1] - seg_off[q]), &bases[seg_off[q]]);
-        };
-        std::vector<std::thread> th;
-        for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
-        work(0);
-        for (auto& x : th) x.join();
-    }
-    // shard: edges dealt to GPUs by estimated DP cost (sum of len^2-ish), largest first; one host thread per GPU
+    // shard: edges dealt to GPUs by estimated DP cost (sum of len^2-ish), largest first (LPT); one host thread per GPU
     const size_t G = std::max<size_t>(1, ctxs.size());
     std::vector<std::vector<uint32_t>> shard(G);
-    {
+    if (G == 1) {
+        shard[0].resize(n);
+        for (size_t e = 0; e < n; ++e) shard[0][e] = (uint32_t)e;
+    } else {
         std::vector<std::pair<double, uint32_t>> cost(n);
         for (size_t e = 0; e < n; ++e) {
             double c = 0, v = 0;
@@ -203,25 +194,46 @@ int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& 
         }
         for (auto& s : shard) std::sort(s.begin(), s.end());
     }
+    // per-GPU segment tables; every segment is copied (or reverse-complemented) ONCE, from the read into its GPU's buffer
+    struct Shard { std::string b; std::vector<uint64_t> so{0}; std::vector<uint32_t> eso{0}; std::vector<uint32_t> seg; };
+    std::vector<Shard> sh(G);
+    std::vector<std::pair<uint32_t, uint64_t>> seg_home(seg_src.size());      // segment -> (gpu, offset in its buffer), for the log
+    for (size_t gi = 0; gi < G; ++gi) {
+        Shard& S = sh[gi];
+        for (uint32_t e : shard[gi]) {
+            for (uint32_t s = edge_seg_off[e]; s < edge_seg_off[e + 1]; ++s) {
+                seg_home[s] = {(uint32_t)gi, S.so.back()};
+                S.seg.push_back(s);
+                S.so.push_back(S.so.back() + (seg_off[s + 1] - seg_off[s]));
+            }
+            S.eso.push_back((uint32_t)(S.so.size() - 1));
+        }
+        S.b.resize(S.so.back());
+    }
+    {   // the copies are independent: all host threads
+        const size_t n_seg = seg_src.size();
+        const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(threads, n_seg / 256 + 1));
+        auto work = [&](unsigned t) {
+            for (size_t q = n_seg * t / nt; q < n_seg * (t + 1) / nt; ++q)
+                write_segment(reads, *seg_src[q], (uint32_t)(seg_off[q + 1] - seg_off[q]), &sh[seg_home[q].first].b[seg_home[q].second]);
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+    }
     std::vector<std::string> cons(n);
     std::vector<int> rc(G, 0);
     const double t1 = now_s();
     auto run = [&](size_t gi) {
         const std::vector<uint32_t>& my = shard[gi];
         if (my.empty()) return;
-        std::string b; std::vector<uint64_t> so{0}; std::vector<uint32_t> eso{0};
-        for (uint32_t e : my) {
-            for (uint32_t s = edge_seg_off[e]; s < edge_seg_off[e + 1]; ++s) {
-                b.append(bases, seg_off[s], seg_off[s + 1] - seg_off[s]);
-                so.push_back(b.size());
-            }
-            eso.push_back((uint32_t)(so.size() - 1));
-        }
-        std::vector<uint8_t> out(b.size() + 64);
+        Shard& S = sh[gi];
+        std::vector<uint8_t> out(S.b.size() + 64);
         std::vector<uint64_t> off(my.size() + 1);
         std::vector<uint32_t> status(my.size());
-        hgpu_poa_set_timing(ctxs[gi], 1);
-        int r = hgpu_poa_batch(ctxs[gi], (const uint8_t*)b.data(), so.data(), eso.data(), (uint32_t)my.size(), 5, -4, -8, 0,   // Assemble.cpp:8-11
+        hgpu_poa_set_timing(ctxs[gi], 1);      // one event pair per scheduling pass, read after the pass's own synchronisation
+        int r = hgpu_poa_batch(ctxs[gi], (const uint8_t*)S.b.data(), S.so.data(), S.eso.data(), (uint32_t)my.size(), 5, -4, -8, 0,   // Assemble.cpp:8-11
                                out.data(), out.size(), off.data(), status.data());
         if (r != HGPU_OK) { fprintf(stderr, "[ERROR] hgpu_poa_batch (gpu %zu): %s\n", gi, hgpu_last_error(ctxs[gi])); rc[gi] = r; return; }
         hgpu_poa_stats st;
@@ -253,7 +265,7 @@ int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& 
             for (const CnsSupp& c : e1[e]->cns_supp) {
                 fprintf(fp, "        [debug] lr_id:%u lr_len:%u region_start:%u region_end:%u subseq_len:%u\n", c.lr_id, reads.len(c.lr_id), c.spos, c.epos, c.epos - c.spos + 1);
                 fprintf(fp, ">%u %c %u %u %u\n", c.lr_id, sgn(c.lr_strand), c.spos, c.epos, c.epos - c.spos + 1);
-                fwrite(bases.data() + seg_off[s], 1, seg_off[s + 1] - seg_off[s], fp);
+                fwrite(sh[seg_home[s].first].b.data() + seg_home[s].second, 1, seg_off[s + 1] - seg_off[s], fp);
                 fputc('\n', fp);
                 ++s;
             }

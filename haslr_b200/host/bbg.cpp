@@ -54,13 +54,13 @@ int remove_weak_edges(Graph& g, uint32_t min_edge_sup) {                        
     return removed;
 }
 
-void write_compact(const CompactReads& cl, const PafTable& paf, const std::string& path) {          // Longread.cpp:675-693
+void write_compact(const CompactReads& cl, const std::string& path) {          // Longread.cpp:675-693
     FILE* fp = open_write(path);
     for (size_t r = 0; r + 1 < cl.off.size(); ++r) {
         fprintf(fp, ">%zu\t", r);
         for (uint32_t j = cl.off[r]; j < cl.off[r + 1]; ++j) {
             const hgpu_cl_elem& e = cl.elems[j];
-            fprintf(fp, "%u-%u:%u:%c:%u-%u\t", e.q_start, e.q_end, paf.t_id[e.hit], sgn(paf.is_rev[e.hit]), e.t_start, e.t_end);
+            fprintf(fp, "%u-%u:%u:%c:%u-%u\t", e.q_start, e.q_end, cl.tid[j], sgn(cl.rev[j]), e.t_start, e.t_end);
         }
         fprintf(fp, "\n");
     }

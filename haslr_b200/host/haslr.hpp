@@ -44,17 +44,12 @@ struct ContigStore : SeqStore {
     std::vector<double> mean_kmer;     // km:f:
 };
 
-// PAF rows as structure-of-arrays columns + run-length CIGARs (the layout hgpu_compact_lr takes)
-struct PafTable {
-    std::vector<uint32_t> q_id, q_len, q_start, q_end, t_id, t_len, t_start, t_end, n_match, n_block;
-    std::vector<uint8_t> is_rev, mapq;
-    std::vector<uint32_t> cg_off{0}, cg_ops;
-    std::vector<uint32_t> read_off;    // n_reads+1
-    size_t size() const { return q_id.size(); }
-};
-
+// Compact long reads as the host keeps them: the elements, and per element the contig and strand of the hit behind it
+// (all the host ever needs of the PAF hit table, which itself stays on the device: hgpu_paf_tokenize -> hgpu_compact_lr_dev).
 struct CompactReads {
     std::vector<hgpu_cl_elem> elems;
+    std::vector<uint32_t> tid;         // per element: t_id of its hit
+    std::vector<uint8_t> rev;          // per element: is_rev of its hit
     std::vector<uint32_t> off;         // n_reads+1
 };
 
@@ -73,8 +68,7 @@ typedef std::vector<Node> Graph;
 // io.cpp
 void load_fasta(const std::string& path, SeqStore& out, ContigStore* contig_meta);
 void load_fofn(const std::string& path, std::vector<std::string>& files);
-void load_paf(const std::string& path, PafTable& paf, hgpu_t* ctx);
-void finish_paf(PafTable& paf, size_t n_reads);
+void read_text_file(const std::string& path, std::vector<char>& text);      // appended; a missing final line feed is added
 double calc_uniq_freq(const ContigStore& c);
 std::string revcomp(const std::string& s);
 FILE* open_write(const std::string& path);
@@ -86,7 +80,7 @@ void graph_from_edge_table(Graph& g, size_t n_contigs, const std::vector<uint64_
 int remove_weak_edges(Graph& g, uint32_t min_edge_sup);
 void write_stats(const Graph& g, const ContigStore& contigs, const std::string& path);
 void write_gfa(const Graph& g, const ContigStore& contigs, const std::string& path);
-void write_compact(const CompactReads& cl, const PafTable& paf, const std::string& path);
+void write_compact(const CompactReads& cl, const std::string& path);
 int clean_tips(Graph& g, int max_depth, const std::string& logpath);
 int clean_simple_bubbles(Graph& g, int max_depth, const std::string& logpath);
 int clean_super_bubbles(Graph& g, const std::string& logpath);
@@ -97,11 +91,30 @@ void report_branching(const Graph& g, const std::string& logpath);
 struct EdgeRef { uint32_t node1, rev1, node2, rev2; };
 void enumerate_edges(Graph& g, uint32_t flag, std::vector<EdgeRef>& out);
 int calc_edge_coordinates(Graph& g, const std::vector<EdgeRef>& edges, const ContigStore& contigs, const SeqStore& reads,
-                          const CompactReads& cl, const PafTable& paf, hgpu_t* ctx, const std::string& logpath);
+                          const CompactReads& cl, hgpu_t* ctx, const std::string& logpath);
 uint32_t segment_length(const SeqStore& reads, const CnsSupp& s);                     // Assemble.cpp:529-532 (uint32 arithmetic, quirk Q7)
 void write_segment(const SeqStore& reads, const CnsSupp& s, uint32_t cnt, char* out);   // the read, or its reverse complement, from spos
 int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& reads, const std::vector<hgpu_t*>& ctxs,
                    const std::string& logpath, bool write_log, unsigned threads, uint64_t* bases_in);
 void write_assembly(Graph& g, const ContigStore& contigs, const std::string& out_dir);
+
+// pipeline.cpp: the path "PAF text + sequences in host memory -> consensus of every backbone edge in host memory" (SURVEY 8d),
+// i.e. main.cpp:116-207 of the reference: K0 tokenise, K1 compact reads, K2 edge table, host graph cleaning, K4 coordinates,
+// segment gather, K3 batched POA. out_dir empty: no files are written (bench / library use).
+struct PathInputs {
+    ContigStore contigs;
+    SeqStore reads;
+    std::vector<char> paf_text;
+};
+struct PathTimes { double tokenize = 0, k1 = 0, k2 = 0, clean = 0, coords = 0, poa = 0, total = 0; };      // wall seconds
+struct PathResult {
+    Graph g;
+    CompactReads cl;
+    std::vector<EdgeRef> edges;        // the POA'd edges in asm_get_next_edge order
+    uint64_t n_rows = 0, poa_bases = 0, cons_bytes = 0;
+    uint32_t cons_crc = 0;             // CRC-32 of the consensus strings concatenated in edge order
+    PathTimes t;
+};
+int run_path(const PathInputs& in, Options& opt, const std::vector<hgpu_t*>& ctxs, const std::string& out_dir, bool logs, PathResult& r);
 
 }  // namespace haslr

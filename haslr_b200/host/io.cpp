@@ -12,13 +12,14 @@
 
 namespace haslr {
 
+// an empty path means "no file wanted" (library use: run_path without an output directory): the bytes go to /dev/null
 FILE* open_write(const std::string& path) {
-    FILE* fp = fopen(path.c_str(), "w");
+    FILE* fp = fopen(path.empty() ? "/dev/null" : path.c_str(), "w");
     if (!fp) { fprintf(stderr, "[ERROR] could not open file for writing: %s\n", path.c_str()); exit(EXIT_FAILURE); }
     return fp;
 }
 FILE* open_append(const std::string& path) {
-    FILE* fp = fopen(path.c_str(), "a");
+    FILE* fp = fopen(path.empty() ? "/dev/null" : path.c_str(), "a");
     if (!fp) { fprintf(stderr, "[ERROR] could not open file for appending: %s\n", path.c_str()); exit(EXIT_FAILURE); }
     return fp;
 }
@@ -127,61 +128,23 @@ void load_fofn(const std::string& path, std::vector<std::string>& files) {
     while (getline(fin, line)) if (!line.empty()) files.push_back(line);
 }
 
-// minimap2 PAF with cg:Z: (Longread.cpp:234-302 reads columns 1-12 and the cg tag). All rows are kept: the load
-// filters run in hgpu_compact_lr. The file is read whole and tokenised on the GPU (hgpu_paf_tokenize / hgpu_paf_fetch);
-// further files of a fofn are appended.
-void load_paf(const std::string& path, PafTable& paf, hgpu_t* ctx) {
+// A text file read whole (the PAF: it is tokenised on the GPU, hgpu_paf_tokenize). Further files of a fofn are appended.
+void read_text_file(const std::string& path, std::vector<char>& text) {
     FILE* fp = fopen(path.c_str(), "rb");
-    if (!fp) { fprintf(stderr, "[ERROR] (load_paf) could not open file: %s\n", path.c_str()); exit(EXIT_FAILURE); }
-    std::vector<char> text;
-    {
-        struct stat sb;
-        size_t guess = (fstat(fileno(fp), &sb) == 0 && sb.st_size > 0) ? (size_t)sb.st_size : (size_t)(1 << 24);
-        text.resize(guess + 1);
-        size_t n = 0;
-        while (true) {
-            if (n == text.size()) text.resize(text.size() * 2);
-            const size_t got = fread(text.data() + n, 1, text.size() - n, fp);
-            if (got == 0) break;
-            n += got;
-        }
-        text.resize(n);
+    if (!fp) { fprintf(stderr, "[ERROR] (read_text_file) could not open file: %s\n", path.c_str()); exit(EXIT_FAILURE); }
+    struct stat sb;
+    const size_t guess = (fstat(fileno(fp), &sb) == 0 && sb.st_size > 0) ? (size_t)sb.st_size : (size_t)(1 << 24);
+    size_t n = text.size();
+    text.resize(n + guess + 1);
+    while (true) {
+        if (n == text.size()) text.resize(text.size() + text.size() / 2 + 1);
+        const size_t got = fread(text.data() + n, 1, text.size() - n, fp);
+        if (got == 0) break;
+        n += got;
     }
     fclose(fp);
-    uint64_t rows = 0, ops = 0;
-    if (hgpu_paf_tokenize(ctx, text.data(), text.size(), &rows, &ops) != HGPU_OK) {
-        fprintf(stderr, "[ERROR] (load_paf) %s: %s\n", path.c_str(), hgpu_last_error(ctx)); exit(EXIT_FAILURE);
-    }
-    const size_t r0 = paf.size(), o0 = paf.cg_ops.size();
-    if ((uint64_t)o0 + ops > 0xFFFFFFFFull || (uint64_t)r0 + rows > 0xFFFFFFFEull) { fprintf(stderr, "[ERROR] (load_paf) hit table too large\n"); exit(EXIT_FAILURE); }
-    std::vector<uint32_t>* cols[10] = {&paf.q_id, &paf.q_len, &paf.q_start, &paf.q_end, &paf.t_id, &paf.t_len, &paf.t_start, &paf.t_end, &paf.n_match, &paf.n_block};
-    for (auto* c : cols) c->resize(r0 + rows);
-    paf.is_rev.resize(r0 + rows); paf.mapq.resize(r0 + rows);
-    paf.cg_off.resize(r0 + rows + 1); paf.cg_ops.resize(o0 + ops);
-    std::vector<uint32_t> off(rows + 1);
-    if (hgpu_paf_fetch(ctx, paf.q_id.data() + r0, paf.q_len.data() + r0, paf.q_start.data() + r0, paf.q_end.data() + r0, paf.is_rev.data() + r0,
-                       paf.t_id.data() + r0, paf.t_len.data() + r0, paf.t_start.data() + r0, paf.t_end.data() + r0, paf.n_match.data() + r0,
-                       paf.n_block.data() + r0, paf.mapq.data() + r0, off.data(), paf.cg_ops.data() + o0) != HGPU_OK) {
-        fprintf(stderr, "[ERROR] (load_paf) %s: %s\n", path.c_str(), hgpu_last_error(ctx)); exit(EXIT_FAILURE);
-    }
-    for (uint64_t i = 0; i <= rows; ++i) paf.cg_off[r0 + i] = (uint32_t)(o0 + off[i]);
-}
-
-// rows must be grouped by read with read ids ascending (the reference silently assumes it: update_longreads,
-// Longread.cpp:57-84, slices the hit array by cumulative counts in read-id order)
-void finish_paf(PafTable& paf, size_t n_reads) {
-    for (size_t i = 1; i < paf.size(); ++i)
-        if (paf.q_id[i] < paf.q_id[i - 1]) {
-            fprintf(stderr, "[ERROR] (load_paf) PAF rows are not grouped by ascending read id (row %zu: read %u after read %u)\n", i, paf.q_id[i], paf.q_id[i - 1]);
-            exit(EXIT_FAILURE);
-        }
-    if (paf.size() && paf.q_id.back() >= n_reads) {
-        fprintf(stderr, "[ERROR] (load_paf) PAF names read %u but only %zu reads were loaded\n", paf.q_id.back(), n_reads);
-        exit(EXIT_FAILURE);
-    }
-    paf.read_off.assign(n_reads + 1, 0);
-    for (size_t i = 0; i < paf.size(); ++i) paf.read_off[paf.q_id[i] + 1]++;
-    for (size_t r = 0; r < n_reads; ++r) paf.read_off[r + 1] += paf.read_off[r];
+    text.resize(n);
+    if (n && text[n - 1] != '\n') text.push_back('\n');
 }
 
 // mean km of the 20 longest contigs, pairs ordered descending by (len, km) — Contig.cpp:162-174

@@ -111,7 +111,8 @@ int main(int argc, char** argv) {
     fprintf(stderr, "[NOTE] number of threads: %d, GPUs: %d\n\n", opt.num_threads, opt.gpus);
 
     fprintf(stderr, "[NOTE] loading contig sequences...\n");
-    ContigStore contigs;
+    PathInputs in;
+    ContigStore& contigs = in.contigs;
     load_fasta(opt.contig_path, contigs, &contigs);
     fprintf(stderr, "       loaded %zu contigs\n", contigs.size());
     lap();
@@ -121,7 +122,7 @@ int main(int argc, char** argv) {
     lap();
 
     fprintf(stderr, "[NOTE] loading long read sequences...\n");
-    SeqStore reads;
+    SeqStore& reads = in.reads;
     {
         std::vector<std::string> files;
         if (opt.long_fofn) load_fofn(opt.long_path, files); else files.push_back(opt.long_path);
@@ -129,106 +130,27 @@ int main(int argc, char** argv) {
     }
     fprintf(stderr, "       loaded %zu long reads\n", reads.size());
     lap();
-    fprintf(stderr, "[NOTE] loading alignment between contigs and long reads (tokenised on the GPU)...\n");
-    if (!join_contexts()) return EXIT_FAILURE;       // no CPU path: without the device the run ends here
-    PafTable paf;
+    fprintf(stderr, "[NOTE] loading alignment between contigs and long reads...\n");
     {
         std::vector<std::string> files;
         if (opt.mapping_fofn) load_fofn(opt.mapping_path, files); else files.push_back(opt.mapping_path);
-        for (const auto& f : files) load_paf(f, paf, ctxs[0]);
-        finish_paf(paf, reads.size());
+        for (const auto& f : files) read_text_file(f, in.paf_text);
     }
-    fprintf(stderr, "       loaded %zu alignment rows\n", paf.size());
+    fprintf(stderr, "       read %zu bytes of PAF text\n", in.paf_text.size());
     lap();
 
-    const double path_t0 = real_time();              // the clock of the backbone+POA path starts with the hits in host memory
-    // (i) filters + per-read sort + overlap fix + chaining, on the GPU
-    fprintf(stderr, "[NOTE] fixing overlapping alignments and building compact long reads (GPU)...\n");
+    // the clock of the backbone + POA path starts with the inputs in host memory and ends with every consensus
+    // string in host memory. Tokenising, compact reads, edge table and coordinates run on the GPU with the hit table resident.
+    fprintf(stderr, "[NOTE] PAF -> compact long reads -> backbone graph -> cleaning -> coordinates -> consensus (GPU)...\n");
     if (!join_contexts()) return EXIT_FAILURE;       // no CPU path: without the device the run ends here
-    CompactReads cl;
-    {
-        hgpu_hits_t h{(uint32_t)paf.size(), paf.q_start.data(), paf.q_end.data(), paf.t_id.data(), paf.t_len.data(), paf.t_start.data(),
-                      paf.t_end.data(), paf.n_match.data(), paf.n_block.data(), paf.is_rev.data(), paf.mapq.data(), paf.cg_off.data(),
-                      paf.cg_ops.empty() ? paf.cg_off.data() : paf.cg_ops.data()};
-        hgpu_k1_params p{opt.min_aln_sim, opt.uniq_freq, opt.max_uniq_dev, opt.min_aln_block, opt.min_aln_mapq};
-        cl.elems.resize(paf.size() + 1); cl.off.resize(reads.size() + 1);
-        uint64_t n = 0;
-        int rc = hgpu_compact_lr(ctxs[0], &h, paf.read_off.data(), (uint32_t)reads.size(), contigs.mean_kmer.data(), (uint32_t)contigs.size(), &p,
-                                 cl.elems.data(), cl.off.data(), &n);
-        if (rc != HGPU_OK) { fprintf(stderr, "[ERROR] hgpu_compact_lr: %s\n", hgpu_last_error(ctxs[0])); return EXIT_FAILURE; }
-        cl.elems.resize(n);
-    }
-    write_compact(cl, paf, d + "/compact_uniq.txt");
+    PathResult res;
+    if (run_path(in, opt, ctxs, d, logs, res) != HGPU_OK) return EXIT_FAILURE;
+    Graph& g = res.g;
+    fprintf(stderr, "       %llu alignment rows, %zu edges; tokenise %.2f s, compact reads %.2f s, edge table %.2f s, cleaning %.2f s, coordinates %.2f s, consensus %.2f s\n",
+            (unsigned long long)res.n_rows, res.edges.size(), res.t.tokenize, res.t.k1, res.t.k2, res.t.clean, res.t.coords, res.t.poa);
     lap();
-
-    // (ii) edge table on the GPU, graph container on the host
-    fprintf(stderr, "[NOTE] building the backbone graph (GPU)...\n");
-    Graph g;
-    {
-        std::vector<uint32_t> tid(cl.elems.size()); std::vector<uint8_t> rev(cl.elems.size());
-        for (size_t j = 0; j < cl.elems.size(); ++j) { tid[j] = paf.t_id[cl.elems[j].hit]; rev[j] = paf.is_rev[cl.elems[j].hit]; }
-        uint64_t pairs = 0;
-        for (size_t r = 0; r + 1 < cl.off.size(); ++r) if (cl.off[r + 1] - cl.off[r] > 1) pairs += cl.off[r + 1] - cl.off[r] - 1;
-        const size_t cap = 2 * pairs + 1;
-        std::vector<uint64_t> key(cap); std::vector<uint32_t> soff(cap + 1); std::vector<hgpu_edge_supp> supp(cap); std::vector<uint8_t> keep(cap);
-        uint64_t n = 0;
-        int rc = hgpu_backbone_edges(ctxs[0], tid.data(), rev.data(), cl.off.data(), (uint32_t)reads.size(), opt.min_edge_sup,
-                                     key.data(), soff.data(), supp.data(), keep.data(), &n);
-        if (rc != HGPU_OK) { fprintf(stderr, "[ERROR] hgpu_backbone_edges: %s\n", hgpu_last_error(ctxs[0])); return EXIT_FAILURE; }
-        key.resize(n); soff.resize(n + 1); keep.resize(n);
-        graph_from_edge_table(g, contigs.size(), key, soff, supp, nullptr);
-    }
-    write_stats(g, contigs, d + "/backbone.01.init.stat");
-    write_gfa(g, contigs, d + "/backbone.01.init.gfa");
-    lap();
-    fprintf(stderr, "[NOTE] cleaning weak edges...\n");
-    fprintf(stderr, "       removed %d edges\n", remove_weak_edges(g, opt.min_edge_sup));
-    write_stats(g, contigs, d + "/backbone.02.weakEdge.stat");
-    write_gfa(g, contigs, d + "/backbone.02.weakEdge.gfa");
-    lap();
-
-    fprintf(stderr, "[NOTE] cleaning tips...\n");
-    int nb = clean_tips(g, 1, d + "/backbone.03.tip.log");
-    nb += clean_tips(g, 2, d + "/backbone.03.tip.log");
-    nb += clean_tips(g, 3, d + "/backbone.03.tip.log");
-    fprintf(stderr, "       removed %d tips\n", nb);
-    write_stats(g, contigs, d + "/backbone.03.tip.stat");
-    write_gfa(g, contigs, d + "/backbone.03.tip.gfa");
-    lap();
-    fprintf(stderr, "[NOTE] cleaning simple bubbles...\n");
-    fprintf(stderr, "       removed %d simple bubbles\n", clean_simple_bubbles(g, 4, d + "/backbone.04.simplebubble.log"));
-    write_stats(g, contigs, d + "/backbone.04.simplebubble.stat");
-    write_gfa(g, contigs, d + "/backbone.04.simplebubble.gfa");
-    lap();
-    fprintf(stderr, "[NOTE] cleaning super bubbles...\n");
-    fprintf(stderr, "       removed %d super bubbles\n", clean_super_bubbles(g, d + "/backbone.05.superbubble.log"));
-    write_stats(g, contigs, d + "/backbone.05.superbubble.stat");
-    write_gfa(g, contigs, d + "/backbone.05.superbubble.gfa");
-    lap();
-    fprintf(stderr, "[NOTE] cleaning small bubbles...\n");
-    fprintf(stderr, "       removed %d small bubbles\n", clean_small_bubbles(g, d + "/backbone.06.smallbubble.log"));
-    write_stats(g, contigs, d + "/backbone.06.smallbubble.stat");
-    write_gfa(g, contigs, d + "/backbone.06.smallbubble.gfa");
-    lap();
-    report_branching(g, d + "/backbone.branching.log");
-
-    fprintf(stderr, "[NOTE] calculating long read coordinates between anchors (GPU)...\n");
-    std::vector<EdgeRef> edges;
-    enumerate_edges(g, 11, edges);
-    if (calc_edge_coordinates(g, edges, contigs, reads, cl, paf, ctxs[0], logs ? d + "/log_coordinate.txt" : std::string()) != 0) return EXIT_FAILURE;
-    lap();
-
-    // (iii) all edges in one batched POA call per GPU
-    fprintf(stderr, "[NOTE] calling consensus sequence between anchors (GPU, %zu edges)...\n", edges.size());
-    enumerate_edges(g, 12, edges);
-    uint64_t poa_bases = 0;
-    if (!edges.empty() && call_consensus(g, edges, reads, ctxs, d + "/log_consensus.txt", logs, opt.num_threads, &poa_bases) != 0) return EXIT_FAILURE;
-    lap();
-    {
-        const double dt = real_time() - path_t0;
-        fprintf(stderr, "[NOTE] backbone + POA path (hits in host memory -> consensus in host memory): %.1f long-read Mbases in %.2f s = %.1f Mbases/s\n\n",
-                poa_bases / 1e6, dt, dt > 0 ? poa_bases / 1e6 / dt : 0.0);
-    }
+    fprintf(stderr, "[NOTE] backbone + POA path (inputs in host memory -> consensus in host memory): %.1f long-read Mbases in %.2f s = %.1f Mbases/s\n\n",
+            res.poa_bases / 1e6, res.t.total, res.t.total > 0 ? res.poa_bases / 1e6 / res.t.total : 0.0);
 
     fprintf(stderr, "[NOTE] generating the assembly from the cleaned backbone graph...\n");
     write_assembly(g, contigs, d);

@@ -20,9 +20,9 @@ FILES = ["compact_uniq.txt", "backbone.01.init.gfa", "backbone.01.init.stat", "b
          "log_coordinate.txt", "log_consensus.txt", "asm.final.fa", "asm.final.ann", "log_asmfinal.txt"]
 
 
-def run_both(tmp, genome, n_reads, seed, extra=()):
+def run_both(tmp, genome, n_reads, seed, extra=(), threads=1):
     subprocess.run([oracle_ffi.GEN_BIN, tmp, str(genome), str(n_reads), "8000", str(seed)], check=True, stdout=subprocess.DEVNULL)
-    args = ["-t", "1", "-c", "contigs.fa", "-l", "reads.fa", "-m", "map.paf", "--aln-block", "500", "--aln-sim", "0.85", "--edge-sup", "3"]
+    args = ["-t", str(threads), "-c", "contigs.fa", "-l", "reads.fa", "-m", "map.paf", "--aln-block", "500", "--aln-sim", "0.85", "--edge-sup", "3"]
     with open(os.path.join(tmp, "ref.err"), "w") as e:
         subprocess.run([oracle_ffi.REF_BIN] + args + ["-d", "ref"], cwd=tmp, check=True, stdout=subprocess.DEVNULL, stderr=e)
     with open(os.path.join(tmp, "new.err"), "w") as e:
@@ -43,6 +43,34 @@ def test_all_output_files_identical(genome, n_reads, seed):
                                         and filecmp.cmp(os.path.join(tmp, "ref", f), os.path.join(tmp, "new", f), shallow=False))]
         assert not bad, f"files differ from the reference binary's: {bad}"
         assert os.path.getsize(os.path.join(tmp, "new", "asm.final.fa")) > genome // 2
+
+
+def sorted_log_lines(path):
+    """A per-edge log written line by line from several threads (Assemble.cpp:176-362,501-557: one fprintf per line on a shared
+    FILE*): its lines as a sorted multiset, thread ids masked."""
+    import re
+    with open(path, "rb") as f:
+        return sorted(re.sub(rb"th_id:\d+", b"th_id:0", ln) for ln in f)
+
+
+def test_baseline_config2_full_size():
+    """BASELINE config 2 at its stated size (10 Mb genome, 20k SRCs, 50k reads x 8 kb; seed 1 of the committed generator): every
+    output file of the reference binary, byte for byte. The reference runs on all host cores here (its DP is 400 CPU-seconds), so
+    the lines of its two per-edge logs interleave between threads: those two files are compared as multisets of lines; what they
+    log (coordinates, segments, consensus) also decides asm.final.fa / .ann, which are compared byte for byte."""
+    for p in (oracle_ffi.GEN_BIN, oracle_ffi.REF_BIN, BIN):
+        if not os.path.exists(p):
+            pytest.skip(f"{p} not built")
+    with tempfile.TemporaryDirectory() as tmp:
+        run_both(tmp, 10000000, 50000, 1, threads=os.cpu_count() or 8)
+        ordered = [f for f in FILES if f not in ("log_coordinate.txt", "log_consensus.txt")]
+        bad = [f for f in ordered if not (os.path.exists(os.path.join(tmp, "ref", f)) and os.path.exists(os.path.join(tmp, "new", f))
+                                          and filecmp.cmp(os.path.join(tmp, "ref", f), os.path.join(tmp, "new", f), shallow=False))]
+        assert not bad, f"files differ from the reference binary's: {bad}"
+        for name in ("log_coordinate.txt", "log_consensus.txt"):
+            a, b = sorted_log_lines(os.path.join(tmp, "ref", name)), sorted_log_lines(os.path.join(tmp, "new", name))
+            assert len(a) == len(b) > 100000 and a == b, name
+        assert os.path.getsize(os.path.join(tmp, "new", "asm.final.fa")) > 5_000_000
 
 
 def test_help_exits_zero_like_haslr_py_probe():

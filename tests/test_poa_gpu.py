@@ -191,6 +191,7 @@ def test_team_kernel_matches_oracle(oracle, monkeypatch):
     """Edges large enough for the block-per-edge kernel (forced here with a low threshold): multi-stripe score matrices
     filled by 8 warps in a pipeline must give the same consensus as the warp-per-edge kernel and the oracle."""
     import haslr_b200
+    monkeypatch.setenv("HGPU_POOL", "0")           # the pool kernel takes these edges otherwise
     monkeypatch.setenv("HGPU_TEAM", "8")
     monkeypatch.setenv("HGPU_TEAM_MIN_CELLS", "1000")
     c = haslr_b200.Context(0)
@@ -205,5 +206,36 @@ def test_team_kernel_matches_oracle(oracle, monkeypatch):
         st = check_batch(c, oracle, bases, seg_off, eso)
         assert st["dp_launches"] >= 2          # team kernel + warp-per-edge kernel
         assert st["alignments_rel16"] > 0      # the long gaps run in row-relative int16 cells, stripes pipelined over the team
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("ctx_per_block", [0, 1, 3, 8])
+def test_pool_kernel_matches_oracle(oracle, monkeypatch, ctx_per_block):
+    """k_poa_pool (a block's warps pull stripe tasks and graph tasks from several edges in flight), forced onto every edge of mixed
+    batches: single-stripe and 4-10-stripe alignments, edges without / with one segment, more edges than contexts and fewer."""
+    import haslr_b200
+    monkeypatch.setenv("HGPU_DEEP_MIN_READS", "0")
+    if ctx_per_block:
+        monkeypatch.setenv("HGPU_POOL_CTX", str(ctx_per_block))
+    c = haslr_b200.Context(0)
+    try:
+        b1, so1, es1, _ = synth.poa_batch(31, 6, depth=5, length=2600, length_jitter=0.3)
+        b2, so2, es2, _ = synth.poa_batch(32, 40, depth=6, length=300, length_jitter=0.3)
+        b3, so3, es3, _ = synth.poa_batch(33, 2, depth=3, length=5200)
+        bases = np.concatenate((b1, b2, b3))
+        seg_off = np.concatenate((so1, so2[1:] + so1[-1], so3[1:] + so1[-1] + so2[-1])).astype(np.uint64)
+        eso = np.concatenate((es1, es2[1:] + es1[-1], es3[1:] + es1[-1] + es2[-1])).astype(np.uint32)
+        st = check_batch(c, oracle, bases, seg_off, eso)
+        assert st["alignments_rel16"] == st["alignments"] > 0
+        edges = [[], [b"ACGT"], [b""], [b"ACGTACGT", b"", b"ACGTACGT"], [b"ACGT" * 300, b"ACGT" * 10, b"ACGT" * 500],
+                 [b"GATTACA", b"GATACA", b"GATTTACA", b"CATTACA", b"GATTACAT", b"TGATTACA"]]
+        bases, seg_off, eso = synth.from_strings(edges)
+        check_batch(c, oracle, bases, seg_off, eso)
+        b, so, eo, _ = synth.poa_batch(9, 48, depth=24, length=300, err=(0.08, 0.06, 0.04), length_jitter=0.3, depth_jitter=6)
+        check_batch(c, oracle, b, so, eo)
+        b, so, eo, _ = synth.poa_batch(19, 6, depth=14, length=2600, length_jitter=0.2)
+        check_batch(c, oracle, b, so, eo)
+        check_batch(c, oracle, b, so, eo, (3, -5, -4))
     finally:
         c.close()
