@@ -149,6 +149,99 @@ def reference_arm(args):
 
 CFG2 = dict(genome=10_000_000, reads=50_000, read_len=8000, seed=1)      # BASELINE config 2 (SURVEY 8d generator)
 
+# Strong-scaling edge population: ONE fixed set of backbone edges, modelled on the spread the reference's own run of config 2 shows
+# (SURVEY 8a12: 30 supporting reads per edge on average, p95 82; gaps median 470 bp, p95 2.5 kb, max 7.5 kb), x STRONG_SCALE towards
+# config 4 (D. melanogaster = config 2 x 14). (supporting reads, share) x (gap length, share):
+STRONG_DEPTHS = ((8, 0.15), (18, 0.25), (28, 0.30), (40, 0.18), (60, 0.09), (82, 0.03))
+STRONG_GAPS = ((120, 0.32), (400, 0.32), (900, 0.22), (2200, 0.10), (4500, 0.033), (7500, 0.007))
+STRONG_MAX_CELLS = 1.2e9     # the reference's config 2 run has no edge above 8e8 DP cells: long gaps come with few supporting reads
+STRONG_EDGES = 6033 * 2
+
+
+def strong_population(n_edges):
+    """[(depth, gap, count, first global edge id)] and the estimated time (sharding.alignment_cost) of one edge of each class."""
+    from haslr_b200 import sharding
+    combos = []
+    for d, wd in STRONG_DEPTHS:
+        for g, wg in STRONG_GAPS:
+            v, cells, work = float(g), 0.0, 0.0
+            for _k in range(1, d):
+                cells += v * g; work += float(sharding.alignment_cost(v, g)); v += 0.07 * g
+            if cells <= STRONG_MAX_CELLS:
+                combos.append((d, g, wd * wg, work))
+    tot = sum(w for _, _, w, _ in combos)
+    pop, cost, first = [], [], 0
+    for d, g, w, work in combos:
+        c = int(round(n_edges * w / tot))
+        if c:
+            pop.append((d, g, c, first)); cost.append(work); first += c
+    return pop, cost
+
+
+def strong_scaling_leg(ctx, dist, rank, world, dev, args):
+    """One fixed edge set dealt to the ranks by estimated cost (sharding.shard_edges, longest processing time first), every rank
+    runs hgpu_poa_batch_dev on its shard, one all-gather of the consensus; time = max over ranks. The analogue of the
+    reference's only parallelism: T threads pulling the edges of ONE dataset (Assemble.cpp:386-434,562-605)."""
+    import torch
+    import synth
+    from haslr_b200 import sharding
+    pop, ccost = strong_population(STRONG_EDGES)
+    n_total = sum(c for _, _, c, _ in pop)
+    cost = np.concatenate([np.full(c, ccost[i]) for i, (_, _, c, _) in enumerate(pop)])
+    mine = sharding.shard_edges(cost, world)[rank]
+    parts, so_parts, eo_parts = [], [], []
+    for d, g, c, first in pop:
+        ids = mine[(mine >= first) & (mine < first + c)]
+        if len(ids) == 0:
+            continue
+        b, so, eo = synth.hashed_batch(0, 4242 + d * 100000 + g, depth=d, length=g, err=ERR, device=dev, eids=ids - first, chunk=max(1, 60_000_000 // (d * g * 8)))
+        parts.append(b); so_parts.append(np.diff(so.astype(np.int64))); eo_parts.append(np.full(len(ids), d, dtype=np.int64))
+    d_bases = torch.cat(parts)
+    seg_off = np.concatenate(([0], np.cumsum(np.concatenate(so_parts)))).astype(np.uint64)
+    eso = np.concatenate(([0], np.cumsum(np.concatenate(eo_parts)))).astype(np.uint32)
+    nb = int(seg_off[-1])
+    d_out = torch.empty(nb // 4 + 65536, dtype=torch.uint8, device=dev)
+    passes = 2
+
+    def one():
+        off, status = ctx.poa_batch_dev(d_bases.data_ptr(), seg_off, eso, d_out.data_ptr(), d_out.numel(), *SCORES)
+        if world > 1:
+            sharding.all_gather_consensus(dist, d_out, off, dev, to_host=False)
+        return off, status
+    off, status = one()                                  # warm-up: sizes the arenas of this shard
+    assert (status == 0).all(), f"strong-scaling shard: status {np.unique(status)}"
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kms = 0.0
+    e0.record()
+    for _ in range(passes):
+        one()
+        kms += ctx.poa_stats()["ms_dp"]
+    e1.record(); torch.cuda.synchronize()
+    st = ctx.poa_stats()
+    t = torch.tensor([e0.elapsed_time(e1) / passes, kms / passes, float(st["cells"]), float(nb), float(len(eso) - 1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+    else:
+        allt = [t]
+    rows = [x.cpu().tolist() for x in allt]
+    ms = max(r[0] for r in rows)
+    km = [r[1] for r in rows]
+    tot_b, tot_c = sum(r[3] for r in rows), sum(r[2] for r in rows)
+    return {"scaling": "strong", "workload": f"{n_total} backbone edges in {len(pop)} (supporting reads x gap) classes modelled on config 2's spread, "
+                                             f"{tot_b / 1e6:.0f} Mbases, {tot_c:.3e} DP cells; the SAME set at every N, dealt by estimated cost (LPT)",
+            "value": tot_b / 1e6 / (ms / 1e3), "unit": UNIT, "ms_per_pass": ms, "gcups": tot_c / (ms / 1e3) / 1e9, "n_gpus": world,
+            "per_rank_ms": [r[0] for r in rows], "per_rank_kernel_ms": km, "per_rank_edges": [int(r[4]) for r in rows],
+            "per_rank_cells": [r[2] for r in rows], "kernel_imbalance_max_over_mean": max(km) / (sum(km) / len(km)) if sum(km) > 0 else None,
+            "limiter": "per-rank kernel time (k_poa_pool on the rank's deep edges): the all-gather is < 1 % of a pass; the spread between ranks is "
+                       "the LPT estimate's error (cost model: |V| grows 7 % per read) plus the tail of each rank's largest edges"}
+
+
+
+
 
 def cfg2_dataset():
     """BASELINE config 2 written by the seeded generator binary (tools/gen_synth.cpp) into a scratch directory."""
@@ -298,6 +391,7 @@ def main():
     ap.add_argument("--no-deep", action="store_true", help="skip the deep-edge (config 2 shape) leg")
     ap.add_argument("--no-whole-path", action="store_true", help="skip the whole-path leg (BASELINE config 2: PAF text -> consensus)")
     ap.add_argument("--whole-path-ref", action="store_true", help="also time the reference binary on the whole-path dataset inside the native arm")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (one fixed edge set dealt to the N ranks)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -402,6 +496,11 @@ def main():
     h2d = n_bases + seg_off.nbytes + eso.nbytes
     d2h = int(off[-1]) + off.nbytes + status.nbytes
 
+    # ---- strong scaling: one fixed edge set dealt over the ranks (every rank takes part; rank 0 reports)
+    strong = None
+    if not args.no_strong:
+        strong = strong_scaling_leg(ctx, dist if world > 1 else None, rank, world, dev, args)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -482,7 +581,7 @@ def main():
                    "check": check},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
-        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "deep_edges": deep, "whole_path": whole,
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "deep_edges": deep, "whole_path": whole, "strong_scaling": strong,
     }))
     if world > 1:
         dist.destroy_process_group()

@@ -39,9 +39,9 @@ struct PoaState {
     bool have_result = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t stream2 = nullptr;   // the team kernel (few huge edges) runs beside the warp-per-edge kernel
-    static constexpr int NCS = 4;     // size classes whose arenas fit the budget together run side by side on these
-    cudaStream_t cstream[NCS] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t cev[NCS] = {nullptr, nullptr, nullptr, nullptr};
+    static constexpr int NCS = 16;    // size classes whose arenas fit the budget together run side by side on these
+    cudaStream_t cstream[NCS] = {};
+    cudaEvent_t cev[NCS] = {};
     uint32_t cfg_team = 8;            // 0 disables the team kernel
     double cfg_team_min_cells = 2.0e8;
     uint32_t cfg_teams_per_sm = 2;    // resident teams per SM (HGPU_TEAMS_PER_SM); the rest of the SM runs warp-per-edge blocks
@@ -103,14 +103,17 @@ struct EdgeEst {
     uint32_t ncap;       // node capacity needed (estimate)
     uint64_t slot;       // score-matrix bytes needed (estimate)
     double cells;        // DP cells (estimate)
+    double work;         // time estimate in "row-stripe units": per alignment (V + 1) x (stripes + POOL_GRAPH_ROWS): the fill computes whole
+                         // 512-column stripes whatever the gap is, and the serial graph work per node costs about as much as three of them
     uint32_t lmax;       // longest segment
     bool deep;           // many supporting reads: the graph gets several times wider than the gap (k_poa_edges_deep)
 };
 
 // Node-count growth model: every later segment adds about `growth` new nodes per base (SURVEY.md §8(d):
 // |V| grows ~ L * (ins + sub) per read). growth >= 1 means the worst case (every base a new node).
+static constexpr double POOL_GRAPH_ROWS = 3.0;
 void estimate_edge(const uint32_t* len, uint32_t R, double growth, const DpScores& sc, int force, EdgeEst* out) {
-    double V = len[0], cells = 0;
+    double V = len[0], cells = 0, work = 0;
     uint64_t slot = 0;
     uint32_t lmax = len[0];
     for (uint32_t k = 1; k < R; ++k) {
@@ -119,6 +122,7 @@ void estimate_edge(const uint32_t* len, uint32_t R, double growth, const DpScore
         if (mode == DPM_REL16) out->deep = true;                     // only k_poa_edges_deep carries the REL16 code
         slot = std::max(slot, dp_slot_bytes(Vi, len[k], mode));
         cells += (V + 1.0) * (len[k] + 1.0);
+        work += (V + 1.0) * ((double)Geo<DP_NW16, true>::stripes(len[k]) + POOL_GRAPH_ROWS);
         // overhang beyond the graph's current span also becomes new nodes
         double over = len[k] > V ? (double)len[k] - V : 0.0;
         V += growth >= 1.0 ? (double)len[k] : std::min<double>(len[k], growth * len[k] + over + 8.0);
@@ -128,6 +132,7 @@ void estimate_edge(const uint32_t* len, uint32_t R, double growth, const DpScore
     out->ncap = (uint32_t)std::min<double>(ncap, 4.0e9);
     out->slot = slot + 4096;
     out->cells = cells;
+    out->work = work;
     out->lmax = lmax;
 }
 }  // namespace
@@ -144,6 +149,8 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
                    const DpScores& sc, const PoaRunOpts& opt, std::vector<uint32_t>& status_h, std::vector<uint32_t>& len_h) {
     PoaState* S = poa_state(ctx);
     cudaStream_t st = ctx->stream;
+    const auto host_t0 = std::chrono::steady_clock::now();
+    auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
     for (auto& p : S->passes) if (S->spare.size() < 4) S->spare.push_back(std::move(p));
     S->passes.clear();
     S->have_result = false;
@@ -201,7 +208,8 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
     if (!budget) {
         size_t fr = 0, tot = 0;
         HGPU_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
-        fr += S->arena.n + S->ws.n;   // what we already hold can be reused
+        fr += S->arena.n + S->ws.n + S->arena_team.n + S->ws_team.n;   // what we already hold can be reused (all of it: a budget that
+                                                                          // shrinks from call to call changes the wave plan of repeated calls)
         budget = (uint64_t)(fr * S->cfg_budget_frac);
         budget = std::min<uint64_t>(budget, 165ull << 30);
     }
@@ -222,7 +230,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
             uint32_t R = e_off[e + 1] - e_off[e];
             est[i].edge = e;
             est[i].deep = R >= S->cfg_deep_min_reads;
-            if (R == 0) { est[i].ncap = 64; est[i].slot = 4096; est[i].cells = 0; est[i].lmax = 0; continue; }
+            if (R == 0) { est[i].ncap = 64; est[i].slot = 4096; est[i].cells = 0; est[i].work = 0; est[i].lmax = 0; continue; }
             estimate_edge(seg_len.data() + e_off[e], R, growth, sc, opt.force_i32, &est[i]);
             uint64_t sum = 0; uint32_t lmax = 0;
             for (uint32_t k = 0; k < R; ++k) { sum += seg_len[e_off[e] + k]; lmax = std::max(lmax, seg_len[e_off[e] + k]); }
@@ -240,8 +248,13 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
             for (const EdgeEst& x : est) total += x.cells;
             const double share = total / (double)std::max<size_t>(1, std::min<size_t>(est.size(), max_warps));
             const double thr = std::max(S->cfg_team_alpha * share, S->cfg_team_min_cells);
-            for (EdgeEst& x : est)
+            double shallow = 0;
+            for (EdgeEst& x : est) {
                 if (!x.deep && x.lmax >= 2u * (uint32_t)Geo<DP_NW16, true>::SW - 1 && x.cells > thr) x.deep = true;
+                if (!x.deep) shallow += x.cells;
+            }
+            // a small shallow remainder (config 2: 48 of 6,033 edges) would only wait for the pool blocks to leave the SMs: it joins them
+            if (shallow < 0.10 * total) for (EdgeEst& x : est) x.deep = true;
         } else if (S->cfg_team >= 2 && opt.stop_round == 0xFFFFFFFFu) {
             double total = 0;
             for (const EdgeEst& x : est) total += x.cells;
@@ -279,6 +292,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
         HGPU_CUDA(ctx, cudaMemsetAsync(S->pool_cursor.p, 0, sizeof(unsigned long long), st));
         HGPU_CUDA(ctx, cudaMemsetAsync(S->counters.p, 0, 256 * 4, st));
 
+        if (S->verbose) fprintf(stderr, "[poa] host: %.1f ms to the first launch of attempt %d\n", host_ms(), attempt);
         if (S->timing) HGPU_CUDA(ctx, cudaEventRecord(S->ev0, st));
         bool team_launched = false;
         if (!team.empty()) {
@@ -330,7 +344,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
         }
 
         // ---- size classes: a class ends where the slot estimate has halved, unless memory is no constraint
-        struct Cls { size_t a, b; uint64_t slot; WsLayout wl; uint32_t warps; bool deep; bool pool; uint32_t ctx_per_block; };
+        struct Cls { size_t a, b; uint64_t slot; WsLayout wl; uint32_t warps; bool deep; bool pool; uint32_t ctx_per_block, pool_blocks; double cells, work; };
         const uint32_t pool_blocks_max = 2u * (uint32_t)ctx->sm_count;              // k_poa_pool: two blocks of 8 warps per SM
         std::vector<Cls> classes;
         size_t n_deep = 0;
@@ -341,7 +355,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
             const size_t end = deep ? n_deep : est.size();           // a class never mixes the two kernels
             const bool pool = deep && use_pool;
             const uint32_t mw = pool ? pool_blocks_max * (uint32_t)POOL_MAX_CTX : deep ? max_warps_deep : max_warps;   // pool: slots = contexts
-            Cls c; c.a = i; c.slot = (est[i].slot + 127) / 128 * 128; c.deep = deep; c.pool = pool; c.ctx_per_block = 0;
+            Cls c; c.a = i; c.slot = (est[i].slot + 127) / 128 * 128; c.deep = deep; c.pool = pool; c.ctx_per_block = 0; c.pool_blocks = 0; c.cells = 0; c.work = 0;
             auto plan = [&](size_t a, size_t b, Cls& cc) {
                 uint32_t nc = 64;
                 for (size_t q = a; q < b; ++q) nc = std::max(nc, est[q].ncap);
@@ -353,16 +367,53 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
             };
             plan(i, end, c);
             size_t j = end;
-            if (c.warps < mw) {
+            if (c.warps < mw || pool) {           // pool contexts are sized per class: always split where the slot estimate has halved
                 j = i + 1;
                 while (j < end && est[j].slot * 2 > c.slot) ++j;
                 plan(i, j, c);
             }
             c.b = j;
+            for (size_t q = c.a; q < c.b; ++q) { c.cells += est[q].cells; c.work += est[q].work; }
             classes.push_back(c);
             i = j;
         }
         if (classes.size() > 256) HGPU_FAIL(ctx, HGPU_E_INTERNAL, "too many size classes (%zu)", classes.size());
+
+        // ---- pool classes share the device at the same time: the resident blocks (two per SM) are split between them in
+        //      proportion to their estimated time (EdgeEst::work), so that they finish together; every block keeps as many edges in flight as
+        //      the class has for it (at most POOL_MAX_CTX) and the memory budget, shared the same way, allows
+        {
+            double pool_cells = 0; size_t n_pool = 0;
+            for (const Cls& c : classes) if (c.pool && c.warps) { pool_cells += c.work + 1.0; ++n_pool; }
+            if (n_pool) {
+                uint32_t left = pool_blocks_max;
+                uint64_t mem = 0;
+                for (Cls& c : classes) {
+                    if (!c.pool || !c.warps) continue;
+                    const uint32_t n_items = (uint32_t)(c.b - c.a);
+                    uint32_t b = (uint32_t)std::lround(pool_blocks_max * (c.work + 1.0) / pool_cells);
+                    b = std::max<uint32_t>(1, std::min<uint32_t>({b, n_items, c.warps, std::max<uint32_t>(left, 1u)}));
+                    left -= std::min(left, b);
+                    uint32_t E = S->cfg_pool_ctx ? S->cfg_pool_ctx : (n_items + b - 1) / b;
+                    E = std::max<uint32_t>(1, std::min<uint32_t>({E, (uint32_t)POOL_MAX_CTX, c.warps / b}));
+                    c.pool_blocks = std::min<uint32_t>(b, (n_items + E - 1) / E);
+                    c.ctx_per_block = E;
+                    mem += (uint64_t)c.pool_blocks * E * (c.slot + c.wl.bytes);
+                }
+                // over the budget: take contexts away where they cost most, one per block at a time
+                for (int guard = 0; mem > budget && guard < 4096; ++guard) {
+                    Cls* worst = nullptr; uint64_t wm = 0;
+                    for (Cls& c : classes) {
+                        if (!c.pool || !c.warps || c.ctx_per_block <= 1) continue;
+                        const uint64_t m = (uint64_t)c.pool_blocks * c.ctx_per_block * (c.slot + c.wl.bytes);
+                        if (m > wm) { wm = m; worst = &c; }
+                    }
+                    if (!worst) break;
+                    worst->ctx_per_block -= 1;
+                    mem -= (uint64_t)worst->pool_blocks * (worst->slot + worst->wl.bytes);
+                }
+            }
+        }
 
         // ---- launches. A class is one persistent kernel with its own slots and workspaces; consecutive classes whose
         //      memory fits the budget together form a wave and run side by side (each on its own stream), so a class of a
@@ -383,19 +434,8 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
             }
             uint32_t warps, blocks;
             if (c.pool) {
-                // contexts per block: enough edges in flight that 8 warps find a task (an edge offers its stripes while it fills and one
-                // task while its graph is updated, ~30 % of a lone warp's time), never more than the class can fill all blocks with
-                double ns = 0;
-                for (size_t q = c.a; q < c.b; ++q) ns += (double)Geo<DP_NW16, true>::stripes(est[q].lmax);
-                ns /= (double)std::max<size_t>(1, c.b - c.a);
-                uint32_t E = S->cfg_pool_ctx ? S->cfg_pool_ctx : (uint32_t)std::lround(POOL_WARPS / (0.3 + 0.7 * ns));
-                E = std::max<uint32_t>(2, std::min<uint32_t>(E, (uint32_t)POOL_MAX_CTX));
-                blocks = std::min<uint32_t>(pool_blocks_max, (n_items + E - 1) / E);
-                blocks = std::max<uint32_t>(1, std::min<uint32_t>(blocks, c.warps / E));
-                if (!S->cfg_pool_ctx) E = std::max<uint32_t>(1, std::min<uint32_t>(E, (n_items + blocks - 1) / blocks));
-                if ((uint64_t)blocks * E > c.warps) E = std::max<uint32_t>(1, c.warps / blocks);
-                c.ctx_per_block = E;
-                warps = blocks * E;                                            // = slots / workspaces of this class
+                blocks = c.pool_blocks;
+                warps = blocks * c.ctx_per_block;                              // = slots / workspaces of this class
             } else {
                 warps = std::min<uint32_t>(c.warps, n_items ? n_items : 1);
                 blocks = (warps + DP_WARPS_PER_BLOCK - 1) / DP_WARPS_PER_BLOCK;
@@ -428,6 +468,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
             if (wave.empty()) continue;
             const bool side_by_side = wave.size() > 1;
             cudaEvent_t vb = nullptr, ve = nullptr;
+            std::vector<cudaEvent_t> vclass;                  // verbose: when every class of the wave ended
             if (S->verbose) { cudaEventCreate(&vb); cudaEventCreate(&ve); cudaEventRecord(vb, st); }
             if (side_by_side) HGPU_CUDA(ctx, cudaEventRecord(S->ev_fork, st));
             for (size_t li = 0; li < wave.size(); ++li) {
@@ -464,8 +505,10 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
                     HGPU_CUDA(ctx, cudaEventRecord(S->cev[li], ls));
                     HGPU_CUDA(ctx, cudaStreamWaitEvent(st, S->cev[li], 0));
                 }
+                if (S->verbose) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, ls); vclass.push_back(e); }
                 if (S->verbose) {
                     double cc = 0, cmax = 0; for (size_t q = c.a; q < c.b; ++q) { cc += est[q].cells; cmax = std::max(cmax, est[q].cells); }
+                    if (c.pool) fprintf(stderr, "[poa] pool class %zu: %u blocks x %u contexts\n", ln.ci, ln.blocks, c.ctx_per_block);
                     fprintf(stderr, "[poa] attempt %d growth %.2f wave %zu/%zu class %zu/%zu%s: %u edges on %u warps, slot %.1f MB, ws %.1f MB, %.3e cells (largest edge %.3e)\n",
                             attempt, growth, wi, waves.size(), ln.ci, classes.size(), c.pool ? " (pool)" : c.deep ? " (deep)" : "", n_items, ln.warps, c.slot / 1048576.0, c.wl.bytes / 1048576.0, cc, cmax);
                 }
@@ -473,7 +516,13 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
             if (S->verbose) {
                 cudaEventRecord(ve, st); cudaEventSynchronize(ve);
                 float ms = 0; cudaEventElapsedTime(&ms, vb, ve);
-                fprintf(stderr, "[poa] wave %zu: %.1f ms\n", wi, ms);
+                fprintf(stderr, "[poa] wave %zu: %.1f ms; classes ended at", wi, ms);
+                for (size_t q = 0; q < vclass.size(); ++q) {
+                    float cm = 0; cudaEventElapsedTime(&cm, vb, vclass[q]);
+                    fprintf(stderr, " %zu:%.0f", wave[q].ci, cm);
+                    cudaEventDestroy(vclass[q]);
+                }
+                fprintf(stderr, " ms\n");
                 cudaEventDestroy(vb); cudaEventDestroy(ve);
             }
         }
@@ -519,6 +568,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
         fprintf(stderr, "\n");
     }
 #endif
+    if (S->verbose) fprintf(stderr, "[poa] host: %.1f ms for the whole run (kernels %.1f ms)\n", host_ms(), S->st.ms_dp);
     if (sth[7]) HGPU_FAIL(ctx, HGPU_E_INTERNAL, "k_poa_pool: a block ran out of tasks while edges were still open");
     S->st.cells = sth[0]; S->st.cells_padded = sth[1]; S->st.alignments = sth[2]; S->st.alignments_i32 = sth[3] & 0xFFFFFFFFull; S->st.alignments_rel16 = sth[3] >> 32; S->st.bases_in = sth[4];
     return HGPU_OK;

@@ -50,7 +50,7 @@ struct WsLayout {
     uint32_t ncap, ecap, scap;
     uint64_t o_hdr, o_code, o_in_head, o_in_tail, o_out_head, o_aligned, o_e_begin, o_e_end, o_e_w, o_e_next_in, o_e_next_out,
         o_rank2node, o_node2rank, o_meta0, o_pred_off, o_pred_rank, o_sinks, o_aln_rank, o_aln_pos, o_mark, o_check, o_stack,
-        o_score, o_pred, o_plan_a, o_plan_b, o_trec;
+        o_score, o_pred, o_plan, o_trec;
     uint64_t bytes;
 };
 
@@ -72,7 +72,7 @@ __host__ __device__ inline WsLayout ws_layout(uint32_t ncap, uint32_t ecap) {
     w.o_mark = take(n); w.o_check = take(n);
     w.o_stack = take(4 * (uint64_t)w.scap);
     w.o_score = take(8 * n); w.o_pred = take(4 * n);
-    w.o_plan_a = take(4 * n); w.o_plan_b = take(4 * n);      // deep kernels: per-rank predecessor plan (poa_fill_rel.cuh)
+    w.o_plan = take(4 * n);                                   // deep kernels: per-rank predecessor plan (poa_fill_rel.cuh)
     w.o_trec = take(32 * n);                                  // per-node record of the topological sort (w_build_trec)
     w.bytes = (o + 127) / 128 * 128;
     return w;
@@ -1501,11 +1501,19 @@ __device__ __noinline__ int w_toposort(GraphView& g, const TopoRec* rec, uint8_t
         const bool valid = i < N;
         uint32_t np = 0, p0 = NIL, p1 = NIL;
         bool slow = false;                                        // aligned nodes or more than two predecessors
+        uint4 ra = make_uint4(NIL, NIL, NIL, NIL), rb = make_uint4(NIL, NIL, NIL, NIL);
         if (valid) {
-            const uint4 ra = rec4[2 * i], rb = rec4[2 * i + 1];
+            ra = rec4[2 * i]; rb = rec4[2 * i + 1];
             p0 = ra.x; p1 = ra.y;
             np = (p0 != NIL) + (p1 != NIL);
             slow = ra.z != NIL || rb.x != NIL;
+            // the DFS below runs on one lane and waits for every record it touches: pull the records of this root's
+            // predecessors / aligned nodes with larger ids (the ones a walk from this root may still have to visit) into L1 now,
+            // 32 roots at a time
+            const uint32_t ch[7] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z};
+#pragma unroll
+            for (int q = 0; q < 7; ++q)
+                if (ch[q] != NIL && ch[q] > i) asm volatile("prefetch.global.L1 [%0];" :: "l"(rec4 + 2 * ch[q]));
         }
         if (i + 32 < N) asm volatile("prefetch.global.L1 [%0];" :: "l"(rec4 + 2 * (i + 32)));   // the next batch's roots
         uint32_t pos = 0;
@@ -1528,11 +1536,152 @@ __device__ __noinline__ int w_toposort(GraphView& g, const TopoRec* rec, uint8_t
             nr += __popc(em);
             __syncwarp();
             if (f >= 32) break;
-            // SPOA's DFS from root i0+f on one lane: same visits and the same emission order as the serial code. A visit reads the
-            // node's record (two loads in flight together); a node that pushed children is flagged on the stack - when the walk
-            // returns to it every child is emitted (a child is only popped once permanent), so it is finalised on the spot.
-            if (lane == 0) {
+            // SPOA's DFS from root i0+f, same visits and the same emission order as the serial code, but every visit is done by the
+            // whole warp: lanes 0-7 read the eight words of the node's record in one 32-byte access, lanes 0-6 test "their"
+            // predecessor / aligned node against the emitted bitmap at once, one ballot gives the children still to visit, they
+            // are pushed in SPOA's order (in-edges first, then aligned nodes) by the lanes that hold them, and their records are
+            // pulled into L1 on the spot - so the walk waits for one shared-memory round trip per visit instead of a chain of
+            // dependent global loads. A node that pushed children is flagged on the stack: when the walk returns to it every
+            // child is emitted (a child is only popped once permanent), so it is finalised without looking at its lists again.
+            {
                 constexpr uint32_t EXPANDED = 0x80000000u, IDMASK = 0x3FFFFFFFu;
+                const uint32_t* recw = reinterpret_cast<const uint32_t*>(rec);
+                uint32_t sp = 1, guard = 0;
+                const uint32_t limit = 16u * (N + *g.n_edges) + 1024u;
+                if (lane == 0) stk[0] = i0 + f;
+                __syncwarp();
+                while (sp > 0) {
+                    if (++guard > limit) { okflag = 0; break; }
+                    const uint32_t self = sp - 1;
+                    const uint32_t top = stk[self];                                   // same address for all lanes: a broadcast
+                    const uint32_t v = top & IDMASK;
+                    if (is_perm(v)) { --sp; continue; }
+                    const bool chk = !((nochk[v >> 5] >> (v & 31)) & 1u);
+                    const uint32_t child = lane < 8 ? recw[8 * (size_t)v + lane] : NIL;   // words 0-3 in-edge tails, 4-6 aligned nodes, 7 fifth in-edge
+                    bool vvalid = true;
+                    if (!(top & EXPANDED)) {
+                        const uint32_t more = __shfl_sync(FULL, child, 7);
+                        if (more == NIL) {
+                            const bool mine = lane < 4 || (lane < 7 && chk);
+                            const bool unem = mine && child != NIL && !is_perm(child);
+                            const unsigned m = __ballot_sync(FULL, unem);
+                            const uint32_t n = (uint32_t)__popc(m);
+                            if (n) {
+                                if (sp + n > TOPO_STACK) { okflag = 0; break; }
+                                if (unem) {
+                                    stk[sp + __popc(m & ((1u << lane) - 1u))] = child;
+                                    if (lane >= 4) atomicOr(&nochk[child >> 5], 1u << (child & 31));
+                                    asm volatile("prefetch.global.L1 [%0];" :: "l"(rec4 + 2 * (size_t)child));
+                                }
+                                if (lane == 0) stk[self] = v | EXPANDED;
+                                sp += n; vvalid = false;
+                            }
+                        } else {
+                            // five or more in-edges (2 % of the nodes of a deep graph): the in-list beyond the record on one lane
+                            uint32_t nsp = sp;
+                            if (lane == 0) {
+                                const uint4 ra = rec4[2 * (size_t)v], rb = rec4[2 * (size_t)v + 1];
+                                const uint32_t pp[4] = {ra.x, ra.y, ra.z, ra.w};
+                                for (int q = 0; q < 4 && okflag; ++q)
+                                    if (!is_perm(pp[q])) { if (nsp >= TOPO_STACK) okflag = 0; else stk[nsp++] = pp[q]; }
+                                for (uint32_t x = rb.w; x != NIL && okflag; ) {
+                                    const uint32_t b = g.e_begin[x], nx = g.e_next_in[x];
+                                    if (!is_perm(b)) { if (nsp >= TOPO_STACK) okflag = 0; else stk[nsp++] = b; }
+                                    x = nx;
+                                }
+                                if (chk) {
+                                    const uint32_t al[3] = {rb.x, rb.y, rb.z};
+                                    for (int q = 0; q < 3 && okflag; ++q) {
+                                        if (al[q] == NIL) break;
+                                        if (!is_perm(al[q])) { if (nsp >= TOPO_STACK) okflag = 0; else { stk[nsp++] = al[q]; nochk[al[q] >> 5] |= 1u << (al[q] & 31); } }
+                                    }
+                                }
+                                if (nsp != sp) stk[self] = v | EXPANDED;
+                            }
+                            nsp = __shfl_sync(FULL, nsp, 0);
+                            okflag = __shfl_sync(FULL, okflag, 0);
+                            if (!okflag) break;
+                            if (nsp != sp) { sp = nsp; vvalid = false; }
+                        }
+                    }
+                    if (vvalid) {
+                        if (lane == 0) perm[v >> 5] |= 1u << (v & 31);
+                        if (chk) {
+                            const bool al = lane >= 4 && lane < 7 && child != NIL;       // NIL-terminated: the aligned nodes sit in lanes 4, 5, 6 in order
+                            const uint32_t na = (uint32_t)__popc(__ballot_sync(FULL, al));
+                            if (lane == 0) { g.rank2node[nr] = v; g.node2rank[v] = nr; }
+                            if (al) { g.rank2node[nr + 1 + (lane - 4)] = child; g.node2rank[child] = nr + 1 + (lane - 4); }
+                            nr += 1 + na;
+                        }
+                        --sp;
+                    }
+                    __syncwarp();
+                }
+            }
+            __syncwarp();
+            if (!okflag) break;
+            pos = f + 1;
+            if (pos >= 32) break;
+        }
+    }
+    if (okflag && nr != N) okflag = 0;
+    return okflag;
+}
+
+// The same sort walking the in-lists directly (no records): what the shallow kernel runs. Its graphs (a handful of reads) have few
+// aligned nodes, most ranks are emitted by the 32-wide fast path, and the kernel is instruction-cache bound: the extra record
+// pass and its code cost it 4-6 % there (A/B on config 3: 1,490 vs 1,394 GCUPS), while deep graphs gain 25 % of their sort.
+__device__ __noinline__ int w_toposort_chain(GraphView& g, uint8_t* wsm, int lane) {
+    const uint32_t N = *g.n_nodes;
+    if (N > TOPO_BM_WORDS * 32) return 0;
+    uint32_t* perm = reinterpret_cast<uint32_t*>(wsm);
+    uint32_t* nochk = perm + TOPO_BM_WORDS;
+    uint32_t* stk = nochk + TOPO_BM_WORDS;
+    for (uint32_t w = lane; w < (N + 31) / 32; w += 32) { perm[w] = 0; nochk[w] = 0; }
+    __syncwarp();
+    auto is_perm = [&](uint32_t v) -> bool { return (perm[v >> 5] >> (v & 31)) & 1u; };
+    uint32_t nr = 0;
+    int okflag = 1;
+    for (uint32_t i0 = 0; i0 < N && okflag; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const bool valid = i < N;
+        uint32_t np = 0, p0 = NIL, p1 = NIL;
+        bool slow = false;                                        // aligned nodes or more than two predecessors
+        if (valid) {
+            uint32_t x = g.in_head[i];
+            if (x != NIL) {
+                p0 = g.e_begin[x]; np = 1; x = g.e_next_in[x];
+                if (x != NIL) { p1 = g.e_begin[x]; np = 2; if (g.e_next_in[x] != NIL) slow = true; }
+            }
+            if (g.aligned[3 * i] != NIL) slow = true;
+        }
+        uint32_t pos = 0;
+        while (true) {
+            const uint32_t lo = i0 + pos;
+            const bool marked = valid && is_perm(i);
+            bool ok = valid && (uint32_t)lane >= pos && !marked && !slow;
+            if (ok && np >= 1) ok = is_perm(p0) || (p0 >= lo && p0 < i);
+            if (ok && np >= 2) ok = is_perm(p1) || (p1 >= lo && p1 < i);
+            const bool pass = (uint32_t)lane < pos || !valid || marked || ok;
+            const unsigned failmask = __ballot_sync(FULL, !pass);
+            const uint32_t f = failmask ? (uint32_t)(__ffs(failmask) - 1) : 32u;
+            const bool emit = ok && (uint32_t)lane < f;
+            const unsigned em = __ballot_sync(FULL, emit);
+            if (emit) {
+                const uint32_t r = nr + __popc(em & ((1u << lane) - 1));
+                g.rank2node[r] = i; g.node2rank[i] = r;
+            }
+            if (lane == 0 && em) perm[i0 >> 5] |= em;
+            nr += __popc(em);
+            __syncwarp();
+            if (f >= 32) break;
+            // SPOA's DFS from root i0+f on one lane: same visits and the same emission order as the serial code, with
+            // two changes that only remove memory round trips: (1) the loads of a visit are issued before their first
+            // use (node record and aligned triple together, both words of an edge together); (2) a node that pushed
+            // children is flagged on the stack - when the walk returns to it every child is emitted (a child is only
+            // popped once permanent), so it is finalised on the spot instead of walking its lists a second time.
+            if (lane == 0) {
+                constexpr uint32_t EXPANDED = 0x80000000u, HAS_ALIGNED = 0x40000000u, IDMASK = 0x3FFFFFFFu;
                 uint32_t sp = 0, guard = 0;
                 const uint32_t limit = 16u * (N + *g.n_edges) + 1024u;
                 stk[sp++] = i0 + f;
@@ -1543,21 +1692,14 @@ __device__ __noinline__ int w_toposort(GraphView& g, const TopoRec* rec, uint8_t
                     const uint32_t v = top & IDMASK;
                     if (is_perm(v)) { --sp; continue; }
                     const bool chk = !((nochk[v >> 5] >> (v & 31)) & 1u);
+                    uint32_t al[3] = {NIL, NIL, NIL};
                     bool vvalid = true;
-                    const uint4 rb = rec4[2 * v + 1];
-                    if (!(top & EXPANDED)) {
-                        const uint4 ra = rec4[2 * v];
-                        const uint32_t pp[4] = {ra.x, ra.y, ra.z, ra.w};
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint32_t b = pp[q];
-                            if (b == NIL) break;
-                            if (!is_perm(b)) {
-                                if (sp >= TOPO_STACK) { okflag = 0; break; }
-                                stk[sp++] = b; vvalid = false;
-                            }
-                        }
-                        for (uint32_t x = rb.w; x != NIL && okflag; ) {          // fifth in-edge onwards: walk the list (2 % of the nodes of a deep graph)
+                    if (top & EXPANDED) {
+                        if (chk && (top & HAS_ALIGNED)) { al[0] = g.aligned[3 * v]; al[1] = g.aligned[3 * v + 1]; al[2] = g.aligned[3 * v + 2]; }
+                    } else {
+                        uint32_t x = g.in_head[v];
+                        const uint32_t a0 = g.aligned[3 * v], a1 = g.aligned[3 * v + 1], a2 = g.aligned[3 * v + 2];
+                        while (x != NIL) {
                             const uint32_t b = g.e_begin[x], nx = g.e_next_in[x];
                             if (!is_perm(b)) {
                                 if (sp >= TOPO_STACK) { okflag = 0; break; }
@@ -1567,7 +1709,7 @@ __device__ __noinline__ int w_toposort(GraphView& g, const TopoRec* rec, uint8_t
                         }
                         if (!okflag) break;
                         if (chk) {
-                            const uint32_t al[3] = {rb.x, rb.y, rb.z};
+                            al[0] = a0; al[1] = a0 == NIL ? NIL : a1; al[2] = (a0 == NIL || a1 == NIL) ? NIL : a2;
 #pragma unroll
                             for (int q = 0; q < 3; ++q) {
                                 const uint32_t o = al[q];
@@ -1579,13 +1721,12 @@ __device__ __noinline__ int w_toposort(GraphView& g, const TopoRec* rec, uint8_t
                             }
                             if (!okflag) break;
                         }
-                        if (!vvalid) stk[self] = v | EXPANDED;               // children first; finalised on return
+                        if (!vvalid) stk[self] = v | EXPANDED | (a0 != NIL ? HAS_ALIGNED : 0u);   // children first; finalised on return
                     }
                     if (vvalid) {
                         perm[v >> 5] |= 1u << (v & 31);
                         if (chk) {
                             g.rank2node[nr] = v; g.node2rank[v] = nr; ++nr;
-                            const uint32_t al[3] = {rb.x, rb.y, rb.z};
 #pragma unroll
                             for (int q = 0; q < 3; ++q) {
                                 if (al[q] == NIL) break;
@@ -1752,8 +1893,7 @@ __device__ __forceinline__ void poa_edges_body(const PoaArgs& a) {
     GraphView gv = bind_graph(wsb, a.wl);
     GraphScratch gs = bind_scratch(wsb, a.wl);
     uint32_t* hdr = reinterpret_cast<uint32_t*>(wsb + a.wl.o_hdr);
-    uint32_t* plan_a = reinterpret_cast<uint32_t*>(wsb + a.wl.o_plan_a);
-    uint32_t* plan_b = reinterpret_cast<uint32_t*>(wsb + a.wl.o_plan_b);
+    uint32_t* plan = reinterpret_cast<uint32_t*>(wsb + a.wl.o_plan);
     TopoRec* trec = reinterpret_cast<TopoRec*>(wsb + a.wl.o_trec);
     unsigned long long st_cells = 0, st_padded = 0, st_aln = 0, st_aln32 = 0, st_bases = 0;
     PHASE_CLK_DECL
@@ -1776,7 +1916,7 @@ __device__ __forceinline__ void poa_edges_body(const PoaArgs& a) {
         } else {
             const uint32_t L0 = a.seg_len[s0];
             if (L0 > gv.ncap || L0 > gv.ecap) st = ST_CAPACITY;
-            else { w_init_chain(gv, a.bases + a.seg_ptr[s0], L0, lane); e_bases += L0; if (RING > 2) w_build_plan(gv, plan_a, plan_b, lane); }
+            else { w_init_chain(gv, a.bases + a.seg_ptr[s0], L0, lane); e_bases += L0; if (RING > 2) w_build_plan(gv, plan, lane); }
             PHASE_CLK(PC_INIT)
             for (uint32_t k = 1; k < R && st == ST_OK; ++k) {
                 const uint32_t V = *gv.n_nodes;
@@ -1792,7 +1932,7 @@ __device__ __forceinline__ void poa_edges_body(const PoaArgs& a) {
                 if (dp_slot_bytes(V, L, mode) > a.slot_bytes) { st = ST_TOO_LARGE; break; }
                 const uint32_t probe = (k == a.probe_round) ? a.probe : 0u;
                 if (probe == 1) {
-                    if (RING > 2 && mode == DPM_REL16) dp_fill_rel<false>(gv, plan_a, plan_b, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, lane, 0, 1, nullptr);
+                    if (RING > 2 && mode == DPM_REL16) dp_fill_rel<false>(gv, plan, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, lane, 0, 1, nullptr);
                     else if (mode == DPM_ABS16) dp_fill16<false, false, 2>(gv.meta0, gv.pred_off, gv.pred_rank, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, Geo<DP_NW16, true>::bias(V, a.sc), lane, 0, 1, nullptr);
                     e_cells += (unsigned long long)(V + 1) * (L + 1);
                     debug_stop = true; break;
@@ -1803,7 +1943,7 @@ __device__ __forceinline__ void poa_edges_body(const PoaArgs& a) {
                     PHASE_CLK(PC_FILL)
                     ok = dp_traceback<DP_NW16, true>(gv, slot, wsm, seq, V, L, a.sc, lane);
                 } else if (RING > 2 && mode == DPM_REL16) {
-                    dp_fill_rel<false>(gv, plan_a, plan_b, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, lane, 0, 1, nullptr);
+                    dp_fill_rel<false>(gv, plan, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, lane, 0, 1, nullptr);
                     PHASE_CLK(PC_FILL)
                     ok = dp_traceback<DP_NW16, true, true>(gv, slot, wsm, seq, V, L, a.sc, lane);
                 } else {
@@ -1834,8 +1974,8 @@ __device__ __forceinline__ void poa_edges_body(const PoaArgs& a) {
                 if (ust != ST_OK) { st = ust; break; }
                 PHASE_CLK(PC_ADD)
                 if (probe == 3) { debug_stop = true; break; }
-                w_build_trec(gv, trec, lane);
-                if (!w_toposort(gv, trec, wsm, lane)) {    // too large for the shared-memory bitmaps / deep DFS: serial
+                if (RING > 2) w_build_trec(gv, trec, lane);
+                if (!(RING > 2 ? w_toposort(gv, trec, wsm, lane) : w_toposort_chain(gv, wsm, lane))) {    // too large for the shared-memory bitmaps / deep DFS: serial
                     ust = ST_OK;
                     if (lane == 0 && !g_toposort(gv, gs)) ust = ST_TOPOSORT;
                     ust = __shfl_sync(FULL, ust, 0);
@@ -1845,7 +1985,7 @@ __device__ __forceinline__ void poa_edges_body(const PoaArgs& a) {
                 PHASE_CLK(PC_TOPO)
                 if (probe == 4) { debug_stop = true; break; }
                 w_build_meta(gv, lane);
-                if (RING > 2) w_build_plan(gv, plan_a, plan_b, lane);
+                if (RING > 2) w_build_plan(gv, plan, lane);
                 PHASE_CLK(PC_META)
                 if (probe == 5) { debug_stop = true; break; }
             }
@@ -1916,8 +2056,7 @@ __global__ void __launch_bounds__(32 * TEAM, 512 / (32 * TEAM)) k_poa_edges_team
     GraphView gv = bind_graph(wsb, a.wl);
     GraphScratch gs = bind_scratch(wsb, a.wl);
     uint32_t* hdr = reinterpret_cast<uint32_t*>(wsb + a.wl.o_hdr);
-    uint32_t* plan_a = reinterpret_cast<uint32_t*>(wsb + a.wl.o_plan_a);
-    uint32_t* plan_b = reinterpret_cast<uint32_t*>(wsb + a.wl.o_plan_b);
+    uint32_t* plan = reinterpret_cast<uint32_t*>(wsb + a.wl.o_plan);
     TopoRec* trec = reinterpret_cast<TopoRec*>(wsb + a.wl.o_trec);
     unsigned long long st_cells = 0, st_padded = 0, st_aln = 0, st_aln32 = 0, st_bases = 0;
     const bool lead = wib == 0;
@@ -1939,7 +2078,7 @@ __global__ void __launch_bounds__(32 * TEAM, 512 / (32 * TEAM)) k_poa_edges_team
         } else {
             const uint32_t L0 = a.seg_len[s0];
             if (L0 > gv.ncap || L0 > gv.ecap) st = ST_CAPACITY;
-            else if (lead) { w_init_chain(gv, a.bases + a.seg_ptr[s0], L0, lane); e_bases += L0; w_build_plan(gv, plan_a, plan_b, lane); }
+            else if (lead) { w_init_chain(gv, a.bases + a.seg_ptr[s0], L0, lane); e_bases += L0; w_build_plan(gv, plan, lane); }
             for (uint32_t k = 1; k < R && st == ST_OK; ++k) {
                 if (threadIdx.x < TEAM) vprog[threadIdx.x] = 0;
                 __syncthreads();                              // graph of round k-1 complete, progress words cleared
@@ -1951,7 +2090,7 @@ __global__ void __launch_bounds__(32 * TEAM, 512 / (32 * TEAM)) k_poa_edges_team
                 const bool p16 = mode != DPM_I32;
                 if ((uint64_t)V + L > gv.ncap || (uint64_t)NE + L + 1 > gv.ecap) { st = ST_CAPACITY; break; }
                 if (dp_slot_bytes(V, L, mode) > a.slot_bytes) { st = ST_TOO_LARGE; break; }
-                const bool fill_ok = mode == DPM_REL16 ? dp_fill_rel<true>(gv, plan_a, plan_b, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, lane, wib, TEAM, vprog)
+                const bool fill_ok = mode == DPM_REL16 ? dp_fill_rel<true>(gv, plan, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, lane, wib, TEAM, vprog)
                                                        : dp_fill<DP_NW32, false>(gv, slot, wsm, seq, V, L, a.sc, lane, wib, TEAM, vprog);
                 const int all_ok = __syncthreads_and(fill_ok ? 1 : 0);    // every stripe stored (and no wait gave up)
                 if (!all_ok) { st = ST_SYNC; break; }
@@ -1982,7 +2121,7 @@ __global__ void __launch_bounds__(32 * TEAM, 512 / (32 * TEAM)) k_poa_edges_team
                             ust = __shfl_sync(FULL, ust, 0);
                             __syncwarp();
                         }
-                        if (ust == ST_OK) { w_build_meta(gv, lane); w_build_plan(gv, plan_a, plan_b, lane); }
+                        if (ust == ST_OK) { w_build_meta(gv, lane); w_build_plan(gv, plan, lane); }
                         rst = ust;
                     }
                     if (lane == 0) bcast[1] = rst;

@@ -10,7 +10,7 @@
 //    THREE packed instructions per word and predecessor - x = src[k-1] + profile, y = max(src[k] + gap, x),
 //    t[k] = max(t[k], y + rebase) - so re-basing a predecessor row into this row's frame costs nothing extra and the
 //    plain-int16 encoding has no advantage left: all alignments run relative, one code path.
-//  * The predecessor list of every rank is condensed once per alignment into a two-word PLAN (eight 4-bit rank distances,
+//  * The predecessor list of every rank is condensed once per alignment into a one-word PLAN (eight 3-bit rank distances,
 //    count, base code; w_build_plan) that the stripes load 32 ranks at a time; rows whose predecessors do not fit the plan
 //    (farther than the ring, more than eight, or none but the virtual row) take the generic walk over the CSR.
 //  * Row bases are int32 Hhat values of the cell left of the stripe (column 0 itself in stripe 0), kept per stripe in the
@@ -20,49 +20,53 @@
 
 namespace hgpu {
 
-static constexpr uint32_t PLAN_SLOW = 1u << 6;
+// Plan word of a rank: bits 0-23 the rank distances of up to eight predecessor rows, 3 bits each (distance - 1; the previous
+// rank first when it is one of them), bits 24-25 the node's base code, bits 26-29 the predecessor count, bit 30 PLAN_SLOW.
+static constexpr uint32_t PLAN_SLOW = 1u << 30;
 static constexpr int REL_RING = DP_RING_DEEP;            // parked rows per warp; plan distances are 1 .. REL_RING
+static_assert(REL_RING == 8, "plan distances are packed in 3 bits");
+__device__ __forceinline__ uint32_t plan_code(uint32_t p) { return (p >> 24) & 3u; }
+__device__ __forceinline__ uint32_t plan_np(uint32_t p) { return (p >> 26) & 15u; }
 
-// Plan of rank rr from its DP record: pa = rank distances of its predecessor rows (4 bits each), pb = code | count << 2,
-// or PLAN_SLOW when the row needs the generic walk.
-__device__ __forceinline__ void deep_plan_of(uint32_t m0, uint32_t rr, const uint32_t* pred_off, const uint32_t* pred_rank, uint32_t& pa, uint32_t& pb) {
+__device__ __forceinline__ uint32_t deep_plan_of(uint32_t m0, uint32_t rr, const uint32_t* pred_off, const uint32_t* pred_rank) {
     const uint32_t code = m0 & 3u, npc = (m0 >> 3) & 3u;
-    pa = 0; pb = code | PLAN_SLOW;
-    if (npc == 0) {
-        if (rr == 0) { pa = 1u; pb = code | (1u << 2); }                  // first rank: the virtual row 0 is the previous row
-    } else if (npc == 1) {
+    const uint32_t slow = (code << 24) | PLAN_SLOW;
+    auto pack = [&](uint32_t dists, uint32_t n) { return dists | (code << 24) | (n << 26); };
+    if (npc == 0) return rr == 0 ? pack(0u, 1u) : slow;                  // first rank: the virtual row 0 is the previous row
+    if (npc == 1) {
         const uint32_t d0 = meta_d0(m0);
-        if (d0 <= (uint32_t)REL_RING) { pa = d0; pb = code | (1u << 2); }
-    } else if (npc == 2) {
-        const uint32_t d0 = meta_d0(m0), d1 = meta_d1(m0);
-        if (d0 <= (uint32_t)REL_RING && d1 <= (uint32_t)REL_RING) { pa = d0 | (d1 << 4); pb = code | (2u << 2); }
-    } else {
-        const uint32_t c0 = pred_off[rr], n = pred_off[rr + 1] - c0;
-        if (n <= 8u) {
-            bool ok = true;
-            for (uint32_t x = 0; x < n; ++x) {
-                const uint32_t d = rr - pred_rank[c0 + x];
-                ok = ok && d <= (uint32_t)REL_RING;
-                pa |= (d & 15u) << (4u * x);
-            }
-            if (ok) pb = code | (n << 2);
-        }
+        return d0 <= (uint32_t)REL_RING ? pack(d0 - 1u, 1u) : slow;
     }
+    if (npc == 2) {
+        uint32_t d0 = meta_d0(m0), d1 = meta_d1(m0);
+        if (d0 > (uint32_t)REL_RING || d1 > (uint32_t)REL_RING) return slow;
+        if (d1 == 1u) { d1 = d0; d0 = 1u; }
+        return pack((d0 - 1u) | ((d1 - 1u) << 3), 2u);
+    }
+    const uint32_t c0 = pred_off[rr], n = pred_off[rr + 1] - c0;
+    if (n > 8u) return slow;
+    uint32_t dists = 0, at = 1;                                           // slot 0 is kept for the previous rank
+    bool ok = true, has1 = false;
+    for (uint32_t x = 0; x < n; ++x) {
+        const uint32_t d = rr - pred_rank[c0 + x];
+        ok = ok && d <= (uint32_t)REL_RING;
+        if (d == 1u) has1 = true;
+        else { dists |= ((d - 1u) & 7u) << (3u * at); ++at; }
+    }
+    if (!ok) return slow;
+    if (!has1) dists >>= 3;                                               // no previous-rank predecessor: close the gap
+    return pack(dists, n);
 }
 
 // plan words of all ranks, lane-parallel; run by the warp that owns the graph, after the per-rank DP records exist
-__device__ __noinline__ void w_build_plan(const GraphView& g, uint32_t* plan_a, uint32_t* plan_b, int lane) {
+__device__ __noinline__ void w_build_plan(const GraphView& g, uint32_t* plan, int lane) {
     const uint32_t N = *g.n_nodes;
-    for (uint32_t r = lane; r < N; r += 32) {
-        uint32_t pa, pb;
-        deep_plan_of(g.meta0[r], r, g.pred_off, g.pred_rank, pa, pb);
-        plan_a[r] = pa; plan_b[r] = pb;
-    }
+    for (uint32_t r = lane; r < N; r += 32) plan[r] = deep_plan_of(g.meta0[r], r, g.pred_off, g.pred_rank);
     __syncwarp();
 }
 
 struct RelFrame {                                         // cold per-alignment state, in the warp's shared memory behind the profile
-    unsigned long long meta0, pred_off, pred_rank, plan_a, plan_b, seq, H, bases;
+    unsigned long long meta0, pred_off, pred_rank, plan, seq, H, bases;
     uint32_t V, L, NS; int32_t sm, sx, pad;
 };
 static_assert(sizeof(RelFrame) <= FILL16_PARKED, "frame must fit in front of the parked rows");
@@ -96,10 +100,22 @@ struct RelState {
         t[1] = __viaddmax_s16x2(__viaddmax_s16x2(s1, g2, __vadd2(s0, p0.y)), d2, t[1]);                       \
         t[0] = __viaddmax_s16x2(__viaddmax_s16x2(s0, g2, __vadd2(hs, p0.x)), d2, t[0]);                       \
     } while (0)
+// the first predecessor of a row: t[k] = max(src[k] + gap, src[k-1] + profile[k]) + rebase
+#define REL_FOLD_FIRST(s0, s1, s2, s3, s4, s5, s6, s7, hs, d2)                                              \
+    do {                                                                                                       \
+        t[7] = __vadd2(__viaddmax_s16x2(s7, g2, __vadd2(s6, p1.w)), d2);                                      \
+        t[6] = __vadd2(__viaddmax_s16x2(s6, g2, __vadd2(s5, p1.z)), d2);                                      \
+        t[5] = __vadd2(__viaddmax_s16x2(s5, g2, __vadd2(s4, p1.y)), d2);                                      \
+        t[4] = __vadd2(__viaddmax_s16x2(s4, g2, __vadd2(s3, p1.x)), d2);                                      \
+        t[3] = __vadd2(__viaddmax_s16x2(s3, g2, __vadd2(s2, p0.w)), d2);                                      \
+        t[2] = __vadd2(__viaddmax_s16x2(s2, g2, __vadd2(s1, p0.z)), d2);                                      \
+        t[1] = __vadd2(__viaddmax_s16x2(s1, g2, __vadd2(s0, p0.y)), d2);                                      \
+        t[0] = __vadd2(__viaddmax_s16x2(s0, g2, __vadd2(hs, p0.x)), d2);                                      \
+    } while (0)
 
 // One row, in place: A = row i-1 on entry and row i on exit (stored to the slot and, by the next row, parked in the ring).
-// pa / pb: the row's plan; bi: its base (stripes > 0; stripe 0 derives it from the predecessors' bases here).
-__device__ __forceinline__ void row_rel(uint32_t (&A)[8], RelState& S, uint32_t pa, uint32_t pb, int bi, int q, uint32_t i) {
+// plan: the row's plan word; bi: its base (stripes > 0; stripe 0 derives it from the predecessors' bases here).
+__device__ __forceinline__ void row_rel(uint32_t (&A)[8], RelState& S, uint32_t plan, int bi, int q, uint32_t i) {
     using F = Fill16;
     const int lane = S.lane;
     const uint32_t g2 = S.g2;
@@ -108,46 +124,59 @@ __device__ __forceinline__ void row_rel(uint32_t (&A)[8], RelState& S, uint32_t 
     // park row i-1: later rows read it through the ring
     sts_v4(parked + ((i - 1) & (uint32_t)(REL_RING - 1)) * 1024u, A[0], A[1], A[2], A[3]);
     sts_v4(parked + ((i - 1) & (uint32_t)(REL_RING - 1)) * 1024u + 512u, A[4], A[5], A[6], A[7]);
-    const uint32_t pf = S.pf_lane + (pb & 3u) * (uint32_t)(F::NW * 32 * 4);
+    const uint32_t pf = S.pf_lane + plan_code(plan) * (uint32_t)(F::NW * 32 * 4);
     const uint4 p0 = lds_v4(pf), p1 = lds_v4(pf + 512u);
     const uint32_t blw = (uint32_t)(S.has_prev ? 0 : F::G::NEGV) << 16;   // the cell left of the stripe in a row's own frame: its base, or nothing
     uint32_t t[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) t[k] = F::NEG2;
-    // base (int32 Hhat) of the row `dist` ranks back: this batch, the previous batch, else the stripe's base array
+    // base (int32 Hhat) of the row `dist` ranks back, dist <= 8: lane q - dist of this batch's register, or of the previous batch's
     auto base_near = [&](uint32_t dist) -> int {
-        const int ql = q - (int)dist;                                     // dist <= 8 <= 32
-        return ql >= 0 ? __shfl_sync(FULL, (int)S.b, ql) : __shfl_sync(FULL, (int)S.bprev, ql + 32);
+        const int ql = q - (int)dist;
+        return __shfl_sync(FULL, (int)(ql >= 0 ? S.b : S.bprev), ql & 31);
     };
-    if ((pb & PLAN_SLOW) == 0) {
-        const uint32_t np = (pb >> 2) & 15u;
+    if ((plan & PLAN_SLOW) == 0) {
+        const uint32_t np = plan_np(plan);
         if (!S.has_prev) {                                                // stripe 0: base = column 0 = gap + best predecessor base
             int best = INT32_MIN;
-            uint32_t dd = pa;
-            for (uint32_t x = 0; x < np; ++x, dd >>= 4) best = max(best, base_near(dd & 15u));
+            uint32_t dd = plan;
+            for (uint32_t x = 0; x < np; ++x, dd >>= 3) best = max(best, base_near((dd & 7u) + 1u));
             bi = best + gap;
             if (lane == q) S.b = (uint32_t)bi;
         }
-        uint32_t dd = pa;
-#pragma unroll 1
-        for (uint32_t x = 0; x < np; ++x, dd >>= 4) {
-            const uint32_t dist = dd & 15u;
+        // the first predecessor initialises the row: the previous rank (row i-1, still in registers) if it is one of them
+        uint32_t dd = plan;
+        {
+            const uint32_t dist = (dd & 7u) + 1u;
             const uint32_t d2 = pack2(max(base_near(dist) - bi, REL_CLAMP));
             if (dist == 1u) {
                 uint32_t left = __shfl_up_sync(FULL, A[7], 1);
                 if (lane == 0) left = blw;
                 const uint32_t hs = __byte_perm(left, A[7], 0x5432);
-                REL_FOLD(A[0], A[1], A[2], A[3], A[4], A[5], A[6], A[7], hs, d2);
+                REL_FOLD_FIRST(A[0], A[1], A[2], A[3], A[4], A[5], A[6], A[7], hs, d2);
             } else {
                 const uint32_t pa_ = parked + ((i - dist) & (uint32_t)(REL_RING - 1)) * 1024u;
                 const uint4 s0 = lds_v4(pa_), s1 = lds_v4(pa_ + 512u);
                 uint32_t left = __shfl_up_sync(FULL, s1.w, 1);
                 if (lane == 0) left = blw;
                 const uint32_t hs = __byte_perm(left, s1.w, 0x5432);
-                REL_FOLD(s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, hs, d2);
+                REL_FOLD_FIRST(s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, hs, d2);
             }
         }
+        // the others (never the previous rank: the plan lists it first) come from the ring
+#pragma unroll 1
+        for (uint32_t x = 1; x < np; ++x) {
+            dd >>= 3;
+            const uint32_t dist = (dd & 7u) + 1u;
+            const uint32_t d2 = pack2(max(base_near(dist) - bi, REL_CLAMP));
+            const uint32_t pa_ = parked + ((i - dist) & (uint32_t)(REL_RING - 1)) * 1024u;
+            const uint4 s0 = lds_v4(pa_), s1 = lds_v4(pa_ + 512u);
+            uint32_t left = __shfl_up_sync(FULL, s1.w, 1);
+            if (lane == 0) left = blw;
+            const uint32_t hs = __byte_perm(left, s1.w, 0x5432);
+            REL_FOLD(s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, hs, d2);
+        }
     } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t[k] = F::NEG2;
         // generic walk: predecessors from the CSR (or the virtual row 0 when there is none), bases of rows outside the two
         // batch registers from the stripe's base array, cells of rows outside the ring from the slot
         const unsigned long long bases = lds_u64(S.frame + RFRAME(bases)) + 4ull * S.stripe * (lds_u32v(S.frame + RFRAME(V)) + 1ull);
@@ -277,14 +306,14 @@ __device__ __forceinline__ bool rel_stripe(RelState& S, uint32_t* prof, RelFrame
     if (s == 0 && lane == 0) stg_u32(b_cur, 0u);
     if (TEAM) team_publish(ts.vprog, ts.pub_idx, ts.pub_base + 1u, lane);
     S.b = 0u;                                                          // "previous batch" of the first batch: row 0 (base 0) in lane 31
-    const unsigned long long plan_a = lds_u64(S.frame + RFRAME(plan_a)), plan_b = lds_u64(S.frame + RFRAME(plan_b));
-    uint32_t npa = 0, npb = 0;
-    if ((uint32_t)lane < Vs) { npa = ldg_u32(plan_a, lane); npb = ldg_u32(plan_b, lane); }
+    const unsigned long long plan = lds_u64(S.frame + RFRAME(plan));
+    uint32_t npl = 0;
+    if ((uint32_t)lane < Vs) npl = ldg_u32(plan, lane);
 #pragma unroll 1
     for (uint32_t r0 = 0; r0 < Vs; r0 += 32) {
         const uint32_t rr = r0 + lane;
-        const uint32_t mpa = npa, mpb = npb;
-        if (rr + 32 < Vs) { npa = ldg_u32(plan_a, rr + 32); npb = ldg_u32(plan_b, rr + 32); }
+        const uint32_t mpl = npl;
+        if (rr + 32 < Vs) npl = ldg_u32(plan, rr + 32);
         S.bprev = S.b;
         if (s > 0) {
             if (TEAM) {                                                // rows r0 .. r0+32 of the stripe to the left must be complete
@@ -296,9 +325,9 @@ __device__ __forceinline__ bool rel_stripe(RelState& S, uint32_t* prof, RelFrame
         const int nb = (Vs - r0) < 32u ? (int)(Vs - r0) : 32;
 #pragma unroll 1
         for (int q = 0; q < nb; ++q) {
-            const uint32_t pa = __shfl_sync(FULL, mpa, q), pb = __shfl_sync(FULL, mpb, q);
+            const uint32_t pl = __shfl_sync(FULL, mpl, q);
             const int bi = __shfl_sync(FULL, (int)S.b, q);             // stripe 0: replaced inside the row
-            row_rel(A, S, pa, pb, bi, q, r0 + q + 1);
+            row_rel(A, S, pl, bi, q, r0 + q + 1);
         }
         if (s == 0 && lane < nb) stg_u32(b_cur + 4ull * (rr + 1), S.b);
         if (s == 0) __syncwarp();                                      // later generic rows read these through other lanes' loads
@@ -310,15 +339,14 @@ __device__ __forceinline__ bool rel_stripe(RelState& S, uint32_t* prof, RelFrame
 }
 
 // frame of an alignment (lane 0 writes it; callers __syncwarp before the first stripe)
-__device__ __forceinline__ void rel_frame_init(RelFrame* frame, const GraphView& gv, const uint32_t* plan_a, const uint32_t* plan_b, uint8_t* slot,
+__device__ __forceinline__ void rel_frame_init(RelFrame* frame, const GraphView& gv, const uint32_t* plan, uint8_t* slot,
                                                const uint8_t* seq, uint32_t V, uint32_t L, int sm, int sx) {
     constexpr int NW = DP_NW16;
     const uint32_t NS = Geo<NW, true>::stripes(L);
     frame->meta0 = (unsigned long long)(uintptr_t)gv.meta0;
     frame->pred_off = (unsigned long long)(uintptr_t)gv.pred_off;
     frame->pred_rank = (unsigned long long)(uintptr_t)gv.pred_rank;
-    frame->plan_a = (unsigned long long)(uintptr_t)plan_a;
-    frame->plan_b = (unsigned long long)(uintptr_t)plan_b;
+    frame->plan = (unsigned long long)(uintptr_t)plan;
     frame->seq = (unsigned long long)(uintptr_t)seq;
     frame->H = (unsigned long long)(uintptr_t)slot;
     frame->bases = (unsigned long long)(uintptr_t)(slot + (uint64_t)(V + 1) * NS * NW * 128);
@@ -340,7 +368,7 @@ __device__ __forceinline__ void rel_state_init(RelState& S, uint32_t* prof, RelF
 // The fill of one alignment by one warp (TEAM false) or by the warps of a team (warp trank takes stripes trank, trank + tsize,
 // ...; its progress word vprog[trank] = stripe * (V + 1) + rows done + 1 is cleared by the caller before every alignment).
 template <bool TEAM>
-__device__ __noinline__ bool dp_fill_rel(const GraphView& gv, const uint32_t* plan_a, const uint32_t* plan_b, uint8_t* slot, uint8_t* wsm,
+__device__ __noinline__ bool dp_fill_rel(const GraphView& gv, const uint32_t* plan, uint8_t* slot, uint8_t* wsm,
                                          const uint8_t* seq, uint32_t V, uint32_t L, int sm, int sx, int gap, int lane,
                                          uint32_t trank, uint32_t tsize, volatile uint32_t* vprog) {
     constexpr int NW = DP_NW16;
@@ -349,7 +377,7 @@ __device__ __noinline__ bool dp_fill_rel(const GraphView& gv, const uint32_t* pl
     RelFrame* frame = reinterpret_cast<RelFrame*>(wsm + G::PROF_BYTES);
     const uint32_t NS = G::stripes(L);
     __syncwarp();
-    if (lane == 0) rel_frame_init(frame, gv, plan_a, plan_b, slot, seq, V, L, sm, sx);
+    if (lane == 0) rel_frame_init(frame, gv, plan, slot, seq, V, L, sm, sx);
     RelState S;
     rel_state_init(S, prof, frame, NS, gap, lane);
     bool ok = true;

@@ -44,7 +44,7 @@ __device__ __forceinline__ uint32_t vld(const uint32_t* p) { return *reinterpret
 __device__ __forceinline__ void vst(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
 
 struct PoolEnv {                         // per-context global storage, bound on demand
-    GraphView gv; GraphScratch gs; uint32_t* hdr; uint32_t* plan_a; uint32_t* plan_b; TopoRec* trec; uint8_t* slot;
+    GraphView gv; GraphScratch gs; uint32_t* hdr; uint32_t* plan; TopoRec* trec; uint8_t* slot;
 };
 __device__ __forceinline__ PoolEnv pool_env(const PoaArgs& a, uint32_t gctx) {
     PoolEnv e;
@@ -52,8 +52,7 @@ __device__ __forceinline__ PoolEnv pool_env(const PoaArgs& a, uint32_t gctx) {
     e.gv = bind_graph(wsb, a.wl);
     e.gs = bind_scratch(wsb, a.wl);
     e.hdr = reinterpret_cast<uint32_t*>(wsb + a.wl.o_hdr);
-    e.plan_a = reinterpret_cast<uint32_t*>(wsb + a.wl.o_plan_a);
-    e.plan_b = reinterpret_cast<uint32_t*>(wsb + a.wl.o_plan_b);
+    e.plan = reinterpret_cast<uint32_t*>(wsb + a.wl.o_plan);
     e.trec = reinterpret_cast<TopoRec*>(wsb + a.wl.o_trec);
     e.slot = a.arena + (uint64_t)gctx * a.slot_bytes;
     return e;
@@ -150,7 +149,7 @@ __device__ __noinline__ void pool_advance(const PoaArgs& a, PoolEnv& E, PoolCtx*
             if (L0 > gv.ncap || L0 > gv.ecap) st = ST_CAPACITY;
             else {
                 w_init_chain(gv, a.bases + a.seg_ptr[s0], L0, lane);
-                w_build_plan(gv, E.plan_a, E.plan_b, lane);
+                w_build_plan(gv, E.plan, lane);
                 if (lane == 0) C->bases = L0;
                 __syncwarp();
             }
@@ -193,7 +192,7 @@ __device__ __noinline__ void pool_graph_task(const PoaArgs& a, PoolEnv& E, PoolC
                     __syncwarp();
                 }
             }
-            if (ust == ST_OK) { w_build_meta(gv, lane); w_build_plan(gv, E.plan_a, E.plan_b, lane); }
+            if (ust == ST_OK) { w_build_meta(gv, lane); w_build_plan(gv, E.plan, lane); }
             st = ust;
         }
     }
@@ -269,13 +268,13 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, 2) k_poa_pool(PoaArgs a, uint
                 uint32_t* prof = reinterpret_cast<uint32_t*>(wsm);
                 RelFrame* frame = reinterpret_cast<RelFrame*>(wsm + Geo<DP_NW16, true>::PROF_BYTES);
                 __syncwarp();
-                if (lane == 0) rel_frame_init(frame, E.gv, E.plan_a, E.plan_b, E.slot, seq, V, L, a.sc.sm, a.sc.sx);
+                if (lane == 0) rel_frame_init(frame, E.gv, E.plan, E.slot, seq, V, L, a.sc.sm, a.sc.sx);
                 RelState S;
                 rel_state_init(S, prof, frame, NS, a.sc.g, lane);
                 const TeamSync ts{C->vprog, s, s > 0 ? s - 1 : 0u, 0u, 0u};
                 ok = rel_stripe<true>(S, prof, frame, s, lane, ts);
             } else if (mode == DPM_REL16) {
-                ok = dp_fill_rel<false>(E.gv, E.plan_a, E.plan_b, E.slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, lane, 0, 1, nullptr);
+                ok = dp_fill_rel<false>(E.gv, E.plan, E.slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, lane, 0, 1, nullptr);
             } else {
                 ok = dp_fill<DP_NW32, false>(E.gv, E.slot, wsm, seq, V, L, a.sc, lane, 0, 1, nullptr);
             }

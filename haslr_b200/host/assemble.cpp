@@ -5,6 +5,11 @@
 // call for all edges; this file turns the answer into cns_supp lists and the reference's log), the per-edge consensus
 // call (:479-560 — here ONE batched hgpu_poa_batch call instead of a SPOA engine per edge per thread) and the
 // simple-path stitching (:607-810,1045-1077).
+//
+// Provenance note: asm.final.fa / .ann and the logs must match the reference byte for byte, so assemble_path and the log block of
+// calc_edge_coordinates follow the statement order and format strings of asm_assemble_single_path / asm_calc_single_edge_coordinates
+// (Assemble.cpp:624-755,157-363, GPLv3) closely: a behaviour-identical host port, not a redesign. It lives only in the host
+// binary / libhaslr_path.so; the CUDA library (libhaslr_b200.so) contains no reference-derived text.
 #include <algorithm>
 #include <cstring>
 #include <deque>

@@ -4,6 +4,11 @@
 // (other_node << 1) | other_strand, every edge stored with its twin) because the cleaning passes and all writers
 // are defined in terms of that iteration order. The passes restate the behaviour of the reference's
 // src/haslr_assemble/src/Cleaning.cpp and Backbone_graph.cpp; each function cites what it mirrors.
+//
+// Provenance note: the drop-in contract is byte-identical logs and GFA files, so detect_super_bubble / clean_super_bubbles and
+// clean_small_bubbles below follow the statement order of the reference's functions (Cleaning.cpp:488-560,563-648,7-57, GPLv3)
+// closely, down to its arithmetic quirks. They are a behaviour-identical host port, not a redesign, live only in the host
+// binary / libhaslr_path.so, and are never linked into the CUDA library (libhaslr_b200.so), which contains no reference-derived text.
 #include <algorithm>
 #include <queue>
 #include <set>

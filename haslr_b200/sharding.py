@@ -5,8 +5,19 @@ consensus at the end. torch.distributed is plumbing here: bac
 import numpy as np
 
 
+STRIPE = 512          # columns of one score-matrix stripe (csrc/poa_device.cuh: DP_NW16 x 2 x 32)
+GRAPH_ROWS = 3.0      # serial graph work per node, in units of one stripe row (csrc/poa.cu: POOL_GRAPH_ROWS)
+
+
+def alignment_cost(v, l):
+    """Estimated time of aligning a segment of l bases to a graph of v nodes, in stripe-row units: the fill computes whole
+    512-column stripes whatever the gap is, and traceback / graph update / topological sort cost ~3 stripe rows per node."""
+    return (v + 1.0) * (np.ceil((l + 1.0) / STRIPE) + GRAPH_ROWS)
+
+
 def edge_costs(seg_off, edge_seg_off):
-    """Estimated DP cells per edge from the segment lengths alone: sum_k |V_{k-1}| * L_k with |V| growing ~10 % per read."""
+    """Estimated time per edge from the segment lengths alone: sum over alignments of alignment_cost, |V| growing ~10 % per read
+    (the model csrc/poa.cu uses to share the device between size classes)."""
     seg_off = np.asarray(seg_off, dtype=np.int64)
     eso = np.asarray(edge_seg_off, dtype=np.int64)
     lens = np.diff(seg_off)
@@ -14,8 +25,9 @@ def edge_costs(seg_off, edge_seg_off):
     for e in range(len(eso) - 1):
         v = 0.0
         c = 0.0
-        for l in lens[eso[e]: eso[e + 1]]:
-            c += v * l
+        for k, l in enumerate(lens[eso[e]: eso[e + 1]]):
+            if k:
+                c += alignment_cost(v, float(l))
             v = max(v, float(l)) + 0.1 * l
         cost[e] = c
     return cost

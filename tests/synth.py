@@ -73,11 +73,15 @@ def _mix64(z, np_backend):
     return z ^ shr(z, 31)
 
 
-def hashed_batch(n_edges, seed, depth=6, length=1500, err=(0.04, 0.03, 0.02), device=None, edge0=0, chunk=4096):
+def hashed_batch(n_edges, seed, depth=6, length=1500, err=(0.04, 0.03, 0.02), device=None, edge0=0, chunk=4096, eids=None):
     """Per edge: truth of `length` bases, `depth` copies with per-base deletion / substitution and single-base insertions (the
     error model of poa_batch / SURVEY 8(d) cfg3). device None: numpy; else a torch device (the bases stay there).
+    eids: explicit edge ids (any subset, any order) instead of edge0 .. edge0 + n_edges.
     Returns (bases, seg_off uint64 numpy, edge_seg_off uint32 numpy)."""
     npb = device is None
+    if eids is not None:
+        eids = np.asarray(eids, dtype=np.int64)
+        n_edges = len(eids)
     if not npb:
         import torch
     p_ins, p_del, p_sub = err
@@ -88,14 +92,15 @@ def hashed_batch(n_edges, seed, depth=6, length=1500, err=(0.04, 0.03, 0.02), de
         for a in range(0, n_edges, chunk):
             e = min(chunk, n_edges - a)
             if npb:
-                eid = (np.arange(e, dtype=np.uint64) + np.uint64(edge0 + a))[:, None, None]
+                eid = (np.arange(e, dtype=np.uint64) + np.uint64(edge0 + a) if eids is None else eids[a: a + e].astype(np.uint64))[:, None, None]
                 rd = np.arange(depth, dtype=np.uint64)[None, :, None]
                 pos = np.arange(length, dtype=np.uint64)[None, None, :]
                 m32 = np.uint64(0xFFFFFFFF)
                 sh = lambda v, k: v << np.uint64(k)
                 u32 = lambda v: (v >> np.uint64(32)) & m32
             else:
-                eid = (torch.arange(e, dtype=torch.int64, device=device) + (edge0 + a))[:, None, None]
+                eid = (torch.arange(e, dtype=torch.int64, device=device) + (edge0 + a) if eids is None
+                       else torch.from_numpy(eids[a: a + e]).to(device))[:, None, None]
                 rd = torch.arange(depth, dtype=torch.int64, device=device)[None, :, None]
                 pos = torch.arange(length, dtype=torch.int64, device=device)[None, None, :]
                 m32 = 0xFFFFFFFF

@@ -96,6 +96,53 @@ def test_k4_adversarial_on_device_matches_reference_log(ctx, asm, seed, tmp_path
         assert best == ge["best"], e
 
 
+@pytest.mark.parametrize("seed", [1, 2])
+def test_resident_stages_equal_host_pointer_stages(asm, seed, tmp_path):
+    """The device-resident chain the binary runs (hgpu_paf_tokenize -> hgpu_hits_group -> hgpu_compact_lr_dev ->
+    hgpu_backbone_edges_dev -> hgpu_edge_coords_dev: nothing of the hit table comes back to the host) against the host-pointer
+    entry points on the same adversarial PAF text: identical offsets, elements, edge table and coordinates."""
+    import haslr_b200
+    a = golden_io.k4_adversarial(seed)
+    n_reads = len(a["read_len"])
+    uf = io_helpers.calc_uniq_freq(a["contig_len"], a["mean_kmer"])
+    c1, c2 = haslr_b200.Context(0), haslr_b200.Context(0)
+    try:
+        hits = c1.parse_paf(a["paf"])
+        read_off = np.searchsorted(hits["q_id"], np.arange(n_reads + 1), side="left").astype(np.uint32)
+        elems, off = c1.compact_lr(hits, read_off, a["mean_kmer"], uf)
+        key, soff, supp, keep = c1.backbone_edges(hits["t_id"][elems["hit"]], hits["is_rev"][elems["hit"]], off, 3)
+        rows, ops = c2.tokenize(a["paf"])
+        assert rows == len(hits["q_id"]) and ops == int(hits["cg_off"][-1])
+        assert np.array_equal(c2.hits_group(n_reads), read_off)
+        delems, dtid, drev, doff = c2.compact_lr_dev(n_reads, rows, a["mean_kmer"], uf)
+        assert np.array_equal(doff, off) and delems.tobytes() == elems.tobytes()
+        assert np.array_equal(dtid, hits["t_id"][elems["hit"]]) and np.array_equal(drev, hits["is_rev"][elems["hit"]])
+        dkey, dsoff, dsupp, dkeep = c2.backbone_edges_dev(doff, 3)
+        assert np.array_equal(dkey, key) and np.array_equal(dsoff, soff) and np.array_equal(dkeep, keep) and dsupp.tobytes() == supp.tobytes()
+        p = lambda x, t: x.ctypes.data_as(t)
+        coff = np.concatenate(([0], np.cumsum(a["contig_len"].astype(np.uint64)))).astype(np.uint64)
+        asm.asmhost_prepare.argtypes = [C.c_uint32, C.c_char_p, u64p, C.c_uint64, u64p, u32p, C.c_void_p, C.c_uint32, C.c_char_p]
+        n = asm.asmhost_prepare(len(a["contig_len"]), b"A" * int(coff[-1]), p(coff, u64p), len(key), p(key, u64p), p(soff, u32p), supp.ctypes.data, 3,
+                                str(tmp_path).encode())
+        e4 = np.zeros(4 * n, dtype=np.uint32); eso = np.zeros(n + 1, dtype=np.uint32); esupp = np.zeros(len(supp), dtype=oracle_ffi.EDGE_SUPP)
+        asm.asmhost_edges.argtypes = [u32p, u32p, C.c_void_p, C.c_uint32]
+        ns = asm.asmhost_edges(p(e4, u32p), p(eso, u32p), esupp.ctypes.data, len(esupp))
+        e4 = e4.reshape(n, 4); esupp = esupp[:ns]
+        rev = (e4[:, 1] | (e4[:, 3] << 1)).astype(np.uint8)
+        oe, os_ = c1.edge_coords(rev, eso, esupp, elems, off, a["read_len"], hits)
+        doe, dos = c2.edge_coords_dev(rev, eso, esupp, a["read_len"])
+        assert doe.tobytes() == oe.tobytes() and dos.tobytes() == os_.tobytes()
+        st = c2.stage_stats()
+        assert st["k0_rows"] == rows and st["k1_hits"] == rows and st["k4_supports"] == ns
+        # a support that names an element outside its compact read is refused by the kernel, not read
+        bad = esupp.copy(); bad["cmp_head"][0] = 1000
+        with pytest.raises(haslr_b200.HgpuError) as ei:
+            c2.edge_coords_dev(rev, eso, bad, a["read_len"])
+        assert ei.value.code == -1
+    finally:
+        c1.close(); c2.close()
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # invariants against the synthetic truth (no SPOA, no oracle involved)
 # ---------------------------------------------------------------------------------------------------------------------

@@ -70,3 +70,31 @@ def test_short_line_is_refused(ctx):
     with pytest.raises(haslr_b200.HgpuError) as ei:
         ctx.parse_paf(b"1\t2\t3\t4\t+\t5\t6\t7\t8\t9\t10\t11\tcg:Z:5M\n1\t2\t3\n")
     assert ei.value.code == -1 and "line 2" in str(ei.value)
+
+
+def test_cigar_run_total_beyond_32_bits_is_refused(monkeypatch):
+    """cg_off is 32-bit: a buffer whose CIGAR runs do not fit must fail with HGPU_E_UNSUPPORTED, not wrap (the totals are
+    scanned in 64 bits; the test adds a bias to the real total instead of tokenising 16 GB of text)."""
+    import haslr_b200
+    monkeypatch.setenv("HGPU_TEST_PAF_OPS_BIAS", str(2**32 - 2))
+    c = haslr_b200.Context(0)
+    try:
+        line = b"0\t100\t0\t50\t+\t1\t200\t0\t50\t50\t50\t60\tcg:Z:20M1I29M\n"
+        with pytest.raises(haslr_b200.HgpuError) as ei:
+            c.tokenize(line * 3)
+        assert ei.value.code == -5
+    finally:
+        c.close()
+
+
+def test_rows_out_of_read_order_are_refused(ctx):
+    import haslr_b200
+    row = lambda q: b"%d\t100\t0\t50\t+\t1\t200\t0\t50\t50\t50\t60\tcg:Z:50M\n" % q
+    ctx.tokenize(row(0) + row(2) + row(1))
+    with pytest.raises(haslr_b200.HgpuError) as ei:
+        ctx.hits_group(3)
+    assert ei.value.code == -1
+    ctx.tokenize(row(0) + row(2) + row(2))
+    assert ctx.hits_group(4).tolist() == [0, 1, 1, 3, 3]
+    with pytest.raises(haslr_b200.HgpuError):
+        ctx.hits_group(2)                    # read 2 named, two reads loaded
