@@ -236,8 +236,10 @@ def strong_scaling_leg(ctx, dist, rank, world, dev, args):
             "value": tot_b / 1e6 / (ms / 1e3), "unit": UNIT, "ms_per_pass": ms, "gcups": tot_c / (ms / 1e3) / 1e9, "n_gpus": world,
             "per_rank_ms": [r[0] for r in rows], "per_rank_kernel_ms": km, "per_rank_edges": [int(r[4]) for r in rows],
             "per_rank_cells": [r[2] for r in rows], "kernel_imbalance_max_over_mean": max(km) / (sum(km) / len(km)) if sum(km) > 0 else None,
-            "limiter": "per-rank kernel time (k_poa_pool on the rank's deep edges): the all-gather is < 1 % of a pass; the spread between ranks is "
-                       "the LPT estimate's error (cost model: |V| grows 7 % per read) plus the tail of each rank's largest edges"}
+            "limiter": "edges in flight per GPU: k_poa_pool needs ~16 deep edges per SM to keep the issue slots busy (deep_edges leg: 4 per SM run at "
+                       "half the rate of 16 per SM) and every edge keeps a serial critical path (traceback, graph update, topological sort); "
+                       "with 1/N of the set per rank the per-GPU rate falls before the deal's imbalance (kernel_imbalance_max_over_mean) or "
+                       "the all-gather (< 1 % of a pass) matter"}
 
 
 
@@ -528,32 +530,40 @@ def main():
     #      median 28 supporting reads over a 2.5 kb gap, graphs of ~10^4 nodes, most cells outside the plain int16 range)
     deep = None
     if world == 1 and not args.no_deep:
-        dd, dso, deo = gen_cfg3_torch(DEEP_EDGES, 77, dev, chunk=64, DEPTH=DEEP_DEPTH, GAP_LEN=DEEP_GAP)
-        dn = int(dso[-1])
-        dout = torch.empty(dn // DEEP_DEPTH * 2 + 4096, dtype=torch.uint8, device=dev)
-        for _ in range(2):
-            doff, dstat = ctx.poa_batch_dev(dd.data_ptr(), dso, deo, dout.data_ptr(), dout.numel(), *SCORES)
-        assert (dstat == 0).all(), f"deep edges: status {np.unique(dstat)}"
-        torch.cuda.synchronize()
-        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        d0.record()
-        for _ in range(2):
-            ctx.poa_batch_dev(dd.data_ptr(), dso, deo, dout.data_ptr(), dout.numel(), *SCORES)
-        d1.record(); torch.cuda.synchronize()
-        dst = ctx.poa_stats()
-        dms = d0.elapsed_time(d1) / 2
-        dchk, dcpu = None, None
-        if not args.no_cpu:
-            rc, roff, ccells, cdt, cnb = run_oracle_sample(dd.cpu().numpy(), dso, deo, 4, os.cpu_count() or 1)
-            assert np.array_equal(doff[:5], roff) and dout[: int(doff[4])].cpu().numpy().tobytes() == rc.tobytes(), "deep edges: consensus differs from the oracle"
-            dchk = "first 4 edges bit-exact vs oracle"
-            # the checker's own speed on those 4 edges (one edge per thread, so 4 host threads busy): context, not a baseline run
-            dcpu = {"edges": 4, "threads_busy": 4, "value": cnb / cdt / 1e6, "unit": UNIT, "gcups": ccells / cdt / 1e9}
-        deep = {"workload": f"{DEEP_EDGES} edges x {DEEP_DEPTH} supporting reads x {DEEP_GAP} bp gap (BASELINE config 2 edge shape)",
-                "value": dn / (dms / 1e3) / 1e6, "unit": UNIT, "ms_per_step": dms, "gcups": dst["cells"] / (dms / 1e3) / 1e9,
-                "alignments": dst["alignments"], "alignments_rel16": dst["alignments_rel16"], "alignments_i32": dst["alignments_i32"],
-                "kernels": "k_poa_edges_deep (+ k_poa_edges_team for the largest)", "check": dchk, "cpu_oracle_on_check": dcpu}
-        del dd, dout
+        deep = {}
+        for n_deep_edges, key in ((DEEP_EDGES, None), (4 * DEEP_EDGES, "saturated")):
+            dd, dso, deo = gen_cfg3_torch(n_deep_edges, 77, dev, chunk=64, DEPTH=DEEP_DEPTH, GAP_LEN=DEEP_GAP)
+            dn = int(dso[-1])
+            dout = torch.empty(dn // DEEP_DEPTH * 2 + 4096, dtype=torch.uint8, device=dev)
+            for _ in range(2):
+                doff, dstat = ctx.poa_batch_dev(dd.data_ptr(), dso, deo, dout.data_ptr(), dout.numel(), *SCORES)
+            assert (dstat == 0).all(), f"deep edges: status {np.unique(dstat)}"
+            torch.cuda.synchronize()
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            d0.record()
+            for _ in range(2):
+                ctx.poa_batch_dev(dd.data_ptr(), dso, deo, dout.data_ptr(), dout.numel(), *SCORES)
+            d1.record(); torch.cuda.synchronize()
+            dst = ctx.poa_stats()
+            dms = d0.elapsed_time(d1) / 2
+            dchk, dcpu = None, None
+            if not args.no_cpu and key is None:
+                rc, roff, ccells, cdt, cnb = run_oracle_sample(dd.cpu().numpy(), dso, deo, 4, os.cpu_count() or 1)
+                assert np.array_equal(doff[:5], roff) and dout[: int(doff[4])].cpu().numpy().tobytes() == rc.tobytes(), "deep edges: consensus differs from the oracle"
+                dchk = "first 4 edges bit-exact vs oracle"
+                # the checker's own speed on those 4 edges (one edge per thread, so 4 host threads busy): context, not a baseline run
+                dcpu = {"edges": 4, "threads_busy": 4, "value": cnb / cdt / 1e6, "unit": UNIT, "gcups": ccells / cdt / 1e9}
+            leg = {"workload": f"{n_deep_edges} edges x {DEEP_DEPTH} supporting reads x {DEEP_GAP} bp gap (BASELINE config 2 edge shape, "
+                               f"{n_deep_edges // 148} edges per SM)",
+                   "value": dn / (dms / 1e3) / 1e6, "unit": UNIT, "ms_per_step": dms, "gcups": dst["cells"] / (dms / 1e3) / 1e9,
+                   "kernel_ms": dst["ms_dp"], "alignments": dst["alignments"], "alignments_rel16": dst["alignments_rel16"],
+                   "alignments_i32": dst["alignments_i32"], "kernels": "k_poa_pool", "check": dchk, "cpu_oracle_on_check": dcpu}
+            if key is None:
+                deep = leg
+            else:
+                deep[key] = leg
+            del dd, dout
+            torch.cuda.empty_cache()
 
     # ---- the whole path (BASELINE config 2) through the path library
     whole = None

@@ -1,4 +1,6 @@
 // Context management of the C ABI (include/haslr_b200.h).
+#include <cstdlib>
+
 #include "common.cuh"
 
 extern "C" int hgpu_abi_version(void) { return 3; }   // 3: device-resident stages (hgpu_hits_group, *_dev), hgpu_stage_stats / hgpu_set_timing
@@ -19,6 +21,9 @@ extern "C" const char* hgpu_strerror(int code) {
 extern "C" int hgpu_create(int device, hgpu_t** out) {
     if (!out) return HGPU_E_INVALID;
     *out = nullptr;
+    // the POA scheduler runs up to 6 size classes + helpers side by side: give them hardware work queues of their own (only
+    // effective if the process has not initialised CUDA yet; poa.cu stays within the default 8 otherwise)
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) return HGPU_E_CUDA;   // no silent CPU path: the product needs a GPU

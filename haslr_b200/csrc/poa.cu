@@ -24,7 +24,8 @@ struct PoaPass {                 // one scheduling pass keeps its consensus pool
 struct PoaState {
     DevBuf<uint8_t> arena, ws, arena_team, ws_team, d_bases, d_out;
     DevBuf<uint64_t> seg_ptr, cons_pos, d_off;
-    DevBuf<uint32_t> seg_len, e_seg_off, items, status, cons_len, out_nodes, counters;
+    DevBuf<uint32_t> seg_len, e_seg_off, items, status, cons_len, out_nodes, counters, pool_tab32;
+    DevBuf<uint8_t> pool_tab8;
     DevBuf<unsigned long long> stats, pool_cursor;
     std::vector<std::unique_ptr<PoaPass>> passes;
     std::vector<std::unique_ptr<PoaPass>> spare;   // consensus pools of earlier calls, reused (a cudaMalloc/cudaFree pair per call costs tens of ms)
@@ -347,6 +348,8 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
         struct Cls { size_t a, b; uint64_t slot; WsLayout wl; uint32_t warps; bool deep; bool pool; uint32_t ctx_per_block, pool_blocks; double cells, work; };
         const uint32_t pool_blocks_max = 2u * (uint32_t)ctx->sm_count;              // k_poa_pool: two blocks of 8 warps per SM
         std::vector<Cls> classes;
+        constexpr uint64_t POOL_SMALL_SLOT = 8ull << 20;
+        uint32_t n_pool_classes = 0;
         size_t n_deep = 0;
         while (n_deep < est.size() && est[n_deep].deep) ++n_deep;
         size_t i = 0;
@@ -367,11 +370,15 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
             };
             plan(i, end, c);
             size_t j = end;
-            if (c.warps < mw || pool) {           // pool contexts are sized per class: always split where the slot estimate has halved
+            // pool contexts are sized per class: split where the slot estimate has halved - but not below POOL_SMALL_SLOT (small slots
+            // waste little when shared) and into at most POOL_MAX_CLASSES classes (the kernel's parameter block holds that many)
+            const bool split = pool ? (c.slot > POOL_SMALL_SLOT && n_pool_classes + 1 < (uint32_t)POOL_MAX_CLASSES) : c.warps < mw;
+            if (split) {
                 j = i + 1;
                 while (j < end && est[j].slot * 2 > c.slot) ++j;
                 plan(i, j, c);
             }
+            if (pool) ++n_pool_classes;
             c.b = j;
             for (size_t q = c.a; q < c.b; ++q) { c.cells += est[q].cells; c.work += est[q].work; }
             classes.push_back(c);
@@ -379,39 +386,108 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
         }
         if (classes.size() > 256) HGPU_FAIL(ctx, HGPU_E_INTERNAL, "too many size classes (%zu)", classes.size());
 
-        // ---- pool classes share the device at the same time: the resident blocks (two per SM) are split between them in
-        //      proportion to their estimated time (EdgeEst::work), so that they finish together; every block keeps as many edges in flight as
-        //      the class has for it (at most POOL_MAX_CTX) and the memory budget, shared the same way, allows
+        // ---- pool classes: ONE persistent kernel for all of them. Every block holds contexts of several classes (a context = a
+        //      slot + workspace of its class's size), dealt so that each class gets contexts in proportion to its estimated time
+        //      (EdgeEst::work) and every SM sees the same mix; a context whose class has run dry takes edges of the classes with
+        //      smaller slots. So the classes cannot finish at different times any more (they did: 367 ... 611 ms on config 2 as six
+        //      side-by-side kernels), and the few huge edges get the warps the small ones leave.
+        bool pool_launched = false;
         {
-            double pool_cells = 0; size_t n_pool = 0;
-            for (const Cls& c : classes) if (c.pool && c.warps) { pool_cells += c.work + 1.0; ++n_pool; }
-            if (n_pool) {
-                uint32_t left = pool_blocks_max;
-                uint64_t mem = 0;
-                for (Cls& c : classes) {
-                    if (!c.pool || !c.warps) continue;
-                    const uint32_t n_items = (uint32_t)(c.b - c.a);
-                    uint32_t b = (uint32_t)std::lround(pool_blocks_max * (c.work + 1.0) / pool_cells);
-                    b = std::max<uint32_t>(1, std::min<uint32_t>({b, n_items, c.warps, std::max<uint32_t>(left, 1u)}));
-                    left -= std::min(left, b);
-                    uint32_t E = S->cfg_pool_ctx ? S->cfg_pool_ctx : (n_items + b - 1) / b;
-                    E = std::max<uint32_t>(1, std::min<uint32_t>({E, (uint32_t)POOL_MAX_CTX, c.warps / b}));
-                    c.pool_blocks = std::min<uint32_t>(b, (n_items + E - 1) / E);
-                    c.ctx_per_block = E;
-                    mem += (uint64_t)c.pool_blocks * E * (c.slot + c.wl.bytes);
+            std::vector<size_t> pc;
+            for (size_t ci = 0; ci < classes.size(); ++ci) if (classes[ci].pool && classes[ci].warps) pc.push_back(ci);
+            if (!pc.empty()) {
+                const size_t K = pc.size();
+                double tot_work = 0; uint64_t tot_items = 0;
+                for (size_t k = 0; k < K; ++k) { tot_work += classes[pc[k]].work + 1.0; tot_items += classes[pc[k]].b - classes[pc[k]].a; }
+                // a context of class k may run edges of later classes: its workspace must hold their graphs too
+                for (size_t k = K; k-- > 1;)
+                    if (classes[pc[k]].wl.ncap > classes[pc[k - 1]].wl.ncap) classes[pc[k - 1]].wl = ws_layout(classes[pc[k]].wl.ncap, classes[pc[k]].wl.ecap);
+                const uint32_t blocks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(pool_blocks_max, tot_items));
+                uint32_t E = S->cfg_pool_ctx ? S->cfg_pool_ctx : (uint32_t)std::min<uint64_t>(POOL_MAX_CTX, (tot_items + blocks - 1) / blocks);
+                E = std::max<uint32_t>(1, std::min<uint32_t>(E, (uint32_t)POOL_MAX_CTX));
+                const uint32_t T = blocks * E;
+                // quotas: proportional to work, at least one, at most the class's edges; then within the memory budget
+                std::vector<uint32_t> quota(K);
+                uint32_t given = 0;
+                for (size_t k = 0; k < K; ++k) {
+                    const uint32_t n_items = (uint32_t)(classes[pc[k]].b - classes[pc[k]].a);
+                    uint32_t qk = (uint32_t)std::lround(T * (classes[pc[k]].work + 1.0) / tot_work);
+                    quota[k] = std::max<uint32_t>(1, std::min<uint32_t>({qk, n_items, classes[pc[k]].warps}));
+                    given += quota[k];
                 }
-                // over the budget: take contexts away where they cost most, one per block at a time
-                for (int guard = 0; mem > budget && guard < 4096; ++guard) {
-                    Cls* worst = nullptr; uint64_t wm = 0;
-                    for (Cls& c : classes) {
-                        if (!c.pool || !c.warps || c.ctx_per_block <= 1) continue;
-                        const uint64_t m = (uint64_t)c.pool_blocks * c.ctx_per_block * (c.slot + c.wl.bytes);
-                        if (m > wm) { wm = m; worst = &c; }
+                for (size_t k = 0; given > T && k < 64 * K; ++k) {            // rounding / minimums may overshoot: trim the largest quotas
+                    size_t w = 0;
+                    for (size_t q = 1; q < K; ++q) if (quota[q] > quota[w]) w = q;
+                    if (quota[w] <= 1) break;
+                    --quota[w]; --given;
+                }
+                for (bool grew = true; given < T && grew;) {                 // contexts left over: classes that still have more edges than contexts
+                    grew = false;
+                    for (size_t k = 0; k < K && given < T; ++k) {
+                        const uint32_t n_items = (uint32_t)(classes[pc[k]].b - classes[pc[k]].a);
+                        if (quota[k] < n_items && quota[k] < classes[pc[k]].warps) { ++quota[k]; ++given; grew = true; }
                     }
-                    if (!worst) break;
-                    worst->ctx_per_block -= 1;
-                    mem -= (uint64_t)worst->pool_blocks * (worst->slot + worst->wl.bytes);
                 }
+                auto mem_of = [&](size_t k) { return (uint64_t)quota[k] * (classes[pc[k]].slot + classes[pc[k]].wl.bytes); };
+                uint64_t mem = 0;
+                for (size_t k = 0; k < K; ++k) mem += mem_of(k);
+                for (int guard = 0; mem > budget && guard < 100000; ++guard) {
+                    size_t w = K;
+                    for (size_t q = 0; q < K; ++q) if (quota[q] > 1 && (w == K || mem_of(q) > mem_of(w))) w = q;
+                    if (w == K) break;
+                    mem -= classes[pc[w]].slot + classes[pc[w]].wl.bytes; --quota[w]; --given;
+                }
+                // deal the contexts: context g (block g / E) goes to the class furthest behind its quota, so every block gets the mix
+                std::vector<uint8_t> ctx_class(T, 0xFF);
+                std::vector<uint32_t> ctx_slot(T, 0), dealt(K, 0);
+                for (uint32_t g = 0; g < given && g < T; ++g) {
+                    // spread over blocks first: context g of the deal sits in block g % blocks, position g / blocks
+                    const uint32_t where = (g % blocks) * E + g / blocks;
+                    size_t best = K; double lag = -1e300;
+                    for (size_t k = 0; k < K; ++k) {
+                        if (dealt[k] >= quota[k]) continue;
+                        const double l = (double)(g + 1) * quota[k] / given - dealt[k];
+                        if (l > lag) { lag = l; best = k; }
+                    }
+                    if (best == K) break;
+                    ctx_class[where] = (uint8_t)best; ctx_slot[where] = dealt[best]++;
+                }
+                PoolArgs pa{};
+                uint64_t a_off = 0, w_off = 0;
+                for (size_t k = 0; k < K; ++k) { a_off += (uint64_t)quota[k] * classes[pc[k]].slot; w_off += (uint64_t)quota[k] * classes[pc[k]].wl.bytes; }
+                HGPU_CUDA(ctx, S->arena_team.ensure(a_off)); HGPU_CUDA(ctx, S->ws_team.ensure(w_off));
+                HGPU_CUDA(ctx, S->pool_tab8.ensure(T)); HGPU_CUDA(ctx, S->pool_tab32.ensure(T));
+                HGPU_CUDA(ctx, cudaMemcpyAsync(S->pool_tab8.p, ctx_class.data(), T, cudaMemcpyHostToDevice, st));
+                HGPU_CUDA(ctx, cudaMemcpyAsync(S->pool_tab32.p, ctx_slot.data(), (size_t)T * 4, cudaMemcpyHostToDevice, st));
+                S->st.arena_bytes = std::max<uint64_t>(S->st.arena_bytes, a_off);
+                budget -= std::min<uint64_t>(budget, a_off + w_off);
+                a_off = 0; w_off = 0;
+                for (size_t k = 0; k < K; ++k) {
+                    const Cls& c = classes[pc[k]];
+                    PoolClass& q = pa.cls[k];
+                    q.items = S->items.p + c.a; q.n_items = (uint32_t)(c.b - c.a); q.counter = S->counters.p + pc[k];
+                    q.ws = S->ws_team.p + w_off; q.wl = c.wl; q.arena = S->arena_team.p + a_off; q.slot_bytes = c.slot;
+                    a_off += (uint64_t)quota[k] * c.slot; w_off += (uint64_t)quota[k] * c.wl.bytes;
+                    if (S->verbose)
+                        fprintf(stderr, "[poa] attempt %d growth %.2f pool class %zu/%zu: %u edges, %u contexts, slot %.1f MB, ws %.1f MB, %.3e cells, work share %.1f %%\n",
+                                attempt, growth, k, K, q.n_items, quota[k], c.slot / 1048576.0, c.wl.bytes / 1048576.0, c.cells, 100.0 * (c.work + 1.0) / tot_work);
+                }
+                pa.n_cls = (uint32_t)K; pa.ctx_class = S->pool_tab8.p; pa.ctx_slot = S->pool_tab32.p;
+                PoaArgs& a = pa.a;
+                a.bases = d_bases; a.seg_ptr = S->seg_ptr.p; a.seg_len = S->seg_len.p; a.e_seg_off = S->e_seg_off.p;
+                a.status = S->status.p; a.cons_len = S->cons_len.p; a.cons_pos = S->cons_pos.p; a.out_nodes = S->out_nodes.p;
+                a.pool = pass->pool.p; a.pool_cap = pass->pool.n; a.pool_cursor = S->pool_cursor.p;
+                a.sc = sc; a.stats = S->stats.p; a.stop_round = opt.stop_round; a.force_i32 = opt.force_i32;
+                const size_t psmem = (size_t)POOL_WARPS * DP_SMEM_PER_WARP_DEEP + sizeof(PoolShared);
+                HGPU_CUDA(ctx, cudaFuncSetAttribute(k_poa_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+                HGPU_CUDA(ctx, cudaEventRecord(S->ev_fork, st));          // uploads and memsets above are on `st`
+                HGPU_CUDA(ctx, cudaStreamWaitEvent(S->stream2, S->ev_fork, 0));
+                k_poa_pool<<<blocks, 32 * POOL_WARPS, psmem, S->stream2>>>(pa, E);
+                HGPU_CUDA(ctx, cudaGetLastError());
+                HGPU_CUDA(ctx, cudaEventRecord(S->ev_join, S->stream2));
+                ctx->launches++; S->st.dp_launches++;
+                pool_launched = true;
+                if (S->verbose) fprintf(stderr, "[poa] k_poa_pool: %u blocks x %u contexts (%u in use), %.1f GB of slots\n", blocks, E, given, (a_off + w_off) / 1073741824.0);
             }
         }
 
@@ -424,6 +500,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
         for (size_t ci = 0; ci < classes.size(); ++ci) {
             Cls& c = classes[ci];
             const uint32_t n_items = (uint32_t)(c.b - c.a);
+            if (c.pool && c.warps) continue;                  // launched above, all pool classes in one kernel
             if (c.warps == 0) {
                 // does not fit the device budget even alone: report per edge, keep going
                 std::vector<uint32_t> code(1, ST_TOO_LARGE);
@@ -433,10 +510,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
                 continue;
             }
             uint32_t warps, blocks;
-            if (c.pool) {
-                blocks = c.pool_blocks;
-                warps = blocks * c.ctx_per_block;                              // = slots / workspaces of this class
-            } else {
+            {
                 warps = std::min<uint32_t>(c.warps, n_items ? n_items : 1);
                 blocks = (warps + DP_WARPS_PER_BLOCK - 1) / DP_WARPS_PER_BLOCK;
                 warps = blocks * DP_WARPS_PER_BLOCK;
@@ -493,11 +567,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
 #endif
                 if (const char* e = getenv("HGPU_PROBE")) { a.probe = (uint32_t)atoi(e); a.probe_round = 1; }
                 if (const char* e = getenv("HGPU_PROBE_ROUND")) a.probe_round = (uint32_t)atoi(e);
-                if (c.pool) {
-                    const size_t psmem = (size_t)POOL_WARPS * DP_SMEM_PER_WARP_DEEP + sizeof(PoolShared);
-                    HGPU_CUDA(ctx, cudaFuncSetAttribute(k_poa_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-                    k_poa_pool<<<ln.blocks, 32 * POOL_WARPS, psmem, ls>>>(a, c.ctx_per_block);
-                } else if (c.deep) k_poa_edges_deep<<<ln.blocks, 32 * DP_WARPS_PER_BLOCK, smem_deep, ls>>>(a);
+                if (c.deep) k_poa_edges_deep<<<ln.blocks, 32 * DP_WARPS_PER_BLOCK, smem_deep, ls>>>(a);
                 else k_poa_edges<<<ln.blocks, 32 * DP_WARPS_PER_BLOCK, smem, ls>>>(a);
                 HGPU_CUDA(ctx, cudaGetLastError());
                 ctx->launches++; S->st.dp_launches++;
@@ -508,7 +578,6 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
                 if (S->verbose) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, ls); vclass.push_back(e); }
                 if (S->verbose) {
                     double cc = 0, cmax = 0; for (size_t q = c.a; q < c.b; ++q) { cc += est[q].cells; cmax = std::max(cmax, est[q].cells); }
-                    if (c.pool) fprintf(stderr, "[poa] pool class %zu: %u blocks x %u contexts\n", ln.ci, ln.blocks, c.ctx_per_block);
                     fprintf(stderr, "[poa] attempt %d growth %.2f wave %zu/%zu class %zu/%zu%s: %u edges on %u warps, slot %.1f MB, ws %.1f MB, %.3e cells (largest edge %.3e)\n",
                             attempt, growth, wi, waves.size(), ln.ci, classes.size(), c.pool ? " (pool)" : c.deep ? " (deep)" : "", n_items, ln.warps, c.slot / 1048576.0, c.wl.bytes / 1048576.0, cc, cmax);
                 }
@@ -526,12 +595,12 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
                 cudaEventDestroy(vb); cudaEventDestroy(ve);
             }
         }
-        if (team_launched) {
+        if (team_launched || pool_launched) {
             HGPU_CUDA(ctx, cudaStreamWaitEvent(st, S->ev_join, 0));
             if (S->verbose) {
                 const auto t0 = std::chrono::steady_clock::now();
                 cudaStreamSynchronize(st);
-                fprintf(stderr, "[poa] team kernel outlasted the classes by %.1f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+                fprintf(stderr, "[poa] team / pool kernel outlasted the other classes by %.1f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
             }
         }
         if (S->timing) {

@@ -23,6 +23,21 @@ static constexpr uint32_t POOL_MAX_STRIPES = 32;          // alignments with mor
 enum : uint32_t { PS_IDLE = 0, PS_BUSY = 1, PS_FILL = 2, PS_GRAPH_READY = 3, PS_DONE = 4 };
 enum : int { PT_NONE = 0, PT_STRIPE = 1, PT_GRAPH = 2, PT_NEW = 3, PT_EXIT = 4 };
 
+// One size class of deep edges: its own queue, slot size and workspace layout. Classes are ordered by slot size, largest
+// first; a context whose own queue has run dry takes edges of the classes after its own (they fit its slot and workspace).
+static constexpr int POOL_MAX_CLASSES = 6;
+struct PoolClass {
+    const uint32_t* items; uint32_t n_items; uint32_t* counter;
+    uint8_t* ws; WsLayout wl; uint8_t* arena; uint64_t slot_bytes;
+};
+struct PoolArgs {
+    PoaArgs a;                           // everything that is not per class (a.items / a.ws / a.arena / a.wl / a.slot_bytes are unused)
+    PoolClass cls[POOL_MAX_CLASSES];
+    uint32_t n_cls;
+    const uint8_t* ctx_class;            // [blocks * n_ctx] class of every context (0xFF: none, the context stays idle)
+    const uint32_t* ctx_slot;            // [blocks * n_ctx] its slot / workspace index inside the class
+};
+
 struct PoolCtx {
     uint32_t state;
     uint32_t edge, k, R, s0;             // edge id, index of the segment being aligned, segments of the edge, its first segment
@@ -44,17 +59,21 @@ __device__ __forceinline__ uint32_t vld(const uint32_t* p) { return *reinterpret
 __device__ __forceinline__ void vst(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
 
 struct PoolEnv {                         // per-context global storage, bound on demand
-    GraphView gv; GraphScratch gs; uint32_t* hdr; uint32_t* plan; TopoRec* trec; uint8_t* slot;
+    GraphView gv; GraphScratch gs; uint32_t* hdr; uint32_t* plan; TopoRec* trec; uint8_t* slot; uint64_t slot_bytes; uint32_t cls;
 };
-__device__ __forceinline__ PoolEnv pool_env(const PoaArgs& a, uint32_t gctx) {
+__device__ __forceinline__ PoolEnv pool_env(const PoolArgs& pa, uint32_t gctx) {
     PoolEnv e;
-    uint8_t* wsb = a.ws + (uint64_t)gctx * a.wl.bytes;
-    e.gv = bind_graph(wsb, a.wl);
-    e.gs = bind_scratch(wsb, a.wl);
-    e.hdr = reinterpret_cast<uint32_t*>(wsb + a.wl.o_hdr);
-    e.plan = reinterpret_cast<uint32_t*>(wsb + a.wl.o_plan);
-    e.trec = reinterpret_cast<TopoRec*>(wsb + a.wl.o_trec);
-    e.slot = a.arena + (uint64_t)gctx * a.slot_bytes;
+    e.cls = pa.ctx_class[gctx];
+    const PoolClass& c = pa.cls[e.cls];
+    const uint32_t idx = pa.ctx_slot[gctx];
+    uint8_t* wsb = c.ws + (uint64_t)idx * c.wl.bytes;
+    e.gv = bind_graph(wsb, c.wl);
+    e.gs = bind_scratch(wsb, c.wl);
+    e.hdr = reinterpret_cast<uint32_t*>(wsb + c.wl.o_hdr);
+    e.plan = reinterpret_cast<uint32_t*>(wsb + c.wl.o_plan);
+    e.trec = reinterpret_cast<TopoRec*>(wsb + c.wl.o_trec);
+    e.slot = c.arena + (uint64_t)idx * c.slot_bytes;
+    e.slot_bytes = c.slot_bytes;
     return e;
 }
 
@@ -98,7 +117,8 @@ __device__ __noinline__ void pool_finish_edge(const PoaArgs& a, PoolEnv& E, Pool
 
 // Bring context C to its next fill: set up alignment k of the current edge, or finish the edge and start the next one from the
 // queue (several times over if edges have a single segment). Leaves state = PS_FILL or PS_DONE. Lane-uniform.
-__device__ __noinline__ void pool_advance(const PoaArgs& a, PoolEnv& E, PoolCtx* C, PoolShared* sh, uint32_t st, bool have_edge, int lane) {
+__device__ __noinline__ void pool_advance(const PoolArgs& pa, PoolEnv& E, PoolCtx* C, PoolShared* sh, uint32_t st, bool have_edge, int lane) {
+    const PoaArgs& a = pa.a;
     GraphView& gv = E.gv;
     while (true) {
         if (have_edge && st == ST_OK && vld(&C->k) < vld(&C->R)) {
@@ -107,7 +127,7 @@ __device__ __noinline__ void pool_advance(const PoaArgs& a, PoolEnv& E, PoolCtx*
             const uint32_t V = *gv.n_nodes, NE = *gv.n_edges, L = a.seg_len[s0 + k];
             const int mode = dp_mode_deep(a.sc, a.force_i32);
             if ((uint64_t)V + L > gv.ncap || (uint64_t)NE + L + 1 > gv.ecap) st = ST_CAPACITY;
-            else if (dp_slot_bytes(V, L, mode) > a.slot_bytes) st = ST_TOO_LARGE;
+            else if (dp_slot_bytes(V, L, mode) > E.slot_bytes) st = ST_TOO_LARGE;
             else {
                 const uint32_t NS = mode == DPM_REL16 ? Geo<DP_NW16, true>::stripes(L) : Geo<DP_NW32, false>::stripes(L);
                 if (lane == 0) {
@@ -128,15 +148,22 @@ __device__ __noinline__ void pool_advance(const PoaArgs& a, PoolEnv& E, PoolCtx*
         }
         // ---- the edge is complete (or failed): consensus, publish, next edge
         if (have_edge) pool_finish_edge(a, E, C, sh, st, lane);
-        uint32_t item = 0;
-        if (lane == 0) item = atomicAdd(a.counter, 1u);
-        item = __shfl_sync(FULL, item, 0);
-        if (item >= a.n_items) {
+        // next edge: the context's own class first, then the classes with smaller slots (their edges fit)
+        uint32_t e = 0xFFFFFFFFu;
+        if (lane == 0) {
+            for (uint32_t k = E.cls; k < pa.n_cls && e == 0xFFFFFFFFu; ++k) {
+                const PoolClass& c = pa.cls[k];
+                if (*reinterpret_cast<volatile uint32_t*>(c.counter) >= c.n_items) continue;
+                const uint32_t item = atomicAdd(c.counter, 1u);
+                if (item < c.n_items) e = c.items[item];
+            }
+        }
+        e = __shfl_sync(FULL, e, 0);
+        if (e == 0xFFFFFFFFu) {
             __threadfence_block();
             if (lane == 0) vst(&C->state, PS_DONE);
             return;
         }
-        const uint32_t e = a.items[item];
         const uint32_t s0 = a.e_seg_off[e], R = a.e_seg_off[e + 1] - s0;
         if (lane == 0) { C->edge = e; C->k = 1; C->R = R; C->s0 = s0; C->cells = 0; C->padded = 0; C->aln = 0; C->aln32 = 0; C->bases = 0; }
         __syncwarp();
@@ -158,7 +185,8 @@ __device__ __noinline__ void pool_advance(const PoaArgs& a, PoolEnv& E, PoolCtx*
 }
 
 // everything between two fills of a context
-__device__ __noinline__ void pool_graph_task(const PoaArgs& a, PoolEnv& E, PoolCtx* C, PoolShared* sh, uint8_t* wsm, int lane) {
+__device__ __noinline__ void pool_graph_task(const PoolArgs& pa, PoolEnv& E, PoolCtx* C, PoolShared* sh, uint8_t* wsm, int lane) {
+    const PoaArgs& a = pa.a;
     GraphView& gv = E.gv;
     const uint32_t V = vld(&C->V), L = vld(&C->L), k = vld(&C->k), s0 = vld(&C->s0);
     const int mode = (int)vld(&C->mode);
@@ -198,16 +226,20 @@ __device__ __noinline__ void pool_graph_task(const PoaArgs& a, PoolEnv& E, PoolC
     }
     if (lane == 0) C->k = k + 1;
     __syncwarp();
-    pool_advance(a, E, C, sh, st, true, lane);
+    pool_advance(pa, E, C, sh, st, true, lane);
 }
 
-__global__ void __launch_bounds__(32 * POOL_WARPS, 2) k_poa_pool(PoaArgs a, uint32_t n_ctx) {
+__global__ void __launch_bounds__(32 * POOL_WARPS, 2) k_poa_pool(const __grid_constant__ PoolArgs pa, uint32_t n_ctx) {
+    const PoaArgs& a = pa.a;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = lane_id();
     const uint32_t wib = threadIdx.x >> 5;
     uint8_t* wsm = smem_raw + (size_t)wib * DP_SMEM_PER_WARP_DEEP;
     PoolShared* sh = reinterpret_cast<PoolShared*>(smem_raw + (size_t)POOL_WARPS * DP_SMEM_PER_WARP_DEEP);
-    if (threadIdx.x < POOL_MAX_CTX) { sh->ctx[threadIdx.x].state = threadIdx.x < n_ctx ? PS_IDLE : PS_DONE; sh->ctx[threadIdx.x].claim = 0; sh->ctx[threadIdx.x].n_tasks = 0; }
+    if (threadIdx.x < POOL_MAX_CTX) {
+        const bool live = threadIdx.x < n_ctx && pa.ctx_class[blockIdx.x * n_ctx + threadIdx.x] != 0xFFu;
+        sh->ctx[threadIdx.x].state = live ? PS_IDLE : PS_DONE; sh->ctx[threadIdx.x].claim = 0; sh->ctx[threadIdx.x].n_tasks = 0;
+    }
     if (threadIdx.x < 5) sh->tot[threadIdx.x] = 0;
     __syncthreads();
     uint32_t idle_spins = 0;
@@ -254,11 +286,11 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, 2) k_poa_pool(PoaArgs a, uint
         idle_spins = 0;
         __threadfence_block();
         PoolCtx* C = &sh->ctx[c];
-        PoolEnv E = pool_env(a, blockIdx.x * n_ctx + c);
+        PoolEnv E = pool_env(pa, blockIdx.x * n_ctx + c);
         if (kind == PT_NEW) {
-            pool_advance(a, E, C, sh, ST_OK, false, lane);
+            pool_advance(pa, E, C, sh, ST_OK, false, lane);
         } else if (kind == PT_GRAPH) {
-            pool_graph_task(a, E, C, sh, wsm, lane);
+            pool_graph_task(pa, E, C, sh, wsm, lane);
         } else {
             const uint32_t V = vld(&C->V), L = vld(&C->L), k = vld(&C->k), s0 = vld(&C->s0), NS = vld(&C->NS);
             const int mode = (int)vld(&C->mode);

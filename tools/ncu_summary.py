@@ -55,9 +55,11 @@ SUBPHASE = [("--- sequence profile of this stripe", "fill.profile"), ("--- row 0
             ("// horizontal gaps = prefix maximum", "fill.scan"), ("// stream the row out", "fill.store"),
             ("// end cell: best Hhat", "tb.endcell"), ("// tile of the stored matrix", "tb.tile_load"),
             ("// (1) a run of diagonal moves", "tb.diag_run"), ("// (2) one generic step", "tb.generic"),
-            ("// SPOA's DFS from root", "topo.dfs"), ("// (A)+(B): node of every position", "add.AB"), ("// (B2): initialise new nodes", "add.B2"),
+            ("// SPOA's DFS from root", "topo.dfs"), ("// park row i-1: later rows read it", "rel.row_head"), ("// the first predecessor initialises the row", "rel.first_pred"),
+            ("// the others (never the previous rank", "rel.more_preds"), ("// generic walk: predecessors from the CSR", "rel.generic_row"),
+            ("// horizontal gaps = prefix maximum in hat space (see row16)", "rel.scan_store"), ("// --- row 0: Hhat = 0 everywhere, base 0", "rel.stripe_setup"), ("// (A)+(B): node of every position", "add.AB"), ("// (B2): initialise new nodes", "add.B2"),
             ("// (C): edges between consecutive", "add.C"), ("// heaviest-bundle consensus; node ids", "edge.consensus"), ("// publish", "edge.publish")]
-for fn in ("poa_device.cuh", "poa_graph.cuh"):
+for fn in ("poa_device.cuh", "poa_graph.cuh", "poa_fill_rel.cuh", "poa_pool.cuh"):
     marks = []
     for n, text in enumerate(open(os.path.join(ROOT, "haslr_b200", "csrc", fn)), 1):
         m = re.match(r"^(?:template.*>\s*)?(?:__device__|__global__|HGPU_HD|__host__ __device__)[^;]*?\b([a-zA-Z_0-9]+)\s*\(", text)
