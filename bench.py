@@ -353,7 +353,9 @@ def whole_path_leg(ctx, args, peak):
       f"4 B x {ps['cells']} DP cells + bases in + consensus out (SURVEY 8d)")
     kern[-1]["gcups"] = ps["cells"] / (ps["ms_dp"] / 1e3) / 1e9 if ps["ms_dp"] > 0 else None
     out = {
-        "workload": f"BASELINE config 2: synthetic {CFG2['genome'] // 1_000_000} Mb genome, {int(sz[0].value)} SRC contigs, {int(sz[1].value)} long reads "
+        "workload": ("BASELINE config 2" if CFG2["genome"] == 10_000_000 else f"BASELINE config 2's generator x {CFG2['genome'] // 10_000_000} "
+                     "(x 14 = config 4, D. melanogaster scale)") +
+                    f": synthetic {CFG2['genome'] // 1_000_000} Mb genome, {int(sz[0].value)} SRC contigs, {int(sz[1].value)} long reads "
                     f"({int(sz[2].value) / 1e6:.0f} Mbases), {int(sz[3].value) / 1e6:.0f} MB of PAF text ({rr['n_rows']} rows), seed {CFG2['seed']}",
         "boundary": "haslr_path_run (libhaslr_path.so above the C ABI): inputs in HOST memory -> consensus strings in HOST memory",
         "value": mb / dt, "unit": UNIT, "Mbases": mb, "s_per_pass": dt, "passes_timed": len(timed), "edges": rr["n_edges"],

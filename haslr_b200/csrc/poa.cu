@@ -55,6 +55,20 @@ struct PoaState {
     int verbose = 0;                  // HGPU_VERBOSE=1: pass / class plan and per-launch device time on stderr
 };
 
+// Grow one of the big per-context buffers. The memory budget counts what the state already holds as reusable, so when the
+// allocation fails the other arenas (sized by an earlier, differently shaped call) are given back and it is tried again.
+static cudaError_t ensure_big(PoaState* S, DevBuf<uint8_t>& buf, size_t bytes) {
+    if (bytes <= buf.n) return cudaSuccess;
+    cudaError_t e = buf.alloc(bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        (void)cudaGetLastError();
+        DevBuf<uint8_t>* all[4] = {&S->arena, &S->ws, &S->arena_team, &S->ws_team};
+        for (DevBuf<uint8_t>* b : all) if (b != &buf) b->release();
+        e = buf.alloc(bytes);
+    }
+    return e;
+}
+
 void poa_state_destroy(PoaState* s) {
     if (!s) return;
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -455,7 +469,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
                 PoolArgs pa{};
                 uint64_t a_off = 0, w_off = 0;
                 for (size_t k = 0; k < K; ++k) { a_off += (uint64_t)quota[k] * classes[pc[k]].slot; w_off += (uint64_t)quota[k] * classes[pc[k]].wl.bytes; }
-                HGPU_CUDA(ctx, S->arena_team.ensure(a_off)); HGPU_CUDA(ctx, S->ws_team.ensure(w_off));
+                HGPU_CUDA(ctx, ensure_big(S, S->arena_team, a_off)); HGPU_CUDA(ctx, ensure_big(S, S->ws_team, w_off));
                 HGPU_CUDA(ctx, S->pool_tab8.ensure(T)); HGPU_CUDA(ctx, S->pool_tab32.ensure(T));
                 HGPU_CUDA(ctx, cudaMemcpyAsync(S->pool_tab8.p, ctx_class.data(), T, cudaMemcpyHostToDevice, st));
                 HGPU_CUDA(ctx, cudaMemcpyAsync(S->pool_tab32.p, ctx_slot.data(), (size_t)T * 4, cudaMemcpyHostToDevice, st));
@@ -534,8 +548,8 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
             wave_a += na; wave_w += nw;
             arena_need = std::max(arena_need, wave_a); ws_need = std::max(ws_need, wave_w);
         }
-        HGPU_CUDA(ctx, S->arena.ensure(arena_need));
-        HGPU_CUDA(ctx, S->ws.ensure(ws_need));
+        HGPU_CUDA(ctx, ensure_big(S, S->arena, arena_need));
+        HGPU_CUDA(ctx, ensure_big(S, S->ws, ws_need));
         S->st.arena_bytes = std::max<uint64_t>(S->st.arena_bytes, arena_need);
         for (size_t wi = 0; wi < waves.size(); ++wi) {
             const std::vector<Launch>& wave = waves[wi];

@@ -128,6 +128,13 @@ __device__ __forceinline__ void st_row(uint4* p, uint4 v) {
 #endif
 }
 static constexpr int TB_ROWS = 32, TB_COLS = 32;
+#ifndef HGPU_TB_CPASYNC
+#define HGPU_TB_CPASYNC 1            // traceback tiles as asynchronous global -> shared copies (LDGSTS); 0 = LDG + STS (A/B: +0.4 % on config 3,
+#endif                               // +1.4 % on the deep shape, profiles/r2n_ab_cpasync.log)
+#ifndef HGPU_SHALLOW_TREC
+#define HGPU_SHALLOW_TREC 1          // the shallow kernel also runs the record-based topological sort (0: the in-list walking one; A/B on config 3 with
+                                     // the warp-cooperative walk: 1,506 vs 1,461 GCUPS, profiles/r2o_ab_strec.log)
+#endif
 
 // Geometry of one alignment inside a slot. P16: two int16 cells per word; I32: one int32 cell per word.
 template <int NW, bool P16>
@@ -1009,13 +1016,18 @@ __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8
     using G = Geo<NW, P16>;
     using T = TbTile<NW, P16, REL>;
     const int g = sc.g;
+    // the view's address escapes to the graph functions, so the compiler re-reads its fields from local memory around every
+    // store: keep what the walk uses in registers
+    const uint32_t* const T_meta0 = gv.meta0; const uint32_t* const T_pred_off = gv.pred_off; const uint32_t* const T_pred_rank = gv.pred_rank;
+    const uint32_t* const T_sinks = gv.sinks; int32_t* const T_aln_rank = gv.aln_rank; int32_t* const T_aln_pos = gv.aln_pos;
+    const uint32_t T_ncap = gv.ncap;
     SlotView<NW, P16, REL> sv;
     sv.bind(slot, V, L);
     // end cell: best Hhat[i][L] over sink nodes, first maximum in rank order (SPOA kNW)
     int best = INT32_MIN; uint32_t best_i = 0;
     const uint32_t n_sinks = *gv.n_sinks;
     for (uint32_t x = lane; x < n_sinks; x += 32) {                      // the sink list is built with the DP records
-        const uint32_t r = gv.sinks[x];
+        const uint32_t r = T_sinks[x];
         const int v = sv.load(r + 1, L);
         if (v > best) { best = v; best_i = r + 1; }
     }
@@ -1046,17 +1058,27 @@ __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8
                 if (gg * G::CPL <= jt) {
                     const uint4* src = Hu + ((uint64_t)row * NS + gg / 32u) * (G::UNITS * 32) + (gg & 31u);
                     uint4* dst = reinterpret_cast<uint4*>(tile + lane * T::LDW + gi * NW);
+#if HGPU_TB_CPASYNC
+                    // A/B: the same 16-byte pieces as asynchronous global -> shared copies (LDGSTS), no register staging
+#pragma unroll
+                    for (int u = 0; u < G::UNITS; ++u)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(dst + u)), "l"(src + u * 32) : "memory");
+#else
 #pragma unroll
                     for (int u = 0; u < G::UNITS; ++u) dst[u] = src[u * 32];
+#endif
                 }
             }
-            if (row >= 1) tm0[lane] = gv.meta0[row - 1];
+            if (row >= 1) tm0[lane] = T_meta0[row - 1];
             if (REL) {
                 const uint32_t sA = g0 / 32u;
                 tbase[lane] = sv.bcol[(uint64_t)sA * (V + 1) + row];
                 tbase[TB_ROWS + lane] = sv.bcol[(uint64_t)(sA + 1) * (V + 1) + row];
             }
         }
+#if HGPU_TB_CPASYNC
+        asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
         if (jt >= (uint32_t)lane + 1) tseq[lane] = (uint8_t)base_code(seq[jt - lane - 1]);
         // prefetch what the walk will most likely read next: the rows above the tile, one tile to the left
         if (it >= (uint32_t)(TB_ROWS - 1) + lane && jt >= (uint32_t)(TB_COLS - 1)) {
@@ -1124,13 +1146,13 @@ __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8
             const uint32_t run = (uint32_t)(__ffs(fm) - 1);
             const int kr = __shfl_sync(FULL, kind, run);
             const uint32_t extra = kr == 1 ? 1u : 0u;
-            if ((uint64_t)n_out + run + extra > gv.ncap) { bad = true; break; }
+            if ((uint64_t)n_out + run + extra > T_ncap) { bad = true; break; }
             if ((uint32_t)lane < run) {
-                gv.aln_rank[n_out + lane] = (int32_t)(ci - lane - 1);
-                gv.aln_pos[n_out + lane] = (int32_t)(cj - lane - 1);
+                T_aln_rank[n_out + lane] = (int32_t)(ci - lane - 1);
+                T_aln_pos[n_out + lane] = (int32_t)(cj - lane - 1);
             } else if ((uint32_t)lane == run && extra) {
-                gv.aln_rank[n_out + run] = di == 0 ? -1 : (int32_t)(ci - run - 1);
-                gv.aln_pos[n_out + run] = dj == 0 ? -1 : (int32_t)(cj - run - 1);
+                T_aln_rank[n_out + run] = di == 0 ? -1 : (int32_t)(ci - run - 1);
+                T_aln_pos[n_out + run] = dj == 0 ? -1 : (int32_t)(cj - run - 1);
             }
             const uint32_t xdi = __shfl_sync(FULL, di, run), xdj = __shfl_sync(FULL, dj, run);
             n_out += run + extra; ci -= run; cj -= run;
@@ -1150,28 +1172,28 @@ __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8
                 uint32_t pi = i, pj = j;
                 bool found = false;
                 if (i != 0) {
-                    const uint32_t m0 = gv.meta0[i - 1];
+                    const uint32_t m0 = T_meta0[i - 1];
                     const uint32_t code = m0 & 3u, npc = (m0 >> 3) & 3u, d0 = meta_d0(m0), m1 = meta_d1(m0);
                     uint32_t np = npc, cs = 0;
                     if (npc == 0) np = 1;
-                    if (npc == 3) { cs = gv.pred_off[i - 1]; np = gv.pred_off[i] - cs; }
+                    if (npc == 3) { cs = T_pred_off[i - 1]; np = T_pred_off[i] - cs; }
                     if (j != 0) {
                         const int dsc = ((uint32_t)base_code(seq[j - 1]) == code) ? sc.sm : sc.sx;
                         for (uint32_t x = 0; x < np && !found; ++x) {
-                            uint32_t prow = npc == 0 ? 0 : npc == 3 ? gv.pred_rank[cs + x] + 1 : i - (x == 0 ? d0 : m1);
+                            uint32_t prow = npc == 0 ? 0 : npc == 3 ? T_pred_rank[cs + x] + 1 : i - (x == 0 ? d0 : m1);
                             if (val == getH(prow, j - 1) + dsc) { pi = prow; pj = j - 1; found = true; }
                         }
                     }
                     for (uint32_t x = 0; x < np && !found; ++x) {
-                        uint32_t prow = npc == 0 ? 0 : npc == 3 ? gv.pred_rank[cs + x] + 1 : i - (x == 0 ? d0 : m1);
+                        uint32_t prow = npc == 0 ? 0 : npc == 3 ? T_pred_rank[cs + x] + 1 : i - (x == 0 ? d0 : m1);
                         if (val == getH(prow, j) + g) { pi = prow; pj = j; found = true; }
                     }
                 }
                 if (!found && j != 0 && val == getH(i, j - 1)) { pi = i; pj = j - 1; found = true; }
-                if (!found || n_out >= gv.ncap) { bad = true; }
+                if (!found || n_out >= T_ncap) { bad = true; }
                 else {
-                    gv.aln_rank[n_out] = (pi == i) ? -1 : (int32_t)(i - 1);
-                    gv.aln_pos[n_out] = (pj == j) ? -1 : (int32_t)(j - 1);
+                    T_aln_rank[n_out] = (pi == i) ? -1 : (int32_t)(i - 1);
+                    T_aln_pos[n_out] = (pj == j) ? -1 : (int32_t)(j - 1);
                     ++n_out;
                     ci = pi; cj = pj;
                 }
@@ -1219,31 +1241,33 @@ __device__ __forceinline__ void w_init_chain(GraphView& g, const uint8_t* seq, u
 // iteration) through the same stages together: the round trips of the four overlap.
 __device__ __noinline__ void w_build_meta(GraphView& g, int lane) {
     const uint32_t N = *g.n_nodes;
+    // the view lives in the caller's frame: keep the arrays this function walks in registers
+    auto* const L_rank2node = g.rank2node; auto* const L_in_head = g.in_head; auto* const L_code = g.code; auto* const L_out_head = g.out_head; auto* const L_e_begin = g.e_begin; auto* const L_e_next_in = g.e_next_in; auto* const L_node2rank = g.node2rank; auto* const L_pred_off = g.pred_off; auto* const L_pred_rank = g.pred_rank; auto* const L_meta0 = g.meta0; auto* const L_sinks = g.sinks;
     constexpr int K = 4;
     uint32_t running = 0, n_sinks = 0;
     for (uint32_t r0 = 0; r0 < N; r0 += 32 * K) {
         uint32_t v[K], ih[K], cd[K], oh[K], b0[K], b1[K], n1[K], n2[K], q0[K], q1[K], deg[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) { const uint32_t r = r0 + k * 32 + lane; v[k] = r < N ? g.rank2node[r] : NIL; }
+        for (int k = 0; k < K; ++k) { const uint32_t r = r0 + k * 32 + lane; v[k] = r < N ? L_rank2node[r] : NIL; }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             ih[k] = NIL; cd[k] = 0; oh[k] = NIL;
-            if (v[k] != NIL) { ih[k] = g.in_head[v[k]]; cd[k] = g.code[v[k]]; oh[k] = g.out_head[v[k]]; }
+            if (v[k] != NIL) { ih[k] = L_in_head[v[k]]; cd[k] = L_code[v[k]]; oh[k] = L_out_head[v[k]]; }
         }
 #pragma unroll
-        for (int k = 0; k < K; ++k) { b0[k] = NIL; n1[k] = NIL; if (ih[k] != NIL) { b0[k] = g.e_begin[ih[k]]; n1[k] = g.e_next_in[ih[k]]; } }
+        for (int k = 0; k < K; ++k) { b0[k] = NIL; n1[k] = NIL; if (ih[k] != NIL) { b0[k] = L_e_begin[ih[k]]; n1[k] = L_e_next_in[ih[k]]; } }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             q0[k] = 0; b1[k] = NIL; n2[k] = NIL;
-            if (b0[k] != NIL) q0[k] = g.node2rank[b0[k]];
-            if (n1[k] != NIL) { b1[k] = g.e_begin[n1[k]]; n2[k] = g.e_next_in[n1[k]]; }
+            if (b0[k] != NIL) q0[k] = L_node2rank[b0[k]];
+            if (n1[k] != NIL) { b1[k] = L_e_begin[n1[k]]; n2[k] = L_e_next_in[n1[k]]; }
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             q1[k] = 0;
-            if (b1[k] != NIL) q1[k] = g.node2rank[b1[k]];
+            if (b1[k] != NIL) q1[k] = L_node2rank[b1[k]];
             deg[k] = (ih[k] != NIL) + (n1[k] != NIL);
-            for (uint32_t x = n2[k]; x != NIL; x = g.e_next_in[x]) ++deg[k];       // three or more in-edges: rare
+            for (uint32_t x = n2[k]; x != NIL; x = L_e_next_in[x]) ++deg[k];       // three or more in-edges: rare
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -1258,22 +1282,22 @@ __device__ __noinline__ void w_build_meta(GraphView& g, int lane) {
             bool is_sink = false;
             if (v[k] != NIL) {
                 const uint32_t base = cd[k] | (oh[k] == NIL ? META_SINK : 0u);
-                g.pred_off[r] = off;
+                L_pred_off[r] = off;
                 uint32_t d0 = 0, d1 = 0;
-                if (deg[k] >= 1) { g.pred_rank[off] = q0[k]; d0 = r - q0[k]; }
-                if (deg[k] >= 2) { g.pred_rank[off + 1] = q1[k]; d1 = r - q1[k]; }
+                if (deg[k] >= 1) { L_pred_rank[off] = q0[k]; d0 = r - q0[k]; }
+                if (deg[k] >= 2) { L_pred_rank[off + 1] = q1[k]; d1 = r - q1[k]; }
                 uint32_t np = 2;
-                for (uint32_t x = n2[k]; x != NIL; x = g.e_next_in[x]) g.pred_rank[off + np++] = g.node2rank[g.e_begin[x]];
-                g.meta0[r] = meta_pack(base, r, deg[k], d0, d1);
+                for (uint32_t x = n2[k]; x != NIL; x = L_e_next_in[x]) L_pred_rank[off + np++] = L_node2rank[L_e_begin[x]];
+                L_meta0[r] = meta_pack(base, r, deg[k], d0, d1);
                 is_sink = (base & META_SINK) != 0;
             }
             const unsigned sm_ = __ballot_sync(FULL, is_sink);
-            if (is_sink) g.sinks[n_sinks + __popc(sm_ & ((1u << lane) - 1))] = r;
+            if (is_sink) L_sinks[n_sinks + __popc(sm_ & ((1u << lane) - 1))] = r;
             n_sinks += __popc(sm_);
             running += __shfl_sync(FULL, incl, 31);
         }
     }
-    if (lane == 0) { g.pred_off[N] = running; *g.n_sinks = n_sinks; }
+    if (lane == 0) { L_pred_off[N] = running; *g.n_sinks = n_sinks; }
     __syncwarp();
 }
 
@@ -1292,14 +1316,16 @@ static constexpr uint32_t ABSENT = 0xFFFFFFFEu;
 
 __device__ __noinline__ uint32_t w_add_alignment(GraphView& g, GraphScratch& s, const uint8_t* seq, uint32_t L, int lane) {
     const uint32_t n = *g.aln_len, N0 = *g.n_nodes, E0 = *g.n_edges;
+    // the view lives in the caller's frame: keep the arrays this function walks in registers
+    auto* const L_aln_pos = g.aln_pos; auto* const L_aln_rank = g.aln_rank; auto* const L_rank2node = g.rank2node; auto* const L_code = g.code; auto* const L_aligned = g.aligned; auto* const L_in_head = g.in_head; auto* const L_in_tail = g.in_tail; auto* const L_out_head = g.out_head; auto* const L_e_begin = g.e_begin; auto* const L_e_end = g.e_end; auto* const L_e_w = g.e_w; auto* const L_e_next_in = g.e_next_in; auto* const L_e_next_out = g.e_next_out;
     if (n == 0 || 3ull * L > s.stack_cap) return 0xFFFFFFFFu;
     if ((uint64_t)N0 + L > g.ncap || (uint64_t)E0 + L + 1 > g.ecap) return ST_CAPACITY;
-    uint32_t* by_j = s.stack; uint32_t* nid = by_j + L; uint32_t* alto = nid + L;
+    uint32_t* const by_j = s.stack; uint32_t* const nid = by_j + L; uint32_t* const alto = nid + L;
     for (uint32_t j = lane; j < L; j += 32) by_j[j] = ABSENT;
     __syncwarp();
     for (uint32_t t = lane; t < n; t += 32) {
-        const int32_t pos = g.aln_pos[t];
-        if (pos != -1) by_j[pos] = (uint32_t)g.aln_rank[t];     // rank, or 0xFFFFFFFF for an insertion
+        const int32_t pos = L_aln_pos[t];
+        if (pos != -1) by_j[pos] = (uint32_t)L_aln_rank[t];     // rank, or 0xFFFFFFFF for an insertion
     }
     __syncwarp();
     // (A)+(B): node of every position; new nodes numbered in alignment order. Four positions per lane (j0 + 32k + lane)
@@ -1316,20 +1342,20 @@ __device__ __noinline__ uint32_t w_add_alignment(GraphView& g, GraphScratch& s, 
             if (j < L) { rk[k] = by_j[j]; c[k] = base_code(seq[j]); if (rk[k] == ABSENT) full = false; }
         }
 #pragma unroll
-        for (int k = 0; k < K; ++k) an[k] = (rk[k] < 0xFFFFFFFEu) ? g.rank2node[rk[k]] : NIL;      // neither ABSENT nor an insertion
+        for (int k = 0; k < K; ++k) an[k] = (rk[k] < 0xFFFFFFFEu) ? L_rank2node[rk[k]] : NIL;      // neither ABSENT nor an insertion
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             ca[k] = 0; o0[k] = NIL; o1[k] = NIL; o2[k] = NIL;
-            if (an[k] != NIL) { ca[k] = g.code[an[k]]; o0[k] = g.aligned[3 * an[k]]; o1[k] = g.aligned[3 * an[k] + 1]; o2[k] = g.aligned[3 * an[k] + 2]; }
+            if (an[k] != NIL) { ca[k] = L_code[an[k]]; o0[k] = L_aligned[3 * an[k]]; o1[k] = L_aligned[3 * an[k] + 1]; o2[k] = L_aligned[3 * an[k] + 2]; }
         }
         uint32_t c0[K], c1[K], c2[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             if (o0[k] == NIL) { o1[k] = NIL; o2[k] = NIL; } else if (o1[k] == NIL) o2[k] = NIL;
             const bool look = an[k] != NIL && ca[k] != c[k];                                            // the aligned nodes matter only on a mismatch
-            c0[k] = (look && o0[k] != NIL) ? g.code[o0[k]] : 4u;
-            c1[k] = (look && o1[k] != NIL) ? g.code[o1[k]] : 4u;
-            c2[k] = (look && o2[k] != NIL) ? g.code[o2[k]] : 4u;
+            c0[k] = (look && o0[k] != NIL) ? L_code[o0[k]] : 4u;
+            c1[k] = (look && o1[k] != NIL) ? L_code[o1[k]] : 4u;
+            c2[k] = (look && o2[k] != NIL) ? L_code[o2[k]] : 4u;
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -1355,22 +1381,22 @@ __device__ __noinline__ uint32_t w_add_alignment(GraphView& g, GraphScratch& s, 
     for (uint32_t j = lane; j < L; j += 32) {
         const uint32_t v = nid[j];
         if (v < N0) continue;
-        g.code[v] = (uint8_t)base_code(seq[j]);
-        g.in_head[v] = NIL; g.in_tail[v] = NIL; g.out_head[v] = NIL;
+        L_code[v] = (uint8_t)base_code(seq[j]);
+        L_in_head[v] = NIL; L_in_tail[v] = NIL; L_out_head[v] = NIL;
         uint32_t a3[3] = {NIL, NIL, NIL};
         const uint32_t a = alto[j];
         if (a != NIL) {
             int cnt = 0;
             for (int q = 0; q < 3; ++q) {
-                const uint32_t o = g.aligned[3 * a + q];
+                const uint32_t o = L_aligned[3 * a + q];
                 if (o == NIL) break;
                 a3[cnt++] = o;
-                for (int z = 0; z < 3; ++z) if (g.aligned[3 * o + z] == NIL) { g.aligned[3 * o + z] = v; break; }
+                for (int z = 0; z < 3; ++z) if (L_aligned[3 * o + z] == NIL) { L_aligned[3 * o + z] = v; break; }
             }
             a3[cnt] = a;
-            for (int z = 0; z < 3; ++z) if (g.aligned[3 * a + z] == NIL) { g.aligned[3 * a + z] = v; break; }
+            for (int z = 0; z < 3; ++z) if (L_aligned[3 * a + z] == NIL) { L_aligned[3 * a + z] = v; break; }
         }
-        g.aligned[3 * v] = a3[0]; g.aligned[3 * v + 1] = a3[1]; g.aligned[3 * v + 2] = a3[2];
+        L_aligned[3 * v] = a3[0]; L_aligned[3 * v + 1] = a3[1]; L_aligned[3 * v + 2] = a3[2];
     }
     __syncwarp();
     // (C): edges between consecutive positions, weight 2 (both bases contribute 1); four positions per lane again
@@ -1384,7 +1410,7 @@ __device__ __noinline__ uint32_t w_add_alignment(GraphView& g, GraphScratch& s, 
             if (j < L) { b[k] = nid[j - 1]; e[k] = nid[j]; }
         }
 #pragma unroll
-        for (int k = 0; k < K; ++k) { x[k] = NIL; tl[k] = NIL; if (b[k] != NIL) { x[k] = g.out_head[b[k]]; tl[k] = g.in_tail[e[k]]; } }
+        for (int k = 0; k < K; ++k) { x[k] = NIL; tl[k] = NIL; if (b[k] != NIL) { x[k] = L_out_head[b[k]]; tl[k] = L_in_tail[e[k]]; } }
         const uint32_t oh0 = x[0], oh1 = x[1], oh2 = x[2], oh3 = x[3];
         const uint32_t oh[K] = {oh0, oh1, oh2, oh3};
         bool hit[K] = {false, false, false, false};
@@ -1392,7 +1418,7 @@ __device__ __noinline__ uint32_t w_add_alignment(GraphView& g, GraphScratch& s, 
 #pragma unroll
         for (int step = 0; step < 2; ++step) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) { xe[k] = NIL; xn[k] = NIL; if (x[k] != NIL && !hit[k]) { xe[k] = g.e_end[x[k]]; xn[k] = g.e_next_out[x[k]]; } }
+            for (int k = 0; k < K; ++k) { xe[k] = NIL; xn[k] = NIL; if (x[k] != NIL && !hit[k]) { xe[k] = L_e_end[x[k]]; xn[k] = L_e_next_out[x[k]]; } }
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 if (x[k] != NIL && !hit[k]) {
@@ -1402,8 +1428,8 @@ __device__ __noinline__ uint32_t w_add_alignment(GraphView& g, GraphScratch& s, 
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            while (x[k] != NIL && !hit[k]) { if (g.e_end[x[k]] == e[k]) hit[k] = true; else x[k] = g.e_next_out[x[k]]; }
-            if (hit[k]) g.e_w[x[k]] += 2;
+            while (x[k] != NIL && !hit[k]) { if (L_e_end[x[k]] == e[k]) hit[k] = true; else x[k] = L_e_next_out[x[k]]; }
+            if (hit[k]) L_e_w[x[k]] += 2;
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -1411,12 +1437,12 @@ __device__ __noinline__ uint32_t w_add_alignment(GraphView& g, GraphScratch& s, 
             const unsigned m = __ballot_sync(FULL, need);
             if (need) {
                 const uint32_t nx = E0 + e_new + __popc(m & ((1u << lane) - 1));
-                g.e_begin[nx] = b[k]; g.e_end[nx] = e[k]; g.e_w[nx] = 2;
-                g.e_next_in[nx] = NIL;
-                g.e_next_out[nx] = oh[k];
-                g.out_head[b[k]] = nx;
-                if (tl[k] == NIL) g.in_head[e[k]] = nx; else g.e_next_in[tl[k]] = nx;
-                g.in_tail[e[k]] = nx;
+                L_e_begin[nx] = b[k]; L_e_end[nx] = e[k]; L_e_w[nx] = 2;
+                L_e_next_in[nx] = NIL;
+                L_e_next_out[nx] = oh[k];
+                L_out_head[b[k]] = nx;
+                if (tl[k] == NIL) L_in_head[e[k]] = nx; else L_e_next_in[tl[k]] = nx;
+                L_in_tail[e[k]] = nx;
             }
             e_new += __popc(m);
         }
@@ -1449,6 +1475,8 @@ static_assert(sizeof(TopoRec) == 32, "record layout");
 // all records, lane-parallel, four nodes per lane in flight (the chain of an in-list is still dependent loads, but 128 of them overlap)
 __device__ __noinline__ void w_build_trec(const GraphView& g, TopoRec* rec, int lane) {
     const uint32_t N = *g.n_nodes;
+    // the view lives in the caller's frame: keep the arrays this function walks in registers
+    auto* const L_in_head = g.in_head; auto* const L_aligned = g.aligned; auto* const L_e_begin = g.e_begin; auto* const L_e_next_in = g.e_next_in;
     constexpr int K = 4;
     for (uint32_t v0 = 0; v0 < N; v0 += 32 * K) {
         uint32_t x[K];
@@ -1460,13 +1488,13 @@ __device__ __noinline__ void w_build_trec(const GraphView& g, TopoRec* rec, int 
 #pragma unroll
             for (int q = 0; q < 4; ++q) r[k].p[q] = NIL;
             r[k].a[0] = r[k].a[1] = r[k].a[2] = NIL; r[k].more = NIL;
-            if (v < N) { x[k] = g.in_head[v]; r[k].a[0] = g.aligned[3 * v]; r[k].a[1] = g.aligned[3 * v + 1]; r[k].a[2] = g.aligned[3 * v + 2]; }
+            if (v < N) { x[k] = L_in_head[v]; r[k].a[0] = L_aligned[3 * v]; r[k].a[1] = L_aligned[3 * v + 1]; r[k].a[2] = L_aligned[3 * v + 2]; }
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                if (x[k] != NIL) { r[k].p[q] = g.e_begin[x[k]]; x[k] = g.e_next_in[x[k]]; }
+                if (x[k] != NIL) { r[k].p[q] = L_e_begin[x[k]]; x[k] = L_e_next_in[x[k]]; }
             }
         }
 #pragma unroll
@@ -1487,6 +1515,10 @@ __device__ __noinline__ void w_build_trec(const GraphView& g, TopoRec* rec, int 
 __device__ __noinline__ int w_toposort(GraphView& g, const TopoRec* rec, uint8_t* wsm, int lane) {
     const uint32_t N = *g.n_nodes;
     if (N > TOPO_BM_WORDS * 32) return 0;
+    // the view lives in the caller's frame (local memory): keep what the loops store through in registers
+    uint32_t* const r2n = g.rank2node; uint32_t* const n2r = g.node2rank;
+    const uint32_t* const e_begin = g.e_begin; const uint32_t* const e_next_in = g.e_next_in;
+    const uint32_t step_limit = 16u * (N + *g.n_edges) + 1024u;
     uint32_t* perm = reinterpret_cast<uint32_t*>(wsm);
     uint32_t* nochk = perm + TOPO_BM_WORDS;
     uint32_t* stk = nochk + TOPO_BM_WORDS;
@@ -1530,7 +1562,7 @@ __device__ __noinline__ int w_toposort(GraphView& g, const TopoRec* rec, uint8_t
             const unsigned em = __ballot_sync(FULL, emit);
             if (emit) {
                 const uint32_t r = nr + __popc(em & ((1u << lane) - 1));
-                g.rank2node[r] = i; g.node2rank[i] = r;
+                r2n[r] = i; n2r[i] = r;
             }
             if (lane == 0 && em) perm[i0 >> 5] |= em;
             nr += __popc(em);
@@ -1547,34 +1579,38 @@ __device__ __noinline__ int w_toposort(GraphView& g, const TopoRec* rec, uint8_t
                 constexpr uint32_t EXPANDED = 0x80000000u, IDMASK = 0x3FFFFFFFu;
                 const uint32_t* recw = reinterpret_cast<const uint32_t*>(rec);
                 uint32_t sp = 1, guard = 0;
-                const uint32_t limit = 16u * (N + *g.n_edges) + 1024u;
-                if (lane == 0) stk[0] = i0 + f;
+                const uint32_t limit = step_limit;
+                uint32_t top = i0 + f;                                                // the top of the stack stays in a register (uniform)
+                if (lane == 0) stk[0] = top;
                 __syncwarp();
                 while (sp > 0) {
                     if (++guard > limit) { okflag = 0; break; }
-                    const uint32_t self = sp - 1;
-                    const uint32_t top = stk[self];                                   // same address for all lanes: a broadcast
                     const uint32_t v = top & IDMASK;
-                    if (is_perm(v)) { --sp; continue; }
-                    const bool chk = !((nochk[v >> 5] >> (v & 31)) & 1u);
+                    // everything this visit may need is requested at once: the node's two bitmap words, its record, the entry below it
+                    const uint32_t pw = perm[v >> 5], nw = nochk[v >> 5];
                     const uint32_t child = lane < 8 ? recw[8 * (size_t)v + lane] : NIL;   // words 0-3 in-edge tails, 4-6 aligned nodes, 7 fifth in-edge
-                    bool vvalid = true;
+                    const uint32_t below = sp >= 2 ? stk[sp - 2] : 0u;
+                    if ((pw >> (v & 31)) & 1u) { --sp; top = below; continue; }
+                    const bool chk = !((nw >> (v & 31)) & 1u);
                     if (!(top & EXPANDED)) {
                         const uint32_t more = __shfl_sync(FULL, child, 7);
                         if (more == NIL) {
                             const bool mine = lane < 4 || (lane < 7 && chk);
                             const bool unem = mine && child != NIL && !is_perm(child);
                             const unsigned m = __ballot_sync(FULL, unem);
-                            const uint32_t n = (uint32_t)__popc(m);
-                            if (n) {
+                            if (m) {
+                                const uint32_t n = (uint32_t)__popc(m);
                                 if (sp + n > TOPO_STACK) { okflag = 0; break; }
                                 if (unem) {
                                     stk[sp + __popc(m & ((1u << lane) - 1u))] = child;
                                     if (lane >= 4) atomicOr(&nochk[child >> 5], 1u << (child & 31));
                                     asm volatile("prefetch.global.L1 [%0];" :: "l"(rec4 + 2 * (size_t)child));
                                 }
-                                if (lane == 0) stk[self] = v | EXPANDED;
-                                sp += n; vvalid = false;
+                                if (lane == 0) stk[sp - 1] = v | EXPANDED;
+                                top = __shfl_sync(FULL, child, 31 - __clz(m));        // the last child pushed is visited first
+                                sp += n;
+                                __syncwarp();
+                                continue;
                             }
                         } else {
                             // five or more in-edges (2 % of the nodes of a deep graph): the in-list beyond the record on one lane
@@ -1585,7 +1621,7 @@ __device__ __noinline__ int w_toposort(GraphView& g, const TopoRec* rec, uint8_t
                                 for (int q = 0; q < 4 && okflag; ++q)
                                     if (!is_perm(pp[q])) { if (nsp >= TOPO_STACK) okflag = 0; else stk[nsp++] = pp[q]; }
                                 for (uint32_t x = rb.w; x != NIL && okflag; ) {
-                                    const uint32_t b = g.e_begin[x], nx = g.e_next_in[x];
+                                    const uint32_t b = e_begin[x], nx = e_next_in[x];
                                     if (!is_perm(b)) { if (nsp >= TOPO_STACK) okflag = 0; else stk[nsp++] = b; }
                                     x = nx;
                                 }
@@ -1596,25 +1632,25 @@ __device__ __noinline__ int w_toposort(GraphView& g, const TopoRec* rec, uint8_t
                                         if (!is_perm(al[q])) { if (nsp >= TOPO_STACK) okflag = 0; else { stk[nsp++] = al[q]; nochk[al[q] >> 5] |= 1u << (al[q] & 31); } }
                                     }
                                 }
-                                if (nsp != sp) stk[self] = v | EXPANDED;
+                                if (nsp != sp) stk[sp - 1] = v | EXPANDED;
                             }
                             nsp = __shfl_sync(FULL, nsp, 0);
                             okflag = __shfl_sync(FULL, okflag, 0);
                             if (!okflag) break;
-                            if (nsp != sp) { sp = nsp; vvalid = false; }
+                            __syncwarp();
+                            if (nsp != sp) { sp = nsp; top = stk[sp - 1]; continue; }
                         }
                     }
-                    if (vvalid) {
-                        if (lane == 0) perm[v >> 5] |= 1u << (v & 31);
-                        if (chk) {
-                            const bool al = lane >= 4 && lane < 7 && child != NIL;       // NIL-terminated: the aligned nodes sit in lanes 4, 5, 6 in order
-                            const uint32_t na = (uint32_t)__popc(__ballot_sync(FULL, al));
-                            if (lane == 0) { g.rank2node[nr] = v; g.node2rank[v] = nr; }
-                            if (al) { g.rank2node[nr + 1 + (lane - 4)] = child; g.node2rank[child] = nr + 1 + (lane - 4); }
-                            nr += 1 + na;
-                        }
-                        --sp;
+                    // every child is emitted: the node (and, if it leads its aligned set, the set) is final
+                    if (lane == 0) perm[v >> 5] = pw | (1u << (v & 31));                  // only this walk writes the bitmap: pw is current
+                    if (chk) {
+                        const bool al = lane >= 4 && lane < 7 && child != NIL;           // NIL-terminated: the aligned nodes sit in lanes 4, 5, 6 in order
+                        const uint32_t na = (uint32_t)__popc(__ballot_sync(FULL, al));
+                        if (lane == 0) { r2n[nr] = v; n2r[v] = nr; }
+                        if (al) { r2n[nr + 1 + (lane - 4)] = child; n2r[child] = nr + 1 + (lane - 4); }
+                        nr += 1 + na;
                     }
+                    --sp; top = below;
                     __syncwarp();
                 }
             }
@@ -1628,9 +1664,9 @@ __device__ __noinline__ int w_toposort(GraphView& g, const TopoRec* rec, uint8_t
     return okflag;
 }
 
-// The same sort walking the in-lists directly (no records): what the shallow kernel runs. Its graphs (a handful of reads) have few
-// aligned nodes, most ranks are emitted by the 32-wide fast path, and the kernel is instruction-cache bound: the extra record
-// pass and its code cost it 4-6 % there (A/B on config 3: 1,490 vs 1,394 GCUPS), while deep graphs gain 25 % of their sort.
+// The same sort walking the in-lists directly (no records), kept for A/B runs (-DHGPU_SHALLOW_TREC=0). With the serial one-lane DFS
+// the record pass cost the shallow kernel 4 % (1,394 vs 1,453 GCUPS on config 3); with the warp-cooperative walk it gains 3 %
+// (1,506 vs 1,461), so every kernel runs w_toposort now.
 __device__ __noinline__ int w_toposort_chain(GraphView& g, uint8_t* wsm, int lane) {
     const uint32_t N = *g.n_nodes;
     if (N > TOPO_BM_WORDS * 32) return 0;
@@ -1760,6 +1796,9 @@ __device__ __noinline__ int w_toposort_chain(GraphView& g, uint8_t* wsm, int lan
 // ---------------------------------------------------------------------------------------------------------
 __device__ __noinline__ uint32_t w_consensus_scores(GraphView& g, GraphScratch& s, int lane) {
     const uint32_t N = *g.n_nodes;
+    int64_t* const S_score = s.score; int32_t* const S_pred = s.pred; uint32_t* const S_stack = s.stack;
+    // the view lives in the caller's frame: keep the arrays this function walks in registers
+    auto* const L_rank2node = g.rank2node; auto* const L_in_head = g.in_head; auto* const L_e_begin = g.e_begin; auto* const L_e_w = g.e_w; auto* const L_e_next_in = g.e_next_in; auto* const L_node2rank = g.node2rank;
     constexpr int K = 4;                                                  // in-edges held in registers; longer lists walk memory
     uint32_t max_id = 0; int max_sc = -1;
     for (uint32_t r0 = 0; r0 < N; r0 += 32) {
@@ -1768,19 +1807,19 @@ __device__ __noinline__ uint32_t w_consensus_scores(GraphView& g, GraphScratch& 
         uint32_t u = 0, eb[K], ew[K], rk[K]; int sb[K];
         int deg = 0; bool more = false;
         if (valid) {
-            u = g.rank2node[r];
-            uint32_t x = g.in_head[u];
+            u = L_rank2node[r];
+            uint32_t x = L_in_head[u];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 eb[k] = 0; ew[k] = 0; rk[k] = 0; sb[k] = -1;
-                if (x != NIL) { eb[k] = g.e_begin[x]; ew[k] = g.e_w[x]; x = g.e_next_in[x]; deg = k + 1; }
+                if (x != NIL) { eb[k] = L_e_begin[x]; ew[k] = L_e_w[x]; x = L_e_next_in[x]; deg = k + 1; }
             }
             more = x != NIL;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 if (k < deg) {
-                    rk[k] = g.node2rank[eb[k]];
-                    if (rk[k] < r0) sb[k] = (int)s.score[eb[k]];         // resolved in an earlier batch
+                    rk[k] = L_node2rank[eb[k]];
+                    if (rk[k] < r0) sb[k] = (int)S_score[eb[k]];         // resolved in an earlier batch
                 }
             }
         } else {
@@ -1806,20 +1845,20 @@ __device__ __noinline__ uint32_t w_consensus_scores(GraphView& g, GraphScratch& 
                         }
                     }
                 } else {                                                  // long in-list: scores of earlier ranks are in memory by now
-                    for (uint32_t y = g.in_head[u]; y != NIL; y = g.e_next_in[y]) {
-                        const uint32_t b = g.e_begin[y];
-                        const int w = (int)g.e_w[y];
-                        const int sbk = (int)s.score[b];
+                    for (uint32_t y = L_in_head[u]; y != NIL; y = L_e_next_in[y]) {
+                        const uint32_t b = L_e_begin[y];
+                        const int w = (int)L_e_w[y];
+                        const int sbk = (int)S_score[b];
                         if (cur < w || (cur == w && ps <= sbk)) { cur = w; cp = (int32_t)b; ps = sbk; }
                     }
                 }
                 if (cp != -1) cur += ps;
                 myscore = cur; mypred = cp;
-                s.score[u] = (int64_t)cur; s.pred[u] = cp;
+                S_score[u] = (int64_t)cur; S_pred[u] = cp;
             }
             __syncwarp();
         }
-        if (valid) s.stack[r] = mypred == -1 ? NIL : g.node2rank[mypred];   // the chosen predecessor by rank, for the backtrack
+        if (valid) S_stack[r] = mypred == -1 ? NIL : L_node2rank[mypred];   // the chosen predecessor by rank, for the backtrack
         // first strict maximum in rank order
         const int bm = __reduce_max_sync(FULL, valid ? myscore : INT32_MIN);
         if (bm > max_sc) {
@@ -1974,8 +2013,9 @@ __device__ __forceinline__ void poa_edges_body(const PoaArgs& a) {
                 if (ust != ST_OK) { st = ust; break; }
                 PHASE_CLK(PC_ADD)
                 if (probe == 3) { debug_stop = true; break; }
-                if (RING > 2) w_build_trec(gv, trec, lane);
-                if (!(RING > 2 ? w_toposort(gv, trec, wsm, lane) : w_toposort_chain(gv, wsm, lane))) {    // too large for the shared-memory bitmaps / deep DFS: serial
+                constexpr bool USE_TREC = RING > 2 || HGPU_SHALLOW_TREC;
+                if (USE_TREC) w_build_trec(gv, trec, lane);
+                if (!(USE_TREC ? w_toposort(gv, trec, wsm, lane) : w_toposort_chain(gv, wsm, lane))) {    // too large for the shared-memory bitmaps / deep DFS: serial
                     ust = ST_OK;
                     if (lane == 0 && !g_toposort(gv, gs)) ust = ST_TOPOSORT;
                     ust = __shfl_sync(FULL, ust, 0);

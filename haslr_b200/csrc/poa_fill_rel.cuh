@@ -61,7 +61,8 @@ __device__ __forceinline__ uint32_t deep_plan_of(uint32_t m0, uint32_t rr, const
 // plan words of all ranks, lane-parallel; run by the warp that owns the graph, after the per-rank DP records exist
 __device__ __noinline__ void w_build_plan(const GraphView& g, uint32_t* plan, int lane) {
     const uint32_t N = *g.n_nodes;
-    for (uint32_t r = lane; r < N; r += 32) plan[r] = deep_plan_of(g.meta0[r], r, g.pred_off, g.pred_rank);
+    const uint32_t* const meta0 = g.meta0; const uint32_t* const pred_off = g.pred_off; const uint32_t* const pred_rank = g.pred_rank;
+    for (uint32_t r = lane; r < N; r += 32) plan[r] = deep_plan_of(meta0[r], r, pred_off, pred_rank);
     __syncwarp();
 }
 

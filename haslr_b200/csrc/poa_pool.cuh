@@ -18,7 +18,10 @@
 namespace hgpu {
 
 static constexpr int POOL_WARPS = 8;
-static constexpr int POOL_MAX_CTX = 8;
+#ifndef HGPU_POOL_MAX_CTX
+#define HGPU_POOL_MAX_CTX 16          // contexts (edges in flight) per block of 8 warps: A/B on config 2, 16 vs 8: 530 vs 552 ms (profiles/r2p_ab.log)
+#endif
+static constexpr int POOL_MAX_CTX = HGPU_POOL_MAX_CTX;
 static constexpr uint32_t POOL_MAX_STRIPES = 32;          // alignments with more stripes are filled by one warp, stripe after stripe
 enum : uint32_t { PS_IDLE = 0, PS_BUSY = 1, PS_FILL = 2, PS_GRAPH_READY = 3, PS_DONE = 4 };
 enum : int { PT_NONE = 0, PT_STRIPE = 1, PT_GRAPH = 2, PT_NEW = 3, PT_EXIT = 4 };
@@ -236,6 +239,7 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, 2) k_poa_pool(const __grid_co
     const uint32_t wib = threadIdx.x >> 5;
     uint8_t* wsm = smem_raw + (size_t)wib * DP_SMEM_PER_WARP_DEEP;
     PoolShared* sh = reinterpret_cast<PoolShared*>(smem_raw + (size_t)POOL_WARPS * DP_SMEM_PER_WARP_DEEP);
+    static_assert(POOL_MAX_CTX <= 32 * POOL_WARPS, "one thread initialises one context");
     if (threadIdx.x < POOL_MAX_CTX) {
         const bool live = threadIdx.x < n_ctx && pa.ctx_class[blockIdx.x * n_ctx + threadIdx.x] != 0xFFu;
         sh->ctx[threadIdx.x].state = live ? PS_IDLE : PS_DONE; sh->ctx[threadIdx.x].claim = 0; sh->ctx[threadIdx.x].n_tasks = 0;

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <deque>
 #include <iterator>
+#include <memory>
 #include <set>
 #include <thread>
 #include <ctime>
@@ -141,6 +142,7 @@ uint32_t segment_length(const SeqStore& reads, const CnsSupp& s) {
     const uint32_t want = s.epos - s.spos + 1;
     return std::min<uint32_t>(want, len - s.spos);
 }
+namespace { struct CompTable { char t[256]; CompTable() { for (int i = 0; i < 256; ++i) t[i] = 'A'; t['A'] = 'T'; t['C'] = 'G'; t['G'] = 'C'; t['T'] = 'A'; } } COMP; }
 void write_segment(const SeqStore& reads, const CnsSupp& s, uint32_t cnt, char* out) {
     const uint32_t len = reads.len(s.lr_id);
     const char* r = reads.data(s.lr_id);
@@ -148,10 +150,8 @@ void write_segment(const SeqStore& reads, const CnsSupp& s, uint32_t cnt, char* 
         memcpy(out, r + s.spos, cnt);
     } else {
         // revcomp(read)[spos .. spos+cnt) = complement of read[len-1-spos], read[len-2-spos], ...
-        for (uint32_t k = 0; k < cnt; ++k) {
-            const char c = r[len - 1 - s.spos - k];
-            out[k] = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : 'A';
-        }
+        const unsigned char* p = reinterpret_cast<const unsigned char*>(r) + (len - 1 - s.spos);
+        for (uint32_t k = 0; k < cnt; ++k) out[k] = COMP.t[p[-(long)k]];
     }
 }
 
@@ -200,7 +200,9 @@ int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& 
         for (auto& s : shard) std::sort(s.begin(), s.end());
     }
     // per-GPU segment tables; every segment is copied (or reverse-complemented) ONCE, from the read into its GPU's buffer
-    struct Shard { std::string b; std::vector<uint64_t> so{0}; std::vector<uint32_t> eso{0}; std::vector<uint32_t> seg; };
+    // the segment bytes live in uninitialised storage: a std::string would zero-fill gigabytes on one thread before the gather threads
+    // touch (and page in) their own parts
+    struct Shard { std::unique_ptr<char[]> b; uint64_t n = 0; std::vector<uint64_t> so{0}; std::vector<uint32_t> eso{0}; std::vector<uint32_t> seg; };
     std::vector<Shard> sh(G);
     std::vector<std::pair<uint32_t, uint64_t>> seg_home(seg_src.size());      // segment -> (gpu, offset in its buffer), for the log
     for (size_t gi = 0; gi < G; ++gi) {
@@ -213,14 +215,15 @@ int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& 
             }
             S.eso.push_back((uint32_t)(S.so.size() - 1));
         }
-        S.b.resize(S.so.back());
+        S.n = S.so.back();
+        S.b.reset(new char[S.n + 64]);
     }
     {   // the copies are independent: all host threads
         const size_t n_seg = seg_src.size();
         const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(threads, n_seg / 256 + 1));
         auto work = [&](unsigned t) {
             for (size_t q = n_seg * t / nt; q < n_seg * (t + 1) / nt; ++q)
-                write_segment(reads, *seg_src[q], (uint32_t)(seg_off[q + 1] - seg_off[q]), &sh[seg_home[q].first].b[seg_home[q].second]);
+                write_segment(reads, *seg_src[q], (uint32_t)(seg_off[q + 1] - seg_off[q]), sh[seg_home[q].first].b.get() + seg_home[q].second);
         };
         std::vector<std::thread> th;
         for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
@@ -234,12 +237,13 @@ int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& 
         const std::vector<uint32_t>& my = shard[gi];
         if (my.empty()) return;
         Shard& S = sh[gi];
-        std::vector<uint8_t> out(S.b.size() + 64);
+        const uint64_t out_cap = S.n + 64;                      // worst case (every consensus as long as its segments together); never touched beyond the result
+        std::unique_ptr<uint8_t[]> out(new uint8_t[out_cap]);
         std::vector<uint64_t> off(my.size() + 1);
         std::vector<uint32_t> status(my.size());
         hgpu_poa_set_timing(ctxs[gi], 1);      // one event pair per scheduling pass, read after the pass's own synchronisation
-        int r = hgpu_poa_batch(ctxs[gi], (const uint8_t*)S.b.data(), S.so.data(), S.eso.data(), (uint32_t)my.size(), 5, -4, -8, 0,   // Assemble.cpp:8-11
-                               out.data(), out.size(), off.data(), status.data());
+        int r = hgpu_poa_batch(ctxs[gi], (const uint8_t*)S.b.get(), S.so.data(), S.eso.data(), (uint32_t)my.size(), 5, -4, -8, 0,   // Assemble.cpp:8-11
+                               out.get(), out_cap, off.data(), status.data());
         if (r != HGPU_OK) { fprintf(stderr, "[ERROR] hgpu_poa_batch (gpu %zu): %s\n", gi, hgpu_last_error(ctxs[gi])); rc[gi] = r; return; }
         hgpu_poa_stats st;
         if (hgpu_poa_get_stats(ctxs[gi], &st) == HGPU_OK)
@@ -248,7 +252,7 @@ int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& 
                     st.ms_dp, st.ms_dp > 0 ? st.cells / (st.ms_dp * 1e6) : 0.0, (unsigned long long)st.dp_launches);
         for (size_t k = 0; k < my.size(); ++k) {
             if (status[k] != 0) { fprintf(stderr, "[ERROR] POA failed for edge %u with status %u\n", my[k], status[k]); rc[gi] = HGPU_E_INTERNAL; }
-            cons[my[k]].assign((const char*)out.data() + off[k], off[k + 1] - off[k]);
+            cons[my[k]].assign((const char*)out.get() + off[k], off[k + 1] - off[k]);
         }
     };
     if (G == 1) run(0);
@@ -270,7 +274,7 @@ int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& 
             for (const CnsSupp& c : e1[e]->cns_supp) {
                 fprintf(fp, "        [debug] lr_id:%u lr_len:%u region_start:%u region_end:%u subseq_len:%u\n", c.lr_id, reads.len(c.lr_id), c.spos, c.epos, c.epos - c.spos + 1);
                 fprintf(fp, ">%u %c %u %u %u\n", c.lr_id, sgn(c.lr_strand), c.spos, c.epos, c.epos - c.spos + 1);
-                fwrite(sh[seg_home[s].first].b.data() + seg_home[s].second, 1, seg_off[s + 1] - seg_off[s], fp);
+                fwrite(sh[seg_home[s].first].b.get() + seg_home[s].second, 1, seg_off[s + 1] - seg_off[s], fp);
                 fputc('\n', fp);
                 ++s;
             }
