@@ -53,7 +53,16 @@ struct K1Args {
     uint32_t* status;                         // [0] first row (min) that names a contig >= n_contigs, [1] first read whose offsets decrease
 };
 
+// Per-warp staging of a read's rows in shared memory: the order-dependent tail runs on one lane and walks the run-length CIGARs
+// run by run (find_contig_pos) and the sort keys comparison by comparison - from global memory every step was a dependent L2
+// round trip (~300k cycles per read). The runs of the surviving hits and the sort keys of the read's rows are copied here by the
+// whole warp first; reads that do not fit (more than K1_ROWS_CAP rows or K1_RUNS_CAP runs) take the global arrays as before.
+static constexpr uint32_t K1_ROWS_CAP = 96, K1_RUNS_CAP = 1536;
+struct K1Stage { uint32_t runs[K1_RUNS_CAP]; uint32_t off[K1_ROWS_CAP + 2]; uint32_t q_start[K1_ROWS_CAP]; uint32_t q_end[K1_ROWS_CAP]; };
+
 __global__ void __launch_bounds__(128) k1_compact_lr(K1Args a) {
+    __shared__ K1Stage stage_all[4];
+    K1Stage& sg = stage_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
@@ -76,19 +85,46 @@ __global__ void __launch_bounds__(128) k1_compact_lr(K1Args a) {
         }
         if (__any_sync(FULLM, bad)) { if (lane == 0) a.out_cnt[r] = 0; continue; }
         __syncwarp();
-        // expanded CIGAR length of every surviving hit: the runs are summed by the whole warp (the serial tail needs only the totals)
+        // runs of the surviving hits, packed in row order: survivor c occupies [start_c, start_c + n_c)
+        const uint32_t n_rows = e - b;
+        uint32_t total_runs = 0;
+        for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
+            const uint32_t c = c0 + lane;
+            uint32_t nr_ = 0, row = 0;
+            if (c < cnt) { row = idx[c]; nr_ = a.h.cg_off[row + 1] - a.h.cg_off[row]; }
+            uint32_t incl = nr_;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(FULLM, incl, d); if (lane >= d) incl += o; }
+            const uint32_t start = total_runs + incl - nr_;
+            if (c < cnt && n_rows <= K1_ROWS_CAP) { sg.off[row - b] = start; sg.off[row - b + 1] = start + nr_; }
+            total_runs += __shfl_sync(FULLM, incl, 31);
+        }
+        const bool staged = n_rows <= K1_ROWS_CAP && total_runs <= K1_RUNS_CAP;
+        __syncwarp();
+        // expanded CIGAR length of every surviving hit, summed by the whole warp; the same pass stages the runs
         for (uint32_t c = 0; c < cnt; ++c) {
             const uint32_t row = idx[c];
             const uint32_t k0 = a.h.cg_off[row], k1 = a.h.cg_off[row + 1];
+            const uint32_t dst = staged ? sg.off[row - b] : 0u;
             uint32_t tot = 0;
-            for (uint32_t k = k0 + lane; k < k1; k += 32) tot += a.h.cg_ops[k] >> 2;
+            for (uint32_t k = k0 + lane; k < k1; k += 32) {
+                const uint32_t op = a.h.cg_ops[k];
+                tot += op >> 2;
+                if (staged) sg.runs[dst + (k - k0)] = op;
+            }
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(FULLM, tot, d);
             if (lane == 0) a.cg_total[row] = tot;
         }
+        HitCols hl = a.h;
+        if (staged) {
+            for (uint32_t j = lane; j < n_rows; j += 32) { sg.q_start[j] = a.h.q_start[b + j]; sg.q_end[j] = a.h.q_end[b + j]; }
+            hl.cg_ops = sg.runs; hl.cg_off = sg.off - b;            // indexed by global row, like the arrays they stand in for
+            hl.q_start = sg.q_start - b; hl.q_end = sg.q_end - b;
+        }
         __syncwarp();
         if (lane == 0)
-            a.out_cnt[r] = k1_process_read(a.h, a.mean_kmer, a.p, idx, cnt, a.hit + b, a.dp + b, a.prevc + b, a.cand + b,
+            a.out_cnt[r] = k1_process_read(hl, a.mean_kmer, a.p, idx, cnt, a.hit + b, a.dp + b, a.prevc + b, a.cand + b,
                                            a.take + b, a.tmp + b, a.cg_total);
         __syncwarp();
     }
