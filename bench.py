@@ -297,7 +297,7 @@ def whole_path_leg(ctx, args, peak):
     per-kernel CUDA-event time against the algorithmic bytes of DESIGN.md."""
     import ctypes as C
     import shutil
-    lib_p = os.path.join(ROOT, "haslr_b200", "libhaslr_path.so")
+    lib_p = os.environ.get("HASLR_PATH_LIB") or os.path.join(ROOT, "haslr_b200", "libhaslr_path.so")   # override: developer A/B builds
     d = cfg2_dataset()
     if d is None or not os.path.exists(lib_p):
         return {"unavailable": "generator binary or libhaslr_path.so not built"}

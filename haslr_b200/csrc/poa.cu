@@ -24,7 +24,7 @@ struct PoaPass {                 // one scheduling pass keeps its consensus pool
 struct PoaState {
     DevBuf<uint8_t> arena, ws, arena_team, ws_team, d_bases, d_out;
     DevBuf<uint64_t> seg_ptr, cons_pos, d_off;
-    DevBuf<uint32_t> seg_len, e_seg_off, items, status, cons_len, out_nodes, counters, pool_tab32;
+    DevBuf<uint32_t> seg_len, e_seg_off, items, status, cons_len, out_nodes, counters, pool_tab32, pool_first;
     DevBuf<uint8_t> pool_tab8;
     DevBuf<unsigned long long> stats, pool_cursor;
     std::vector<std::unique_ptr<PoaPass>> passes;
@@ -52,7 +52,8 @@ struct PoaState {
     int cfg_force = 0;                // HGPU_FORCE_MODE: 1 = every alignment in int32, 2 = every alignment in REL16 (tests)
     int cfg_pool = 1;                 // HGPU_POOL=0: deep edges in the warp-per-edge / block-per-edge kernels instead of k_poa_pool (A/B runs, tests)
     uint32_t cfg_pool_ctx = 0;        // HGPU_POOL_CTX: contexts (edges in flight) per pool block, 0 = by the stripes per alignment of the class
-    int verbose = 0;                  // HGPU_VERBOSE=1: pass / class plan and per-launch device time on stderr
+    int verbose = 0;                  // HGPU_VERBOSE=1: pass / class plan and per-launch device time on stderr; 2: + when k_poa_pool finished which edge
+    DevBuf<unsigned long long> edge_clk;
 };
 
 // Grow one of the big per-context buffers. The memory budget counts what the state already holds as reusable, so when the
@@ -162,6 +163,7 @@ struct PoaRunOpts {
 // Leaves per-edge status/cons_len/cons_pos on the device and in `status_h`/`len_h`.
 static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off, const uint32_t* edge_seg_off, uint32_t n_edges,
                    const DpScores& sc, const PoaRunOpts& opt, std::vector<uint32_t>& status_h, std::vector<uint32_t>& len_h) {
+    bool pool_ran = false; (void)pool_ran;
     PoaState* S = poa_state(ctx);
     cudaStream_t st = ctx->stream;
     const auto host_t0 = std::chrono::steady_clock::now();
@@ -360,7 +362,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
 
         // ---- size classes: a class ends where the slot estimate has halved, unless memory is no constraint
         struct Cls { size_t a, b; uint64_t slot; WsLayout wl; uint32_t warps; bool deep; bool pool; uint32_t ctx_per_block, pool_blocks; double cells, work; };
-        const uint32_t pool_blocks_max = 2u * (uint32_t)ctx->sm_count;              // k_poa_pool: two blocks of 8 warps per SM
+        const uint32_t pool_blocks_max = (uint32_t)HGPU_POOL_BLOCKS_PER_SM * (uint32_t)ctx->sm_count;   // k_poa_pool: two blocks of 8 warps per SM
         std::vector<Cls> classes;
         constexpr uint64_t POOL_SMALL_SLOT = 8ull << 20;
         uint32_t n_pool_classes = 0;
@@ -466,6 +468,42 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
                     if (best == K) break;
                     ctx_class[where] = (uint8_t)best; ctx_slot[where] = dealt[best]++;
                 }
+                // first edges. Every class has its edges sorted by estimated time; the quota[k] heaviest are dealt to its contexts here,
+                // heaviest edge of all classes first, each to the block with the least work so far that still has a free context of the
+                // class (LPT), so the blocks' heavy work ends together; the rest of the class waits in its queue and goes to whichever
+                // context is free first.
+                std::vector<uint32_t> ctx_first(T, 0xFFFFFFFFu);
+                {
+                    for (size_t k = 0; k < K; ++k) {
+                        const Cls& c = classes[pc[k]];
+                        std::sort(est.begin() + c.a, est.begin() + c.b, [](const EdgeEst& x, const EdgeEst& y) { return x.work != y.work ? x.work > y.work : x.edge < y.edge; });
+                        for (size_t q = c.a; q < c.b; ++q) items_h[q] = est[q].edge;
+                    }
+                    HGPU_CUDA(ctx, cudaMemcpyAsync(S->items.p, items_h.data(), est.size() * 4, cudaMemcpyHostToDevice, st));
+                    std::vector<std::vector<std::vector<uint32_t>>> free_pos(K, std::vector<std::vector<uint32_t>>(blocks));
+                    for (uint32_t b = 0; b < blocks; ++b)
+                        for (uint32_t j = E; j-- > 0;) { const uint32_t w = b * E + j; if (ctx_class[w] != 0xFF) free_pos[ctx_class[w]][b].push_back(w); }
+                    struct Cand { double work; uint32_t k; size_t q; };
+                    std::vector<Cand> cand;
+                    for (size_t k = 0; k < K; ++k)
+                        for (uint32_t x = 0; x < dealt[k]; ++x) cand.push_back({est[classes[pc[k]].a + x].work, (uint32_t)k, classes[pc[k]].a + x});
+                    std::sort(cand.begin(), cand.end(), [](const Cand& x, const Cand& y) { return x.work != y.work ? x.work > y.work : x.q < y.q; });
+                    std::vector<double> block_work(blocks, 0.0);
+                    for (const Cand& cd : cand) {
+                        uint32_t bb = blocks;
+                        for (uint32_t b = 0; b < blocks; ++b)
+                            if (!free_pos[cd.k][b].empty() && (bb == blocks || block_work[b] < block_work[bb])) bb = b;
+                        if (bb == blocks) break;              // cannot happen: dealt[k] contexts of the class exist
+                        ctx_first[free_pos[cd.k][bb].back()] = est[cd.q].edge;
+                        free_pos[cd.k][bb].pop_back();
+                        block_work[bb] += cd.work;
+                    }
+                    if (S->verbose) {
+                        double lo = 1e300, hi = 0, sum = 0;
+                        for (double w : block_work) { lo = std::min(lo, w); hi = std::max(hi, w); sum += w; }
+                        fprintf(stderr, "[poa] first edges dealt: estimated work per block min %.3g mean %.3g max %.3g\n", lo, sum / blocks, hi);
+                    }
+                }
                 PoolArgs pa{};
                 uint64_t a_off = 0, w_off = 0;
                 for (size_t k = 0; k < K; ++k) { a_off += (uint64_t)quota[k] * classes[pc[k]].slot; w_off += (uint64_t)quota[k] * classes[pc[k]].wl.bytes; }
@@ -473,25 +511,36 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
                 HGPU_CUDA(ctx, S->pool_tab8.ensure(T)); HGPU_CUDA(ctx, S->pool_tab32.ensure(T));
                 HGPU_CUDA(ctx, cudaMemcpyAsync(S->pool_tab8.p, ctx_class.data(), T, cudaMemcpyHostToDevice, st));
                 HGPU_CUDA(ctx, cudaMemcpyAsync(S->pool_tab32.p, ctx_slot.data(), (size_t)T * 4, cudaMemcpyHostToDevice, st));
+                HGPU_CUDA(ctx, S->pool_first.ensure(T));
+                HGPU_CUDA(ctx, cudaMemcpyAsync(S->pool_first.p, ctx_first.data(), (size_t)T * 4, cudaMemcpyHostToDevice, st));
                 S->st.arena_bytes = std::max<uint64_t>(S->st.arena_bytes, a_off);
                 budget -= std::min<uint64_t>(budget, a_off + w_off);
                 a_off = 0; w_off = 0;
                 for (size_t k = 0; k < K; ++k) {
                     const Cls& c = classes[pc[k]];
                     PoolClass& q = pa.cls[k];
-                    q.items = S->items.p + c.a; q.n_items = (uint32_t)(c.b - c.a); q.counter = S->counters.p + pc[k];
+                    q.items = S->items.p + c.a + dealt[k]; q.n_items = (uint32_t)(c.b - c.a) - dealt[k]; q.counter = S->counters.p + pc[k];   // the first dealt[k] went out with ctx_first
                     q.ws = S->ws_team.p + w_off; q.wl = c.wl; q.arena = S->arena_team.p + a_off; q.slot_bytes = c.slot;
                     a_off += (uint64_t)quota[k] * c.slot; w_off += (uint64_t)quota[k] * c.wl.bytes;
                     if (S->verbose)
                         fprintf(stderr, "[poa] attempt %d growth %.2f pool class %zu/%zu: %u edges, %u contexts, slot %.1f MB, ws %.1f MB, %.3e cells, work share %.1f %%\n",
                                 attempt, growth, k, K, q.n_items, quota[k], c.slot / 1048576.0, c.wl.bytes / 1048576.0, c.cells, 100.0 * (c.work + 1.0) / tot_work);
                 }
-                pa.n_cls = (uint32_t)K; pa.ctx_class = S->pool_tab8.p; pa.ctx_slot = S->pool_tab32.p;
+                pa.n_cls = (uint32_t)K; pa.ctx_class = S->pool_tab8.p; pa.ctx_slot = S->pool_tab32.p; pa.ctx_first = S->pool_first.p;
                 PoaArgs& a = pa.a;
                 a.bases = d_bases; a.seg_ptr = S->seg_ptr.p; a.seg_len = S->seg_len.p; a.e_seg_off = S->e_seg_off.p;
                 a.status = S->status.p; a.cons_len = S->cons_len.p; a.cons_pos = S->cons_pos.p; a.out_nodes = S->out_nodes.p;
                 a.pool = pass->pool.p; a.pool_cap = pass->pool.n; a.pool_cursor = S->pool_cursor.p;
                 a.sc = sc; a.stats = S->stats.p; a.stop_round = opt.stop_round; a.force_i32 = opt.force_i32;
+#if HGPU_PHASE_CLOCKS
+                HGPU_CUDA(ctx, cudaMemsetAsync(S->stats.p + 8, 0, 16 * sizeof(unsigned long long), st));
+                a.phase_clk = S->stats.p + 8;
+#endif
+                if (S->verbose >= 2) {
+                    HGPU_CUDA(ctx, S->edge_clk.ensure((size_t)n_edges * 2));
+                    HGPU_CUDA(ctx, cudaMemsetAsync(S->edge_clk.p, 0, (size_t)n_edges * 16, st));
+                    a.edge_clk = S->edge_clk.p;
+                }
                 const size_t psmem = (size_t)POOL_WARPS * DP_SMEM_PER_WARP_DEEP + sizeof(PoolShared);
                 HGPU_CUDA(ctx, cudaFuncSetAttribute(k_poa_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
                 HGPU_CUDA(ctx, cudaEventRecord(S->ev_fork, st));          // uploads and memsets above are on `st`
@@ -500,7 +549,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
                 HGPU_CUDA(ctx, cudaGetLastError());
                 HGPU_CUDA(ctx, cudaEventRecord(S->ev_join, S->stream2));
                 ctx->launches++; S->st.dp_launches++;
-                pool_launched = true;
+                pool_launched = true; pool_ran = true;
                 if (S->verbose) fprintf(stderr, "[poa] k_poa_pool: %u blocks x %u contexts (%u in use), %.1f GB of slots\n", blocks, E, given, (a_off + w_off) / 1073741824.0);
             }
         }
@@ -644,7 +693,9 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
     {
         unsigned long long pc[16];
         HGPU_CUDA(ctx, cudaMemcpy(pc, S->stats.p + 8, sizeof pc, cudaMemcpyDeviceToHost));
-        static const char* nm[9] = {"queue", "init", "fill", "traceback", "add_alignment", "toposort", "dp_records", "consensus", "publish"};
+        static const char* nm_edges[9] = {"queue", "init", "fill", "traceback", "add_alignment", "toposort", "dp_records", "consensus", "publish"};
+        static const char* nm_pool[9] = {"claim/idle", "open", "stripes", "traceback", "add_alignment", "records+toposort", "dp_records+plan", "advance", "-"};
+        const char* const* nm = pool_ran ? nm_pool : nm_edges;
         double tot = 0; for (int i = 0; i < 9; ++i) tot += (double)pc[i];
         fprintf(stderr, "[phase clocks, warp-cycles of the last class]");
         for (int i = 0; i < 9; ++i) fprintf(stderr, " %s %.1f%%", nm[i], 100.0 * (double)pc[i] / (tot > 0 ? tot : 1));
@@ -652,6 +703,34 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
     }
 #endif
     if (S->verbose) fprintf(stderr, "[poa] host: %.1f ms for the whole run (kernels %.1f ms)\n", host_ms(), S->st.ms_dp);
+    if (S->verbose >= 2 && S->edge_clk.p) {
+        // the pool's time line: how many edges were open at each tenth of the kernel, and the edges that ended last
+        std::vector<unsigned long long> clk((size_t)n_edges * 2);
+        HGPU_CUDA(ctx, cudaMemcpy(clk.data(), S->edge_clk.p, clk.size() * 8, cudaMemcpyDeviceToHost));
+        unsigned long long t0 = ~0ull, t1 = 0;
+        for (uint32_t e = 0; e < n_edges; ++e) if (clk[2 * e] && clk[2 * e + 1]) { t0 = std::min(t0, clk[2 * e]); t1 = std::max(t1, clk[2 * e + 1]); }
+        if (t1 > t0) {
+            const double span = (double)(t1 - t0);
+            fprintf(stderr, "[poa] pool time line (%.1f ms): edges open at each 5 %%:", span / 1e6);
+            for (int q = 0; q < 20; ++q) {
+                const unsigned long long t = t0 + (unsigned long long)(span * (q + 0.5) / 20);
+                uint32_t open = 0;
+                for (uint32_t e = 0; e < n_edges; ++e) if (clk[2 * e] && clk[2 * e] <= t && clk[2 * e + 1] > t) ++open;
+                fprintf(stderr, " %u", open);
+            }
+            fprintf(stderr, "\n");
+            std::vector<uint32_t> ord;
+            for (uint32_t e = 0; e < n_edges; ++e) if (clk[2 * e] && clk[2 * e + 1]) ord.push_back(e);
+            std::sort(ord.begin(), ord.end(), [&](uint32_t x, uint32_t y) { return clk[2 * x + 1] > clk[2 * y + 1]; });
+            for (size_t i = 0; i < ord.size() && i < 12; ++i) {
+                const uint32_t e = ord[i];
+                const uint32_t s0 = edge_seg_off[e], R = edge_seg_off[e + 1] - s0;
+                uint64_t bases = 0; for (uint32_t k = 0; k < R; ++k) bases += seg_off[s0 + k + 1] - seg_off[s0 + k];
+                fprintf(stderr, "[poa]   edge %u: %u reads, %.0f bp mean, started %.1f ms, ended %.1f ms (%.1f ms)\n", e, R, R ? (double)bases / R : 0.0,
+                        (clk[2 * e] - t0) / 1e6, (clk[2 * e + 1] - t0) / 1e6, (clk[2 * e + 1] - clk[2 * e]) / 1e6);
+            }
+        }
+    }
     if (sth[7]) HGPU_FAIL(ctx, HGPU_E_INTERNAL, "k_poa_pool: a block ran out of tasks while edges were still open");
     S->st.cells = sth[0]; S->st.cells_padded = sth[1]; S->st.alignments = sth[2]; S->st.alignments_i32 = sth[3] & 0xFFFFFFFFull; S->st.alignments_rel16 = sth[3] >> 32; S->st.bases_in = sth[4];
     return HGPU_OK;

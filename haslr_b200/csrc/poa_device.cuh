@@ -172,7 +172,10 @@ static constexpr int DP_SMEM_PER_WARP = 6272;  // int16 fill: profile 4 KB + fra
 // Deep edges (tens of supporting reads) have graphs several times wider than the gap: most ranks read predecessor rows 2-8
 // ranks back. Their kernel (k_poa_edges_deep, and the team kernel) parks EVERY row in a ring of DP_RING_DEEP rows in shared
 // memory, so those reads never leave the SM; a lone warp otherwise waits a full L2 round trip per predecessor row.
-static constexpr int DP_RING_DEEP = 8;
+#ifndef HGPU_RING_DEEP
+#define HGPU_RING_DEEP 8
+#endif
+static constexpr int DP_RING_DEEP = HGPU_RING_DEEP;
 static constexpr int DP_SMEM_PER_WARP_DEEP = 4096 + 128 + DP_RING_DEEP * 1024;
 static constexpr int DP_WARPS_PER_BLOCK = 4;
 
@@ -229,6 +232,7 @@ struct PoaArgs {
     uint32_t stop_round;         // debug: stop after the fill+traceback of this round (0xFFFFFFFF = run to consensus)
     int force_i32;
     unsigned long long* phase_clk; // developer build (-DHGPU_PHASE_CLOCKS=1): per-phase SM cycles summed over warps, [16]
+    unsigned long long* edge_clk;  // HGPU_VERBOSE=2: [2 x edges] globaltimer ns at which k_poa_pool started / finished each edge (else null)
     uint32_t probe, probe_round; // developer timing probes (HGPU_PROBE=phase, HGPU_PROBE_ROUND=k): the edge ends in round k after 1 fill, 2 traceback,
                                  // 3 add_alignment, 4 topological sort, 5 DP records; results are invalid
 };

@@ -24,7 +24,7 @@ namespace hgpu {
 // rank first when it is one of them), bits 24-25 the node's base code, bits 26-29 the predecessor count, bit 30 PLAN_SLOW.
 static constexpr uint32_t PLAN_SLOW = 1u << 30;
 static constexpr int REL_RING = DP_RING_DEEP;            // parked rows per warp; plan distances are 1 .. REL_RING
-static_assert(REL_RING == 8, "plan distances are packed in 3 bits");
+static_assert(REL_RING == 8 || REL_RING == 4, "plan distances are packed in 3 bits; the ring index is a mask");
 __device__ __forceinline__ uint32_t plan_code(uint32_t p) { return (p >> 24) & 3u; }
 __device__ __forceinline__ uint32_t plan_np(uint32_t p) { return (p >> 26) & 15u; }
 

@@ -33,12 +33,24 @@ struct PoolClass {
     const uint32_t* items; uint32_t n_items; uint32_t* counter;
     uint8_t* ws; WsLayout wl; uint8_t* arena; uint64_t slot_bytes;
 };
+#if HGPU_PHASE_CLOCKS
+#define POOL_CLK_DECL long long pk_t = clock64();
+#define POOL_CLK(a, idx) { const long long pk_n = clock64(); if (lane == 0 && (a).phase_clk) atomicAdd((a).phase_clk + (idx), (unsigned long long)(pk_n - pk_t)); pk_t = pk_n; }
+#else
+#define POOL_CLK_DECL
+#define POOL_CLK(a, idx)
+#endif
+// developer clocks of the pool (warp-cycles): 0 looking for a task / idle, 1 opening a context, 2 stripe tasks, 3 traceback, 4 add_alignment,
+// 5 records + topological sort, 6 DP records + plan, 7 next alignment / consensus / publish / next edge
+
 struct PoolArgs {
     PoaArgs a;                           // everything that is not per class (a.items / a.ws / a.arena / a.wl / a.slot_bytes are unused)
     PoolClass cls[POOL_MAX_CLASSES];
     uint32_t n_cls;
     const uint8_t* ctx_class;            // [blocks * n_ctx] class of every context (0xFF: none, the context stays idle)
     const uint32_t* ctx_slot;            // [blocks * n_ctx] its slot / workspace index inside the class
+    const uint32_t* ctx_first;           // [blocks * n_ctx] the edge the context starts with (the host deals the heaviest edges of every class so
+                                         // that the blocks' summed work is even), 0xFFFFFFFF: from the class queue like every later edge
 };
 
 struct PoolCtx {
@@ -49,6 +61,7 @@ struct PoolCtx {
     uint32_t claim, done;                // (generation << 8) | stripe tasks claimed; finished stripe tasks. The generation changes with
                                          // every alignment, so a claim (a CAS on the whole word) can never cross into the next one
     uint32_t sync_fail;
+    uint32_t prio;                       // what is left of the edge's critical path, ~ (alignments to go) x (graph nodes): the claim order
     uint32_t vprog[POOL_MAX_STRIPES];    // rows done + 1 of every stripe (TeamSync)
     unsigned long long cells, padded, aln, aln32, bases;   // of the current edge; added to the block's totals when it completes
 };
@@ -62,10 +75,11 @@ __device__ __forceinline__ uint32_t vld(const uint32_t* p) { return *reinterpret
 __device__ __forceinline__ void vst(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
 
 struct PoolEnv {                         // per-context global storage, bound on demand
-    GraphView gv; GraphScratch gs; uint32_t* hdr; uint32_t* plan; TopoRec* trec; uint8_t* slot; uint64_t slot_bytes; uint32_t cls;
+    GraphView gv; GraphScratch gs; uint32_t* hdr; uint32_t* plan; TopoRec* trec; uint8_t* slot; uint64_t slot_bytes; uint32_t cls, gctx;
 };
 __device__ __forceinline__ PoolEnv pool_env(const PoolArgs& pa, uint32_t gctx) {
     PoolEnv e;
+    e.gctx = gctx;
     e.cls = pa.ctx_class[gctx];
     const PoolClass& c = pa.cls[e.cls];
     const uint32_t idx = pa.ctx_slot[gctx];
@@ -110,6 +124,7 @@ __device__ __noinline__ void pool_finish_edge(const PoaArgs& a, PoolEnv& E, Pool
         a.cons_len[e] = (st == ST_OK) ? n_cons : 0;
         a.cons_pos[e] = (uint64_t)(uintptr_t)(a.pool + pos);
         if (a.out_nodes) a.out_nodes[e] = *gv.n_nodes;
+        if (a.edge_clk) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.edge_clk[2 * e + 1] = t; }
         if (st == ST_OK) {
             atomicAdd(&sh->tot[0], C->cells); atomicAdd(&sh->tot[1], C->padded); atomicAdd(&sh->tot[2], C->aln);
             atomicAdd(&sh->tot[3], C->aln32); atomicAdd(&sh->tot[4], C->bases);
@@ -137,6 +152,7 @@ __device__ __noinline__ void pool_advance(const PoolArgs& pa, PoolEnv& E, PoolCt
                     C->V = V; C->L = L; C->NS = NS; C->mode = (uint32_t)mode;
                     C->n_tasks = (mode == DPM_REL16 && NS <= POOL_MAX_STRIPES) ? NS : 1u;
                     C->done = 0; C->sync_fail = 0;
+                    C->prio = (uint32_t)min((unsigned long long)(vld(&C->R) - k) * ((V >> 4) + 1u), 0xFFFFFFull);
                 }
                 for (uint32_t s = lane; s < POOL_MAX_STRIPES; s += 32) C->vprog[s] = 0;
                 __threadfence_block();
@@ -154,6 +170,7 @@ __device__ __noinline__ void pool_advance(const PoolArgs& pa, PoolEnv& E, PoolCt
         // next edge: the context's own class first, then the classes with smaller slots (their edges fit)
         uint32_t e = 0xFFFFFFFFu;
         if (lane == 0) {
+            if (!have_edge) e = pa.ctx_first[E.gctx];           // the context's first edge was dealt by the host
             for (uint32_t k = E.cls; k < pa.n_cls && e == 0xFFFFFFFFu; ++k) {
                 const PoolClass& c = pa.cls[k];
                 if (*reinterpret_cast<volatile uint32_t*>(c.counter) >= c.n_items) continue;
@@ -169,6 +186,7 @@ __device__ __noinline__ void pool_advance(const PoolArgs& pa, PoolEnv& E, PoolCt
         }
         const uint32_t s0 = a.e_seg_off[e], R = a.e_seg_off[e + 1] - s0;
         if (lane == 0) { C->edge = e; C->k = 1; C->R = R; C->s0 = s0; C->cells = 0; C->padded = 0; C->aln = 0; C->aln32 = 0; C->bases = 0; }
+        if (lane == 0 && a.edge_clk) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.edge_clk[2 * e] = t; }
         __syncwarp();
         st = ST_OK; have_edge = true;
         if (R == 0) {
@@ -195,10 +213,12 @@ __device__ __noinline__ void pool_graph_task(const PoolArgs& pa, PoolEnv& E, Poo
     const int mode = (int)vld(&C->mode);
     const uint8_t* seq = a.bases + a.seg_ptr[s0 + k];
     uint32_t st = ST_OK;
+    POOL_CLK_DECL
     if (vld(&C->sync_fail)) st = ST_SYNC;
     else {
         const bool ok = mode == DPM_REL16 ? dp_traceback<DP_NW16, true, true>(gv, E.slot, wsm, seq, V, L, a.sc, lane)
                                           : dp_traceback<DP_NW32, false>(gv, E.slot, wsm, seq, V, L, a.sc, lane);
+        POOL_CLK(a, 3)
         if (lane == 0) {
             E.hdr[HDR_LAST_P16] = (uint32_t)mode; E.hdr[HDR_LAST_V] = V; E.hdr[HDR_LAST_L] = L; E.hdr[HDR_LAST_BIAS] = 0;
             C->cells += (unsigned long long)(V + 1) * (L + 1);
@@ -215,6 +235,7 @@ __device__ __noinline__ void pool_graph_task(const PoolArgs& pa, PoolEnv& E, Poo
                 ust = __shfl_sync(FULL, ust, 0);
                 __syncwarp();
             }
+            POOL_CLK(a, 4)
             if (ust == ST_OK) {
                 w_build_trec(gv, E.trec, lane);
                 if (!w_toposort(gv, E.trec, wsm, lane)) {
@@ -223,23 +244,32 @@ __device__ __noinline__ void pool_graph_task(const PoolArgs& pa, PoolEnv& E, Poo
                     __syncwarp();
                 }
             }
+            POOL_CLK(a, 5)
             if (ust == ST_OK) { w_build_meta(gv, lane); w_build_plan(gv, E.plan, lane); }
+            POOL_CLK(a, 6)
             st = ust;
         }
     }
     if (lane == 0) C->k = k + 1;
     __syncwarp();
     pool_advance(pa, E, C, sh, st, true, lane);
+    POOL_CLK(a, 7)
 }
 
-__global__ void __launch_bounds__(32 * POOL_WARPS, 2) k_poa_pool(const __grid_constant__ PoolArgs pa, uint32_t n_ctx) {
+#ifndef HGPU_POOL_POLICY
+#define HGPU_POOL_POLICY 0
+#endif
+#ifndef HGPU_POOL_BLOCKS_PER_SM
+#define HGPU_POOL_BLOCKS_PER_SM 2
+#endif
+__global__ void __launch_bounds__(32 * POOL_WARPS, HGPU_POOL_BLOCKS_PER_SM) k_poa_pool(const __grid_constant__ PoolArgs pa, uint32_t n_ctx) {
     const PoaArgs& a = pa.a;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = lane_id();
     const uint32_t wib = threadIdx.x >> 5;
     uint8_t* wsm = smem_raw + (size_t)wib * DP_SMEM_PER_WARP_DEEP;
     PoolShared* sh = reinterpret_cast<PoolShared*>(smem_raw + (size_t)POOL_WARPS * DP_SMEM_PER_WARP_DEEP);
-    static_assert(POOL_MAX_CTX <= 32 * POOL_WARPS, "one thread initialises one context");
+    static_assert(POOL_MAX_CTX <= 32, "one lane looks at one context when a warp claims a task");
     if (threadIdx.x < POOL_MAX_CTX) {
         const bool live = threadIdx.x < n_ctx && pa.ctx_class[blockIdx.x * n_ctx + threadIdx.x] != 0xFFu;
         sh->ctx[threadIdx.x].state = live ? PS_IDLE : PS_DONE; sh->ctx[threadIdx.x].claim = 0; sh->ctx[threadIdx.x].n_tasks = 0;
@@ -247,37 +277,63 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, 2) k_poa_pool(const __grid_co
     if (threadIdx.x < 5) sh->tot[threadIdx.x] = 0;
     __syncthreads();
     uint32_t idle_spins = 0;
+    POOL_CLK_DECL
     while (true) {
-        // ---- claim a task: graph work first (it is the critical path of its edge), then stripes, then a context without an edge
+        // ---- claim a task. Every lane looks at one context and offers what it has: a context that was never opened (first: an
+        //      edge can only be ranked once its first alignment is set up), else its graph task or its next stripe, ranked by what
+        //      is left of the edge's critical path. The longest edges of the block get the warps first and run at their own speed;
+        //      the short ones fill what is left and make the tail of the kernel (first come first served left the long ones
+        //      sharing warps eight ways, and the kernel waited 60 % of its time for them).
         int kind = PT_NONE; uint32_t c = 0, s = 0;
-        if (lane == 0) {
-            for (uint32_t q = 0; q < n_ctx && kind == PT_NONE; ++q) {
-                const uint32_t cc = (q + wib) % n_ctx;
-                if (vld(&sh->ctx[cc].state) == PS_GRAPH_READY && atomicCAS(&sh->ctx[cc].state, PS_GRAPH_READY, PS_BUSY) == PS_GRAPH_READY) { kind = PT_GRAPH; c = cc; }
-            }
-            for (uint32_t q = 0; q < n_ctx && kind == PT_NONE; ++q) {
-                const uint32_t cc = (q + wib) % n_ctx;
-                PoolCtx* C = &sh->ctx[cc];
-                if (vld(&C->state) == PS_FILL) {
+        {
+            uint32_t key = 0, w = 0, st_ = PS_DONE;
+            if ((uint32_t)lane < n_ctx) {
+                PoolCtx* Cq = &sh->ctx[lane];
+                st_ = vld(&Cq->state);
+#if HGPU_POOL_POLICY == 3
+                const uint32_t uniq = 31u - (uint32_t)lane;
+#else
+                const uint32_t uniq = (uint32_t)(lane + wib) & 31u;
+#endif
+                if (st_ == PS_IDLE) key = 0x80000000u | uniq;
+#if HGPU_POOL_POLICY == 1
+                else if (st_ == PS_GRAPH_READY) key = 0x40000000u | (vld(&Cq->prio) << 6) | uniq;
+#elif HGPU_POOL_POLICY == 2
+                else if (st_ == PS_GRAPH_READY) key = ((vld(&Cq->prio) >> 4) << 7) | 0x40u | uniq;
+#else
+                else if (st_ == PS_GRAPH_READY) key = (vld(&Cq->prio) << 7) | 0x40u | uniq;
+#endif
+                else if (st_ == PS_FILL) {
                     // read the claim word, then the task count of that generation, then claim by CAS on the whole word: if the
                     // alignment changed in between, the generation differs and the CAS fails
-                    const uint32_t w = vld(&C->claim);
+                    w = vld(&Cq->claim);
                     __threadfence_block();
-                    const uint32_t t = w & 0xFFu;
-                    if (t < vld(&C->n_tasks) && atomicCAS(&C->claim, w, w + 1u) == w) { kind = PT_STRIPE; c = cc; s = t; }
+#if HGPU_POOL_POLICY == 1
+                    if ((w & 0xFFu) < vld(&Cq->n_tasks)) key = (vld(&Cq->prio) << 6) | uniq;
+#elif HGPU_POOL_POLICY == 2
+                    if ((w & 0xFFu) < vld(&Cq->n_tasks)) key = ((vld(&Cq->prio) >> 4) << 7) | uniq;
+#else
+                    if ((w & 0xFFu) < vld(&Cq->n_tasks)) key = (vld(&Cq->prio) << 7) | uniq;
+#endif
                 }
             }
-            for (uint32_t q = 0; q < n_ctx && kind == PT_NONE; ++q) {
-                const uint32_t cc = (q + wib) % n_ctx;
-                if (vld(&sh->ctx[cc].state) == PS_IDLE && atomicCAS(&sh->ctx[cc].state, PS_IDLE, PS_BUSY) == PS_IDLE) { kind = PT_NEW; c = cc; }
-            }
-            if (kind == PT_NONE) {
-                bool all_done = true;
-                for (uint32_t q = 0; q < n_ctx; ++q) all_done = all_done && vld(&sh->ctx[q].state) == PS_DONE;
-                if (all_done) kind = PT_EXIT;
+            const uint32_t best = __reduce_max_sync(FULL, key);
+            if (best == 0) {
+                if (__all_sync(FULL, st_ == PS_DONE)) kind = PT_EXIT;
+            } else {
+                const int winner = __ffs(__ballot_sync(FULL, key == best)) - 1;
+                int got = PT_NONE;
+                if (lane == winner) {
+                    PoolCtx* Cq = &sh->ctx[lane];
+                    if (st_ == PS_IDLE) { if (atomicCAS(&Cq->state, PS_IDLE, PS_BUSY) == PS_IDLE) got = PT_NEW; }
+                    else if (st_ == PS_GRAPH_READY) { if (atomicCAS(&Cq->state, PS_GRAPH_READY, PS_BUSY) == PS_GRAPH_READY) got = PT_GRAPH; }
+                    else if (atomicCAS(&Cq->claim, w, w + 1u) == w) got = PT_STRIPE;
+                }
+                kind = __shfl_sync(FULL, got, winner);
+                if (kind == PT_NONE) continue;                  // another warp was faster: look again
+                c = (uint32_t)winner; s = __shfl_sync(FULL, w, winner) & 0xFFu;
             }
         }
-        kind = __shfl_sync(FULL, kind, 0); c = __shfl_sync(FULL, c, 0); s = __shfl_sync(FULL, s, 0);
         if (kind == PT_EXIT) break;
         if (kind == PT_NONE) {
             __nanosleep(idle_spins < 64 ? 200 : 2000);
@@ -288,13 +344,18 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, 2) k_poa_pool(const __grid_co
             continue;
         }
         idle_spins = 0;
+        POOL_CLK(a, 0)
         __threadfence_block();
         PoolCtx* C = &sh->ctx[c];
         PoolEnv E = pool_env(pa, blockIdx.x * n_ctx + c);
         if (kind == PT_NEW) {
             pool_advance(pa, E, C, sh, ST_OK, false, lane);
+            POOL_CLK(a, 1)
         } else if (kind == PT_GRAPH) {
             pool_graph_task(pa, E, C, sh, wsm, lane);
+#if HGPU_PHASE_CLOCKS
+            pk_t = clock64();
+#endif
         } else {
             const uint32_t V = vld(&C->V), L = vld(&C->L), k = vld(&C->k), s0 = vld(&C->s0), NS = vld(&C->NS);
             const int mode = (int)vld(&C->mode);
@@ -322,8 +383,10 @@ __global__ void __launch_bounds__(32 * POOL_WARPS, 2) k_poa_pool(const __grid_co
                 if (d == vld(&C->n_tasks)) { __threadfence_block(); vst(&C->state, PS_GRAPH_READY); }
             }
             __syncwarp();
+            POOL_CLK(a, 2)
         }
     }
+    POOL_CLK(a, 0)
     __syncthreads();
     if (threadIdx.x == 0 && a.stats) {
         atomicAdd(a.stats + 0, sh->tot[0]); atomicAdd(a.stats + 1, sh->tot[1]); atomicAdd(a.stats + 2, sh->tot[2]);
