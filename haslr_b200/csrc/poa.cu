@@ -535,6 +535,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
 #if HGPU_PHASE_CLOCKS
                 HGPU_CUDA(ctx, cudaMemsetAsync(S->stats.p + 8, 0, 16 * sizeof(unsigned long long), st));
                 a.phase_clk = S->stats.p + 8;
+                { unsigned long long* tbp = S->stats.p + 8 + 10; HGPU_CUDA(ctx, cudaMemcpyToSymbolAsync(g_tb_counters, &tbp, sizeof tbp, 0, cudaMemcpyHostToDevice, st)); }
 #endif
                 if (S->verbose >= 2) {
                     HGPU_CUDA(ctx, S->edge_clk.ensure((size_t)n_edges * 2));
@@ -700,6 +701,8 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
         fprintf(stderr, "[phase clocks, warp-cycles of the last class]");
         for (int i = 0; i < 9; ++i) fprintf(stderr, " %s %.1f%%", nm[i], 100.0 * (double)pc[i] / (tot > 0 ? tot : 1));
         fprintf(stderr, "\n");
+        if (pc[13]) fprintf(stderr, "[traceback] path steps %llu, walk iterations %llu (%.2f steps each), tiles loaded %llu (%.1f steps each), generic steps %llu\n",
+                            pc[13], pc[11], (double)pc[13] / (double)(pc[11] ? pc[11] : 1), pc[10], (double)pc[13] / (double)(pc[10] ? pc[10] : 1), pc[12]);
     }
 #endif
     if (S->verbose) fprintf(stderr, "[poa] host: %.1f ms for the whole run (kernels %.1f ms)\n", host_ms(), S->st.ms_dp);

@@ -50,7 +50,7 @@ struct WsLayout {
     uint32_t ncap, ecap, scap;
     uint64_t o_hdr, o_code, o_in_head, o_in_tail, o_out_head, o_aligned, o_e_begin, o_e_end, o_e_w, o_e_next_in, o_e_next_out,
         o_rank2node, o_node2rank, o_meta0, o_pred_off, o_pred_rank, o_sinks, o_aln_rank, o_aln_pos, o_mark, o_check, o_stack,
-        o_score, o_pred, o_plan, o_trec;
+        o_score, o_pred, o_plan, o_trec, o_tbp;
     uint64_t bytes;
 };
 
@@ -74,6 +74,7 @@ __host__ __device__ inline WsLayout ws_layout(uint32_t ncap, uint32_t ecap) {
     w.o_score = take(8 * n); w.o_pred = take(4 * n);
     w.o_plan = take(4 * n);                                   // deep kernels: per-rank predecessor plan (poa_fill_rel.cuh)
     w.o_trec = take(32 * n);                                  // per-node record of the topological sort (w_build_trec)
+    w.o_tbp = take(4 * n);                                    // deep kernels: per-rank predecessor distances in in-edge order for the traceback (w_build_plan)
     w.bytes = (o + 127) / 128 * 128;
     return w;
 }
@@ -128,6 +129,7 @@ __device__ __forceinline__ void st_row(uint4* p, uint4 v) {
 #endif
 }
 static constexpr int TB_ROWS = 32, TB_COLS = 32;
+static constexpr uint32_t TBP_GENERIC = 0xC0000000u;       // traceback predecessor word: the row takes the one-lane generic step
 #ifndef HGPU_TB_CPASYNC
 #define HGPU_TB_CPASYNC 1            // traceback tiles as asynchronous global -> shared copies (LDGSTS); 0 = LDG + STS (A/B: +0.4 % on config 3,
 #endif                               // +1.4 % on the deep shape, profiles/r2n_ab_cpasync.log)
@@ -1005,20 +1007,23 @@ namespace hgpu {
 // plus the first move of another kind. Only rows with three or more predecessors, or predecessors outside the
 // tile, take the one-lane generic step.
 // ---------------------------------------------------------------------------------------------------------
-template <int NW, bool P16, bool REL = false>
+#if HGPU_PHASE_CLOCKS
+__device__ unsigned long long* g_tb_counters = nullptr;   // developer build: [4] tiles loaded, walk iterations, generic steps, path length
+#endif
+template <int NW, bool P16, bool REL = false, bool TBP = false>
 struct TbTile {
     using G = Geo<NW, P16>;
     static constexpr int NG = (TB_COLS + G::CPL - 2) / G::CPL + 1;        // column groups a 32-column window can touch (3 / 5)
     static constexpr int LDW = NG * NW + 4;                               // row stride in words (16-byte multiple, spreads banks)
-    static constexpr int BYTES = TB_ROWS * LDW * 4 + TB_ROWS * 4 + TB_COLS + (REL ? 2 * TB_ROWS * 4 : 0);   // REL: row bases of the (at most two) stripes a tile touches
+    static constexpr int BYTES = TB_ROWS * LDW * 4 + TB_ROWS * 4 + TB_COLS + (REL ? 2 * TB_ROWS * 4 : 0) + (TBP ? TB_ROWS * 4 : 0);   // REL: row bases of the (at most two) stripes a tile touches; TBP: the rows' predecessor words
     static_assert(BYTES <= DP_SMEM_PER_WARP, "traceback tile does not fit the warp's shared memory");
 };
 
-template <int NW, bool P16, bool REL = false>
+template <int NW, bool P16, bool REL = false, bool TBP = false>
 __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8_t* wsm, const uint8_t* seq,
-                                       uint32_t V, uint32_t L, const DpScores sc, int lane) {
+                                       uint32_t V, uint32_t L, const DpScores sc, int lane, const uint32_t* tbp = nullptr) {
     using G = Geo<NW, P16>;
-    using T = TbTile<NW, P16, REL>;
+    using T = TbTile<NW, P16, REL, TBP>;
     const int g = sc.g;
     // the view's address escapes to the graph functions, so the compiler re-reads its fields from local memory around every
     // store: keep what the walk uses in registers
@@ -1045,11 +1050,20 @@ __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8
     uint32_t* tm0 = tile + TB_ROWS * T::LDW;
     uint8_t* tseq = reinterpret_cast<uint8_t*>(tm0 + TB_ROWS);
     int32_t* tbase = reinterpret_cast<int32_t*>(tseq + TB_COLS);         // REL: [2][TB_ROWS] bases of the tile's rows in its first / second stripe
+    uint32_t* ttp = reinterpret_cast<uint32_t*>(tbase + (REL ? 2 * TB_ROWS : 0));   // TBP: predecessor words of the tile's rows
+    uint32_t J0 = TB_ROWS, J1 = TB_ROWS, J2 = TB_ROWS, J3 = TB_ROWS, J4 = TB_ROWS;  // TBP: lane a holds the tile row 2^k first-predecessor hops from row a (32: outside)
     const uint4* Hu = reinterpret_cast<const uint4*>(sv.H);
     const uint32_t NS = sv.NS;
     uint32_t ci = best_i, cj = L, n_out = 0;
     bool bad = (best_i == 0);
+#if HGPU_PHASE_CLOCKS
+    uint32_t tbc_tiles = 0, tbc_iters = 0, tbc_generic = 0;
+#define TB_COUNT(x) ++(x)
+#else
+#define TB_COUNT(x)
+#endif
     while (!bad && !(ci == 0 && cj == 0)) {
+        TB_COUNT(tbc_tiles);
         // ---- tile with (ci, cj) in its corner: rows it-31 .. it, columns jt-31 .. jt
         const uint32_t it = ci, jt = cj;
         const uint32_t g0 = (jt >= (uint32_t)(TB_COLS - 1) ? jt - (TB_COLS - 1) : 0u) / G::CPL;   // first column group of the tile
@@ -1074,11 +1088,25 @@ __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8
                 }
             }
             if (row >= 1) tm0[lane] = T_meta0[row - 1];
+            if (TBP) {
+                const uint32_t tp = row >= 1 ? tbp[row - 1] : TBP_GENERIC;
+                ttp[lane] = tp;
+                J0 = (tp >> 30) ? (uint32_t)TB_ROWS : min((uint32_t)lane + (tp & 31u), (uint32_t)TB_ROWS);
+            }
             if (REL) {
                 const uint32_t sA = g0 / 32u;
                 tbase[lane] = sv.bcol[(uint64_t)sA * (V + 1) + row];
                 tbase[TB_ROWS + lane] = sv.bcol[(uint64_t)(sA + 1) * (V + 1) + row];
             }
+        }
+        if (TBP) {
+            if (it < (uint32_t)lane) J0 = TB_ROWS;
+            // hop tables by doubling: J(k+1)[a] = Jk[Jk[a]]
+            uint32_t y;
+            y = __shfl_sync(FULL, J0, J0 & 31u); J1 = J0 >= (uint32_t)TB_ROWS ? (uint32_t)TB_ROWS : y;
+            y = __shfl_sync(FULL, J1, J1 & 31u); J2 = J1 >= (uint32_t)TB_ROWS ? (uint32_t)TB_ROWS : y;
+            y = __shfl_sync(FULL, J2, J2 & 31u); J3 = J2 >= (uint32_t)TB_ROWS ? (uint32_t)TB_ROWS : y;
+            y = __shfl_sync(FULL, J3, J3 & 31u); J4 = J3 >= (uint32_t)TB_ROWS ? (uint32_t)TB_ROWS : y;
         }
 #if HGPU_TB_CPASYNC
         asm volatile("cp.async.wait_all;" ::: "memory");
@@ -1114,6 +1142,49 @@ __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8
             //      kind: 0 diagonal to the previous rank, 1 another move (di rows up, dj columns left), 2 needs the generic step,
             //            3 reload the tile here, 4 no move reproduces the cell (cannot happen), 5 the walk is complete
             int kind = 3; uint32_t di = 0, dj = 0;
+            uint32_t my_i = 0;                                            // TBP: the row of this lane's cell
+            if (TBP) {
+                // lane t looks at the cell t first-predecessor hops up and t columns left of (ci, cj): the path runs through it as long
+                // as every lane before it moved diagonally to its first predecessor (SPOA's first preference), whatever that
+                // predecessor's rank distance is. Rows with up to six predecessors within the tile are decided here.
+                uint32_t a_ = li, nx;
+                nx = __shfl_sync(FULL, J0, a_ & 31u); if (lane & 1) a_ = a_ >= (uint32_t)TB_ROWS ? (uint32_t)TB_ROWS : nx;
+                nx = __shfl_sync(FULL, J1, a_ & 31u); if (lane & 2) a_ = a_ >= (uint32_t)TB_ROWS ? (uint32_t)TB_ROWS : nx;
+                nx = __shfl_sync(FULL, J2, a_ & 31u); if (lane & 4) a_ = a_ >= (uint32_t)TB_ROWS ? (uint32_t)TB_ROWS : nx;
+                nx = __shfl_sync(FULL, J3, a_ & 31u); if (lane & 8) a_ = a_ >= (uint32_t)TB_ROWS ? (uint32_t)TB_ROWS : nx;
+                nx = __shfl_sync(FULL, J4, a_ & 31u); if (lane & 16) a_ = a_ >= (uint32_t)TB_ROWS ? (uint32_t)TB_ROWS : nx;
+                if (a_ < (uint32_t)TB_ROWS && (uint32_t)lane <= cj) {
+                    const uint32_t i = it - a_, j = cj - lane, b_ = lj + lane;
+                    my_i = i;
+                    if (i == 0 && j == 0) kind = 5;
+                    else if (a_ + 1 < (uint32_t)TB_ROWS && b_ + 1 < (uint32_t)TB_COLS) {
+                        const int val = cell(a_, j);
+                        if (i == 0) { kind = 1; di = 0; dj = 1; }          // row 0: only horizontal moves are left
+                        else {
+                            const uint32_t tp = ttp[a_];
+                            if (tp >> 30) kind = 2;
+                            else {
+                                bool far = false;
+                                for (uint32_t q = tp; q; q >>= 5) far = far || a_ + (q & 31u) >= (uint32_t)TB_ROWS;
+                                if (far) kind = a_ == 0 ? 2 : 3;            // a predecessor row is outside the tile
+                                else {
+                                    kind = 4;
+                                    if (j != 0) {
+                                        const int dsc = (tseq[b_] == (tm0[a_] & 3u)) ? sc.sm : sc.sx;
+                                        for (uint32_t q = tp; q; q >>= 5)
+                                            if (val == cell(a_ + (q & 31u), j - 1) + dsc) { kind = q == tp ? 0 : 1; di = q & 31u; dj = 1; break; }
+                                    }
+                                    if (kind == 4) {
+                                        for (uint32_t q = tp; q; q >>= 5)
+                                            if (val == cell(a_ + (q & 31u), j) + g) { kind = 1; di = q & 31u; dj = 0; break; }
+                                        if (kind == 4 && j != 0 && val == cell(a_, j - 1)) { kind = 1; di = 0; dj = 1; }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            } else
             if ((uint32_t)lane <= ci && (uint32_t)lane <= cj) {
                 const uint32_t i = ci - lane, j = cj - lane, a_ = li + lane, b_ = lj + lane;
                 if (i == 0 && j == 0) kind = 5;
@@ -1146,25 +1217,31 @@ __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8
                     }
                 }
             }
+            TB_COUNT(tbc_iters);
             const unsigned fm = __ballot_sync(FULL, kind != 0);           // never 0: the tile's edge cells say "reload"
             const uint32_t run = (uint32_t)(__ffs(fm) - 1);
             const int kr = __shfl_sync(FULL, kind, run);
             const uint32_t extra = kr == 1 ? 1u : 0u;
             if ((uint64_t)n_out + run + extra > T_ncap) { bad = true; break; }
+            const uint32_t row_i = TBP ? my_i : ci - lane;                 // the row of this lane's cell
             if ((uint32_t)lane < run) {
-                T_aln_rank[n_out + lane] = (int32_t)(ci - lane - 1);
+                T_aln_rank[n_out + lane] = (int32_t)(row_i - 1);
                 T_aln_pos[n_out + lane] = (int32_t)(cj - lane - 1);
             } else if ((uint32_t)lane == run && extra) {
-                T_aln_rank[n_out + run] = di == 0 ? -1 : (int32_t)(ci - run - 1);
+                T_aln_rank[n_out + run] = di == 0 ? -1 : (int32_t)(row_i - 1);
                 T_aln_pos[n_out + run] = dj == 0 ? -1 : (int32_t)(cj - run - 1);
             }
             const uint32_t xdi = __shfl_sync(FULL, di, run), xdj = __shfl_sync(FULL, dj, run);
-            n_out += run + extra; ci -= run; cj -= run;
+            n_out += run + extra;
+            if (TBP) { const uint32_t after = __shfl_sync(FULL, row_i - di, (run + 31u) & 31u); if (run) ci = after; }   // where the last diagonal move of the run went
+            else ci -= run;
+            cj -= run;
             if (extra) { ci -= xdi; cj -= xdj; continue; }
             if (kr == 3) break;                                           // reload the tile around (ci, cj)
             if (kr == 5) continue;                                        // (0, 0) reached: the loop head ends the walk
             if (kr == 4) { bad = true; break; }
             // ---- kr == 2: one generic step on one lane (three or more predecessors, or predecessor rows outside the tile)
+            TB_COUNT(tbc_generic);
             if (lane == 0) {
                 const uint32_t i = ci, j = cj;
                 auto getH = [&](uint32_t ii, uint32_t jj) -> int {
@@ -1210,6 +1287,12 @@ __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8
         }
     }
     if (lane == 0) *gv.aln_len = bad ? 0 : n_out;
+#if HGPU_PHASE_CLOCKS
+    if (lane == 0 && g_tb_counters) {
+        atomicAdd(g_tb_counters + 0, (unsigned long long)tbc_tiles); atomicAdd(g_tb_counters + 1, (unsigned long long)tbc_iters);
+        atomicAdd(g_tb_counters + 2, (unsigned long long)tbc_generic); atomicAdd(g_tb_counters + 3, (unsigned long long)n_out);
+    }
+#endif
     __syncwarp();
     return !bad;
 }
@@ -1937,6 +2020,7 @@ __device__ __forceinline__ void poa_edges_body(const PoaArgs& a) {
     GraphScratch gs = bind_scratch(wsb, a.wl);
     uint32_t* hdr = reinterpret_cast<uint32_t*>(wsb + a.wl.o_hdr);
     uint32_t* plan = reinterpret_cast<uint32_t*>(wsb + a.wl.o_plan);
+    uint32_t* tbp = reinterpret_cast<uint32_t*>(wsb + a.wl.o_tbp);
     TopoRec* trec = reinterpret_cast<TopoRec*>(wsb + a.wl.o_trec);
     unsigned long long st_cells = 0, st_padded = 0, st_aln = 0, st_aln32 = 0, st_bases = 0;
     PHASE_CLK_DECL
@@ -1959,7 +2043,7 @@ __device__ __forceinline__ void poa_edges_body(const PoaArgs& a) {
         } else {
             const uint32_t L0 = a.seg_len[s0];
             if (L0 > gv.ncap || L0 > gv.ecap) st = ST_CAPACITY;
-            else { w_init_chain(gv, a.bases + a.seg_ptr[s0], L0, lane); e_bases += L0; if (RING > 2) w_build_plan(gv, plan, lane); }
+            else { w_init_chain(gv, a.bases + a.seg_ptr[s0], L0, lane); e_bases += L0; if (RING > 2) w_build_plan(gv, plan, tbp, lane); }
             PHASE_CLK(PC_INIT)
             for (uint32_t k = 1; k < R && st == ST_OK; ++k) {
                 const uint32_t V = *gv.n_nodes;
@@ -2029,7 +2113,7 @@ __device__ __forceinline__ void poa_edges_body(const PoaArgs& a) {
                 PHASE_CLK(PC_TOPO)
                 if (probe == 4) { debug_stop = true; break; }
                 w_build_meta(gv, lane);
-                if (RING > 2) w_build_plan(gv, plan, lane);
+                if (RING > 2) w_build_plan(gv, plan, tbp, lane);
                 PHASE_CLK(PC_META)
                 if (probe == 5) { debug_stop = true; break; }
             }
@@ -2101,6 +2185,7 @@ __global__ void __launch_bounds__(32 * TEAM, 512 / (32 * TEAM)) k_poa_edges_team
     GraphScratch gs = bind_scratch(wsb, a.wl);
     uint32_t* hdr = reinterpret_cast<uint32_t*>(wsb + a.wl.o_hdr);
     uint32_t* plan = reinterpret_cast<uint32_t*>(wsb + a.wl.o_plan);
+    uint32_t* tbp = reinterpret_cast<uint32_t*>(wsb + a.wl.o_tbp);
     TopoRec* trec = reinterpret_cast<TopoRec*>(wsb + a.wl.o_trec);
     unsigned long long st_cells = 0, st_padded = 0, st_aln = 0, st_aln32 = 0, st_bases = 0;
     const bool lead = wib == 0;
@@ -2122,7 +2207,7 @@ __global__ void __launch_bounds__(32 * TEAM, 512 / (32 * TEAM)) k_poa_edges_team
         } else {
             const uint32_t L0 = a.seg_len[s0];
             if (L0 > gv.ncap || L0 > gv.ecap) st = ST_CAPACITY;
-            else if (lead) { w_init_chain(gv, a.bases + a.seg_ptr[s0], L0, lane); e_bases += L0; w_build_plan(gv, plan, lane); }
+            else if (lead) { w_init_chain(gv, a.bases + a.seg_ptr[s0], L0, lane); e_bases += L0; w_build_plan(gv, plan, tbp, lane); }
             for (uint32_t k = 1; k < R && st == ST_OK; ++k) {
                 if (threadIdx.x < TEAM) vprog[threadIdx.x] = 0;
                 __syncthreads();                              // graph of round k-1 complete, progress words cleared
@@ -2165,7 +2250,7 @@ __global__ void __launch_bounds__(32 * TEAM, 512 / (32 * TEAM)) k_poa_edges_team
                             ust = __shfl_sync(FULL, ust, 0);
                             __syncwarp();
                         }
-                        if (ust == ST_OK) { w_build_meta(gv, lane); w_build_plan(gv, plan, lane); }
+                        if (ust == ST_OK) { w_build_meta(gv, lane); w_build_plan(gv, plan, tbp, lane); }
                         rst = ust;
                     }
                     if (lane == 0) bcast[1] = rst;

@@ -58,11 +58,34 @@ __device__ __forceinline__ uint32_t deep_plan_of(uint32_t m0, uint32_t rr, const
     return pack(dists, n);
 }
 
+// The traceback's word of rank rr: the rank distances of up to six predecessors in in-edge order (SPOA's preference order), five bits
+// each, first predecessor in the low bits; TBP_GENERIC when there are more, or one is 32 or more ranks away (it could never be inside
+// a 32-row tile). A node without in-edges has the virtual row 0 as its predecessor: distance = its row.
+__device__ __forceinline__ uint32_t tb_plan_of(uint32_t m0, uint32_t rr, const uint32_t* pred_off, const uint32_t* pred_rank) {
+    const uint32_t npc = (m0 >> 3) & 3u;
+    if (npc == 0) return rr + 1u <= 31u ? rr + 1u : TBP_GENERIC;
+    if (npc == 1) { const uint32_t d0 = meta_d0(m0); return d0 <= 31u ? d0 : TBP_GENERIC; }
+    if (npc == 2) { const uint32_t d0 = meta_d0(m0), d1 = meta_d1(m0); return (d0 <= 31u && d1 <= 31u) ? (d0 | (d1 << 5)) : TBP_GENERIC; }
+    const uint32_t c0 = pred_off[rr], n = pred_off[rr + 1] - c0;
+    if (n == 0 || n > 6u) return TBP_GENERIC;
+    uint32_t w = 0;
+    for (uint32_t x = 0; x < n; ++x) {
+        const uint32_t d = rr - pred_rank[c0 + x];
+        if (d == 0 || d > 31u) return TBP_GENERIC;
+        w |= d << (5u * x);
+    }
+    return w;
+}
+
 // plan words of all ranks, lane-parallel; run by the warp that owns the graph, after the per-rank DP records exist
-__device__ __noinline__ void w_build_plan(const GraphView& g, uint32_t* plan, int lane) {
+__device__ __noinline__ void w_build_plan(const GraphView& g, uint32_t* plan, uint32_t* tbp, int lane) {
     const uint32_t N = *g.n_nodes;
     const uint32_t* const meta0 = g.meta0; const uint32_t* const pred_off = g.pred_off; const uint32_t* const pred_rank = g.pred_rank;
-    for (uint32_t r = lane; r < N; r += 32) plan[r] = deep_plan_of(meta0[r], r, pred_off, pred_rank);
+    for (uint32_t r = lane; r < N; r += 32) {
+        const uint32_t m0 = meta0[r];
+        plan[r] = deep_plan_of(m0, r, pred_off, pred_rank);
+        tbp[r] = tb_plan_of(m0, r, pred_off, pred_rank);
+    }
     __syncwarp();
 }
 

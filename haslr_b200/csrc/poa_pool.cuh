@@ -75,7 +75,7 @@ __device__ __forceinline__ uint32_t vld(const uint32_t* p) { return *reinterpret
 __device__ __forceinline__ void vst(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
 
 struct PoolEnv {                         // per-context global storage, bound on demand
-    GraphView gv; GraphScratch gs; uint32_t* hdr; uint32_t* plan; TopoRec* trec; uint8_t* slot; uint64_t slot_bytes; uint32_t cls, gctx;
+    GraphView gv; GraphScratch gs; uint32_t* hdr; uint32_t* plan; uint32_t* tbp; TopoRec* trec; uint8_t* slot; uint64_t slot_bytes; uint32_t cls, gctx;
 };
 __device__ __forceinline__ PoolEnv pool_env(const PoolArgs& pa, uint32_t gctx) {
     PoolEnv e;
@@ -89,6 +89,7 @@ __device__ __forceinline__ PoolEnv pool_env(const PoolArgs& pa, uint32_t gctx) {
     e.hdr = reinterpret_cast<uint32_t*>(wsb + c.wl.o_hdr);
     e.plan = reinterpret_cast<uint32_t*>(wsb + c.wl.o_plan);
     e.trec = reinterpret_cast<TopoRec*>(wsb + c.wl.o_trec);
+    e.tbp = reinterpret_cast<uint32_t*>(wsb + c.wl.o_tbp);
     e.slot = c.arena + (uint64_t)idx * c.slot_bytes;
     e.slot_bytes = c.slot_bytes;
     return e;
@@ -197,7 +198,7 @@ __device__ __noinline__ void pool_advance(const PoolArgs& pa, PoolEnv& E, PoolCt
             if (L0 > gv.ncap || L0 > gv.ecap) st = ST_CAPACITY;
             else {
                 w_init_chain(gv, a.bases + a.seg_ptr[s0], L0, lane);
-                w_build_plan(gv, E.plan, lane);
+                w_build_plan(gv, E.plan, E.tbp, lane);
                 if (lane == 0) C->bases = L0;
                 __syncwarp();
             }
@@ -216,8 +217,8 @@ __device__ __noinline__ void pool_graph_task(const PoolArgs& pa, PoolEnv& E, Poo
     POOL_CLK_DECL
     if (vld(&C->sync_fail)) st = ST_SYNC;
     else {
-        const bool ok = mode == DPM_REL16 ? dp_traceback<DP_NW16, true, true>(gv, E.slot, wsm, seq, V, L, a.sc, lane)
-                                          : dp_traceback<DP_NW32, false>(gv, E.slot, wsm, seq, V, L, a.sc, lane);
+        const bool ok = mode == DPM_REL16 ? dp_traceback<DP_NW16, true, true, true>(gv, E.slot, wsm, seq, V, L, a.sc, lane, E.tbp)
+                                          : dp_traceback<DP_NW32, false, false, true>(gv, E.slot, wsm, seq, V, L, a.sc, lane, E.tbp);
         POOL_CLK(a, 3)
         if (lane == 0) {
             E.hdr[HDR_LAST_P16] = (uint32_t)mode; E.hdr[HDR_LAST_V] = V; E.hdr[HDR_LAST_L] = L; E.hdr[HDR_LAST_BIAS] = 0;
@@ -245,7 +246,7 @@ __device__ __noinline__ void pool_graph_task(const PoolArgs& pa, PoolEnv& E, Poo
                 }
             }
             POOL_CLK(a, 5)
-            if (ust == ST_OK) { w_build_meta(gv, lane); w_build_plan(gv, E.plan, lane); }
+            if (ust == ST_OK) { w_build_meta(gv, lane); w_build_plan(gv, E.plan, E.tbp, lane); }
             POOL_CLK(a, 6)
             st = ust;
         }
