@@ -533,7 +533,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
                 a.pool = pass->pool.p; a.pool_cap = pass->pool.n; a.pool_cursor = S->pool_cursor.p;
                 a.sc = sc; a.stats = S->stats.p; a.stop_round = opt.stop_round; a.force_i32 = opt.force_i32;
 #if HGPU_PHASE_CLOCKS
-                HGPU_CUDA(ctx, cudaMemsetAsync(S->stats.p + 8, 0, 16 * sizeof(unsigned long long), st));
+                HGPU_CUDA(ctx, cudaMemsetAsync(S->stats.p + 8, 0, 24 * sizeof(unsigned long long), st));
                 a.phase_clk = S->stats.p + 8;
                 { unsigned long long* tbp = S->stats.p + 8 + 10; HGPU_CUDA(ctx, cudaMemcpyToSymbolAsync(g_tb_counters, &tbp, sizeof tbp, 0, cudaMemcpyHostToDevice, st)); }
 #endif
@@ -692,7 +692,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
     HGPU_CUDA(ctx, cudaStreamSynchronize(st));
 #if HGPU_PHASE_CLOCKS
     {
-        unsigned long long pc[16];
+        unsigned long long pc[24];
         HGPU_CUDA(ctx, cudaMemcpy(pc, S->stats.p + 8, sizeof pc, cudaMemcpyDeviceToHost));
         static const char* nm_edges[9] = {"queue", "init", "fill", "traceback", "add_alignment", "toposort", "dp_records", "consensus", "publish"};
         static const char* nm_pool[9] = {"claim/idle", "open", "stripes", "traceback", "add_alignment", "records+toposort", "dp_records+plan", "advance", "-"};
@@ -701,6 +701,8 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
         fprintf(stderr, "[phase clocks, warp-cycles of the last class]");
         for (int i = 0; i < 9; ++i) fprintf(stderr, " %s %.1f%%", nm[i], 100.0 * (double)pc[i] / (tot > 0 ? tot : 1));
         fprintf(stderr, "\n");
+        if (pc[14]) fprintf(stderr, "[toposort] nodes %llu, batch passes %llu, DFS roots %llu (one per %.1f nodes), visits %llu (%.2f per root)\n",
+                            pc[14], pc[15], pc[16], (double)pc[14] / (double)(pc[16] ? pc[16] : 1), pc[17], (double)pc[17] / (double)(pc[16] ? pc[16] : 1));
         if (pc[13]) fprintf(stderr, "[traceback] path steps %llu, walk iterations %llu (%.2f steps each), tiles loaded %llu (%.1f steps each), generic steps %llu\n",
                             pc[13], pc[11], (double)pc[13] / (double)(pc[11] ? pc[11] : 1), pc[10], (double)pc[13] / (double)(pc[10] ? pc[10] : 1), pc[12]);
     }

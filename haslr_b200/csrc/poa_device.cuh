@@ -1008,6 +1008,11 @@ namespace hgpu {
 // tile, take the one-lane generic step.
 // ---------------------------------------------------------------------------------------------------------
 #if HGPU_PHASE_CLOCKS
+#define TB_COUNT(x) ++(x)
+#else
+#define TB_COUNT(x)
+#endif
+#if HGPU_PHASE_CLOCKS
 __device__ unsigned long long* g_tb_counters = nullptr;   // developer build: [4] tiles loaded, walk iterations, generic steps, path length
 #endif
 template <int NW, bool P16, bool REL = false, bool TBP = false>
@@ -1058,9 +1063,6 @@ __device__ DP_INLINE bool dp_traceback(const GraphView& gv, uint8_t* slot, uint8
     bool bad = (best_i == 0);
 #if HGPU_PHASE_CLOCKS
     uint32_t tbc_tiles = 0, tbc_iters = 0, tbc_generic = 0;
-#define TB_COUNT(x) ++(x)
-#else
-#define TB_COUNT(x)
 #endif
     while (!bad && !(ci == 0 && cj == 0)) {
         TB_COUNT(tbc_tiles);
@@ -1615,6 +1617,9 @@ __device__ __noinline__ int w_toposort(GraphView& g, const TopoRec* rec, uint8_t
     const uint4* rec4 = reinterpret_cast<const uint4*>(rec);
     uint32_t nr = 0;
     int okflag = 1;
+#if HGPU_PHASE_CLOCKS
+    uint32_t tpc_roots = 0, tpc_visits = 0, tpc_passes = 0;
+#endif
     for (uint32_t i0 = 0; i0 < N && okflag; i0 += 32) {
         const uint32_t i = i0 + lane;
         const bool valid = i < N;
@@ -1637,6 +1642,7 @@ __device__ __noinline__ int w_toposort(GraphView& g, const TopoRec* rec, uint8_t
         if (i + 32 < N) asm volatile("prefetch.global.L1 [%0];" :: "l"(rec4 + 2 * (i + 32)));   // the next batch's roots
         uint32_t pos = 0;
         while (true) {
+            TB_COUNT(tpc_passes);
             const uint32_t lo = i0 + pos;
             const bool marked = valid && is_perm(i);
             bool ok = valid && (uint32_t)lane >= pos && !marked && !slow;
@@ -1670,7 +1676,9 @@ __device__ __noinline__ int w_toposort(GraphView& g, const TopoRec* rec, uint8_t
                 uint32_t top = i0 + f;                                                // the top of the stack stays in a register (uniform)
                 if (lane == 0) stk[0] = top;
                 __syncwarp();
+                TB_COUNT(tpc_roots);
                 while (sp > 0) {
+                    TB_COUNT(tpc_visits);
                     if (++guard > limit) { okflag = 0; break; }
                     const uint32_t v = top & IDMASK;
                     // everything this visit may need is requested at once: the node's two bitmap words, its record, the entry below it
@@ -1747,6 +1755,12 @@ __device__ __noinline__ int w_toposort(GraphView& g, const TopoRec* rec, uint8_t
             if (pos >= 32) break;
         }
     }
+#if HGPU_PHASE_CLOCKS
+    if (lane == 0 && g_tb_counters) {
+        atomicAdd(g_tb_counters + 4, (unsigned long long)N); atomicAdd(g_tb_counters + 5, (unsigned long long)tpc_passes);
+        atomicAdd(g_tb_counters + 6, (unsigned long long)tpc_roots); atomicAdd(g_tb_counters + 7, (unsigned long long)tpc_visits);
+    }
+#endif
     if (okflag && nr != N) okflag = 0;
     return okflag;
 }
@@ -1991,6 +2005,9 @@ __device__ __noinline__ uint32_t w_consensus_backtrack(GraphView& g, GraphScratc
 #ifndef HGPU_PHASE_CLOCKS
 #define HGPU_PHASE_CLOCKS 0
 #endif
+#ifndef HGPU_SHALLOW_TBP
+#define HGPU_SHALLOW_TBP 0   // A/B: the warp-per-edge kernel's traceback with predecessor words too
+#endif
 #if HGPU_PHASE_CLOCKS
 #define PHASE_CLK_DECL long long pc_t = clock64(); unsigned long long pc_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #define PHASE_CLK(idx) { const long long pc_n = clock64(); pc_acc[idx] += (unsigned long long)(pc_n - pc_t); pc_t = pc_n; }
@@ -2043,7 +2060,7 @@ __device__ __forceinline__ void poa_edges_body(const PoaArgs& a) {
         } else {
             const uint32_t L0 = a.seg_len[s0];
             if (L0 > gv.ncap || L0 > gv.ecap) st = ST_CAPACITY;
-            else { w_init_chain(gv, a.bases + a.seg_ptr[s0], L0, lane); e_bases += L0; if (RING > 2) w_build_plan(gv, plan, tbp, lane); }
+            else { w_init_chain(gv, a.bases + a.seg_ptr[s0], L0, lane); e_bases += L0; if (RING > 2) w_build_plan(gv, plan, tbp, lane); else if (HGPU_SHALLOW_TBP) w_build_tbp(gv, tbp, lane); }
             PHASE_CLK(PC_INIT)
             for (uint32_t k = 1; k < R && st == ST_OK; ++k) {
                 const uint32_t V = *gv.n_nodes;
@@ -2068,15 +2085,15 @@ __device__ __forceinline__ void poa_edges_body(const PoaArgs& a) {
                 if (RING == 2 && mode == DPM_ABS16) {
                     dp_fill16<false, false, 2>(gv.meta0, gv.pred_off, gv.pred_rank, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, Geo<DP_NW16, true>::bias(V, a.sc), lane, 0, 1, nullptr);
                     PHASE_CLK(PC_FILL)
-                    ok = dp_traceback<DP_NW16, true>(gv, slot, wsm, seq, V, L, a.sc, lane);
+                    ok = dp_traceback<DP_NW16, true, false, HGPU_SHALLOW_TBP != 0>(gv, slot, wsm, seq, V, L, a.sc, lane, tbp);
                 } else if (RING > 2 && mode == DPM_REL16) {
                     dp_fill_rel<false>(gv, plan, slot, wsm, seq, V, L, a.sc.sm, a.sc.sx, a.sc.g, lane, 0, 1, nullptr);
                     PHASE_CLK(PC_FILL)
-                    ok = dp_traceback<DP_NW16, true, true>(gv, slot, wsm, seq, V, L, a.sc, lane);
+                    ok = dp_traceback<DP_NW16, true, true, true>(gv, slot, wsm, seq, V, L, a.sc, lane, tbp);
                 } else {
                     dp_fill<DP_NW32, false>(gv, slot, wsm, seq, V, L, a.sc, lane, 0, 1, nullptr);
                     PHASE_CLK(PC_FILL)
-                    ok = dp_traceback<DP_NW32, false>(gv, slot, wsm, seq, V, L, a.sc, lane);
+                    ok = dp_traceback<DP_NW32, false, false, (RING > 2) || HGPU_SHALLOW_TBP != 0>(gv, slot, wsm, seq, V, L, a.sc, lane, tbp);
                 }
                 PHASE_CLK(PC_TRACEBACK)
                 if (probe == 2) { e_cells += (unsigned long long)(V + 1) * (L + 1); debug_stop = true; break; }
@@ -2114,6 +2131,7 @@ __device__ __forceinline__ void poa_edges_body(const PoaArgs& a) {
                 if (probe == 4) { debug_stop = true; break; }
                 w_build_meta(gv, lane);
                 if (RING > 2) w_build_plan(gv, plan, tbp, lane);
+                else if (HGPU_SHALLOW_TBP) w_build_tbp(gv, tbp, lane);
                 PHASE_CLK(PC_META)
                 if (probe == 5) { debug_stop = true; break; }
             }
@@ -2225,8 +2243,8 @@ __global__ void __launch_bounds__(32 * TEAM, 512 / (32 * TEAM)) k_poa_edges_team
                 if (!all_ok) { st = ST_SYNC; break; }
                 uint32_t rst = ST_OK;
                 if (lead) {
-                    bool ok = mode == DPM_REL16 ? dp_traceback<DP_NW16, true, true>(gv, slot, wsm, seq, V, L, a.sc, lane)
-                                                : dp_traceback<DP_NW32, false>(gv, slot, wsm, seq, V, L, a.sc, lane);
+                    bool ok = mode == DPM_REL16 ? dp_traceback<DP_NW16, true, true, true>(gv, slot, wsm, seq, V, L, a.sc, lane, tbp)
+                                                : dp_traceback<DP_NW32, false, false, true>(gv, slot, wsm, seq, V, L, a.sc, lane, tbp);
                     if (lane == 0) {
                         hdr[HDR_LAST_P16] = (uint32_t)mode; hdr[HDR_LAST_V] = V; hdr[HDR_LAST_L] = L;
                         hdr[HDR_LAST_BIAS] = (uint32_t)(mode == DPM_ABS16 ? Geo<DP_NW16, true>::bias(V, a.sc) : 0);

@@ -89,6 +89,14 @@ __device__ __noinline__ void w_build_plan(const GraphView& g, uint32_t* plan, ui
     __syncwarp();
 }
 
+// the traceback words alone (the warp-per-edge kernel has no fill plan)
+__device__ __noinline__ void w_build_tbp(const GraphView& g, uint32_t* tbp, int lane) {
+    const uint32_t N = *g.n_nodes;
+    const uint32_t* const meta0 = g.meta0; const uint32_t* const pred_off = g.pred_off; const uint32_t* const pred_rank = g.pred_rank;
+    for (uint32_t r = lane; r < N; r += 32) tbp[r] = tb_plan_of(meta0[r], r, pred_off, pred_rank);
+    __syncwarp();
+}
+
 struct RelFrame {                                         // cold per-alignment state, in the warp's shared memory behind the profile
     unsigned long long meta0, pred_off, pred_rank, plan, seq, H, bases;
     uint32_t V, L, NS; int32_t sm, sx, pad;

@@ -1,0 +1,12 @@
+mkdir -p gpurun_out
+L=gpurun_out/r2A.log
+: > $L
+(timeout 900 python -m pytest tests/test_poa_gpu.py tests/test_golden_gpu.py -m gpu -x -q 2>&1 | tail -5) > gpurun_out/r2A_pytest.log
+bash tools/ab.sh haslr_b200/libhaslr_b200.so >> $L 2>&1
+DEEP_PROBE_CHECK=4 timeout 300 python tools/deep_probe.py 592 28 2500 1 2>&1 | tail -2 | cut -c1-150 >> $L
+timeout 300 python tools/deep_probe.py 2368 28 2500 1 2>&1 | tail -1 | cut -c1-150 >> $L
+HGPU_VERBOSE=2 PATH_PROBE_STEPS=2 timeout 300 python tools/path_probe.py 2>&1 | grep "gpu 0\|time line\|value" | tail -3 | cut -c1-260 >> $L
+for shape in "592 28 2500" "20000 6 1500"; do
+  echo "== $shape" >> $L
+  HASLR_B200_LIB=build/var/pclk.so timeout 300 python tools/deep_probe.py $shape 1 2>&1 | grep "phase\|rep 1\|traceback\|toposort" | tail -4 | cut -c1-400 >> $L
+done
