@@ -17,7 +17,10 @@
 
 namespace hgpu {
 
-static constexpr int POOL_WARPS = 8;
+#ifndef HGPU_POOL_WARPS
+#define HGPU_POOL_WARPS 8
+#endif
+static constexpr int POOL_WARPS = HGPU_POOL_WARPS;
 #ifndef HGPU_POOL_MAX_CTX
 #define HGPU_POOL_MAX_CTX 16          // contexts (edges in flight) per block of 8 warps: A/B on config 2, 16 vs 8: 530 vs 552 ms (profiles/r2p_ab.log)
 #endif
