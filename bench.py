@@ -526,7 +526,12 @@ def main():
     roofline = {"kernel": "k_poa_edges", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "gcups": cells / (kernel_ms / 1e3) / 1e9,
                 "kernel_ms_per_launch": kernel_ms / max(1, args.steps * klaunch), "launches_per_step": klaunch,
-                "algorithmic_bytes_per_launch": alg_bytes / max(1, args.steps * klaunch)}
+                "algorithmic_bytes_per_launch": alg_bytes / max(1, args.steps * klaunch),
+                # frac can exceed 1: SURVEY 8d counts an int32 cell (4 B), the kernel stores int16 cells (2 B) and reads a fraction back,
+                # so the DRAM pipe itself moves `traffic` bytes per launch, not the algorithmic figure
+                "dram_frac": (traffic / (kernel_ms / 1e3 / max(1, args.steps * klaunch)) / 1e9 / peak) if traffic else None,
+                "note": "achieved = SURVEY 8d algorithmic bytes (4 B per DP cell) / kernel time; dram_frac = ncu DRAM bytes of the same cells / "
+                        "kernel time / peak. The kernel is issue-bound (ncu: ALU pipe 58 %, DRAM 49 %), see DESIGN.md 2d"}
 
     # ---- second shape, reported beside the headline: deep edges as a real 25x dataset produces them (BASELINE config 2:
     #      median 28 supporting reads over a 2.5 kb gap, graphs of ~10^4 nodes, most cells outside the plain int16 range)
