@@ -23,6 +23,11 @@ namespace hgpu {
 // Plan word of a rank: bits 0-23 the rank distances of up to eight predecessor rows, 3 bits each (distance - 1; the previous
 // rank first when it is one of them), bits 24-25 the node's base code, bits 26-29 the predecessor count, bit 30 PLAN_SLOW.
 static constexpr uint32_t PLAN_SLOW = 1u << 30;
+// 1: lane 31 stores every row's base for the next stripe itself instead of shuffling it into a batch register that is stored every 32
+// rows (one shuffle + two ALU instructions less per row; +1 % on the pool kernel, profiles/r2C_row_variants_ab.log)
+#ifndef HGPU_REL_BCO_STORE
+#define HGPU_REL_BCO_STORE 1
+#endif
 static constexpr int REL_RING = DP_RING_DEEP;            // parked rows per warp; plan distances are 1 .. REL_RING
 static_assert(REL_RING == 8 || REL_RING == 4, "plan distances are packed in 3 bits; the ring index is a mask");
 __device__ __forceinline__ uint32_t plan_code(uint32_t p) { return (p >> 24) & 3u; }
@@ -117,6 +122,9 @@ struct RelState {
     uint32_t b, bprev;       // batch registers: lane q holds the base of row r0+q+1 (this batch / the previous batch) in this stripe
     uint32_t bco;            // batch register: lane q collects the last cell (absolute) of row r0+q+1, the base of that row in the next stripe
     uint32_t stripe;         // s
+#if HGPU_REL_BCO_STORE
+    unsigned long long bnext; // base array of the next stripe
+#endif
     int lane; bool has_prev, has_next;
 };
 
@@ -281,10 +289,14 @@ __device__ __forceinline__ void row_rel(uint32_t (&A)[8], RelState& S, uint32_t 
     stg_cs_v4(S.dst, A[0], A[1], A[2], A[3]);
     stg_cs_v4_512(S.dst, A[4], A[5], A[6], A[7]);
     S.dst += S.row_bytes;
+#if HGPU_REL_BCO_STORE
+    if (S.has_next && lane == 31) stg_u32(S.bnext + 4ull * i, (uint32_t)(((int32_t)A[7] >> 16) + bi));   // the row's base in the next stripe
+#else
     if (S.has_next) {
         const uint32_t last = __shfl_sync(FULL, A[7], 31);
         if (lane == q) S.bco = (uint32_t)(((int32_t)last >> 16) + bi);
     }
+#endif
 }
 
 // profile of stripe s (same layout as fill16_profile), from the RelFrame
@@ -326,6 +338,9 @@ __device__ __forceinline__ bool rel_stripe(RelState& S, uint32_t* prof, RelFrame
     S.has_prev = s > 0;
     S.has_next = s + 1 < lds_u32v(S.frame + RFRAME(NS));
     S.stripe = s;
+#if HGPU_REL_BCO_STORE
+    S.bnext = b_next;
+#endif
     // --- row 0: Hhat = 0 everywhere, base 0
     uint32_t A[NW];
 #pragma unroll
@@ -363,7 +378,9 @@ __device__ __forceinline__ bool rel_stripe(RelState& S, uint32_t* prof, RelFrame
         }
         if (s == 0 && lane < nb) stg_u32(b_cur + 4ull * (rr + 1), S.b);
         if (s == 0) __syncwarp();                                      // later generic rows read these through other lanes' loads
+#if !HGPU_REL_BCO_STORE
         if (S.has_next && lane < nb) stg_u32(b_next + 4ull * (rr + 1), S.bco);
+#endif
         if (TEAM) team_publish(ts.vprog, ts.pub_idx, ts.pub_base + ((r0 + 32 < Vs) ? r0 + 32 : Vs) + 1, lane);
     }
     __syncwarp();
