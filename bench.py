@@ -236,10 +236,11 @@ def strong_scaling_leg(ctx, dist, rank, world, dev, args):
             "value": tot_b / 1e6 / (ms / 1e3), "unit": UNIT, "ms_per_pass": ms, "gcups": tot_c / (ms / 1e3) / 1e9, "n_gpus": world,
             "per_rank_ms": [r[0] for r in rows], "per_rank_kernel_ms": km, "per_rank_edges": [int(r[4]) for r in rows],
             "per_rank_cells": [r[2] for r in rows], "kernel_imbalance_max_over_mean": max(km) / (sum(km) / len(km)) if sum(km) > 0 else None,
-            "limiter": "edges in flight per GPU: k_poa_pool needs ~16 deep edges per SM to keep the issue slots busy (deep_edges leg: 4 per SM run at "
-                       "half the rate of 16 per SM) and every edge keeps a serial critical path (traceback, graph update, topological sort); "
-                       "with 1/N of the set per rank the per-GPU rate falls before the deal's imbalance (kernel_imbalance_max_over_mean) or "
-                       "the all-gather (< 1 % of a pass) matter"}
+            "limiter": "the critical path of the heaviest edges: the alignments of one edge are a serial chain (fill ~0.7 us per graph row, then "
+                       "traceback, graph update and topological sort on one warp), ~12 ms per alignment of a 40-read x 5-kb edge = ~0.5 s for "
+                       "the edge, whatever the number of GPUs. k_poa_pool runs such edges first and at their own speed (longest remaining "
+                       "critical path first), so a rank's time is max(its share of the work, that chain); the deal's imbalance "
+                       "(kernel_imbalance_max_over_mean) and the all-gather (< 1 % of a pass) do not matter before that"}
 
 
 

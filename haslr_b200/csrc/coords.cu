@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "coords_core.cuh"
+#include "sort.cuh"
 
 using namespace hgpu;
 
@@ -84,11 +85,17 @@ __global__ void __launch_bounds__(128) k4_edge_coords(CoordIn in, uint32_t n_edg
 #pragma unroll 1
         for (int l = 0; l < 4; ++l) {
             const uint64_t* r = raw + (size_t)l * n_supp;
-            for (uint32_t k = lane; k < n; k += 32) {
-                const uint64_t key = r[k];
-                uint32_t rank = 0;
-                for (uint32_t q = 0; q < n; ++q) rank += r[q] < key ? 1u : 0u;
-                srt[(size_t)l * n_supp + rank] = key;
+            if (n <= SORT_RANK_MAX) {
+                for (uint32_t k = lane; k < n; k += 32) {
+                    const uint64_t key = r[k];
+                    uint32_t rank = 0;
+                    for (uint32_t q = 0; q < n; ++q) rank += r[q] < key ? 1u : 0u;
+                    srt[(size_t)l * n_supp + rank] = key;
+                }
+            } else {                                              // many supports: bitonic network in place (sort.cuh)
+                uint64_t* d = srt + (size_t)l * n_supp;
+                for (uint32_t k = lane; k < n; k += 32) d[k] = r[k];
+                warp_bitonic_u64<false>(reinterpret_cast<unsigned long long*>(d), nullptr, n, lane);
             }
         }
         __syncwarp();

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "k1_core.cuh"
 #include "scan.cuh"
+#include "sort.cuh"
 
 using namespace hgpu;
 
@@ -32,7 +33,8 @@ struct K12State {
     // K2
     DevBuf<uint32_t> cl_tid, cl_read_off, slot_of, h_cnt, from_hist, from_off, bucket_cur, ent_slot, ent_cnt, supp_off, supp_cur, slot_rank;
     DevBuf<uint8_t> cl_rev, keep;
-    DevBuf<unsigned long long> h_key, ent_key;
+    DevBuf<unsigned long long> h_key, ent_key, sort_key;
+    DevBuf<uint32_t> sort_idx;
     DevBuf<hgpu_edge_supp> supp, supp_tmp;
     DevBuf<uint32_t> scalars;
     DevBuf<unsigned long long> scan_tmp;
@@ -385,17 +387,24 @@ __device__ __forceinline__ unsigned long long supp_order(const hgpu_edge_supp& s
     const uint32_t side = s.lr_id_strand >> 31, pj = side ? s.cmp_tail : s.cmp_head;
     return ((unsigned long long)(s.lr_id_strand & 0x7FFFFFFFu) << 32) | ((unsigned long long)pj << 1) | side;
 }
-__global__ void __launch_bounds__(128) k2_supp_sort(const uint32_t* supp_off, uint32_t n_ent, const hgpu_edge_supp* in, hgpu_edge_supp* out) {
+__global__ void __launch_bounds__(128) k2_supp_sort(const uint32_t* supp_off, uint32_t n_ent, const hgpu_edge_supp* in, hgpu_edge_supp* out,
+                                                    unsigned long long* sort_key, uint32_t* sort_idx) {
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
     for (uint32_t ent = gw; ent < n_ent; ent += nw) {
         const uint32_t b = supp_off[ent], n = supp_off[ent + 1] - b;
-        for (uint32_t i = lane; i < n; i += 32) {            // rank sort: keys are distinct
-            const hgpu_edge_supp s = in[b + i];
-            const unsigned long long k = supp_order(s);
-            uint32_t rank = 0;
-            for (uint32_t q = 0; q < n; ++q) rank += supp_order(in[b + q]) < k ? 1u : 0u;
-            out[b + rank] = s;
+        if (n <= SORT_RANK_MAX) {
+            for (uint32_t i = lane; i < n; i += 32) {            // rank sort: keys are distinct
+                const hgpu_edge_supp s = in[b + i];
+                const unsigned long long k = supp_order(s);
+                uint32_t rank = 0;
+                for (uint32_t q = 0; q < n; ++q) rank += supp_order(in[b + q]) < k ? 1u : 0u;
+                out[b + rank] = s;
+            }
+        } else {                                                  // a contig end with many supports: n log^2 n instead of n^2 (sort.cuh)
+            for (uint32_t i = lane; i < n; i += 32) { sort_key[b + i] = supp_order(in[b + i]); sort_idx[b + i] = i; }
+            warp_bitonic_u64<true>(sort_key + b, sort_idx + b, n, lane);
+            for (uint32_t i = lane; i < n; i += 32) out[b + i] = in[b + sort_idx[b + i]];
         }
     }
 }
@@ -465,6 +474,7 @@ static int backbone_edges_run(hgpu_t* ctx, const uint32_t* d_tid, const uint8_t*
     HGPU_CUDA(ctx, S->ent_slot.ensure(ecap)); HGPU_CUDA(ctx, S->ent_key.ensure(ecap)); HGPU_CUDA(ctx, S->ent_cnt.ensure(ecap + 1));
     HGPU_CUDA(ctx, S->keep.ensure(ecap)); HGPU_CUDA(ctx, S->supp_off.ensure(ecap + 2)); HGPU_CUDA(ctx, S->supp_cur.ensure(ecap + 1));
     HGPU_CUDA(ctx, S->supp.ensure(ecap)); HGPU_CUDA(ctx, S->supp_tmp.ensure(ecap));
+    HGPU_CUDA(ctx, S->sort_key.ensure(ecap)); HGPU_CUDA(ctx, S->sort_idx.ensure(ecap));
     HGPU_CUDA(ctx, S->scan_tmp.ensure(scan_tmp_entries((uint32_t)std::max<uint64_t>(n_from, ecap))));
 
     HGPU_CUDA(ctx, cudaMemsetAsync(S->h_key.p, 0xFF, (size_t)cap * 8, st));
@@ -494,7 +504,8 @@ static int backbone_edges_run(hgpu_t* ctx, const uint32_t* d_tid, const uint8_t*
     k2_scatter_supp<<<(2 * n_elems + 255) / 256, 256, 0, st>>>(S->slot_of.p, elem_read, d_read_off, n_elems, S->slot_rank.p, S->supp_off.p,
                                                                S->supp_cur.p, S->supp_tmp.p);
     HGPU_CUDA(ctx, cudaGetLastError());
-    k2_supp_sort<<<std::min<uint32_t>((n_ent + 3) / 4, (uint32_t)ctx->sm_count * 16), 128, 0, st>>>(S->supp_off.p, n_ent, S->supp_tmp.p, S->supp.p);
+    k2_supp_sort<<<std::min<uint32_t>((n_ent + 3) / 4, (uint32_t)ctx->sm_count * 16), 128, 0, st>>>(S->supp_off.p, n_ent, S->supp_tmp.p, S->supp.p,
+                                                                                                    S->sort_key.p, S->sort_idx.p);
     HGPU_CUDA(ctx, cudaGetLastError());
     stage_end(ctx, ctx->ev_k2);
     ctx->launches += 6 + scan_launches; ctx->stage.launches_k2 += 6 + scan_launches;

@@ -30,7 +30,7 @@ def test_edge_coords_golden(ctx, oracle):
     assert [(int(e["c1"]), int(e["c2"]), int(e["n_best"])) for e in ref[0]] == [(x["c1"], x["c2"], x["n_best"]) for x in gold]
 
 
-@pytest.mark.parametrize("seed,n_edges,max_supp", [(1, 200, 90), (2, 3000, 40), (3, 50, 700), (4, 1, 2)])
+@pytest.mark.parametrize("seed,n_edges,max_supp", [(1, 200, 90), (2, 3000, 40), (3, 50, 700), (4, 1, 2), (5, 4, 3000)])
 def test_edge_coords_stress(ctx, oracle, seed, n_edges, max_supp):
     """Ties, equal-depth optima, several bitmask words per edge, degenerate elements, refused walks, rows without CIGAR."""
     c = coords_cases.random_case(seed, n_edges=n_edges, max_supp=max_supp)

@@ -49,7 +49,8 @@ def test_backbone_edges_golden(ctx, oracle):
 def test_backbone_edges_random_with_self_loops_and_repeats(ctx, oracle):
     """Random compact reads over few contigs: many supports per key, both strands, self loops (quirk Q6), empty reads."""
     rng = np.random.default_rng(5)
-    for n_contigs, n_reads in ((6, 400), (50, 2000), (3000, 5000)):
+    # (2, 3000): ~1,500 supports per key - lists longer than 64 take the bitonic network of csrc/sort.cuh instead of the rank sort
+    for n_contigs, n_reads in ((6, 400), (50, 2000), (3000, 5000), (2, 3000)):
         lens = rng.integers(0, 9, n_reads)
         off = np.concatenate(([0], np.cumsum(lens))).astype(np.uint32)
         tid = rng.integers(0, n_contigs, int(off[-1])).astype(np.uint32)

@@ -13,5 +13,6 @@ HGPU_VERBOSE=1 timeout 300 python tools/deep_probe.py 592 28 2500 2 > gpurun_out
 timeout 300 python tools/deep_probe.py 2368 28 2500 2 >> gpurun_out/r2_deep_probe.log 2>&1
 HGPU_POOL=0 timeout 300 python tools/deep_probe.py 592 28 2500 1 >> gpurun_out/r2_deep_probe.log 2>&1
 HGPU_POOL=0 timeout 300 python tools/deep_probe.py 2368 28 2500 1 >> gpurun_out/r2_deep_probe.log 2>&1
-HGPU_VERBOSE=1 PATH_PROBE_STEPS=2 timeout 300 python tools/path_probe.py 2>&1 | grep -v "cleaning" | tail -24 | cut -c1-260 > gpurun_out/r2_cfg2_path.log
+HGPU_VERBOSE=2 PATH_PROBE_STEPS=2 timeout 300 python tools/path_probe.py 2>&1 | grep -v "cleaning" | tail -44 | cut -c1-260 > gpurun_out/r2_cfg2_path.log
+timeout 1500 python tools/scale_probe.py 14 > gpurun_out/r2_scale14_cfg4.json 2> gpurun_out/r2_scale14_cfg4.err
 ls -la gpurun_out | tail -20
