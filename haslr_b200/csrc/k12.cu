@@ -24,7 +24,7 @@ using namespace hgpu;
 struct K12State {
     // K1
     DevBuf<uint32_t> col[8], cg_off, cg_ops, read_off, out_cnt, out_off, idx, cg_total, status;
-    DevBuf<uint8_t> is_rev, mapq, take;
+    DevBuf<uint8_t> is_rev, mapq, take, pass;
     DevBuf<double> mean_kmer;
     DevBuf<K1Hit> hit;
     DevBuf<uint32_t> dp, cand; DevBuf<int32_t> prevc;
@@ -55,81 +55,53 @@ struct K1Args {
     uint32_t* status;                         // [0] first row (min) that names a contig >= n_contigs, [1] first read whose offsets decrease
 };
 
-// Per-warp staging of a read's rows in shared memory: the order-dependent tail runs on one lane and walks the run-length CIGARs
-// run by run (find_contig_pos) and the sort keys comparison by comparison - from global memory every step was a dependent L2
-// round trip (~300k cycles per read). The runs of the surviving hits and the sort keys of the read's rows are copied here by the
-// whole warp first; reads that do not fit (more than K1_ROWS_CAP rows or K1_RUNS_CAP runs) take the global arrays as before.
-static constexpr uint32_t K1_ROWS_CAP = 96, K1_RUNS_CAP = 1536;
-struct K1Stage { uint32_t runs[K1_RUNS_CAP]; uint32_t off[K1_ROWS_CAP + 2]; uint32_t q_start[K1_ROWS_CAP]; uint32_t q_end[K1_ROWS_CAP]; };
+// K1 runs in three launches so that every step has the parallelism it can use:
+//   k1_filter        one thread per PAF row: the load filters F1-F4 and the contig-id check (SoA columns, coalesced);
+//   k1_cigar_totals  one warp per surviving row: its expanded CIGAR length (the tail only needs the totals);
+//   k1_tail          one THREAD per long read: everything that depends on the order of the read's hits (libstdc++-ordered sort,
+//                    palindrome cut, F5, overlap trimming on the run-length CIGARs, chaining) is inherently one instruction stream
+//                    per read, a few hundred dependent global accesses long. With a warp per read (rounds 1 and early 2) 31 lanes
+//                    sat idle beside it and 4,000 reads were in flight per GPU; with a thread per read it is 150,000, and the
+//                    lanes of a warp overlap each other's memory latency wherever their control flow agrees.
+// (Staging the read's CIGAR runs, sort keys and scratch in shared memory for the one-lane tail was measured first: 0.94 -> 1.06 ->
+// 1.24 ms on config 2 - the shared memory cut the resident warps and with them the latency hiding. profiles/r2G_pool_shape_crit_k1_ab.log)
+__global__ void __launch_bounds__(256) k1_filter(K1Args a, uint8_t* pass) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_hits) return;
+    uint8_t f;
+    if (a.h.t_id[i] >= a.n_contigs) { atomicMin(a.status, i); f = 2; }          // Q1: the reference indexes mean_kmer[t_id] unchecked
+    else f = k1_load_filter(a.h, i, a.mean_kmer, a.p) ? 1 : 0;
+    pass[i] = f;
+}
 
-__global__ void __launch_bounds__(128) k1_compact_lr(K1Args a) {
-    __shared__ K1Stage stage_all[4];
-    K1Stage& sg = stage_all[threadIdx.x >> 5];
+__global__ void __launch_bounds__(256) k1_cigar_totals(K1Args a, const uint8_t* pass) {
     const int lane = threadIdx.x & 31;
-    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t r = gw; r < a.n_reads; r += nw) {
-        const uint32_t b = a.read_off[r], e = a.read_off[r + 1];
-        if (e < b || e > a.n_hits) { if (lane == 0) { atomicMin(a.status + 1, r); a.out_cnt[r] = 0; } continue; }
-        uint32_t* idx = a.idx + b;
-        uint32_t cnt = 0;
-        bool bad = false;
-        for (uint32_t base = b; base < e; base += 32) {
-            const uint32_t i = base + lane;
-            bool ok = false;
-            if (i < e) {
-                if (a.h.t_id[i] >= a.n_contigs) { atomicMin(a.status, i); bad = true; }     // Q1: the reference indexes mean_kmer[t_id] unchecked
-                else ok = k1_load_filter(a.h, i, a.mean_kmer, a.p);
-            }
-            const unsigned m = __ballot_sync(FULLM, ok);
-            if (ok) idx[cnt + __popc(m & ((1u << lane) - 1))] = i;
-            cnt += __popc(m);
-        }
-        if (__any_sync(FULLM, bad)) { if (lane == 0) a.out_cnt[r] = 0; continue; }
-        __syncwarp();
-        // runs of the surviving hits, packed in row order: survivor c occupies [start_c, start_c + n_c)
-        const uint32_t n_rows = e - b;
-        uint32_t total_runs = 0;
-        for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
-            const uint32_t c = c0 + lane;
-            uint32_t nr_ = 0, row = 0;
-            if (c < cnt) { row = idx[c]; nr_ = a.h.cg_off[row + 1] - a.h.cg_off[row]; }
-            uint32_t incl = nr_;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t row = gw; row < a.n_hits; row += nw) {
+        if (pass[row] != 1) continue;
+        const uint32_t k0 = a.h.cg_off[row], k1 = a.h.cg_off[row + 1];
+        uint32_t tot = 0;
+        for (uint32_t k = k0 + lane; k < k1; k += 32) tot += a.h.cg_ops[k] >> 2;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(FULLM, incl, d); if (lane >= d) incl += o; }
-            const uint32_t start = total_runs + incl - nr_;
-            if (c < cnt && n_rows <= K1_ROWS_CAP) { sg.off[row - b] = start; sg.off[row - b + 1] = start + nr_; }
-            total_runs += __shfl_sync(FULLM, incl, 31);
-        }
-        const bool staged = n_rows <= K1_ROWS_CAP && total_runs <= K1_RUNS_CAP;
-        __syncwarp();
-        // expanded CIGAR length of every surviving hit, summed by the whole warp; the same pass stages the runs
-        for (uint32_t c = 0; c < cnt; ++c) {
-            const uint32_t row = idx[c];
-            const uint32_t k0 = a.h.cg_off[row], k1 = a.h.cg_off[row + 1];
-            const uint32_t dst = staged ? sg.off[row - b] : 0u;
-            uint32_t tot = 0;
-            for (uint32_t k = k0 + lane; k < k1; k += 32) {
-                const uint32_t op = a.h.cg_ops[k];
-                tot += op >> 2;
-                if (staged) sg.runs[dst + (k - k0)] = op;
-            }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(FULLM, tot, d);
-            if (lane == 0) a.cg_total[row] = tot;
-        }
-        HitCols hl = a.h;
-        if (staged) {
-            for (uint32_t j = lane; j < n_rows; j += 32) { sg.q_start[j] = a.h.q_start[b + j]; sg.q_end[j] = a.h.q_end[b + j]; }
-            hl.cg_ops = sg.runs; hl.cg_off = sg.off - b;            // indexed by global row, like the arrays they stand in for
-            hl.q_start = sg.q_start - b; hl.q_end = sg.q_end - b;
-        }
-        __syncwarp();
-        if (lane == 0)
-            a.out_cnt[r] = k1_process_read(hl, a.mean_kmer, a.p, idx, cnt, a.hit + b, a.dp + b, a.prevc + b, a.cand + b,
-                                           a.take + b, a.tmp + b, a.cg_total);
-        __syncwarp();
+        for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(FULLM, tot, d);
+        if (lane == 0) a.cg_total[row] = tot;
     }
+}
+
+__global__ void __launch_bounds__(128) k1_tail(K1Args a, const uint8_t* pass) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n_reads) return;
+    const uint32_t b = a.read_off[r], e = a.read_off[r + 1];
+    if (e < b || e > a.n_hits) { atomicMin(a.status + 1, r); a.out_cnt[r] = 0; return; }
+    uint32_t* idx = a.idx + b;
+    uint32_t cnt = 0;
+    bool bad = false;
+    for (uint32_t i = b; i < e; ++i) {                                          // survivors in PAF order
+        const uint8_t f = pass[i];
+        if (f == 2) bad = true; else if (f == 1) idx[cnt++] = i;
+    }
+    if (bad) { a.out_cnt[r] = 0; return; }
+    a.out_cnt[r] = k1_process_read(a.h, a.mean_kmer, a.p, idx, cnt, a.hit + b, a.dp + b, a.prevc + b, a.cand + b, a.take + b, a.tmp + b, a.cg_total);
 }
 
 // pack per-read element runs (stored at the read's first hit row) into the output order; also the per-element contig id and
@@ -160,21 +132,25 @@ static int compact_lr_run(hgpu_t* ctx, const HitCols& h, uint32_t n_hits, const 
     HGPU_H2D(ctx, S->mean_kmer.p, mean_kmer, (size_t)n_contigs * 8);
     const size_t sc = (size_t)n_hits + 1;
     HGPU_CUDA(ctx, S->idx.ensure(sc)); HGPU_CUDA(ctx, S->hit.ensure(sc)); HGPU_CUDA(ctx, S->dp.ensure(sc));
-    HGPU_CUDA(ctx, S->prevc.ensure(sc)); HGPU_CUDA(ctx, S->cand.ensure(sc)); HGPU_CUDA(ctx, S->take.ensure(sc)); HGPU_CUDA(ctx, S->cg_total.ensure(sc));
+    HGPU_CUDA(ctx, S->prevc.ensure(sc)); HGPU_CUDA(ctx, S->cand.ensure(sc)); HGPU_CUDA(ctx, S->take.ensure(sc)); HGPU_CUDA(ctx, S->cg_total.ensure(sc)); HGPU_CUDA(ctx, S->pass.ensure(sc));
     HGPU_CUDA(ctx, S->tmp.ensure(sc)); HGPU_CUDA(ctx, S->out.ensure(sc)); HGPU_CUDA(ctx, S->out_tid.ensure(sc)); HGPU_CUDA(ctx, S->out_rev.ensure(sc));
     HGPU_CUDA(ctx, S->out_cnt.ensure(n_reads + 1)); HGPU_CUDA(ctx, S->out_off.ensure(n_reads + 2)); HGPU_CUDA(ctx, S->status.ensure(4));
     HGPU_CUDA(ctx, S->scan_tmp.ensure(scan_tmp_entries(n_reads)));
     HGPU_CUDA(ctx, cudaMemsetAsync(S->status.p, 0xFF, 16, st));
 
-    uint32_t blocks = (uint32_t)ctx->sm_count * 16;          // 16 blocks of 4 warps: every warp slot of an SM
-    blocks = std::max<uint32_t>(1, std::min<uint32_t>(blocks, (n_reads + 3) / 4));
     K1Args a{};
     a.h = h; a.read_off = d_read_off; a.n_reads = n_reads; a.n_contigs = n_contigs; a.n_hits = n_hits; a.mean_kmer = S->mean_kmer.p;
     a.p = K1Params{prm->min_aln_sim, prm->uniq_freq, prm->max_uniq_dev, prm->min_aln_block, prm->min_aln_mapq};
     a.idx = S->idx.p; a.hit = S->hit.p; a.dp = S->dp.p; a.prevc = S->prevc.p; a.cand = S->cand.p; a.take = S->take.p; a.cg_total = S->cg_total.p;
     a.tmp = S->tmp.p; a.out_cnt = S->out_cnt.p; a.status = S->status.p;
     stage_begin(ctx, ctx->ev_k1);
-    k1_compact_lr<<<blocks, 128, 0, st>>>(a);
+    if (n_hits) {
+        k1_filter<<<(n_hits + 255) / 256, 256, 0, st>>>(a, S->pass.p);
+        HGPU_CUDA(ctx, cudaGetLastError());
+        k1_cigar_totals<<<std::min<uint32_t>((n_hits + 7) / 8, (uint32_t)ctx->sm_count * 32), 256, 0, st>>>(a, S->pass.p);
+        HGPU_CUDA(ctx, cudaGetLastError());
+    }
+    k1_tail<<<(n_reads + 127) / 128, 128, 0, st>>>(a, S->pass.p);
     HGPU_CUDA(ctx, cudaGetLastError());
     const int scan_launches = scan_u32(st, S->out_cnt.p, S->out_off.p, n_reads, S->scan_tmp.p, nullptr);
     HGPU_CUDA(ctx, cudaGetLastError());
@@ -182,7 +158,7 @@ static int compact_lr_run(hgpu_t* ctx, const HitCols& h, uint32_t n_hits, const 
         S->tmp.p, d_read_off, S->out_cnt.p, S->out_off.p, n_reads, h.t_id, h.is_rev, S->out.p, S->out_tid.p, S->out_rev.p);
     HGPU_CUDA(ctx, cudaGetLastError());
     stage_end(ctx, ctx->ev_k1);
-    ctx->launches += 2 + scan_launches; ctx->stage.launches_k1 = 2 + scan_launches;
+    ctx->launches += 4 + scan_launches; ctx->stage.launches_k1 = 4 + scan_launches;
     uint32_t status[2];
     HGPU_CUDA(ctx, cudaMemcpyAsync(status, S->status.p, 8, cudaMemcpyDeviceToHost, st));
     HGPU_D2H(ctx, out_read_off, S->out_off.p, (size_t)(n_reads + 1) * 4);

@@ -362,7 +362,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
 
         // ---- size classes: a class ends where the slot estimate has halved, unless memory is no constraint
         struct Cls { size_t a, b; uint64_t slot; WsLayout wl; uint32_t warps; bool deep; bool pool; uint32_t ctx_per_block, pool_blocks; double cells, work; };
-        const uint32_t pool_blocks_max = (uint32_t)HGPU_POOL_BLOCKS_PER_SM * (uint32_t)ctx->sm_count;   // k_poa_pool: two blocks of 8 warps per SM
+        const uint32_t pool_blocks_max = (uint32_t)HGPU_POOL_BLOCKS_PER_SM * (uint32_t)ctx->sm_count;   // k_poa_pool: HGPU_POOL_BLOCKS_PER_SM blocks of POOL_WARPS warps per SM (1 x 16)
         std::vector<Cls> classes;
         constexpr uint64_t POOL_SMALL_SLOT = 8ull << 20;
         uint32_t n_pool_classes = 0;

@@ -18,11 +18,13 @@
 namespace hgpu {
 
 #ifndef HGPU_POOL_WARPS
-#define HGPU_POOL_WARPS 8
+#define HGPU_POOL_WARPS 16            // one block of 16 warps per SM: an edge whose new alignment needs seven warps at once finds them sooner among 16 than
+                                      // among 8 (config 2 K3 355 -> 347 ms against two blocks of 8; profiles/r2E_w16.log, r2G_pool_shape_crit_k1_ab.log)
 #endif
 static constexpr int POOL_WARPS = HGPU_POOL_WARPS;
 #ifndef HGPU_POOL_MAX_CTX
-#define HGPU_POOL_MAX_CTX 16          // contexts (edges in flight) per block of 8 warps: A/B on config 2, 16 vs 8: 530 vs 552 ms (profiles/r2p_ab.log)
+#define HGPU_POOL_MAX_CTX 32          // contexts (edges in flight) per block, two per warp: A/B on config 2 with blocks of 8 warps, 16 vs 8 contexts: 530 vs 552 ms
+                                      // (profiles/r2p_ab.log); at most 32: one lane looks at one context when a warp claims a task
 #endif
 static constexpr int POOL_MAX_CTX = HGPU_POOL_MAX_CTX;
 static constexpr uint32_t POOL_MAX_STRIPES = 32;          // alignments with more stripes are filled by one warp, stripe after stripe
@@ -264,7 +266,7 @@ __device__ __noinline__ void pool_graph_task(const PoolArgs& pa, PoolEnv& E, Poo
 #define HGPU_POOL_POLICY 0
 #endif
 #ifndef HGPU_POOL_BLOCKS_PER_SM
-#define HGPU_POOL_BLOCKS_PER_SM 2
+#define HGPU_POOL_BLOCKS_PER_SM 1
 #endif
 __global__ void __launch_bounds__(32 * POOL_WARPS, HGPU_POOL_BLOCKS_PER_SM) k_poa_pool(const __grid_constant__ PoolArgs pa, uint32_t n_ctx) {
     const PoaArgs& a = pa.a;

@@ -26,4 +26,6 @@ args = argparse.Namespace(steps=int(os.environ.get("PATH_PROBE_STEPS", "2")), wh
 peak, _ = bench.peaks()
 out = bench.whole_path_leg(ctx, args, peak)
 print(json.dumps({k: out[k] for k in ("value", "s_per_pass", "stage_wall_s")}), file=sys.stderr)
+for k in out["kernels"]:
+    print(json.dumps({q: k[q] for q in ("kernel", "ms", "launches", "frac") if q in k}), file=sys.stderr)
 print(json.dumps(out["kernels"][-1]), file=sys.stderr)
