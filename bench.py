@@ -345,7 +345,7 @@ def whole_path_leg(ctx, args, peak):
                      "frac": (alg_bytes / (ms / 1e3) / 1e9 / peak) if ms > 0 else None})
     k("k0_* PAF tokeniser", st["ms_k0"], st["launches_k0"], 4 * st["k0_text_bytes"] + 42 * st["k0_rows"] + 4 * st["k0_ops"],
       f"{st['k0_text_bytes']} text bytes x 4 passes + 42 B x {st['k0_rows']} rows + 4 B x {st['k0_ops']} CIGAR runs")
-    k("k1_compact_lr + k1_pack", st["ms_k1"], st["launches_k1"], 44 * st["k1_hits"] + 8 * int(sz[0].value),
+    k("k1_filter + k1_cigar_totals + k1_tail + k1_pack", st["ms_k1"], st["launches_k1"], 44 * st["k1_hits"] + 8 * int(sz[0].value),
       f"44 B x {st['k1_hits']} hits + 8 B x {int(sz[0].value)} contigs (SURVEY 8d)")
     k("k2_* edge table", st["ms_k2"], st["launches_k2"], 52 * st["k2_pairs"], f"52 B x {st['k2_pairs']} adjacent pairs (SURVEY 8d)")
     k("k4_edge_coords", st["ms_k4"], st["launches_k4"], 124 * st["k4_supports"] + 4 * st["k4_runs"],
