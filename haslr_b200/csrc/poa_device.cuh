@@ -642,6 +642,9 @@ __device__ __forceinline__ uint32_t ldg_u32(unsigned long long base, uint32_t in
 // parked copy (two ranks back, ~85 % of such rows) or from the slot, and are folded into A in place - no second row of
 // registers. The body is one small code path on purpose: the kernel is instruction-cache bound otherwise, and a spill
 // reload in this loop costs an L2 round trip.
+#ifndef HGPU_FILL16_BCO_STORE
+#define HGPU_FILL16_BCO_STORE 1   // +2.5 % on config 3 (1,682 -> 1,725 GCUPS at 50k edges, profiles/r2I_shallow_bco_ab.log)
+#endif
 struct Row16State {
     uint32_t pf_lane;        // shared address of this lane's 16 bytes of prof[0][0]: prof[code][half][lane][4 words]
     uint32_t frame;          // shared address of the FillFrame16; parked row r is at frame + 128 + (r & 1) * 1024 as [half][lane][4 words]
@@ -825,10 +828,19 @@ __device__ __forceinline__ void row16(uint32_t (&A)[8], Row16State& S, uint32_t 
     stg_cs_v4(S.dst, A[0], A[1], A[2], A[3]);
     stg_cs_v4_512(S.dst, A[4], A[5], A[6], A[7]);
     S.dst += S.row_bytes;
+#if HGPU_FILL16_BCO_STORE
+    // lane 31 stores the row's boundary for the next stripe itself (as the REL fill does, poa_fill_rel.cuh) instead of shuffling it
+    // into a batch register that is stored every 32 rows
+    if (S.has_next && lane == 31) {
+        const unsigned long long bc = lds_u64(S.frame + FRAME16(bc_cur));
+        asm volatile("st.global.u32 [%0], %1;" :: "l"(bc + 4ull * i), "r"((uint32_t)(((int32_t)A[7] >> 16) + (REL ? row_base : 0))) : "memory");
+    }
+#else
     if (S.has_next) {
         const uint32_t last = __shfl_sync(FULL, A[7], 31);
         if (lane == q) S.bco = (uint32_t)(((int32_t)last >> 16) + (REL ? row_base : 0));
     }
+#endif
 }
 
 // does the rank with record m0 read the row two ranks back? (class 3 walks the CSR: assume yes)
@@ -980,10 +992,12 @@ __device__ __noinline__ bool dp_fill16(const uint32_t* meta0, const uint32_t* pr
                 asm volatile("st.global.u32 [%0], %1;" :: "l"(bp + 4ull * (rr + 1)), "r"(S.bcx) : "memory");
             }
             if (REL && !S.has_prev) __syncwarp();                     // later rows read these through other lanes' loads
+#if !HGPU_FILL16_BCO_STORE
             if (S.has_next && lane < nb) {
                 const unsigned long long bc = lds_u64(S.frame + FRAME16(bc_cur));
                 asm volatile("st.global.u32 [%0], %1;" :: "l"(bc + 4ull * (rr + 1)), "r"(S.bco) : "memory");
             }
+#endif
             if (TEAM) team_publish(vprog, trank, s * (Vs + 1) + ((r0 + 32 < Vs) ? r0 + 32 : Vs) + 1, lane);
         }
         __syncwarp();
