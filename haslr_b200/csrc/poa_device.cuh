@@ -178,7 +178,12 @@ static constexpr int DP_SMEM_PER_WARP = 6272;  // int16 fill: profile 4 KB + fra
 #define HGPU_RING_DEEP 8
 #endif
 static constexpr int DP_RING_DEEP = HGPU_RING_DEEP;
-static constexpr int DP_SMEM_PER_WARP_DEEP = 4096 + 128 + DP_RING_DEEP * 1024;
+#ifndef HGPU_REL_SMEM_BASES
+#define HGPU_REL_SMEM_BASES 1       // the REL fill keeps the row bases of the current and the previous batch (64 words) and the batch's plan words (32) in
+                                    // shared memory instead of batch registers read through shuffles: poa_fill_rel.cuh
+#endif
+static constexpr int REL_BASES_BYTES = HGPU_REL_SMEM_BASES ? 64 * 4 + 32 * 4 : 0;
+static constexpr int DP_SMEM_PER_WARP_DEEP = 4096 + 128 + DP_RING_DEEP * 1024 + REL_BASES_BYTES;
 static constexpr int DP_WARPS_PER_BLOCK = 4;
 
 // Cell encodings of a stored score matrix. ABS16: int16 Hhat + bias, when the whole range 13(L+1) + 8(V+2) fits.

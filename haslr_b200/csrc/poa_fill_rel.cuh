@@ -102,6 +102,11 @@ __device__ __noinline__ void w_build_tbp(const GraphView& g, uint32_t* tbp, int 
     __syncwarp();
 }
 
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+// shared address of the base of row `row` of the current stripe (rows of this batch and the one before: 64 words behind the ring)
+#define REL_BASE_ADDR(S, row) ((S).frame + (uint32_t)(FILL16_PARKED + REL_RING * 1024) + (((row) & 63u) << 2))
+#define REL_PLAN_ADDR(S, q) ((S).frame + (uint32_t)(FILL16_PARKED + REL_RING * 1024 + 256) + ((uint32_t)(q) << 2))
+
 struct RelFrame {                                         // cold per-alignment state, in the warp's shared memory behind the profile
     unsigned long long meta0, pred_off, pred_rank, plan, seq, H, bases;
     uint32_t V, L, NS; int32_t sm, sx, pad;
@@ -169,10 +174,14 @@ __device__ __forceinline__ void row_rel(uint32_t (&A)[8], RelState& S, uint32_t 
     const uint32_t blw = (uint32_t)(S.has_prev ? 0 : F::G::NEGV) << 16;   // the cell left of the stripe in a row's own frame: its base, or nothing
     uint32_t t[8];
     // base (int32 Hhat) of the row `dist` ranks back, dist <= 8: lane q - dist of this batch's register, or of the previous batch's
+#if HGPU_REL_SMEM_BASES
+    auto base_near = [&](uint32_t dist) -> int { return (int)lds_u32v(REL_BASE_ADDR(S, i - dist)); };     // one broadcast load, no shuffle
+#else
     auto base_near = [&](uint32_t dist) -> int {
         const int ql = q - (int)dist;
         return __shfl_sync(FULL, (int)(ql >= 0 ? S.b : S.bprev), ql & 31);
     };
+#endif
     if ((plan & PLAN_SLOW) == 0) {
         const uint32_t np = plan_np(plan);
         if (!S.has_prev) {                                                // stripe 0: base = column 0 = gap + best predecessor base
@@ -180,7 +189,11 @@ __device__ __forceinline__ void row_rel(uint32_t (&A)[8], RelState& S, uint32_t 
             uint32_t dd = plan;
             for (uint32_t x = 0; x < np; ++x, dd >>= 3) best = max(best, base_near((dd & 7u) + 1u));
             bi = best + gap;
+#if HGPU_REL_SMEM_BASES
+            sts_u32(REL_BASE_ADDR(S, i), (uint32_t)bi);
+#else
             if (lane == q) S.b = (uint32_t)bi;
+#endif
         }
         // the first predecessor initialises the row: the previous rank (row i-1, still in registers) if it is one of them
         uint32_t dd = plan;
@@ -227,15 +240,23 @@ __device__ __forceinline__ void row_rel(uint32_t (&A)[8], RelState& S, uint32_t 
         auto dist_of = [&](uint32_t x) -> uint32_t { return npr == 0 ? i : i - (ldg_u32(prank, cs + x) + 1); };
         auto base_any = [&](uint32_t dist) -> int {
             const int ql = q - (int)dist;
+#if HGPU_REL_SMEM_BASES
+            if (ql >= -32) return (int)lds_u32v(REL_BASE_ADDR(S, i - dist));
+#else
             if (ql >= 0) return __shfl_sync(FULL, (int)S.b, ql);
             if (ql >= -32) return __shfl_sync(FULL, (int)S.bprev, ql + 32);
+#endif
             return (int)ldg_u32(bases, i - dist);
         };
         if (!S.has_prev) {
             int best = INT32_MIN;
             for (uint32_t x = 0; x < np; ++x) best = max(best, base_any(dist_of(x)));
             bi = best + gap;
+#if HGPU_REL_SMEM_BASES
+            sts_u32(REL_BASE_ADDR(S, i), (uint32_t)bi);
+#else
             if (lane == q) S.b = (uint32_t)bi;
+#endif
         }
 #pragma unroll 1
         for (uint32_t x = 0; x < np; ++x) {
@@ -353,6 +374,9 @@ __device__ __forceinline__ bool rel_stripe(RelState& S, uint32_t* prof, RelFrame
     if (s == 0 && lane == 0) stg_u32(b_cur, 0u);
     if (TEAM) team_publish(ts.vprog, ts.pub_idx, ts.pub_base + 1u, lane);
     S.b = 0u;                                                          // "previous batch" of the first batch: row 0 (base 0) in lane 31
+#if HGPU_REL_SMEM_BASES
+    sts_u32(REL_BASE_ADDR(S, (uint32_t)lane), 0u); sts_u32(REL_BASE_ADDR(S, (uint32_t)lane + 32u), 0u);   // row 0: base 0
+#endif
     const unsigned long long plan = lds_u64(S.frame + RFRAME(plan));
     uint32_t npl = 0;
     if ((uint32_t)lane < Vs) npl = ldg_u32(plan, lane);
@@ -368,15 +392,31 @@ __device__ __forceinline__ bool rel_stripe(RelState& S, uint32_t* prof, RelFrame
                 if (!team_wait(ts.vprog, ts.wait_idx, ts.wait_base + need_rows, lane)) sync_ok = false;
             }
             S.b = (rr < Vs) ? ldg_u32(b_cur, rr + 1) : 0u;
+#if HGPU_REL_SMEM_BASES
+            sts_u32(REL_BASE_ADDR(S, rr + 1u), S.b);
+#endif
         }
+#if HGPU_REL_SMEM_BASES
+        sts_u32(REL_PLAN_ADDR(S, lane), mpl);
+        __syncwarp();
+#endif
         const int nb = (Vs - r0) < 32u ? (int)(Vs - r0) : 32;
 #pragma unroll 1
         for (int q = 0; q < nb; ++q) {
+#if HGPU_REL_SMEM_BASES
+            const uint32_t pl = lds_u32v(REL_PLAN_ADDR(S, q));
+            const int bi = (int)lds_u32v(REL_BASE_ADDR(S, r0 + (uint32_t)q + 1u));   // stripe 0: replaced inside the row
+#else
             const uint32_t pl = __shfl_sync(FULL, mpl, q);
             const int bi = __shfl_sync(FULL, (int)S.b, q);             // stripe 0: replaced inside the row
+#endif
             row_rel(A, S, pl, bi, q, r0 + q + 1);
         }
+#if HGPU_REL_SMEM_BASES
+        if (s == 0 && lane < nb) stg_u32(b_cur + 4ull * (rr + 1), lds_u32v(REL_BASE_ADDR(S, rr + 1u)));
+#else
         if (s == 0 && lane < nb) stg_u32(b_cur + 4ull * (rr + 1), S.b);
+#endif
         if (s == 0) __syncwarp();                                      // later generic rows read these through other lanes' loads
 #if !HGPU_REL_BCO_STORE
         if (S.has_next && lane < nb) stg_u32(b_next + 4ull * (rr + 1), S.bco);
