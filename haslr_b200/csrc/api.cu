@@ -3,7 +3,7 @@
 
 #include "common.cuh"
 
-extern "C" int hgpu_abi_version(void) { return 3; }   // 3: device-resident stages (hgpu_hits_group, *_dev), hgpu_stage_stats / hgpu_set_timing
+extern "C" int hgpu_abi_version(void) { return 4; }   // 3: device-resident stages (hgpu_hits_group, *_dev), hgpu_stage_stats / hgpu_set_timing; 4: hgpu_host_staging
 
 extern "C" const char* hgpu_strerror(int code) {
     switch (code) {
@@ -49,12 +49,28 @@ extern "C" void hgpu_destroy(hgpu_t* ctx) {
     k12_state_destroy(ctx->k12);
     coord_state_destroy(ctx->coords);
     paf_state_destroy(ctx->paf);
+    for (void* p : ctx->staging) if (p) cudaFreeHost(p);
     delete ctx;
 }
 
 extern "C" int hgpu_set_stream(hgpu_t* ctx, void* cuda_stream) {
     if (!ctx) return HGPU_E_INVALID;
     ctx->stream = (cudaStream_t)cuda_stream;
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_host_staging(hgpu_t* ctx, uint32_t which, uint64_t bytes, void** out) {
+    if (!ctx || !out || which > 1) return HGPU_E_INVALID;
+    *out = nullptr;
+    if (ctx->staging_bytes[which] < bytes || !ctx->staging[which]) {
+        HGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+        if (ctx->staging[which]) { HGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFreeHost(ctx->staging[which]); ctx->staging[which] = nullptr; ctx->staging_bytes[which] = 0; }
+        const uint64_t want = bytes + bytes / 8 + 4096;      // head room: the next batch of a similar size reuses the buffer
+        void* p = nullptr;
+        HGPU_CUDA(ctx, cudaHostAlloc(&p, want, cudaHostAllocDefault));
+        ctx->staging[which] = p; ctx->staging_bytes[which] = want;
+    }
+    *out = ctx->staging[which];
     return HGPU_OK;
 }
 

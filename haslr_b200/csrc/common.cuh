@@ -52,6 +52,8 @@ struct hgpu_ctx {
     K12State* k12 = nullptr;
     CoordState* coords = nullptr;
     PafState* paf = nullptr;
+    void* staging[2] = {nullptr, nullptr};     // page-locked host buffers lent to the caller (hgpu_host_staging)
+    uint64_t staging_bytes[2] = {0, 0};
 };
 
 #define HGPU_CUDA(ctx, expr)                                                                         \

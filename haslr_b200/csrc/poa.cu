@@ -51,6 +51,12 @@ struct PoaState {
     uint32_t cfg_deep_min_reads = 10; // edges with at least this many supporting reads run in k_poa_edges_deep (HGPU_DEEP_MIN_READS)
     int cfg_force = 0;                // HGPU_FORCE_MODE: 1 = every alignment in int32, 2 = every alignment in REL16 (tests)
     int cfg_pool = 1;                 // HGPU_POOL=0: deep edges in the warp-per-edge / block-per-edge kernels instead of k_poa_pool (A/B runs, tests)
+    double cfg_pool_chain = 40.0;     // HGPU_POOL_CHAIN: a row of an edge's serial chain (fill + traceback + graph update + sort, one after the other) takes as long
+                                      // as this many row-stripe units of a busy block (config 2: 1.0 us against 25 ns); 0 = no edge is protected
+    double cfg_pool_penalty = 0.8;    // HGPU_POOL_PENALTY: the block that gets a protected edge is dealt this share of a block's work less
+    double cfg_pool_prot = 0.65;      // HGPU_POOL_PROT: an edge is protected when its chain alone is more than this share of the kernel's expected time (on a busy
+                                      // block it would end with or after everything else); config 2, (prot, penalty) -> K3: off 341-343 ms, (0.72, 0.5) 334,
+                                      // (0.72, 0.8) 331, (0.65, 0.5) 329 ms: profiles/r2L_protected_edges.log
     uint32_t cfg_pool_ctx = 0;        // HGPU_POOL_CTX: contexts (edges in flight) per pool block, 0 = by the stripes per alignment of the class
     int verbose = 0;                  // HGPU_VERBOSE=1: pass / class plan and per-launch device time on stderr; 2: + when k_poa_pool finished which edge
     DevBuf<unsigned long long> edge_clk;
@@ -94,6 +100,9 @@ static PoaState* poa_state(hgpu_t* ctx) {
         if (const char* e = getenv("HGPU_FORCE_MODE")) ctx->poa->cfg_force = atoi(e);
         if (const char* e = getenv("HGPU_DEEP_MIN_READS")) ctx->poa->cfg_deep_min_reads = (uint32_t)atoi(e);
         if (const char* e = getenv("HGPU_POOL")) ctx->poa->cfg_pool = atoi(e);
+        if (const char* e = getenv("HGPU_POOL_CHAIN")) ctx->poa->cfg_pool_chain = std::max(0.0, atof(e));
+        if (const char* e = getenv("HGPU_POOL_PENALTY")) ctx->poa->cfg_pool_penalty = std::max(0.0, atof(e));
+        if (const char* e = getenv("HGPU_POOL_PROT")) ctx->poa->cfg_pool_prot = std::max(0.01, atof(e));
         if (const char* e = getenv("HGPU_POOL_CTX")) ctx->poa->cfg_pool_ctx = (uint32_t)std::max(0, std::min((int)POOL_MAX_CTX, atoi(e)));
     }
     return ctx->poa;
@@ -121,6 +130,8 @@ struct EdgeEst {
     double cells;        // DP cells (estimate)
     double work;         // time estimate in "row-stripe units": per alignment (V + 1) x (stripes + POOL_GRAPH_ROWS): the fill computes whole
                          // 512-column stripes whatever the gap is, and the serial graph work per node costs about as much as three of them
+    double chain;        // rows of the edge's serial chain, sum over its alignments of (V + 1): what one warp after the other has to walk, however
+                         // many warps the stripes of an alignment spread over
     uint32_t lmax;       // longest segment
     bool deep;           // many supporting reads: the graph gets several times wider than the gap (k_poa_edges_deep)
 };
@@ -129,7 +140,7 @@ struct EdgeEst {
 // |V| grows ~ L * (ins + sub) per read). growth >= 1 means the worst case (every base a new node).
 static constexpr double POOL_GRAPH_ROWS = 3.0;
 void estimate_edge(const uint32_t* len, uint32_t R, double growth, const DpScores& sc, int force, EdgeEst* out) {
-    double V = len[0], cells = 0, work = 0;
+    double V = len[0], cells = 0, work = 0, chain = 0;
     uint64_t slot = 0;
     uint32_t lmax = len[0];
     for (uint32_t k = 1; k < R; ++k) {
@@ -139,6 +150,7 @@ void estimate_edge(const uint32_t* len, uint32_t R, double growth, const DpScore
         slot = std::max(slot, dp_slot_bytes(Vi, len[k], mode));
         cells += (V + 1.0) * (len[k] + 1.0);
         work += (V + 1.0) * ((double)Geo<DP_NW16, true>::stripes(len[k]) + POOL_GRAPH_ROWS);
+        chain += V + 1.0;
         // overhang beyond the graph's current span also becomes new nodes
         double over = len[k] > V ? (double)len[k] - V : 0.0;
         V += growth >= 1.0 ? (double)len[k] : std::min<double>(len[k], growth * len[k] + over + 8.0);
@@ -149,6 +161,7 @@ void estimate_edge(const uint32_t* len, uint32_t R, double growth, const DpScore
     out->slot = slot + 4096;
     out->cells = cells;
     out->work = work;
+    out->chain = chain;
     out->lmax = lmax;
 }
 }  // namespace
@@ -247,7 +260,7 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
             uint32_t R = e_off[e + 1] - e_off[e];
             est[i].edge = e;
             est[i].deep = R >= S->cfg_deep_min_reads;
-            if (R == 0) { est[i].ncap = 64; est[i].slot = 4096; est[i].cells = 0; est[i].work = 0; est[i].lmax = 0; continue; }
+            if (R == 0) { est[i].ncap = 64; est[i].slot = 4096; est[i].cells = 0; est[i].work = 0; est[i].chain = 0; est[i].lmax = 0; continue; }
             estimate_edge(seg_len.data() + e_off[e], R, growth, sc, opt.force_i32, &est[i]);
             uint64_t sum = 0; uint32_t lmax = 0;
             for (uint32_t k = 0; k < R; ++k) { sum += seg_len[e_off[e] + k]; lmax = std::max(lmax, seg_len[e_off[e] + k]); }
@@ -488,6 +501,16 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
                     for (size_t k = 0; k < K; ++k)
                         for (uint32_t x = 0; x < dealt[k]; ++x) cand.push_back({est[classes[pc[k]].a + x].work, (uint32_t)k, classes[pc[k]].a + x});
                     std::sort(cand.begin(), cand.end(), [](const Cand& x, const Cand& y) { return x.work != y.work ? x.work > y.work : x.q < y.q; });
+                    // Protected edges. The alignments of one edge are a serial chain (fill, traceback, graph update, sort, next fill); on a
+                    // block that is as busy as the others the chain of the heaviest edge of config 2 takes 341 ms (230 ms alone) while the
+                    // rest of the kernel is done after 316 ms. An edge whose chain alone is most of the kernel's expected time (cfg_pool_prot)
+                    // charges its block with `penalty` x a block's share of the work on top of its own, so the deal gives that block the
+                    // lightest first edges of every class: its warps are free for the chain long before the others finish. Few edges
+                    // qualify (config 2: 5 of 6,033); protecting every deep edge only moves work to the other blocks (37 blocks charged:
+                    // the tail went and everything else ended 26 ms later, profiles/r2K_protected_edges.log). What is left of the tail is
+                    // the chain itself: 29 alignments of a graph that grows to ~9,000 nodes, ~11 ms each on an almost empty block.
+                    const double block_share = tot_work / blocks;
+                    uint32_t n_prot = 0;
                     std::vector<double> block_work(blocks, 0.0);
                     for (const Cand& cd : cand) {
                         uint32_t bb = blocks;
@@ -497,11 +520,15 @@ static int poa_run(hgpu_t* ctx, const uint8_t* d_bases, const uint64_t* seg_off,
                         ctx_first[free_pos[cd.k][bb].back()] = est[cd.q].edge;
                         free_pos[cd.k][bb].pop_back();
                         block_work[bb] += cd.work;
+                        if (S->cfg_pool_chain > 0 && blocks > 1 && n_prot < blocks / 8 && est[cd.q].chain * S->cfg_pool_chain > S->cfg_pool_prot * block_share) {
+                            block_work[bb] += S->cfg_pool_penalty * block_share;
+                            ++n_prot;
+                        }
                     }
                     if (S->verbose) {
                         double lo = 1e300, hi = 0, sum = 0;
                         for (double w : block_work) { lo = std::min(lo, w); hi = std::max(hi, w); sum += w; }
-                        fprintf(stderr, "[poa] first edges dealt: estimated work per block min %.3g mean %.3g max %.3g\n", lo, sum / blocks, hi);
+                        fprintf(stderr, "[poa] first edges dealt: estimated work per block min %.3g mean %.3g max %.3g (incl. the charge of %u protected edges)\n", lo, sum / blocks, hi, n_prot);
                     }
                 }
                 PoolArgs pa{};

@@ -15,7 +15,7 @@ EXPORTS = (
     "hgpu_launch_count", "hgpu_compact_lr", "hgpu_backbone_edges", "hgpu_poa_batch", "hgpu_poa_batch_dev",
     "hgpu_poa_fetch", "hgpu_poa_get_stats", "hgpu_poa_set_timing", "hgpu_poa_configure", "hgpu_poa_debug", "hgpu_edge_coords",
     "hgpu_paf_tokenize", "hgpu_paf_fetch", "hgpu_hits_group", "hgpu_compact_lr_dev", "hgpu_backbone_edges_dev", "hgpu_edge_coords_dev",
-    "hgpu_get_stage_stats", "hgpu_set_timing",
+    "hgpu_get_stage_stats", "hgpu_set_timing", "hgpu_host_staging",
 )
 
 
@@ -86,6 +86,7 @@ def load():
     L.hgpu_last_error.restype = C.c_char_p; L.hgpu_last_error.argtypes = [C.c_void_p]
     L.hgpu_abi_version.restype = C.c_int; L.hgpu_abi_version.argtypes = []
     L.hgpu_launch_count.restype = C.c_uint64; L.hgpu_launch_count.argtypes = [C.c_void_p]
+    L.hgpu_host_staging.restype = C.c_int; L.hgpu_host_staging.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_void_p)]
     L.hgpu_compact_lr.restype = C.c_int
     L.hgpu_compact_lr.argtypes = [C.c_void_p, C.POINTER(HitsT), u32p, C.c_uint32, f64p, C.c_uint32, C.POINTER(K1Params),
                                   C.c_void_p, u32p, u64p]
@@ -142,6 +143,12 @@ class Context:
 
     def launch_count(self):
         return int(self.L.hgpu_launch_count(self.h))
+
+    def host_staging(self, which, nbytes):
+        """Address of the context's page-locked staging buffer `which` (0 / 1), at least nbytes long (hgpu_host_staging)."""
+        p = C.c_void_p()
+        self._check(self.L.hgpu_host_staging(self.h, which, nbytes, C.byref(p)))
+        return p.value
 
     # ---- (iii) batched POA -------------------------------------------------------------------------------
     def poa_batch(self, bases, seg_off, edge_seg_off, match=5, mismatch=-4, gap=-8, band=0, out=None):

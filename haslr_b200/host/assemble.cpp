@@ -202,7 +202,9 @@ int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& 
     // per-GPU segment tables; every segment is copied (or reverse-complemented) ONCE, from the read into its GPU's buffer
     // the segment bytes live in uninitialised storage: a std::string would zero-fill gigabytes on one thread before the gather threads
     // touch (and page in) their own parts
-    struct Shard { std::unique_ptr<char[]> b; uint64_t n = 0; std::vector<uint64_t> so{0}; std::vector<uint32_t> eso{0}; std::vector<uint32_t> seg; };
+    // ... and that storage is the context's page-locked staging buffer, so the upload is one DMA at link speed (a pageable source
+    // goes through the driver's bounce buffer: 25-50 ms for config 2's 133 MB against 3 ms); plain memory if it cannot be had
+    struct Shard { char* b = nullptr; std::unique_ptr<char[]> own; uint64_t n = 0; std::vector<uint64_t> so{0}; std::vector<uint32_t> eso{0}; std::vector<uint32_t> seg; };
     std::vector<Shard> sh(G);
     std::vector<std::pair<uint32_t, uint64_t>> seg_home(seg_src.size());      // segment -> (gpu, offset in its buffer), for the log
     for (size_t gi = 0; gi < G; ++gi) {
@@ -216,14 +218,16 @@ int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& 
             S.eso.push_back((uint32_t)(S.so.size() - 1));
         }
         S.n = S.so.back();
-        S.b.reset(new char[S.n + 64]);
+        void* pinned = nullptr;
+        if (!shard[gi].empty() && hgpu_host_staging(ctxs[gi], 0, S.n + 64, &pinned) == HGPU_OK) S.b = (char*)pinned;
+        else { S.own.reset(new char[S.n + 64]); S.b = S.own.get(); }
     }
     {   // the copies are independent: all host threads
         const size_t n_seg = seg_src.size();
         const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(threads, n_seg / 256 + 1));
         auto work = [&](unsigned t) {
             for (size_t q = n_seg * t / nt; q < n_seg * (t + 1) / nt; ++q)
-                write_segment(reads, *seg_src[q], (uint32_t)(seg_off[q + 1] - seg_off[q]), sh[seg_home[q].first].b.get() + seg_home[q].second);
+                write_segment(reads, *seg_src[q], (uint32_t)(seg_off[q + 1] - seg_off[q]), sh[seg_home[q].first].b + seg_home[q].second);
         };
         std::vector<std::thread> th;
         for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
@@ -242,7 +246,7 @@ int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& 
         std::vector<uint64_t> off(my.size() + 1);
         std::vector<uint32_t> status(my.size());
         hgpu_poa_set_timing(ctxs[gi], 1);      // one event pair per scheduling pass, read after the pass's own synchronisation
-        int r = hgpu_poa_batch(ctxs[gi], (const uint8_t*)S.b.get(), S.so.data(), S.eso.data(), (uint32_t)my.size(), 5, -4, -8, 0,   // Assemble.cpp:8-11
+        int r = hgpu_poa_batch(ctxs[gi], (const uint8_t*)S.b, S.so.data(), S.eso.data(), (uint32_t)my.size(), 5, -4, -8, 0,   // Assemble.cpp:8-11
                                out.get(), out_cap, off.data(), status.data());
         if (r != HGPU_OK) { fprintf(stderr, "[ERROR] hgpu_poa_batch (gpu %zu): %s\n", gi, hgpu_last_error(ctxs[gi])); rc[gi] = r; return; }
         hgpu_poa_stats st;
@@ -274,16 +278,29 @@ int call_consensus(Graph& g, const std::vector<EdgeRef>& edges, const SeqStore& 
             for (const CnsSupp& c : e1[e]->cns_supp) {
                 fprintf(fp, "        [debug] lr_id:%u lr_len:%u region_start:%u region_end:%u subseq_len:%u\n", c.lr_id, reads.len(c.lr_id), c.spos, c.epos, c.epos - c.spos + 1);
                 fprintf(fp, ">%u %c %u %u %u\n", c.lr_id, sgn(c.lr_strand), c.spos, c.epos, c.epos - c.spos + 1);
-                fwrite(sh[seg_home[s].first].b.get() + seg_home[s].second, 1, seg_off[s + 1] - seg_off[s], fp);
+                fwrite(sh[seg_home[s].first].b + seg_home[s].second, 1, seg_off[s + 1] - seg_off[s], fp);
                 fputc('\n', fp);
                 ++s;
             }
             fprintf(fp, ">CONSENSUS\n%s\n", cons[e].c_str());
         }
-        e1[e]->cns_seq = cons[e];
-        e2[e]->cns_seq = revcomp(cons[e]);       // empty stays empty (Assemble.cpp:545-556)
     }
     if (fp) fclose(fp);
+    {   // edge and twin get the string and its reverse complement; every undirected edge once, so the edges are independent: all host threads
+        const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(threads, n / 64 + 1));
+        auto work = [&](unsigned t) {
+            for (size_t e = n * t / nt; e < n * (t + 1) / nt; ++e) {
+                std::string rc = revcomp(cons[e]);   // empty stays empty (Assemble.cpp:545-556)
+                e1[e]->cns_seq = std::move(cons[e]);
+                e2[e]->cns_seq = std::move(rc);      // after the edge's own, as in the reference (an edge that is its own twin keeps the reverse complement)
+            }
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+    }
+    fprintf(stderr, "       consensus strings scattered to the graph in %.3f s\n", now_s() - t2);
     return 0;
 }
 

@@ -105,6 +105,10 @@ struct PathInputs {
     ContigStore contigs;
     SeqStore reads;
     std::vector<char> paf_text;
+    // where the text is read from: paf_text, unless the caller moved it into page-locked memory (haslr_path_run does, once)
+    const char* paf_ptr = nullptr; size_t paf_len = 0;
+    const char* paf_data() const { return paf_ptr ? paf_ptr : paf_text.data(); }
+    size_t paf_size() const { return paf_ptr ? paf_len : paf_text.size(); }
 };
 struct PathTimes { double tokenize = 0, k1 = 0, k2 = 0, clean = 0, coords = 0, poa = 0, total = 0; };      // wall seconds
 struct PathResult {

@@ -33,9 +33,16 @@ void        hgpu_destroy(hgpu_t* ctx);
 int         hgpu_set_stream(hgpu_t* ctx, void* cuda_stream /* cudaStream_t, NULL = default */);
 const char* hgpu_strerror(int code);
 const char* hgpu_last_error(const hgpu_t* ctx);
-int         hgpu_abi_version(void);   /* 3 since the device-resident stages (hgpu_hits_group, *_dev) and hgpu_stage_stats were added */
+int         hgpu_abi_version(void);   /* 3 since the device-resident stages (hgpu_hits_group, *_dev) and hgpu_stage_stats were added; 4: hgpu_host_staging */
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t    hgpu_launch_count(const hgpu_t* ctx);
+/* Page-locked host staging buffer `which` (0 or 1) of the context, at least `bytes` long: owned by the context, grown on demand,
+ * kept until hgpu_destroy; growing it invalidates the pointer returned before. A host buffer handed to a non-_dev call is
+ * copied by DMA at link speed when it lies in such a buffer (from pageable memory the driver stages the copy through a
+ * bounce buffer at a fifth of that). The reference has no counterpart: its segments are std::string::substr copies made per
+ * edge inside the thread that aligns them (Assemble.cpp:529-532); here the host gathers all segments of a batch once,
+ * straight into this buffer (host/assemble.cpp call_consensus). */
+int         hgpu_host_staging(hgpu_t* ctx, uint32_t which, uint64_t bytes, void** out);
 
 /* Per-stage figures of the most recent call of each stage: CUDA-event time of the stage's kernels (copies excluded; only
  * when timing is on, hgpu_set_timing), kernel launches, the units the stage processed (what the roofline figures of

@@ -129,6 +129,27 @@ def test_empty_batch(ctx):
     assert len(cons) == 0 and off.tolist() == [0] and len(status) == 0
 
 
+def test_bases_from_the_staging_buffer(ctx):
+    """hgpu_host_staging: the context's page-locked buffers. Same result whether the bases come from pageable memory or from the
+    staging buffer; asking for less returns the same buffer, asking for more grows it; a bad index is refused."""
+    import ctypes
+    import haslr_b200
+    bases, seg_off, eso, _ = synth.poa_batch(29, 48, depth=6, length=500, length_jitter=0.3)
+    cons, off, status = ctx.poa_batch(bases, seg_off, eso)
+    p = ctx.host_staging(0, bases.nbytes)
+    assert p and ctx.host_staging(0, bases.nbytes // 2) == p
+    ctypes.memmove(p, bases.ctypes.data, bases.nbytes)
+    pinned = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(bases.nbytes,))
+    cons2, off2, status2 = ctx.poa_batch(pinned, seg_off, eso)
+    assert np.array_equal(off, off2) and np.array_equal(status, status2) and cons.tobytes() == cons2.tobytes()
+    q = ctx.host_staging(1, 1 << 20)
+    assert q and q != p
+    big = ctx.host_staging(0, bases.nbytes * 4)
+    ctypes.memset(big, 0, bases.nbytes * 4)
+    with pytest.raises(haslr_b200.HgpuError):
+        ctx.host_staging(2, 16)
+
+
 def test_other_scores(ctx, oracle):
     bases, seg_off, eso, _ = synth.poa_batch(17, 16, depth=5, length=300, length_jitter=0.2)
     for scores in ((3, -5, -4), (1, -1, -1), (2, -6, -2)):
