@@ -1,5 +1,6 @@
 // Context management of the C ABI (include/haslr_b200.h).
 #include <cstdlib>
+#include <string>
 
 #include "common.cuh"
 
@@ -67,7 +68,11 @@ extern "C" int hgpu_host_staging(hgpu_t* ctx, uint32_t which, uint64_t bytes, vo
         if (ctx->staging[which]) { HGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFreeHost(ctx->staging[which]); ctx->staging[which] = nullptr; ctx->staging_bytes[which] = 0; }
         const uint64_t want = bytes + bytes / 8 + 4096;      // head room: the next batch of a similar size reuses the buffer
         void* p = nullptr;
-        HGPU_CUDA(ctx, cudaHostAlloc(&p, want, cudaHostAllocDefault));
+        if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();                               // not sticky, but the next launch check must not find it: callers fall back to pageable memory
+            ctx->last_error = "hgpu_host_staging: cannot page-lock " + std::to_string(want) + " bytes";
+            return HGPU_E_NOMEM;
+        }
         ctx->staging[which] = p; ctx->staging_bytes[which] = want;
     }
     *out = ctx->staging[which];
