@@ -1905,6 +1905,10 @@ __device__ __noinline__ int w_toposort_chain(GraphView& g, uint8_t* wsm, int lan
     return okflag;
 }
 
+}  // namespace hgpu
+#include "poa_topo_claims.cuh"
+namespace hgpu {
+
 // ---------------------------------------------------------------------------------------------------------
 // w_consensus_scores: the rank-order pass of SPOA's heaviest bundle (g_consensus_scores), 32 ranks at a time.
 // The serial version is a chain of dependent global loads per node (rank -> node -> in-list -> edge -> score of the
@@ -2139,7 +2143,10 @@ __device__ __forceinline__ void poa_edges_body(const PoaArgs& a) {
                 if (probe == 3) { debug_stop = true; break; }
                 constexpr bool USE_TREC = RING > 2 || HGPU_SHALLOW_TREC;
                 if (USE_TREC) w_build_trec(gv, trec, lane);
-                if (!(USE_TREC ? w_toposort(gv, trec, wsm, lane) : w_toposort_chain(gv, wsm, lane))) {    // too large for the shared-memory bitmaps / deep DFS: serial
+                // deep graphs: the roots' walks side by side (poa_topo_claims.cuh); the batched walk when that declines
+                bool sorted = false;
+                if (HGPU_TOPO_CLAIMS && USE_TREC && (RING > 2 || HGPU_TOPO_CLAIMS_SHALLOW)) sorted = w_toposort_claims(gv, gs, trec, lane) != 0;
+                if (!sorted && !(USE_TREC ? w_toposort(gv, trec, wsm, lane) : w_toposort_chain(gv, wsm, lane))) {    // too large for the shared-memory bitmaps / deep DFS: serial
                     ust = ST_OK;
                     if (lane == 0 && !g_toposort(gv, gs)) ust = ST_TOPOSORT;
                     ust = __shfl_sync(FULL, ust, 0);
@@ -2282,7 +2289,7 @@ __global__ void __launch_bounds__(32 * TEAM, 512 / (32 * TEAM)) k_poa_edges_team
                             __syncwarp();
                         }
                         if (ust == ST_OK) w_build_trec(gv, trec, lane);
-                        if (ust == ST_OK && !w_toposort(gv, trec, wsm, lane)) {
+                        if (ust == ST_OK && !(HGPU_TOPO_CLAIMS && w_toposort_claims(gv, gs, trec, lane)) && !w_toposort(gv, trec, wsm, lane)) {
                             if (lane == 0 && !g_toposort(gv, gs)) ust = ST_TOPOSORT;
                             ust = __shfl_sync(FULL, ust, 0);
                             __syncwarp();

@@ -244,7 +244,7 @@ __device__ __noinline__ void pool_graph_task(const PoolArgs& pa, PoolEnv& E, Poo
             POOL_CLK(a, 4)
             if (ust == ST_OK) {
                 w_build_trec(gv, E.trec, lane);
-                if (!w_toposort(gv, E.trec, wsm, lane)) {
+                if (!(HGPU_TOPO_CLAIMS && w_toposort_claims(gv, E.gs, E.trec, lane)) && !w_toposort(gv, E.trec, wsm, lane)) {
                     if (lane == 0 && !g_toposort(gv, E.gs)) ust = ST_TOPOSORT;
                     ust = __shfl_sync(FULL, ust, 0);
                     __syncwarp();

@@ -94,7 +94,160 @@ bool align_scalar(GraphView& g, const uint8_t* seq, uint32_t L, int m, int x, in
     *g.aln_len = n;
     return true;
 }
+
+// The parallelisable form of the topological sort described in DESIGN.md section 7 (not shipped: checked here against the
+// serial walk on every graph the CPU tests build). (1) claim[u] = smallest node id that reaches u over in-edges and aligned
+// links: a min-propagation, swept until nothing changes (every sweep is independent per node: one lane per node on a GPU).
+// (2) Every node that claims itself is a root of SPOA's outer loop; its walk only ever enters nodes it claims (whatever an
+// earlier root reaches is emitted before it starts), so the walks touch disjoint node sets and could run one per lane.
+// (3) The emission lists are concatenated in root id order. Returns false if the order differs from g.rank2node.
+uint32_t g_claim_sweeps_max = 0, g_claim_roots = 0, g_claim_nodes = 0;
+bool toposort_by_claims_matches(const GraphView& g) {
+    const uint32_t N = *g.n_nodes;
+    std::vector<uint32_t> claim(N);
+    for (uint32_t v = 0; v < N; ++v) claim[v] = v;
+    uint32_t sweeps = 0;
+    for (bool changed = true; changed; ++sweeps) {
+        changed = false;
+        std::vector<uint32_t> next(claim);                                  // Jacobi sweep: what a parallel pass over all nodes computes
+        for (uint32_t v = 0; v < N; ++v) {
+            const uint32_t c = claim[v];
+            for (uint32_t x = g.in_head[v]; x != NIL; x = g.e_next_in[x]) if (next[g.e_begin[x]] > c) { next[g.e_begin[x]] = c; changed = true; }
+            for (int q = 0; q < 3; ++q) { const uint32_t o = g.aligned[3 * v + q]; if (o == NIL) break; if (next[o] > c) { next[o] = c; changed = true; } }
+        }
+        claim.swap(next);
+    }
+    g_claim_sweeps_max = std::max(g_claim_sweeps_max, sweeps);
+    std::vector<uint8_t> mark(N, 0), check(N, 1);
+    std::vector<uint32_t> order, stack;
+    order.reserve(N);
+    for (uint32_t i = 0; i < N; ++i) {
+        if (claim[i] != i) continue;                                        // reached by a smaller id: not a root
+        ++g_claim_roots;
+        // the walk of root i, looking only at its own nodes: anything claimed by a smaller root counts as emitted
+        auto done = [&](uint32_t u) { return claim[u] < i || mark[u] == 2; };
+        stack.assign(1, i);
+        while (!stack.empty()) {
+            const uint32_t v = stack.back();
+            bool valid = true;
+            if (mark[v] != 2) {
+                if (claim[v] != i) return false;                            // a walk left its own node set: the claim rule is wrong
+                for (uint32_t x = g.in_head[v]; x != NIL; x = g.e_next_in[x]) if (!done(g.e_begin[x])) { stack.push_back(g.e_begin[x]); valid = false; }
+                if (check[v])
+                    for (int q = 0; q < 3; ++q) {
+                        const uint32_t o = g.aligned[3 * v + q];
+                        if (o == NIL) break;
+                        if (!done(o)) { stack.push_back(o); check[o] = 0; valid = false; }
+                    }
+                if (!valid && mark[v] == 1) return false;
+                if (valid) {
+                    mark[v] = 2;
+                    if (check[v]) {
+                        order.push_back(v);
+                        for (int q = 0; q < 3; ++q) { const uint32_t o = g.aligned[3 * v + q]; if (o == NIL) break; order.push_back(o); }
+                    }
+                } else mark[v] = 1;
+            }
+            if (valid) stack.pop_back();
+        }
+    }
+    g_claim_nodes += N;
+    if (order.size() != N) return false;
+    for (uint32_t r = 0; r < N; ++r) if (order[r] != g.rank2node[r]) return false;
+    return true;
+}
+
+// The same sort laid out the way the CUDA function does it (haslr_b200/csrc/poa_topo_claims.cuh: w_toposort_claims): the
+// per-node records of w_build_trec (four in-edge tails, three aligned nodes, the fifth in-edge), the "only a dependency with a
+// larger id can be lowered" rule of the sweeps, roots that claim only themselves ranked by the scan alone, every walk on a
+// stack region of 5 words per claimed node at 5 x its first rank, the step guard. Lanes are run one after the other here.
+// Returns 1 ranks equal, 0 the function would have declined (the caller falls back), -1 ranks differ.
+uint32_t g_dev_declined = 0, g_dev_stack_peak_x100 = 0;
+int toposort_claims_device_layout(const GraphView& g) {
+    const uint32_t N = *g.n_nodes;
+    struct Rec { uint32_t p[4], a[3], more; };
+    std::vector<Rec> rec(N);
+    for (uint32_t v = 0; v < N; ++v) {
+        Rec r; for (auto& x : r.p) x = NIL; for (auto& x : r.a) x = NIL;
+        uint32_t x = g.in_head[v];
+        for (int q = 0; q < 4 && x != NIL; ++q) { r.p[q] = g.e_begin[x]; x = g.e_next_in[x]; }
+        r.more = x;
+        for (int q = 0; q < 3; ++q) { if (g.aligned[3 * v + q] == NIL) break; r.a[q] = g.aligned[3 * v + q]; }
+        rec[v] = r;
+    }
+    std::vector<uint32_t> claim(N), cnt(N, 0), base(N, 0), roots, r2n(N, NIL), stk(5 * (size_t)N + 8);
+    std::vector<uint8_t> mark(N, 0), check(N, 1);
+    for (uint32_t v = 0; v < N; ++v) claim[v] = v;
+    bool settled = false;
+    for (uint32_t sweep = 0; sweep < 256 && !settled; ++sweep) {
+        bool changed = false;
+        for (uint32_t v = 0; v < N; ++v) {
+            const uint32_t c = claim[v];
+            const uint32_t d[7] = {rec[v].p[0], rec[v].p[1], rec[v].p[2], rec[v].p[3], rec[v].a[0], rec[v].a[1], rec[v].a[2]};
+            for (int q = 0; q < 7; ++q) if (d[q] != NIL && d[q] > c && claim[d[q]] > c) { claim[d[q]] = c; changed = true; }
+            for (uint32_t x = rec[v].more; x != NIL; x = g.e_next_in[x]) { const uint32_t b = g.e_begin[x]; if (b > c && claim[b] > c) { claim[b] = c; changed = true; } }
+        }
+        settled = !changed;
+    }
+    if (!settled) { ++g_dev_declined; return 0; }
+    for (uint32_t u = 0; u < N; ++u) ++cnt[claim[u]];
+    uint32_t running = 0;
+    for (uint32_t i = 0; i < N; ++i) {
+        const uint32_t c = cnt[i];
+        if (c != 0) base[i] = running;
+        if (c == 1) r2n[running] = i;
+        if (c > 1) roots.push_back(i);
+        running += c;
+    }
+    if (running != N) { ++g_dev_declined; return 0; }
+    for (uint32_t i : roots) {
+        const uint32_t b = base[i], n_own = cnt[i], cap = 5 * n_own, limit = 64 * n_own + 64;
+        uint32_t* st = stk.data() + 5 * (size_t)b;
+        uint32_t sp = 1, k = 0, guard = 0, peak = 1;
+        st[0] = i;
+        bool ok = true;
+        while (sp > 0 && ok) {
+            if (++guard > limit) { ok = false; break; }
+            const uint32_t v = st[sp - 1];
+            if (mark[v] == 2) { --sp; continue; }
+            const Rec& r = rec[v];
+            const uint32_t d[7] = {r.p[0], r.p[1], r.p[2], r.p[3], r.a[0], r.a[1], r.a[2]};
+            const bool chk = check[v] != 0;
+            bool valid = true;
+            auto dep = [&](uint32_t u, bool aligned_link) {
+                const uint32_t cu = claim[u];
+                if (cu < i || mark[u] == 2) return;
+                if (cu != i || sp >= cap) { ok = false; return; }
+                st[sp++] = u; valid = false; peak = std::max(peak, sp);
+                if (aligned_link) check[u] = 0;
+            };
+            for (int q = 0; q < 4; ++q) if (d[q] != NIL) dep(d[q], false);
+            for (uint32_t x = r.more; x != NIL && ok; x = g.e_next_in[x]) dep(g.e_begin[x], false);
+            if (chk) for (int q = 4; q < 7; ++q) if (d[q] != NIL) dep(d[q], true);
+            if (!ok) break;
+            if (!valid) { if (mark[v] == 1) { ok = false; break; } mark[v] = 1; continue; }
+            mark[v] = 2;
+            if (chk) {
+                const uint32_t na = (d[4] != NIL) + (d[5] != NIL) + (d[6] != NIL);
+                if (k + 1 + na > n_own) { ok = false; break; }
+                r2n[b + k++] = v;
+                for (int q = 4; q < 7; ++q) if (d[q] != NIL) r2n[b + k++] = d[q];
+            }
+            --sp;
+        }
+        g_dev_stack_peak_x100 = std::max(g_dev_stack_peak_x100, 100 * peak / n_own);
+        if (!ok || k != n_own) { ++g_dev_declined; return 0; }
+    }
+    for (uint32_t r = 0; r < N; ++r) if (r2n[r] != g.rank2node[r]) return -1;
+    return 1;
+}
 }  // namespace
+
+extern "C" void graphtest_claim_device_stats(uint32_t* declined, uint32_t* stack_peak_x100) { *declined = g_dev_declined; *stack_peak_x100 = g_dev_stack_peak_x100; }
+
+extern "C" void graphtest_claim_stats(uint32_t* sweeps_max, uint32_t* roots, uint32_t* nodes) {
+    *sweeps_max = g_claim_sweeps_max; *roots = g_claim_roots; *nodes = g_claim_nodes;
+}
 
 // Returns consensus length (>= 0) or a negative error. Also exports the final graph in rank order.
 extern "C" int graphtest_poa(const uint8_t* bases, const uint64_t* seg_off, uint32_t n_segs, int m, int x, int gp,
@@ -118,6 +271,8 @@ extern "C" int graphtest_poa(const uint8_t* bases, const uint64_t* seg_off, uint
             if (!g_add_alignment(g, seq, L)) return -1;
         }
         if (!g_toposort(g, st.s)) return -3;
+        if (!toposort_by_claims_matches(g)) return -5;
+        if (toposort_claims_device_layout(g) < 0) return -6;
         g_build_meta(g);
     }
     *out_n_nodes = *g.n_nodes;
