@@ -83,3 +83,23 @@ def test_graph_code_edge_cases(gt, oracle):
         cons, off, _, _ = oracle.poa_batch(bases, seg_off, eso)
         got, _ = run_host(gt, bases, seg_off)
         assert got == cons.tobytes(), segs
+
+
+@pytest.mark.parametrize("seed,depth,length,err", [
+    (5, 28, 800, (0.04, 0.03, 0.02)),      # the config 2 edge shape, shortened
+    (8, 30, 1500, (0.10, 0.08, 0.06)),     # 24 % read error: wide graphs, long branches
+    (9, 6, 1500, (0.04, 0.03, 0.02)),      # config 3
+])
+def test_parallel_toposort_formulation_is_exact(gt, seed, depth, length, err):
+    """graphtest_poa re-derives every topological order of the run twice more - by the claim rule (smallest root id that reaches
+    a node, walks on disjoint node sets: -5 on a difference) and in the memory layout of the CUDA function w_toposort_claims
+    (-6) - and fails the call if either differs from SPOA's serial walk. The device layout must never have to decline, and its
+    walks must stay far inside their stack regions (5 words per claimed node)."""
+    gt.graphtest_claim_device_stats.argtypes = [u32p, u32p]
+    bases, seg_off, eso, _ = synth.poa_batch(seed, 2, depth=depth, length=length, err=err, length_jitter=0.1)
+    for e in range(len(eso) - 1):
+        run_host(gt, bases, seg_off[eso[e]: eso[e + 1] + 1])
+    declined, peak = C.c_uint32(), C.c_uint32()
+    gt.graphtest_claim_device_stats(C.byref(declined), C.byref(peak))
+    assert declined.value == 0
+    assert peak.value <= 400, f"a walk needed {peak.value / 100:.2f} stack words per claimed node"
